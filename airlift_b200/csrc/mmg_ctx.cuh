@@ -1,0 +1,102 @@
+// mmg_ctx.cuh -- internal: context, growable device / pinned buffers, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/mmg.h"
+#include "mmg_core.h"
+
+void mmg_set_error(const char *fmt, ...);
+
+#define MMG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	mmg_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return MMG_ECUDA; } } while (0)
+#define MMG_TRY(call) do { int r_ = (call); if (r_ != MMG_OK) return r_; } while (0)
+
+struct DevBuf {
+	void *p = nullptr; size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return MMG_OK;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess) { mmg_set_error("cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); p = nullptr; return MMG_ENOMEM; }
+		cap = want;
+		return MMG_OK;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <class T> T *as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+	void *p = nullptr; size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return MMG_OK;
+		if (p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMallocHost(&p, want);
+		if (e != cudaSuccess) { mmg_set_error("cudaMallocHost(%zu): %s", want, cudaGetErrorString(e)); p = nullptr; return MMG_ENOMEM; }
+		cap = want;
+		return MMG_OK;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+	template <class T> T *as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct mmg_idx_s {
+	int dev = 0;
+	int32_t w = 0, k = 0, is_hpc = 0, n_seq = 0;
+	uint64_t total_len = 0, n_slots = 0, n_pos = 0;
+	int64_t n_keys = 0;
+	int slot_shift = 0;
+	uint32_t *d_S = nullptr;
+	uint64_t *d_seq_off = nullptr;
+	uint32_t *d_seq_len = nullptr;
+	IdxSlot *d_slots = nullptr;
+	uint64_t *d_pos = nullptr;
+	uint32_t *d_counts = nullptr;      // occurrences per distinct minimizer (for mm_idx_cal_max_occ)
+	std::vector<uint64_t> h_seq_off;   // host copies: job generation needs them
+	std::vector<uint32_t> h_seq_len;
+	IdxView view() const {
+		IdxView v;
+		v.S = d_S, v.seq_off = d_seq_off, v.seq_len = d_seq_len, v.slots = d_slots, v.pos = d_pos;
+		v.slot_mask = n_slots - 1, v.slot_shift = slot_shift, v.n_seq = n_seq, v.w = w, v.k = k;
+		return v;
+	}
+};
+
+// state of the mini-batch currently resident on the device
+struct ResidentBatch {
+	int32_t n_frag = 0, n_seq = 0, n_units = 0;
+	uint64_t n_bases = 0, q_words = 0;
+	std::vector<int32_t> n_seg, seg_off, seq_len, frag_unit0, frag_qlen;
+	std::vector<uint64_t> q_off; // packed (8-base aligned) offset of each read
+};
+
+struct mmg_ctx_s {
+	int dev = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	long launches = 0;
+	ResidentBatch rb;
+	// device arenas (grown on demand, reused across batches)
+	DevBuf d_ascii, d_Q, d_seq_len, d_seq_off, d_q_off, d_flip, d_units, d_unit_cnt, d_unit_off, d_mv, d_m_n, d_m_val,
+	       d_frag_unit0, d_frag_qlen, d_frag_na, d_frag_aoff, d_frag_rep, d_frag_nmini, d_mini, d_a, d_work, d_u, d_b, d_heap,
+	       d_stack, d_frag_nu, d_frag_nv, d_frag_flag, d_frag_iter, d_cub, d_out_u, d_out_a, d_out_mini, d_uoff, d_voff, d_moff,
+	       d_frag_list, d_misc;
+	// second-pass (re-chain with max_occ) arenas
+	DevBuf d2_frag_na, d2_frag_aoff, d2_frag_rep, d2_frag_nmini, d2_mini, d2_a, d2_work, d2_u, d2_b, d2_stack, d2_frag_nu, d2_frag_nv;
+	// ksw arenas
+	DevBuf k_jobs, k_mem, k_H, k_p, k_cig, k_res, k_cig_out, k_cig_off;
+	PinBuf h_in, h_meta, h_out_meta, h_out_u, h_out_a, h_out_mini, h_k_jobs, h_k_res, h_k_cig;
+};
+
+#define MMG_LAUNCH(ctx, kern, grid, block, smem, ...) do { \
+	kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); ++(ctx)->launches; \
+	cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { mmg_set_error("launch %s: %s", #kern, cudaGetErrorString(e_)); return MMG_ECUDA; } } while (0)
+
+static inline unsigned mmg_blocks(size_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }

@@ -1,0 +1,381 @@
+// mmg_ksw.cu -- K4: batched ksw_extd2 (ksw2_extd2_sse.c:19-393) on the device.
+//
+// One DP job is run by a group of 16 lanes -- one lane per int8 lane of the reference's SSE
+// registers -- so that the widened 16-lane band, the stale out-of-band lanes and the block
+// boundary carry-in rule are reproduced by construction.  The lane arrays
+// u|v|x|y|x2|y2|s|sf|qr keep the reference's memory order (ksw2_extd2_sse.c:99-102); they live
+// in shared memory when a job is small enough (all short-read jobs) and in a global arena
+// otherwise.  Neighbour lanes are exchanged with width-16 shuffles instead of byte shifts.
+#include <algorithm>
+#include <cub/cub.cuh>
+#include "mmg_ctx.cuh"
+
+struct KswJobDev {
+	uint64_t q_base;      // packed base offset of the read in Q
+	uint64_t t_base;      // packed base offset of the target slice in S
+	uint64_t mem_off, p_off, cig_off;
+	int32_t q_readlen, q_rev, q_start, q_len, t_len, reversed;
+	int32_t w, zdrop, end_bonus, flag;
+	int32_t out_idx, pad;
+};
+
+struct KswScore { int32_t m; int8_t mat[25]; int8_t q, e, q2, e2; };
+
+#define KSW_GROUP 16
+#define KSW_JOBS_PER_BLOCK 8
+#define KSW_SMEM_PER_JOB 4096
+
+__device__ __forceinline__ uint8_t ksw_qbase(const uint32_t *Q, const KswJobDev &jb, int j)
+{ // element j of the query handed to ksw (align.c:691-697,721,761): a slice of qseq0[rev], possibly reversed
+	const int idx = jb.reversed ? jb.q_start + jb.q_len - 1 - j : jb.q_start + j;
+	if (!jb.q_rev) return (uint8_t)mmg_seq4_get(Q, jb.q_base + idx);
+	const int c = mmg_seq4_get(Q, jb.q_base + (jb.q_readlen - 1 - idx)); // align.c:869
+	return (uint8_t)(c < 4 ? 3 - c : 4);
+}
+
+__device__ __forceinline__ uint8_t ksw_tbase(const uint32_t *S, const KswJobDev &jb, int i)
+{
+	const int ti = jb.reversed ? jb.t_len - 1 - i : i;
+	return (uint8_t)mmg_seq4_get(S, jb.t_base + ti); // mm_idx_getseq, index.c:152-162
+}
+
+template <int kMode>
+__device__ __forceinline__ void ksw_run(const KswGeom &g, const KswJobDev &jb, int8_t *mem, int32_t *H, uint8_t *p, KswEz &ez,
+                                        const int lane, const unsigned gmask)
+{
+	const int tl16 = g.tlen_ * 16;
+	int8_t *u = mem, *v = u + tl16, *x = v + tl16, *y = x + tl16, *x2 = y + tl16, *y2 = x2 + tl16, *s = y2 + tl16;
+	const uint8_t *sf = reinterpret_cast<const uint8_t*>(s + tl16), *qr = sf + tl16;
+	const int qlen = g.qlen, tlen = g.tlen, flag = jb.flag;
+	const bool approx = (flag & MMG_EZ_APPROX_MAX) != 0;
+	int last_st = -1, last_en = -1;
+	int32_t H0 = 0, last_H0_t = 0;
+	for (int r = 0; r < qlen + tlen - 1; ++r) {
+		int st0, en0;
+		if (!mmg_ksw_band(g, r, &st0, &en0)) { ez.zdropped = 1; break; }
+		const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
+		int x1, x21, v1;
+		if (st > 0) {
+			if (st - 1 >= last_st && st - 1 <= last_en) x1 = x[st - 1], x21 = x2[st - 1], v1 = v[st - 1];
+			else x1 = -g.q - g.e, x21 = -g.q2 - g.e2, v1 = -g.q - g.e;
+		} else {
+			x1 = -g.q - g.e, x21 = -g.q2 - g.e2;
+			v1 = mmg_ksw_first_col(g, r);
+		}
+		if (en >= r && lane == 0) {
+			y[r] = (int8_t)(-g.q - g.e), y2[r] = (int8_t)(-g.q2 - g.e2);
+			u[r] = (int8_t)mmg_ksw_first_col(g, r);
+		}
+		{ // scores, 16-byte chunks starting at st0 (ksw2_extd2_sse.c:158-172)
+			const uint8_t *qrr = qr + (qlen - 1 - r);
+			for (int t = st0; t <= en0; t += 16) s[t + lane] = mmg_ksw_score(g, sf[t + lane], qrr[t + lane]);
+		}
+		__syncwarp(gmask);
+		const int st_ = st / 16, en_ = en / 16;
+		for (int blk = st_; blk <= en_; ++blk) {
+			const int i = blk * 16 + lane;
+			const int xo = x[i], vo = v[i], x2o = x2[i];
+			int xt1 = __shfl_up_sync(gmask, xo, 1, KSW_GROUP), vt1 = __shfl_up_sync(gmask, vo, 1, KSW_GROUP), x2t1 = __shfl_up_sync(gmask, x2o, 1, KSW_GROUP);
+			if (lane == 0) xt1 = x1, vt1 = v1, x2t1 = x21;
+			x1 = __shfl_sync(gmask, xo, KSW_GROUP - 1, KSW_GROUP);
+			v1 = __shfl_sync(gmask, vo, KSW_GROUP - 1, KSW_GROUP);
+			x21 = __shfl_sync(gmask, x2o, KSW_GROUP - 1, KSW_GROUP);
+			const KswCell c = mmg_ksw_cell<kMode>(g, s[i], (int8_t)xt1, (int8_t)vt1, u[i], y[i], (int8_t)x2t1, y2[i]);
+			u[i] = c.u, v[i] = c.v, x[i] = c.x, y[i] = c.y, x2[i] = c.x2, y2[i] = c.y2;
+			if (kMode) p[((size_t)r * g.n_col_ + (blk - st_)) * 16 + lane] = c.d;
+		}
+		__syncwarp(gmask);
+		if (!approx) { // exact max over the band with the reference's tie order (ksw2_extd2_sse.c:315-358)
+			int32_t max_H, max_t, H_en0;
+			if (r > 0) {
+				H_en0 = en0 > 0 ? H[en0 - 1] + u[en0] : H[en0] + v[en0];
+				__syncwarp(gmask);
+				int32_t bh = H_en0, bt = en0; uint32_t br = 0;
+				for (int t = st0 + lane; t < en0; t += 16) {
+					const int32_t h = H[t] + v[t];
+					H[t] = h;
+					const uint32_t rk = mmg_ksw_max_rank(t, st0, en0);
+					if (h > bh || (h == bh && rk < br)) bh = h, bt = t, br = rk;
+				}
+				if (lane == 0) H[en0] = H_en0;
+#pragma unroll
+				for (int d = 8; d >= 1; d >>= 1) {
+					const int32_t oh = __shfl_xor_sync(gmask, bh, d, KSW_GROUP), ot = __shfl_xor_sync(gmask, bt, d, KSW_GROUP);
+					const uint32_t orank = __shfl_xor_sync(gmask, br, d, KSW_GROUP);
+					if (oh > bh || (oh == bh && orank < br)) bh = oh, bt = ot, br = orank;
+				}
+				max_H = bh, max_t = bt;
+			} else {
+				H_en0 = v[0] - g.qe_pre;
+				if (lane == 0) H[0] = H_en0;
+				max_H = H_en0, max_t = 0;
+			}
+			__syncwarp(gmask);
+			if (en0 == tlen - 1 && H_en0 > ez.mte) ez.mte = H_en0, ez.mte_q = r - en;
+			if (r - st0 == qlen - 1) { const int32_t hs = H[st0]; if (hs > ez.mqe) ez.mqe = hs, ez.mqe_t = st0; }
+			if (mmg_ksw_zdrop(&ez, max_H, r, max_t, jb.zdrop, g.e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H[tlen - 1];
+		} else { // ksw2_extd2_sse.c:359-375
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					const int32_t d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+					if (d0 > d1) H0 += d0;
+					else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
+					H0 += v[last_H0_t];
+				} else {
+					++last_H0_t, H0 += u[last_H0_t];
+				}
+			} else H0 = v[0] - g.qe_pre, last_H0_t = 0;
+			if ((flag & MMG_EZ_APPROX_DROP) && mmg_ksw_zdrop(&ez, H0, r, last_H0_t, jb.zdrop, g.e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
+		}
+		last_st = st, last_en = en;
+	}
+}
+
+__global__ void __launch_bounds__(KSW_GROUP * KSW_JOBS_PER_BLOCK)
+k_ksw(const KswJobDev *__restrict__ jobs, int n_jobs, KswScore sc, const uint32_t *__restrict__ Q, const uint32_t *__restrict__ S,
+      int8_t *__restrict__ gmem, uint8_t *__restrict__ gp, uint32_t *__restrict__ gcig, KswEz *__restrict__ res)
+{
+	extern __shared__ __align__(16) uint8_t smem[];
+	const int grp = threadIdx.x / KSW_GROUP, lane = threadIdx.x % KSW_GROUP;
+	const int ji = blockIdx.x * KSW_JOBS_PER_BLOCK + grp;
+	if (ji >= n_jobs) return;
+	const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+	const KswJobDev jb = jobs[ji];
+	const KswGeom g = mmg_ksw_geom(jb.q_len, jb.t_len, sc.m, sc.mat, sc.q, sc.e, sc.q2, sc.e2, jb.w);
+	KswEz ez;
+	mmg_ksw_reset(&ez);
+	if (g.bail) { if (lane == 0) res[jb.out_idx] = ez; return; }
+	const int tl16 = g.tlen_ * 16;
+	const size_t mem_bytes = mmg_ksw_mem_bytes(jb.q_len, jb.t_len), H_bytes = (size_t)tl16 * 4;
+	int8_t *mem; int32_t *H;
+	if (mem_bytes + H_bytes <= KSW_SMEM_PER_JOB) {
+		mem = reinterpret_cast<int8_t*>(smem + (size_t)grp * KSW_SMEM_PER_JOB);
+		H = reinterpret_cast<int32_t*>(mem + mem_bytes);
+	} else {
+		mem = gmem + jb.mem_off; // arena slot = lane arrays followed by H[] (sized in ksw_launch)
+		H = reinterpret_cast<int32_t*>(gmem + jb.mem_off + mem_bytes);
+	}
+	// initial lane state (ksw2_extd2_sse.c:99-121)
+	{
+		int8_t *u = mem;
+		const int8_t n1 = (int8_t)(-g.q - g.e), n2 = (int8_t)(-g.q2 - g.e2);
+		for (int i = lane; i < tl16; i += KSW_GROUP) {
+			u[i] = n1, u[tl16 + i] = n1, u[2 * tl16 + i] = n1, u[3 * tl16 + i] = n1; // u v x y
+			u[4 * tl16 + i] = n2, u[5 * tl16 + i] = n2;                              // x2 y2
+			u[6 * tl16 + i] = 0;                                                      // s (kcalloc)
+			u[7 * tl16 + i] = i < jb.t_len ? (int8_t)ksw_tbase(S, jb, i) : 0;         // sf
+			H[i] = MMG_KSW_NEG_INF;
+		}
+		int8_t *qr = u + 8 * tl16;
+		const int qn = g.qlen_ * 16 + 16;
+		for (int i = lane; i < qn; i += KSW_GROUP) qr[i] = i < jb.q_len ? (int8_t)ksw_qbase(Q, jb, jb.q_len - 1 - i) : 0;
+	}
+	__syncwarp(gmask);
+	uint8_t *p = gp + jb.p_off;
+	const bool with_cigar = !(jb.flag & MMG_EZ_SCORE_ONLY);
+	if (!with_cigar) ksw_run<0>(g, jb, mem, H, p, ez, lane, gmask);
+	else if (!(jb.flag & MMG_EZ_RIGHT)) ksw_run<1>(g, jb, mem, H, p, ez, lane, gmask);
+	else ksw_run<2>(g, jb, mem, H, p, ez, lane, gmask);
+	__syncwarp(gmask);
+	if (lane == 0) {
+		int i0, j0;
+		if (with_cigar && mmg_ksw_trace_start(g, jb.flag, jb.end_bonus, &ez, &i0, &j0))
+			ez.n_cigar = mmg_ksw_backtrack(g, !!(jb.flag & MMG_EZ_REV_CIGAR), p, i0, j0, gcig + jb.cig_off);
+		res[jb.out_idx] = ez;
+	}
+}
+
+__global__ void k_cig_gather(int n_jobs, const KswJobDev *__restrict__ jobs, const KswEz *__restrict__ res, const int64_t *__restrict__ off,
+                             const uint32_t *__restrict__ gcig, uint32_t *__restrict__ out)
+{
+	const int ji = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ji >= n_jobs) return;
+	const KswJobDev jb = jobs[ji];
+	const int n = res[jb.out_idx].n_cigar;
+	const int64_t o = off[jb.out_idx];
+	for (int i = 0; i < n; ++i) out[o + i] = gcig[jb.cig_off + i];
+}
+
+__global__ void k_res_ncig(int n_jobs, const KswEz *__restrict__ res, int32_t *__restrict__ ncig)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_jobs) ncig[i] = res[i].n_cigar;
+	else if (i == n_jobs) ncig[i] = 0;
+}
+
+static int64_t band_cells(int qlen, int tlen, int w)
+{ // true-band cell count (the GCUPS unit)
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	int64_t cells = 0;
+	for (int r = 0; r < qlen + tlen - 1; ++r) {
+		int st = 0, en = tlen - 1;
+		if (st < r - qlen + 1) st = r - qlen + 1;
+		if (en > r) en = r;
+		if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+		if (en > (r + w) >> 1) en = (r + w) >> 1;
+		if (st > en) break;
+		cells += en - st + 1;
+	}
+	return cells;
+}
+
+static int ksw_launch(mmg_ctx_t *c, const uint32_t *d_Q, const uint32_t *d_S, const KswScore &sc, std::vector<KswJobDev> &jd,
+                      mmg_ksw_res_t *res, const uint32_t **cigars, double *kernel_ms)
+{
+	const int n = (int)jd.size();
+	// big jobs first; arenas sized from the geometry
+	std::sort(jd.begin(), jd.end(), [](const KswJobDev &a, const KswJobDev &b) {
+		const int64_t ca = (int64_t)(a.q_len + a.t_len) * (a.q_len < a.t_len ? a.q_len : a.t_len);
+		const int64_t cb = (int64_t)(b.q_len + b.t_len) * (b.q_len < b.t_len ? b.q_len : b.t_len);
+		return ca != cb ? ca > cb : a.out_idx < b.out_idx;
+	});
+	uint64_t mem_tot = 0, p_tot = 0, cig_tot = 0;
+	for (int i = 0; i < n; ++i) {
+		KswJobDev &j = jd[i];
+		const int qlen = j.q_len, tlen = j.t_len;
+		if (qlen <= 0 || tlen <= 0) { j.mem_off = j.p_off = j.cig_off = 0; continue; }
+		const size_t mem_bytes = mmg_ksw_mem_bytes(qlen, tlen), H_bytes = (size_t)((tlen + 15) / 16) * 16 * 4;
+		j.mem_off = mem_tot;
+		if (mem_bytes + H_bytes > KSW_SMEM_PER_JOB) mem_tot += (mem_bytes + H_bytes + 63) & ~(size_t)63;
+		int w = j.w < 0 ? (tlen > qlen ? tlen : qlen) : j.w;
+		int nc = qlen < tlen ? qlen : tlen;
+		nc = ((nc < w + 1 ? nc : w + 1) + 15) / 16 + 1;
+		j.p_off = p_tot;
+		if (!(j.flag & MMG_EZ_SCORE_ONLY)) p_tot += ((size_t)(qlen + tlen - 1) * nc + 1) * 16;
+		j.cig_off = cig_tot;
+		cig_tot += (size_t)qlen + tlen + 2;
+	}
+	MMG_TRY(c->k_jobs.ensure((size_t)(n + 1) * sizeof(KswJobDev)));
+	MMG_TRY(c->k_mem.ensure(mem_tot + 64));
+	MMG_TRY(c->k_p.ensure(p_tot + 64));
+	MMG_TRY(c->k_cig.ensure((cig_tot + 4) * 4));
+	MMG_TRY(c->k_res.ensure((size_t)(n + 1) * sizeof(KswEz)));
+	MMG_TRY(c->k_cig_off.ensure((size_t)(n + 2) * 12));
+	MMG_TRY(c->h_k_jobs.ensure((size_t)(n + 1) * sizeof(KswJobDev)));
+	memcpy(c->h_k_jobs.p, jd.data(), (size_t)n * sizeof(KswJobDev));
+	MMG_CUDA(cudaMemcpyAsync(c->k_jobs.p, c->h_k_jobs.p, (size_t)n * sizeof(KswJobDev), cudaMemcpyHostToDevice, c->stream));
+	MMG_CUDA(cudaEventRecord(c->ev[0], c->stream));
+	MMG_LAUNCH(c, k_ksw, mmg_blocks(n, KSW_JOBS_PER_BLOCK), KSW_GROUP * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
+	           c->k_jobs.as<KswJobDev>(), n, sc, d_Q, d_S, c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(), c->k_cig.as<uint32_t>(),
+	           c->k_res.as<KswEz>());
+	MMG_CUDA(cudaEventRecord(c->ev[1], c->stream));
+	// compact the cigars: n_cigar -> offsets -> gather
+	int32_t *d_ncig = c->k_cig_off.as<int32_t>();
+	int64_t *d_off = reinterpret_cast<int64_t*>(c->k_cig_off.as<uint8_t>() + (((size_t)(n + 2) * 4 + 15) & ~(size_t)15));
+	MMG_LAUNCH(c, k_res_ncig, mmg_blocks(n + 1, 256), 256, 0, n, c->k_res.as<KswEz>(), d_ncig);
+	{
+		size_t tmp = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_ncig, d_off, n + 1, c->stream);
+		MMG_TRY(c->d_cub.ensure(tmp));
+		MMG_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, d_ncig, d_off, n + 1, c->stream));
+		++c->launches;
+	}
+	int64_t tot = 0;
+	MMG_CUDA(cudaMemcpyAsync(&tot, d_off + n, 8, cudaMemcpyDeviceToHost, c->stream));
+	MMG_CUDA(cudaStreamSynchronize(c->stream));
+	MMG_TRY(c->k_cig_out.ensure((size_t)(tot + 1) * 4));
+	MMG_LAUNCH(c, k_cig_gather, mmg_blocks(n, 128), 128, 0, n, c->k_jobs.as<KswJobDev>(), c->k_res.as<KswEz>(), d_off, c->k_cig.as<uint32_t>(),
+	           c->k_cig_out.as<uint32_t>());
+	MMG_TRY(c->h_k_cig.ensure((size_t)(tot + 1) * 4));
+	MMG_TRY(c->h_k_res.ensure((((size_t)(n + 1) * sizeof(KswEz) + 15) & ~(size_t)15) + (size_t)(n + 1) * 8));
+	KswEz *h_ez = c->h_k_res.as<KswEz>();
+	int64_t *h_off = reinterpret_cast<int64_t*>(c->h_k_res.as<uint8_t>() + (((size_t)(n + 1) * sizeof(KswEz) + 15) & ~(size_t)15));
+	MMG_CUDA(cudaMemcpyAsync(h_ez, c->k_res.p, (size_t)n * sizeof(KswEz), cudaMemcpyDeviceToHost, c->stream));
+	MMG_CUDA(cudaMemcpyAsync(h_off, d_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+	if (tot) MMG_CUDA(cudaMemcpyAsync(c->h_k_cig.p, c->k_cig_out.p, (size_t)tot * 4, cudaMemcpyDeviceToHost, c->stream));
+	MMG_CUDA(cudaStreamSynchronize(c->stream));
+	for (int i = 0; i < n; ++i) {
+		memcpy(&res[i].ez, &h_ez[i], sizeof(KswEz));
+		res[i].cigar_off = (uint64_t)h_off[i];
+	}
+	*cigars = c->h_k_cig.as<uint32_t>();
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+	if (kernel_ms) *kernel_ms = ms;
+	return MMG_OK;
+}
+
+static KswScore make_score(const mmg_mapopt_t *opt)
+{ // ksw_gen_simple_mat (align.c:9-22), m = 5
+	KswScore sc; sc.m = 5;
+	int a = opt->a < 0 ? -opt->a : opt->a, b = opt->b > 0 ? -opt->b : opt->b, amb = opt->sc_ambi > 0 ? -opt->sc_ambi : opt->sc_ambi;
+	for (int i = 0; i < 4; ++i) {
+		for (int j = 0; j < 4; ++j) sc.mat[i * 5 + j] = (int8_t)(i == j ? a : b);
+		sc.mat[i * 5 + 4] = (int8_t)amb;
+	}
+	for (int j = 0; j < 5; ++j) sc.mat[20 + j] = (int8_t)amb;
+	sc.q = (int8_t)opt->q, sc.e = (int8_t)opt->e, sc.q2 = (int8_t)opt->q2, sc.e2 = (int8_t)opt->e2;
+	return sc;
+}
+
+extern "C" int mmg_ksw_batch(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, int n_jobs, const mmg_ksw_job_t *jobs,
+                             mmg_ksw_res_t *res, const uint32_t **cigars, double *kernel_ms, uint64_t *cells)
+{
+	*cigars = nullptr;
+	if (kernel_ms) *kernel_ms = 0;
+	if (cells) *cells = 0;
+	if (n_jobs <= 0) return MMG_OK;
+	MMG_CUDA(cudaSetDevice(c->dev));
+	const ResidentBatch &rb = c->rb;
+	std::vector<KswJobDev> jd(n_jobs);
+	uint64_t ncell = 0;
+	for (int i = 0; i < n_jobs; ++i) {
+		const mmg_ksw_job_t &j = jobs[i];
+		if (j.seq_id < 0 || j.seq_id >= rb.n_seq || j.rid < 0 || j.rid >= mi->n_seq) { mmg_set_error("mmg_ksw_batch: job %d refers to a read or contig that is not resident", i); return MMG_EINVAL; }
+		KswJobDev &d = jd[i];
+		d.q_base = rb.q_off[j.seq_id], d.q_readlen = rb.seq_len[j.seq_id], d.q_rev = j.q_rev, d.q_start = j.q_start, d.q_len = j.q_len;
+		d.t_base = mi->h_seq_off[j.rid] + (uint64_t)j.t_start, d.t_len = j.t_len, d.reversed = j.reversed;
+		d.w = j.w, d.zdrop = j.zdrop, d.end_bonus = j.end_bonus, d.flag = j.flag, d.out_idx = i, d.pad = 0;
+		if (cells && j.q_len > 0 && j.t_len > 0) ncell += (uint64_t)band_cells(j.q_len, j.t_len, j.w);
+	}
+	if (cells) *cells = ncell;
+	return ksw_launch(c, c->d_Q.as<uint32_t>(), mi->d_S, make_score(opt), jd, res, cigars, kernel_ms);
+}
+
+// single pair, sequences given as 0..4 codes (parity-test entry point for ksw_extd2_sse, ksw2.h:60)
+__global__ void k_pack_codes(const uint8_t *__restrict__ codes, int n, uint32_t *__restrict__ out)
+{
+	const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+	if (wi * 8 >= n) return;
+	uint32_t word = 0;
+	for (int j = 0; j < 8 && wi * 8 + j < n; ++j) word |= (uint32_t)(codes[wi * 8 + j] & 0xf) << (4 * j);
+	out[wi] = word;
+}
+
+extern "C" int mmg_ksw_extd2(mmg_ctx_t *c, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+                             int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag, mmg_extz_t *ez, uint32_t *cigar)
+{
+	MMG_CUDA(cudaSetDevice(c->dev));
+	KswEz z; mmg_ksw_reset(&z);
+	memcpy(ez, &z, sizeof(z));
+	if (m != 5) { mmg_set_error("mmg_ksw_extd2: only the 5-letter alphabet of the mapper is supported"); return MMG_EINVAL; }
+	if (qlen <= 0 || tlen <= 0) return MMG_OK;
+	KswScore sc; sc.m = m; memcpy(sc.mat, mat, 25); sc.q = q, sc.e = e, sc.q2 = q2, sc.e2 = e2;
+	DevBuf dq, dt, dqp, dtp;
+	int rc = MMG_OK;
+	auto fin = [&]() { dq.release(); dt.release(); dqp.release(); dtp.release(); };
+#define KS_TRY(x) do { rc = (x); if (rc != MMG_OK) { fin(); return rc; } } while (0)
+	KS_TRY(dq.ensure((size_t)qlen + 16)); KS_TRY(dt.ensure((size_t)tlen + 16));
+	KS_TRY(dqp.ensure(((size_t)qlen / 8 + 4) * 4)); KS_TRY(dtp.ensure(((size_t)tlen / 8 + 4) * 4));
+	cudaMemcpyAsync(dq.p, query, qlen, cudaMemcpyHostToDevice, c->stream);
+	cudaMemcpyAsync(dt.p, target, tlen, cudaMemcpyHostToDevice, c->stream);
+	k_pack_codes<<<mmg_blocks((qlen + 7) / 8, 128), 128, 0, c->stream>>>(dq.as<uint8_t>(), qlen, dqp.as<uint32_t>());
+	k_pack_codes<<<mmg_blocks((tlen + 7) / 8, 128), 128, 0, c->stream>>>(dt.as<uint8_t>(), tlen, dtp.as<uint32_t>());
+	c->launches += 2;
+	std::vector<KswJobDev> jd(1);
+	KswJobDev &d = jd[0];
+	memset(&d, 0, sizeof(d));
+	d.q_base = 0, d.q_readlen = qlen, d.q_rev = 0, d.q_start = 0, d.q_len = qlen, d.t_base = 0, d.t_len = tlen, d.reversed = 0;
+	d.w = w, d.zdrop = zdrop, d.end_bonus = end_bonus, d.flag = flag, d.out_idx = 0;
+	mmg_ksw_res_t r; const uint32_t *cg = nullptr;
+	rc = ksw_launch(c, dqp.as<uint32_t>(), dtp.as<uint32_t>(), sc, jd, &r, &cg, nullptr);
+	if (rc == MMG_OK) {
+		*ez = r.ez;
+		for (int i = 0; i < r.ez.n_cigar; ++i) cigar[i] = cg[r.cigar_off + i];
+	}
+	fin();
+	return rc;
+#undef KS_TRY
+}

@@ -1,0 +1,541 @@
+// mmg_stages.cu -- the batched sketch -> seed -> chain stages (K1, K2, K3) and their
+// single-call test entry points.  Reference path: mm_map_frag, map.c:272-377.
+#include <cub/cub.cuh>
+#include "mmg_ctx.cuh"
+
+int mmg_run_sketch(mmg_ctx_t *c, const uint32_t *d_S, const SketchUnit *d_units, int n_units, int w, int k, int is_hpc,
+                   DevBuf &cnt, DevBuf &off, DevBuf &out, int64_t *total);
+
+#define MMG_READ_CHUNK 4096   // reads longer than this are sketched in chunks
+
+// ------------------------------------------------------------------ kernels
+
+// ASCII reads -> 4-bit codes, one word (8 bases) per thread; flipped reads are reverse-complemented
+// (mm_revcomp_bseq, bseq.h:46-58, applied to mates per pe_ori at map.c:467-469)
+__global__ void k_encode_reads(const uint8_t *__restrict__ ascii, const uint64_t *__restrict__ seq_off, const int32_t *__restrict__ seq_len,
+                               const uint64_t *__restrict__ q_off, const uint8_t *__restrict__ flip, int n_seq, uint64_t n_words,
+                               uint32_t *__restrict__ Q)
+{
+	const uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (wi >= n_words) return;
+	const uint64_t b0 = wi * 8;
+	int lo = 0, hi = n_seq - 1; // last read with q_off <= b0
+	while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (q_off[mid] <= b0) lo = mid; else hi = mid - 1; }
+	const int r = lo, len = seq_len[r];
+	const uint64_t base = b0 - q_off[r];
+	const uint8_t *s = ascii + seq_off[r];
+	const bool fl = flip[r] != 0;
+	uint32_t word = 0;
+	for (int j = 0; j < 8; ++j) {
+		const uint64_t i = base + j;
+		int c = 4;
+		if (i < (uint64_t)len) {
+			if (!fl) c = mmg_nt4(s[i]);
+			else { c = mmg_nt4(s[len - 1 - i]); c = c < 4 ? 3 - c : 4; }
+		}
+		word |= (uint32_t)c << (4 * j);
+	}
+	Q[wi] = word;
+}
+
+// K2a: one lookup per query minimizer (mm_idx_get at map.c:103)
+__global__ void k_lookup(IdxView ix, const mm128 *__restrict__ mv, int64_t n, int32_t *__restrict__ m_n, uint64_t *__restrict__ m_val)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint64_t val;
+	m_n[i] = mmg_idx_probe(ix, mv[i].x >> 8, &val);
+	m_val[i] = val;
+}
+
+struct FragTab {  // per-fragment tables of the resident batch
+	const int32_t *unit0;      // [n_frag+1] first sketch unit of each fragment
+	const int64_t *unit_off;   // [n_units+1] first minimizer of each unit
+	const int32_t *qlen;       // [n_frag] summed segment lengths
+};
+
+// K2b: collect_matches bookkeeping per fragment (map.c:90-123)
+__global__ void k_plan(FragTab ft, const int32_t *__restrict__ list, int n_list, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
+                       int max_occ, int32_t *__restrict__ na, int32_t *__restrict__ rep, int32_t *__restrict__ nmini,
+                       uint64_t *__restrict__ mini /* may be null */)
+{
+	const int li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= n_list) return;
+	const int f = list ? list[li] : li;
+	const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]];
+	int r, nm;
+	const int64_t n_a = mmg_frag_plan(mv + b, m_n + b, (int)(e - b), max_occ, &r, &nm, mini ? mini + b : nullptr);
+	na[li] = (int32_t)n_a, rep[li] = r, nmini[li] = nm;
+}
+
+// K2c: anchors per fragment, in the reference's order (map.c:149-247)
+__global__ void k_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
+                       const uint64_t *__restrict__ m_val, const uint64_t *__restrict__ pos, int max_occ, int64_t flag,
+                       const int64_t *__restrict__ aoff, int32_t *__restrict__ na, mm128 *__restrict__ a, mm128 *__restrict__ heap, RsFrame *__restrict__ stack)
+{
+	const int li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= n_list) return;
+	const int f = list ? list[li] : li;
+	const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]];
+	const int64_t ao = aoff[li];
+	int64_t n;
+	if (flag & MMG_F_HEAP_SORT)
+		n = mmg_fill_heap(mv + b, m_n + b, m_val + b, (int)(e - b), max_occ, pos, flag, ft.qlen[f], na[li], heap + b, a + ao);
+	else
+		n = mmg_fill_flat(mv + b, m_n + b, m_val + b, (int)(e - b), max_occ, pos, flag, ft.qlen[f], a + ao, stack + ao / 65 + 2 * (int64_t)li);
+	na[li] = (int32_t)n;
+}
+
+struct ChainOptDev { int32_t bw, max_gap, max_gap_ref, max_frag_len, max_skip, max_iter, min_cnt, min_sc, is_cdna, is_sr; };
+
+__device__ __forceinline__ ChainParams mmg_chain_params(const ChainOptDev &o, int qlen_sum, int n_segs)
+{ // map.c:341-351
+	ChainParams P;
+	const int gap_qry = o.is_sr ? (qlen_sum > o.max_gap ? qlen_sum : o.max_gap) : o.max_gap;
+	int gap_ref;
+	if (o.max_gap_ref > 0) gap_ref = o.max_gap_ref;
+	else if (o.max_frag_len > 0) { gap_ref = o.max_frag_len - qlen_sum; if (gap_ref < o.max_gap) gap_ref = o.max_gap; }
+	else gap_ref = o.max_gap;
+	P.max_dist_x = gap_ref, P.max_dist_y = gap_qry, P.bw = o.bw, P.max_skip = o.max_skip, P.max_iter = o.max_iter;
+	P.min_cnt = o.min_cnt, P.min_sc = o.min_sc, P.is_cdna = o.is_cdna, P.n_segs = n_segs;
+	return P;
+}
+
+// K3: mm_chain_dp per fragment (chain.c:22-162), then the re-chain test of map.c:353-366
+__global__ void k_chain(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
+                        const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
+                        uint64_t *__restrict__ u, mm128 *__restrict__ bb, RsFrame *__restrict__ stack, int32_t *__restrict__ nu_out,
+                        int32_t *__restrict__ nv_out, const int32_t *__restrict__ rep, int rechain_enabled, uint8_t *__restrict__ flag_out,
+                        unsigned long long *__restrict__ iter_total)
+{
+	const int li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= n_list) return;
+	const int f = list ? list[li] : li;
+	const int64_t ao = aoff[li], n = na[li];
+	const int segs = n_seg[f];
+	int n_u = 0; int64_t n_v = 0;
+	if (n > 0) {
+		const ChainParams P = mmg_chain_params(co, ft.qlen[f], segs);
+		int32_t *fp = work + ao * 4;
+		mm128 *A = a + ao;
+		const uint64_t it = mmg_chain_fill_seq(P, n, A, fp, fp + n, fp + 2 * n, fp + 3 * n);
+		atomicAdd(iter_total, (unsigned long long)it);
+		n_u = mmg_chain_backtrack(P, n, A, fp, fp + n, fp + 2 * n, fp + 3 * n, u + ao * 2, bb + ao, stack + ao / 65 + 2 * (int64_t)li, &n_v);
+	}
+	nu_out[li] = n_u, nv_out[li] = (int32_t)n_v;
+	if (flag_out) {
+		uint8_t rechain = 0;
+		if (rechain_enabled && rep[li] > 0) {
+			if (n_u > 0) { // does the best chain span every segment? (map.c:355-365)
+				const uint64_t *U = u + ao * 2;
+				const mm128 *A = a + ao;
+				int n_chained = 1, max = 0, max_i = -1, max_off = -1, off = 0;
+				for (int i = 0; i < n_u; ++i) {
+					if (max < (int)(U[i] >> 32)) max = (int)(U[i] >> 32), max_i = i, max_off = off;
+					off += (int32_t)U[i];
+				}
+				if (max_i >= 0)
+					for (int i = 1; i < (int32_t)U[max_i]; ++i)
+						if ((A[max_off + i].y & MMG_SEED_SEG_MASK) != (A[max_off + i - 1].y & MMG_SEED_SEG_MASK)) ++n_chained;
+				if (n_chained < segs) rechain = 1;
+			} else rechain = 1;
+		}
+		flag_out[f] = rechain;
+	}
+}
+
+// gather per-fragment results (first or second pass) into dense output arrays
+__global__ void k_gather(int n_frag, const int32_t *__restrict__ src_li /* second-pass slot or -1 */,
+                         const int64_t *__restrict__ aoff1, const uint64_t *__restrict__ u1, const mm128 *__restrict__ a1,
+                         const int64_t *__restrict__ aoff2, const uint64_t *__restrict__ u2, const mm128 *__restrict__ a2,
+                         const int32_t *__restrict__ nu, const int32_t *__restrict__ nv, const int64_t *__restrict__ uoff,
+                         const int64_t *__restrict__ voff, uint64_t *__restrict__ out_u, mm128 *__restrict__ out_a)
+{
+	const int f = blockIdx.x;
+	if (f >= n_frag) return;
+	const int s = src_li ? src_li[f] : -1;
+	const uint64_t *U = s >= 0 ? u2 + aoff2[s] * 2 : u1 + aoff1[f] * 2;
+	const mm128 *A = s >= 0 ? a2 + aoff2[s] : a1 + aoff1[f];
+	for (int i = threadIdx.x; i < nu[f]; i += blockDim.x) out_u[uoff[f] + i] = U[i];
+	for (int i = threadIdx.x; i < nv[f]; i += blockDim.x) out_a[voff[f] + i] = A[i];
+}
+
+__global__ void k_gather_mini(int n_frag, FragTab ft, const int32_t *__restrict__ src_li, const uint64_t *__restrict__ mini1,
+                              const uint64_t *__restrict__ mini2, const int32_t *__restrict__ nmini, const int64_t *__restrict__ moff,
+                              uint64_t *__restrict__ out)
+{
+	const int f = blockIdx.x;
+	if (f >= n_frag) return;
+	const int64_t b = ft.unit_off[ft.unit0[f]];
+	const uint64_t *M = (src_li && src_li[f] >= 0 ? mini2 : mini1) + b;
+	for (int i = threadIdx.x; i < nmini[f]; i += blockDim.x) out[moff[f] + i] = M[i];
+}
+
+// merge second-pass per-fragment scalars back into the first-pass arrays
+__global__ void k_merge_pass2(int n_list, const int32_t *__restrict__ list, const int32_t *__restrict__ nu2, const int32_t *__restrict__ nv2,
+                              const int32_t *__restrict__ rep2, const int32_t *__restrict__ nmini2, int32_t *__restrict__ nu, int32_t *__restrict__ nv,
+                              int32_t *__restrict__ rep, int32_t *__restrict__ nmini, int32_t *__restrict__ src_li)
+{
+	const int li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= n_list) return;
+	const int f = list[li];
+	nu[f] = nu2[li], nv[f] = nv2[li], rep[f] = rep2[li], nmini[f] = nmini2[li], src_li[f] = li;
+}
+
+// ------------------------------------------------------------------ host side
+
+static int scan_i32_to_i64(mmg_ctx_t *c, const int32_t *d_in, int64_t *d_out, int n)
+{ // exclusive sum over n items (callers pass n_items+1 to get the total in the last slot)
+	size_t tmp = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_in, d_out, n, c->stream);
+	MMG_TRY(c->d_cub.ensure(tmp));
+	MMG_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, d_in, d_out, n, c->stream));
+	++c->launches;
+	return MMG_OK;
+}
+
+extern "C" int mmg_batch_upload(mmg_ctx_t *c, const mmg_mapopt_t *opt, const mmg_batch_t *b)
+{
+	MMG_CUDA(cudaSetDevice(c->dev));
+	ResidentBatch &rb = c->rb;
+	rb.n_frag = b->n_frag, rb.n_seq = b->n_seq, rb.n_bases = b->n_bases;
+	rb.n_seg.assign(b->n_seg, b->n_seg + b->n_frag);
+	rb.seg_off.assign(b->seg_off, b->seg_off + b->n_frag);
+	rb.seq_len.assign(b->seq_len, b->seq_len + b->n_seq);
+	rb.q_off.resize(b->n_seq + 1);
+	rb.frag_unit0.resize(b->n_frag + 1);
+	rb.frag_qlen.resize(b->n_frag);
+	std::vector<uint8_t> flip(b->n_seq, 0);
+	std::vector<SketchUnit> units;
+	units.reserve(b->n_seq);
+	uint64_t qo = 0;
+	for (int r = 0; r < b->n_seq; ++r) { rb.q_off[r] = qo; qo += ((uint64_t)b->seq_len[r] + 7) / 8 * 8; }
+	rb.q_off[b->n_seq] = qo;
+	rb.q_words = qo / 8;
+	for (int f = 0; f < b->n_frag; ++f) {
+		const int off = b->seg_off[f], ns = b->n_seg[f];
+		int sum = 0;
+		rb.frag_unit0[f] = (int32_t)units.size();
+		for (int j = 0; j < ns; ++j) {
+			const int r = off + j, len = b->seq_len[r];
+			if (ns == 2 && ((j == 0 && (opt->pe_ori >> 1 & 1)) || (j == 1 && (opt->pe_ori & 1)))) flip[r] = 1;
+			for (int s = 0; s < len; s += MMG_READ_CHUNK) {
+				SketchUnit u;
+				u.off = rb.q_off[r], u.len = len, u.rid = (uint32_t)j, u.y_add = (uint64_t)sum << 1;
+				u.emit_start = s, u.emit_end = s + MMG_READ_CHUNK < len ? s + MMG_READ_CHUNK : len;
+				units.push_back(u);
+			}
+			sum += len;
+		}
+		rb.frag_qlen[f] = sum;
+	}
+	rb.frag_unit0[b->n_frag] = (int32_t)units.size();
+	rb.n_units = (int)units.size();
+
+	// stage everything through one pinned buffer so that the copies are truly asynchronous
+	const size_t sz_bases = (b->n_bases + 15) & ~(size_t)15;
+	MMG_TRY(c->h_in.ensure(sz_bases + 64));
+	memcpy(c->h_in.p, b->bases, b->n_bases);
+	MMG_TRY(c->d_ascii.ensure(sz_bases + 64));
+	MMG_TRY(c->d_Q.ensure((rb.q_words + 8) * 4));
+	MMG_TRY(c->d_seq_len.ensure((size_t)(b->n_seq + 1) * 4));
+	MMG_TRY(c->d_seq_off.ensure((size_t)(b->n_seq + 1) * 8));
+	MMG_TRY(c->d_q_off.ensure((size_t)(b->n_seq + 1) * 8));
+	MMG_TRY(c->d_flip.ensure((size_t)b->n_seq + 16));
+	MMG_TRY(c->d_units.ensure((size_t)(rb.n_units + 1) * sizeof(SketchUnit)));
+	MMG_TRY(c->d_frag_unit0.ensure((size_t)(b->n_frag + 1) * 4));
+	MMG_TRY(c->d_frag_qlen.ensure((size_t)(b->n_frag + 1) * 4));
+	MMG_TRY(c->d_misc.ensure((size_t)(b->n_frag + 1) * 4)); // n_seg
+	MMG_CUDA(cudaMemcpyAsync(c->d_ascii.p, c->h_in.p, b->n_bases, cudaMemcpyHostToDevice, c->stream));
+	MMG_CUDA(cudaMemcpyAsync(c->d_seq_len.p, b->seq_len, (size_t)b->n_seq * 4, cudaMemcpyHostToDevice, c->stream));
+	MMG_CUDA(cudaMemcpyAsync(c->d_seq_off.p, b->seq_off, (size_t)b->n_seq * 8, cudaMemcpyHostToDevice, c->stream));
+	MMG_CUDA(cudaMemcpyAsync(c->d_q_off.p, rb.q_off.data(), (size_t)(b->n_seq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+	MMG_CUDA(cudaMemcpyAsync(c->d_flip.p, flip.data(), (size_t)b->n_seq, cudaMemcpyHostToDevice, c->stream));
+	MMG_CUDA(cudaMemcpyAsync(c->d_units.p, units.data(), (size_t)rb.n_units * sizeof(SketchUnit), cudaMemcpyHostToDevice, c->stream));
+	MMG_CUDA(cudaMemcpyAsync(c->d_frag_unit0.p, rb.frag_unit0.data(), (size_t)(b->n_frag + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+	MMG_CUDA(cudaMemcpyAsync(c->d_frag_qlen.p, rb.frag_qlen.data(), (size_t)b->n_frag * 4, cudaMemcpyHostToDevice, c->stream));
+	MMG_CUDA(cudaMemcpyAsync(c->d_misc.p, b->n_seg, (size_t)b->n_frag * 4, cudaMemcpyHostToDevice, c->stream));
+	if (rb.q_words)
+		MMG_LAUNCH(c, k_encode_reads, mmg_blocks(rb.q_words, 256), 256, 0, c->d_ascii.as<uint8_t>(), c->d_seq_off.as<uint64_t>(),
+		           c->d_seq_len.as<int32_t>(), c->d_q_off.as<uint64_t>(), c->d_flip.as<uint8_t>(), b->n_seq, rb.q_words, c->d_Q.as<uint32_t>());
+	MMG_CUDA(cudaStreamSynchronize(c->stream)); // units/flip live on this stack frame
+	return MMG_OK;
+}
+
+struct PassBufs {
+	DevBuf *na, *aoff, *rep, *nmini, *mini, *a, *work, *u, *b, *stack, *nu, *nv;
+};
+
+// plan -> scan -> fill -> chain for the fragments in `list` (null = all) with cut-off max_occ
+static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, const FragTab &ft, const int32_t *d_list, int n_list,
+                    int64_t n_mv, int max_occ, const PassBufs &pb, bool want_mini, uint8_t *d_flag, int64_t *n_anchors)
+{
+	*n_anchors = 0;
+	if (n_list == 0) return MMG_OK;
+	MMG_TRY(pb.na->ensure((size_t)(n_list + 1) * 4));
+	MMG_TRY(pb.aoff->ensure((size_t)(n_list + 1) * 8));
+	MMG_TRY(pb.rep->ensure((size_t)(n_list + 1) * 4));
+	MMG_TRY(pb.nmini->ensure((size_t)(n_list + 1) * 4));
+	MMG_TRY(pb.nu->ensure((size_t)(n_list + 1) * 4));
+	MMG_TRY(pb.nv->ensure((size_t)(n_list + 1) * 4));
+	if (want_mini) MMG_TRY(pb.mini->ensure((size_t)(n_mv + 1) * 8));
+	MMG_CUDA(cudaMemsetAsync(pb.na->p, 0, (size_t)(n_list + 1) * 4, c->stream));
+	MMG_CUDA(cudaMemsetAsync(pb.nu->p, 0, (size_t)(n_list + 1) * 4, c->stream)); // slot n_list must read 0 for the scans
+	MMG_CUDA(cudaMemsetAsync(pb.nv->p, 0, (size_t)(n_list + 1) * 4, c->stream));
+	MMG_CUDA(cudaMemsetAsync(pb.nmini->p, 0, (size_t)(n_list + 1) * 4, c->stream));
+	MMG_LAUNCH(c, k_plan, mmg_blocks(n_list, 128), 128, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), max_occ,
+	           pb.na->as<int32_t>(), pb.rep->as<int32_t>(), pb.nmini->as<int32_t>(), want_mini ? pb.mini->as<uint64_t>() : nullptr);
+	MMG_TRY(scan_i32_to_i64(c, pb.na->as<int32_t>(), pb.aoff->as<int64_t>(), n_list + 1));
+	int64_t tot = 0;
+	MMG_CUDA(cudaMemcpyAsync(&tot, pb.aoff->as<int64_t>() + n_list, 8, cudaMemcpyDeviceToHost, c->stream));
+	MMG_CUDA(cudaStreamSynchronize(c->stream));
+	*n_anchors = tot;
+	MMG_TRY(pb.a->ensure((size_t)(tot + 1) * 16));
+	MMG_TRY(pb.work->ensure((size_t)(tot + 1) * 16));
+	MMG_TRY(pb.u->ensure((size_t)(tot + 1) * 16));
+	MMG_TRY(pb.b->ensure((size_t)(tot + 1) * 16));
+	MMG_TRY(pb.stack->ensure((size_t)(tot / 65 + 2 * (size_t)n_list + 4) * sizeof(RsFrame)));
+	MMG_TRY(c->d_heap.ensure((size_t)(n_mv + 1) * 16));
+	MMG_LAUNCH(c, k_fill, mmg_blocks(n_list, 64), 64, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
+	           mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>(), c->d_heap.as<mm128>(),
+	           pb.stack->as<RsFrame>());
+	ChainOptDev co;
+	co.bw = opt->bw, co.max_gap = opt->max_gap, co.max_gap_ref = opt->max_gap_ref, co.max_frag_len = opt->max_frag_len;
+	co.max_skip = opt->max_chain_skip, co.max_iter = opt->max_chain_iter, co.min_cnt = opt->min_cnt, co.min_sc = opt->min_chain_score;
+	co.is_cdna = !!(opt->flag & MMG_F_SPLICE), co.is_sr = !!(opt->flag & MMG_F_SR);
+	MMG_LAUNCH(c, k_chain, mmg_blocks(n_list, 64), 64, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+	           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
+	           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), pb.rep->as<int32_t>(), opt->max_occ > opt->mid_occ ? 1 : 0, d_flag,
+	           c->d_frag_iter.as<unsigned long long>());
+	return MMG_OK;
+}
+
+extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, mmg_chains_t *out, int download)
+{
+	MMG_CUDA(cudaSetDevice(c->dev));
+	ResidentBatch &rb = c->rb;
+	const int nf = rb.n_frag;
+	memset(out, 0, sizeof(*out));
+	out->n_frag = nf;
+	if (nf == 0) return MMG_OK;
+	if (mi->w > MMG_MAX_W) { mmg_set_error("w=%d exceeds the device limit %d", mi->w, MMG_MAX_W); return MMG_ELIMIT; }
+	MMG_CUDA(cudaEventRecord(c->ev[0], c->stream));
+	// K1
+	int64_t n_mv = 0;
+	MMG_TRY(mmg_run_sketch(c, c->d_Q.as<uint32_t>(), c->d_units.as<SketchUnit>(), rb.n_units, mi->w, mi->k, mi->is_hpc, c->d_unit_cnt,
+	                       c->d_unit_off, c->d_mv, &n_mv));
+	// K2a
+	MMG_TRY(c->d_m_n.ensure((size_t)(n_mv + 1) * 4));
+	MMG_TRY(c->d_m_val.ensure((size_t)(n_mv + 1) * 8));
+	if (n_mv) MMG_LAUNCH(c, k_lookup, mmg_blocks(n_mv, 256), 256, 0, mi->view(), c->d_mv.as<mm128>(), n_mv, c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>());
+	FragTab ft;
+	ft.unit0 = c->d_frag_unit0.as<int32_t>(), ft.unit_off = c->d_unit_off.as<int64_t>(), ft.qlen = c->d_frag_qlen.as<int32_t>();
+	const bool want_mini = !(opt->flag & MMG_F_SR); // only mm_est_err reads mini_pos (map.c:388)
+	MMG_TRY(c->d_frag_flag.ensure((size_t)nf + 16));
+	MMG_TRY(c->d_frag_iter.ensure(16));
+	MMG_CUDA(cudaMemsetAsync(c->d_frag_flag.p, 0, (size_t)nf + 16, c->stream));
+	MMG_CUDA(cudaMemsetAsync(c->d_frag_iter.p, 0, 16, c->stream));
+	PassBufs p1 = {&c->d_frag_na, &c->d_frag_aoff, &c->d_frag_rep, &c->d_frag_nmini, &c->d_mini, &c->d_a, &c->d_work, &c->d_u, &c->d_b,
+	               &c->d_stack, &c->d_frag_nu, &c->d_frag_nv};
+	int64_t n_anch1 = 0, n_anch2 = 0;
+	MMG_TRY(run_pass(c, mi, opt, ft, nullptr, nf, n_mv, opt->mid_occ, p1, want_mini, c->d_frag_flag.as<uint8_t>(), &n_anch1));
+	// second pass: fragments whose best chain misses a segment, with the higher cut-off (map.c:353-375)
+	std::vector<int32_t> list;
+	std::vector<uint8_t> hflag(nf);
+	MMG_TRY(c->d_frag_list.ensure((size_t)(nf + 1) * 8)); // [0,nf): list, [nf,2nf): src slot per fragment
+	int32_t *d_list = c->d_frag_list.as<int32_t>(), *d_src = d_list + nf;
+	MMG_CUDA(cudaMemsetAsync(d_src, 0xff, (size_t)nf * 4, c->stream));
+	if (opt->max_occ > opt->mid_occ) {
+		MMG_CUDA(cudaMemcpyAsync(hflag.data(), c->d_frag_flag.p, nf, cudaMemcpyDeviceToHost, c->stream));
+		MMG_CUDA(cudaStreamSynchronize(c->stream));
+		for (int f = 0; f < nf; ++f) if (hflag[f]) list.push_back(f);
+	}
+	PassBufs p2 = {&c->d2_frag_na, &c->d2_frag_aoff, &c->d2_frag_rep, &c->d2_frag_nmini, &c->d2_mini, &c->d2_a, &c->d2_work, &c->d2_u, &c->d2_b,
+	               &c->d2_stack, &c->d2_frag_nu, &c->d2_frag_nv};
+	const int n2 = (int)list.size();
+	if (n2) {
+		MMG_CUDA(cudaMemcpyAsync(d_list, list.data(), (size_t)n2 * 4, cudaMemcpyHostToDevice, c->stream));
+		MMG_TRY(run_pass(c, mi, opt, ft, d_list, n2, n_mv, opt->max_occ, p2, want_mini, nullptr, &n_anch2));
+		MMG_LAUNCH(c, k_merge_pass2, mmg_blocks(n2, 128), 128, 0, n2, d_list, c->d2_frag_nu.as<int32_t>(), c->d2_frag_nv.as<int32_t>(),
+		           c->d2_frag_rep.as<int32_t>(), c->d2_frag_nmini.as<int32_t>(), c->d_frag_nu.as<int32_t>(), c->d_frag_nv.as<int32_t>(),
+		           c->d_frag_rep.as<int32_t>(), c->d_frag_nmini.as<int32_t>(), d_src);
+	}
+	// dense outputs
+	MMG_TRY(c->d_uoff.ensure((size_t)(nf + 1) * 8));
+	MMG_TRY(c->d_voff.ensure((size_t)(nf + 1) * 8));
+	MMG_TRY(c->d_moff.ensure((size_t)(nf + 1) * 8));
+	MMG_TRY(scan_i32_to_i64(c, c->d_frag_nu.as<int32_t>(), c->d_uoff.as<int64_t>(), nf + 1));
+	MMG_TRY(scan_i32_to_i64(c, c->d_frag_nv.as<int32_t>(), c->d_voff.as<int64_t>(), nf + 1));
+	if (want_mini) MMG_TRY(scan_i32_to_i64(c, c->d_frag_nmini.as<int32_t>(), c->d_moff.as<int64_t>(), nf + 1));
+	int64_t tot[3] = {0, 0, 0};
+	MMG_CUDA(cudaMemcpyAsync(&tot[0], c->d_uoff.as<int64_t>() + nf, 8, cudaMemcpyDeviceToHost, c->stream));
+	MMG_CUDA(cudaMemcpyAsync(&tot[1], c->d_voff.as<int64_t>() + nf, 8, cudaMemcpyDeviceToHost, c->stream));
+	if (want_mini) MMG_CUDA(cudaMemcpyAsync(&tot[2], c->d_moff.as<int64_t>() + nf, 8, cudaMemcpyDeviceToHost, c->stream));
+	MMG_CUDA(cudaStreamSynchronize(c->stream));
+	MMG_TRY(c->d_out_u.ensure((size_t)(tot[0] + 1) * 8));
+	MMG_TRY(c->d_out_a.ensure((size_t)(tot[1] + 1) * 16));
+	MMG_TRY(c->d_out_mini.ensure((size_t)(tot[2] + 1) * 8));
+	MMG_LAUNCH(c, k_gather, nf, 64, 0, nf, d_src, c->d_frag_aoff.as<int64_t>(), c->d_u.as<uint64_t>(), c->d_a.as<mm128>(),
+	           c->d2_frag_aoff.as<int64_t>(), c->d2_u.as<uint64_t>(), c->d2_a.as<mm128>(), c->d_frag_nu.as<int32_t>(), c->d_frag_nv.as<int32_t>(),
+	           c->d_uoff.as<int64_t>(), c->d_voff.as<int64_t>(), c->d_out_u.as<uint64_t>(), c->d_out_a.as<mm128>());
+	if (want_mini)
+		MMG_LAUNCH(c, k_gather_mini, nf, 64, 0, nf, ft, d_src, c->d_mini.as<uint64_t>(), c->d2_mini.as<uint64_t>(), c->d_frag_nmini.as<int32_t>(),
+		           c->d_moff.as<int64_t>(), c->d_out_mini.as<uint64_t>());
+	MMG_CUDA(cudaEventRecord(c->ev[1], c->stream));
+	unsigned long long iters = 0;
+	MMG_CUDA(cudaMemcpyAsync(&iters, c->d_frag_iter.p, 8, cudaMemcpyDeviceToHost, c->stream));
+	out->n_minimizers = (uint64_t)n_mv, out->n_anchors = (uint64_t)(n_anch1 + n_anch2);
+	if (download) {
+		// meta: n_u | n_a | rep_len | n_mini | rechained (int32 each) then u_off | a_off | mini_off (uint64 each, nf+1)
+		const size_t meta_i = (size_t)nf * 5 * 4, meta_o = (size_t)(nf + 1) * 3 * 8;
+		MMG_TRY(c->h_out_meta.ensure(meta_i + meta_o + 64));
+		MMG_TRY(c->h_out_u.ensure((size_t)(tot[0] + 1) * 8));
+		MMG_TRY(c->h_out_a.ensure((size_t)(tot[1] + 1) * 16));
+		MMG_TRY(c->h_out_mini.ensure((size_t)(tot[2] + 1) * 8));
+		int32_t *hi = c->h_out_meta.as<int32_t>();
+		uint64_t *ho = reinterpret_cast<uint64_t*>(c->h_out_meta.as<uint8_t>() + ((meta_i + 15) & ~(size_t)15));
+		MMG_CUDA(cudaMemcpyAsync(hi, c->d_frag_nu.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
+		MMG_CUDA(cudaMemcpyAsync(hi + nf, c->d_frag_nv.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
+		MMG_CUDA(cudaMemcpyAsync(hi + 2 * nf, c->d_frag_rep.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
+		MMG_CUDA(cudaMemcpyAsync(hi + 3 * nf, c->d_frag_nmini.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
+		MMG_CUDA(cudaMemcpyAsync(hi + 4 * nf, d_src, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
+		MMG_CUDA(cudaMemcpyAsync(ho, c->d_uoff.p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+		MMG_CUDA(cudaMemcpyAsync(ho + (nf + 1), c->d_voff.p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+		if (want_mini) MMG_CUDA(cudaMemcpyAsync(ho + 2 * (nf + 1), c->d_moff.p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+		if (tot[0]) MMG_CUDA(cudaMemcpyAsync(c->h_out_u.p, c->d_out_u.p, (size_t)tot[0] * 8, cudaMemcpyDeviceToHost, c->stream));
+		if (tot[1]) MMG_CUDA(cudaMemcpyAsync(c->h_out_a.p, c->d_out_a.p, (size_t)tot[1] * 16, cudaMemcpyDeviceToHost, c->stream));
+		if (tot[2]) MMG_CUDA(cudaMemcpyAsync(c->h_out_mini.p, c->d_out_mini.p, (size_t)tot[2] * 8, cudaMemcpyDeviceToHost, c->stream));
+		MMG_CUDA(cudaEventRecord(c->ev[2], c->stream));
+		MMG_CUDA(cudaStreamSynchronize(c->stream));
+		for (int f = 0; f < nf; ++f) hi[4 * nf + f] = hi[4 * nf + f] >= 0 ? 1 : 0; // src slot -> rechained flag
+		if (!want_mini) { for (int f = 0; f < nf; ++f) hi[3 * nf + f] = 0; memset(ho + 2 * (nf + 1), 0, (size_t)(nf + 1) * 8); }
+		out->n_u = hi, out->n_a = hi + nf, out->rep_len = hi + 2 * nf, out->n_mini = hi + 3 * nf, out->rechained = hi + 4 * nf;
+		out->u_off = ho, out->a_off = ho + (nf + 1), out->mini_off = ho + 2 * (nf + 1);
+		out->u = c->h_out_u.as<uint64_t>(), out->a = c->h_out_a.as<mmg128_t>(), out->mini_pos = c->h_out_mini.as<uint64_t>();
+		float ms = 0;
+		cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->t_d2h_ms = ms;
+	} else MMG_CUDA(cudaStreamSynchronize(c->stream));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); out->t_kernels_ms = ms;
+	out->n_chain_iter = iters;
+	return MMG_OK;
+}
+
+extern "C" int mmg_seed_chain_batch(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, const mmg_batch_t *b, mmg_chains_t *out)
+{
+	MMG_CUDA(cudaSetDevice(c->dev));
+	MMG_CUDA(cudaEventRecord(c->ev[3], c->stream));
+	MMG_TRY(mmg_batch_upload(c, opt, b));
+	MMG_TRY(mmg_seed_chain_resident(c, mi, opt, out, 1));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, c->ev[3], c->ev[0]); out->t_h2d_ms = ms;
+	return MMG_OK;
+}
+
+// ------------------------------------------------------------------ single-call entry points (parity tests)
+
+extern "C" int mmg_sketch(mmg_ctx_t *c, const char *str, int len, int w, int k, uint32_t rid, int is_hpc, mmg128_t *out, int cap, int *n_out)
+{
+	*n_out = 0;
+	if (len <= 0) return MMG_OK;
+	if (w < 1 || w > MMG_MAX_W || k < 1 || k > 28) { mmg_set_error("mmg_sketch: need 1<=w<=%d, 1<=k<=28", MMG_MAX_W); return w > MMG_MAX_W ? MMG_ELIMIT : MMG_EINVAL; }
+	MMG_CUDA(cudaSetDevice(c->dev));
+	// a single read, deliberately cut into small chunks so that the warm-up logic is exercised
+	mmg_mapopt_t opt; memset(&opt, 0, sizeof(opt));
+	int32_t one = 1, zero = 0, l = len; uint64_t o = 0;
+	mmg_batch_t b; b.n_frag = 1, b.n_seq = 1, b.n_seg = &one, b.seg_off = &zero, b.seq_len = &l, b.seq_off = &o, b.bases = str, b.n_bases = (uint64_t)len;
+	MMG_TRY(mmg_batch_upload(c, &opt, &b));
+	std::vector<SketchUnit> units;
+	const int chunk = is_hpc ? len : 96;
+	for (int s = 0; s < len; s += chunk) {
+		SketchUnit u; u.off = 0, u.len = len, u.rid = rid, u.y_add = 0, u.emit_start = s, u.emit_end = s + chunk < len ? s + chunk : len;
+		units.push_back(u);
+	}
+	MMG_TRY(c->d_units.ensure(units.size() * sizeof(SketchUnit)));
+	MMG_CUDA(cudaMemcpyAsync(c->d_units.p, units.data(), units.size() * sizeof(SketchUnit), cudaMemcpyHostToDevice, c->stream));
+	int64_t n = 0;
+	MMG_TRY(mmg_run_sketch(c, c->d_Q.as<uint32_t>(), c->d_units.as<SketchUnit>(), (int)units.size(), w, k, is_hpc, c->d_unit_cnt, c->d_unit_off, c->d_mv, &n));
+	*n_out = (int)n;
+	const int64_t m = n < cap ? n : cap;
+	if (m > 0) MMG_CUDA(cudaMemcpyAsync(out, c->d_mv.p, (size_t)m * 16, cudaMemcpyDeviceToHost, c->stream));
+	MMG_CUDA(cudaStreamSynchronize(c->stream));
+	return MMG_OK;
+}
+
+__global__ void k_collect_one(IdxView ix, const mm128 *mv, int n_mv, int heap_sort, int64_t flag, int max_occ, int qlen,
+                              int32_t *m_n, uint64_t *m_val, mm128 *heap, mm128 *a, int64_t a_cap, RsFrame *stack, int64_t *out4, uint64_t *mini)
+{
+	if (blockIdx.x || threadIdx.x) return;
+	for (int i = 0; i < n_mv; ++i) { uint64_t v; m_n[i] = mmg_idx_probe(ix, mv[i].x >> 8, &v); m_val[i] = v; }
+	int rep, nm;
+	int64_t n_a = mmg_frag_plan(mv, m_n, n_mv, max_occ, &rep, &nm, mini);
+	out4[0] = n_a, out4[1] = rep, out4[2] = nm;
+	if (n_a > a_cap) return;
+	if (heap_sort) n_a = mmg_fill_heap(mv, m_n, m_val, n_mv, max_occ, ix.pos, flag, qlen, n_a, heap, a);
+	else n_a = mmg_fill_flat(mv, m_n, m_val, n_mv, max_occ, ix.pos, flag, qlen, a, stack);
+	out4[0] = n_a;
+}
+
+extern "C" int mmg_collect_seeds(mmg_ctx_t *c, const mmg_idx_t *mi, int heap_sort, int64_t flag, int max_occ, int n_mv, const mmg128_t *mv,
+                                 int qlen, mmg128_t *a_out, int64_t a_cap, int64_t *n_a, int *rep_len, int *n_mini_pos, uint64_t *mini_pos)
+{
+	MMG_CUDA(cudaSetDevice(c->dev));
+	DevBuf dmv, dn, dval, dheap, da, dstack, dout, dmini;
+	int rc = MMG_OK;
+	auto fin = [&]() { dmv.release(); dn.release(); dval.release(); dheap.release(); da.release(); dstack.release(); dout.release(); dmini.release(); };
+#define CS_TRY(x) do { rc = (x); if (rc != MMG_OK) { fin(); return rc; } } while (0)
+	CS_TRY(dmv.ensure((size_t)(n_mv + 1) * 16)); CS_TRY(dn.ensure((size_t)(n_mv + 1) * 4)); CS_TRY(dval.ensure((size_t)(n_mv + 1) * 8));
+	CS_TRY(dheap.ensure((size_t)(n_mv + 1) * 16)); CS_TRY(da.ensure((size_t)(a_cap + 1) * 16)); CS_TRY(dstack.ensure((size_t)(a_cap / 65 + 4) * sizeof(RsFrame)));
+	CS_TRY(dout.ensure(64)); CS_TRY(dmini.ensure((size_t)(n_mv + 1) * 8));
+	if (n_mv) cudaMemcpyAsync(dmv.p, mv, (size_t)n_mv * 16, cudaMemcpyHostToDevice, c->stream);
+	k_collect_one<<<1, 32, 0, c->stream>>>(mi->view(), dmv.as<mm128>(), n_mv, heap_sort, flag, max_occ, qlen, dn.as<int32_t>(), dval.as<uint64_t>(),
+	                                      dheap.as<mm128>(), da.as<mm128>(), a_cap, dstack.as<RsFrame>(), dout.as<int64_t>(), dmini.as<uint64_t>());
+	++c->launches;
+	int64_t o4[4] = {0, 0, 0, 0};
+	cudaMemcpyAsync(o4, dout.p, 32, cudaMemcpyDeviceToHost, c->stream);
+	cudaError_t e = cudaStreamSynchronize(c->stream);
+	if (e != cudaSuccess) { mmg_set_error("mmg_collect_seeds: %s", cudaGetErrorString(e)); fin(); return MMG_ECUDA; }
+	*n_a = o4[0], *rep_len = (int)o4[1], *n_mini_pos = (int)o4[2];
+	if (o4[0] <= a_cap && o4[0] > 0) cudaMemcpy(a_out, da.p, (size_t)o4[0] * 16, cudaMemcpyDeviceToHost);
+	if (mini_pos && o4[2] > 0) cudaMemcpy(mini_pos, dmini.p, (size_t)o4[2] * 8, cudaMemcpyDeviceToHost);
+	fin();
+	return MMG_OK;
+#undef CS_TRY
+}
+
+__global__ void k_chain_one(ChainParams P, int64_t n, mm128 *a, int32_t *work, uint64_t *u, mm128 *b, RsFrame *stack, int64_t *out2)
+{
+	if (blockIdx.x || threadIdx.x) return;
+	int64_t n_v = 0;
+	mmg_chain_fill_seq(P, n, a, work, work + n, work + 2 * n, work + 3 * n);
+	out2[0] = mmg_chain_backtrack(P, n, a, work, work + n, work + 2 * n, work + 3 * n, u, b, stack, &n_v);
+	out2[1] = n_v;
+}
+
+extern "C" int mmg_chain_dp(mmg_ctx_t *c, int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
+                            int is_cdna, int n_segs, int64_t n, mmg128_t *a, int *n_u, uint64_t *u)
+{
+	*n_u = 0;
+	if (n <= 0) return MMG_OK;
+	MMG_CUDA(cudaSetDevice(c->dev));
+	ChainParams P; P.max_dist_x = max_dist_x, P.max_dist_y = max_dist_y, P.bw = bw, P.max_skip = max_skip, P.max_iter = max_iter;
+	P.min_cnt = min_cnt, P.min_sc = min_sc, P.is_cdna = is_cdna, P.n_segs = n_segs;
+	DevBuf da, dw, du, db, ds, dout;
+	int rc = MMG_OK;
+	auto fin = [&]() { da.release(); dw.release(); du.release(); db.release(); ds.release(); dout.release(); };
+#define CH_TRY(x) do { rc = (x); if (rc != MMG_OK) { fin(); return rc; } } while (0)
+	CH_TRY(da.ensure((size_t)n * 16)); CH_TRY(dw.ensure((size_t)n * 16)); CH_TRY(du.ensure((size_t)n * 16)); CH_TRY(db.ensure((size_t)n * 16));
+	CH_TRY(ds.ensure((size_t)(n / 65 + 4) * sizeof(RsFrame))); CH_TRY(dout.ensure(64));
+	cudaMemcpyAsync(da.p, a, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream);
+	k_chain_one<<<1, 32, 0, c->stream>>>(P, n, da.as<mm128>(), dw.as<int32_t>(), du.as<uint64_t>(), db.as<mm128>(), ds.as<RsFrame>(), dout.as<int64_t>());
+	++c->launches;
+	int64_t o2[2] = {0, 0};
+	cudaMemcpyAsync(o2, dout.p, 16, cudaMemcpyDeviceToHost, c->stream);
+	cudaError_t e = cudaStreamSynchronize(c->stream);
+	if (e != cudaSuccess) { mmg_set_error("mmg_chain_dp: %s", cudaGetErrorString(e)); fin(); return MMG_ECUDA; }
+	*n_u = (int)o2[0];
+	if (o2[0] > 0) { cudaMemcpy(u, du.p, (size_t)o2[0] * 8, cudaMemcpyDeviceToHost); cudaMemcpy(a, da.p, (size_t)o2[1] * 16, cudaMemcpyDeviceToHost); }
+	fin();
+	return MMG_OK;
+#undef CH_TRY
+}

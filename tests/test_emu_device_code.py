@@ -1,0 +1,144 @@
+"""CPU-side check of the per-thread device code (airlift_b200/csrc/mmg_core.h compiled by g++ into
+build/libmmg_emu.so) against the oracle port.  No GPU needed; the same functions are what the
+kernels call, so this pins the logic before it ever runs on the device."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+import pytest
+import _libs as L
+
+EMU_SO = os.path.join(L.ROOT, "build", "libmmg_emu.so")
+
+
+class Ez(C.Structure):
+    _fields_ = [("max", C.c_uint32), ("zdropped", C.c_int32), ("max_q", C.c_int32), ("max_t", C.c_int32), ("mqe", C.c_int32),
+                ("mqe_t", C.c_int32), ("mte", C.c_int32), ("mte_q", C.c_int32), ("score", C.c_int32), ("n_cigar", C.c_int32),
+                ("reach_end", C.c_int32)]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-C", L.ROOT, "emu"], stdout=subprocess.DEVNULL)
+    E = C.CDLL(EMU_SO)
+    E.emu_sketch.restype = C.c_int
+    E.emu_sketch.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    E.emu_idx_new.restype = C.c_void_p
+    E.emu_idx_new.argtypes = [C.c_int64, C.c_void_p, C.c_void_p]
+    E.emu_idx_free.argtypes = [C.c_void_p]
+    E.emu_collect.restype = C.c_int64
+    E.emu_collect.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
+                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+    E.emu_chain.restype = C.c_int
+    E.emu_chain.argtypes = [C.c_int] * 9 + [C.c_int64, C.c_void_p, C.c_void_p]
+    E.emu_rs_sort_128x.argtypes = [C.c_void_p, C.c_int64]
+    E.emu_ksw.restype = C.c_int
+    E.emu_ksw.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.POINTER(Ez), C.c_void_p]
+    return E
+
+
+def emu_sketch(E, s, w, k, rid=0, hpc=0, chunk=0):
+    out = np.zeros(len(s) + 8, dtype=L.mm128)
+    n = E.emu_sketch(s, len(s), w, k, rid, hpc, chunk, out.ctypes.data, len(out))
+    assert n >= 0
+    return out[:n].copy()
+
+
+@pytest.mark.parametrize("w,k,hpc", [(11, 21, 0), (10, 15, 0), (5, 19, 1), (19, 19, 0), (3, 4, 0), (1, 15, 0), (10, 14, 0), (4, 6, 0)])
+def test_sketch_chunked_equals_oracle(emu, w, k, hpc):
+    rng = np.random.default_rng(77 + w + k)
+    for it in range(80):
+        n = int(rng.integers(1, 1500))
+        s = L.rand_seq(rng, n, n_frac=[0, 0.01, 0.15][it % 3])
+        if it % 5 == 0:
+            s = (b"AT" * n)[:n] if it % 2 else (s[:6] * n)[:n]
+        if it % 11 == 0:  # long N run in the middle
+            s = s[: n // 3] + b"N" * (n // 4) + s[n // 3 + n // 4:]
+        want = L.orc_sketch(s, w, k, 7, hpc)
+        for chunk in [0, 1, 7, 64, 96, 500]:
+            got = emu_sketch(emu, s, w, k, 7, hpc, chunk)
+            assert got.tobytes() == want.tobytes(), (w, k, hpc, it, chunk, len(s))
+
+
+def test_exact_radix_replay(emu):
+    rng = np.random.default_rng(3)
+    for n in [0, 1, 64, 65, 300, 4000, 20000]:
+        for bits in [2, 9, 33, 64]:
+            a = np.zeros(n, dtype=L.mm128)
+            a["x"] = rng.integers(0, (1 << bits) - 1, n, dtype=np.uint64, endpoint=True)
+            a["y"] = np.arange(n)
+            b = a.copy()
+            emu.emu_rs_sort_128x(a.ctypes.data, n)
+            L.oracle().orc_radix_sort_128x(b.ctypes.data, b.ctypes.data + 16 * n)
+            assert a.tobytes() == b.tobytes()
+
+
+def _index_arrays(seqs, w, k):
+    parts = [L.orc_sketch(s, w, k, i) for i, s in enumerate(seqs)]
+    mv = np.concatenate(parts)
+    key = mv["x"] >> np.uint64(8)
+    order = np.lexsort((mv["y"], key))
+    return np.ascontiguousarray(key[order]), np.ascontiguousarray(mv["y"][order])
+
+
+@pytest.mark.parametrize("mode", ["sr", "ont"])
+def test_seed_and_chain(emu, mode):
+    from test_oracle_vs_ref import _mk_ref, _frags, SR_CHAIN, ONT_CHAIN
+    rng = np.random.default_rng(42)
+    seqs = _mk_ref(rng)
+    w, k = (11, 21) if mode == "sr" else (10, 15)
+    key, pos = _index_arrays(seqs, w, k)
+    ei = emu.emu_idx_new(len(key), key.ctypes.data, pos.ctypes.data)
+    oi = L.oracle().orc_idx_build(w, k, 0, len(seqs), L.c_str_array(seqs))
+    rng = np.random.default_rng(11)
+    try:
+        for segs in _frags(rng, seqs, 150 if mode == "sr" else 25, mode == "sr"):
+            mv, qlen = L.frag_minimizers(L.orc_sketch, segs, w, k)
+            for max_occ in ([1000, 20, 5] if mode == "sr" else [50, 8]):
+                a0, _, _ = L.orc_collect(oi, mode == "sr", 0, max_occ, mv, qlen)
+                for flag in [0, 0x100000, 0x200000]:
+                    a1, rep1, mp1 = L.orc_collect(oi, mode == "sr", flag, max_occ, mv, qlen)
+                    a2 = np.zeros(len(a0) + 64, dtype=L.mm128)  # capacity = the unfiltered plan
+                    mp2 = np.zeros(len(mv) + 1, dtype=np.uint64)
+                    rep2, nm2 = C.c_int(0), C.c_int(0)
+                    n2 = emu.emu_collect(ei, mode == "sr", flag, max_occ, len(mv), mv.ctypes.data, qlen, a2.ctypes.data, len(a2),
+                                         C.byref(rep2), C.byref(nm2), mp2.ctypes.data)
+                    assert n2 == len(a1) and rep2.value == rep1 and (mp2[:nm2.value] == mp1).all()
+                    assert a2[:n2].tobytes() == a1.tobytes()
+                params = SR_CHAIN if mode == "sr" else ONT_CHAIN
+                a1, _, _ = L.orc_collect(oi, mode == "sr", 0, max_occ, mv, qlen)
+                u1, b1 = L.chain_call(L.oracle().orc_chain_dp, params, a1)
+                u2, b2 = L.chain_call(emu.emu_chain, params, a1)
+                assert (u1 == u2).all() and b1.tobytes() == b2.tobytes()
+    finally:
+        emu.emu_idx_free(ei)
+        L.oracle().orc_idx_destroy(oi)
+
+
+def emu_ksw(E, q, t, mat, pen, w, zd, eb, fl):
+    ez = Ez()
+    cig = np.zeros(len(q) + len(t) + 4, dtype=np.uint32)
+    q = np.ascontiguousarray(q, dtype=np.uint8); t = np.ascontiguousarray(t, dtype=np.uint8)
+    E.emu_ksw(len(q), q.ctypes.data, len(t), t.ctypes.data, mat.ctypes.data, *pen, w, zd, eb, fl, C.byref(ez), cig.ctypes.data)
+    return dict(max=ez.max, zdropped=ez.zdropped, max_q=ez.max_q, max_t=ez.max_t, mqe=ez.mqe, mqe_t=ez.mqe_t, mte=ez.mte,
+                mte_q=ez.mte_q, score=ez.score, reach_end=ez.reach_end, cigar=cig[:ez.n_cigar].tolist())
+
+
+@pytest.mark.parametrize("preset", ["sr", "ont"])
+def test_ksw_pieces(emu, preset):
+    from test_oracle_vs_ref import _ksw_cases
+    rng = np.random.default_rng(5150)
+    if preset == "sr":
+        mat, pen, bw, zd, eb = L.simple_mat(2, 8, 1), (12, 2, 24, 1), 151, 100, 10
+    else:
+        mat, pen, bw, zd, eb = L.simple_mat(2, 4, 1), (4, 2, 24, 1), 751, 400, -1
+    n = 0
+    for q, t in _ksw_cases(rng, 180):
+        for fl in [0xC2, 0x40, 0x08, 0x00, 0x01, 0x02]:
+            for w in ([bw, 20, -1] if n % 5 == 0 else [bw]):
+                a = L.orc_ksw(q, t, mat, *pen, w, zd, eb if fl & 0x40 else -1, fl)
+                b = emu_ksw(emu, q, t, mat, pen, w, zd, eb if fl & 0x40 else -1, fl)
+                if fl & 0x01:
+                    a["cigar"] = []
+                assert a == b, (len(q), len(t), fl, w)
+        n += 1
