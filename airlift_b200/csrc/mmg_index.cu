@@ -455,3 +455,24 @@ extern "C" int mmg_idx_clone_to(mmg_ctx_t *c, const mmg_idx_t *src, mmg_idx_t **
 	(*dst)->h_seq_off = src->h_seq_off; (*dst)->h_seq_len = src->h_seq_len;
 	return MMG_OK;
 }
+
+__global__ void k_count_ones(const uint32_t *__restrict__ cnt, int64_t n, unsigned long long *out)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int one = i < n && cnt[i] == 1;
+	const unsigned m = __ballot_sync(0xffffffffu, one);
+	if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+extern "C" int64_t mmg_idx_n_singletons(const mmg_idx_t *mi)
+{ // for mm_idx_stat (index.c:117): distinct minimizers that occur once
+	if (mi->d_counts == nullptr || mi->n_keys == 0) return 0;
+	cudaSetDevice(mi->dev);
+	unsigned long long *d = nullptr, h = 0;
+	if (cudaMalloc(&d, 8) != cudaSuccess) return -1;
+	cudaMemset(d, 0, 8);
+	k_count_ones<<<mmg_blocks(mi->n_keys, 256), 256>>>(mi->d_counts, mi->n_keys, d);
+	cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	return (int64_t)h;
+}

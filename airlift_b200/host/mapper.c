@@ -1,0 +1,555 @@
+/* mapper.c -- the mini-batch mapper: read -> map (GPU stages + host bookkeeping) -> write.
+ *
+ * Drop-in for the reference's file-level driver (mm_map_file_frag and worker_pipeline, map.c:557-696):
+ * same three ordered steps, same records on stdout.  Step 1 no longer calls mm_map_frag once per
+ * fragment (worker_for, map.c:458-498); it runs each mini-batch through
+ *     upload -> K1 sketch -> K2 seed -> K3 chain          (one device call, mmg_seed_chain_batch)
+ *     chains -> hits, primary/secondary, per-mate split    (host threads; hits.c)
+ *     rounds of { collect DP jobs -> K4 batch -> resume }  (aln.c + mmg_ksw_batch)
+ *     MAPQ, pairing, mate un-flip                          (host threads)
+ * with the fragments of a batch cut into one contiguous range per GPU.
+ */
+#include <stdio.h>
+#include <errno.h>
+#include <pthread.h>
+#include "mm2b_priv.h"
+
+/* ------------------------------------------------------------------ a tiny parallel-for */
+
+typedef struct { void (*fn)(void*, long, int); void *data; long n; volatile long next; int n_threads; } pfor_t;
+typedef struct { pfor_t *pf; int tid; } pfor_arg_t;
+
+static void *pfor_worker(void *p)
+{
+	pfor_arg_t *a = (pfor_arg_t*)p;
+	for (;;) {
+		const long i = __sync_fetch_and_add(&a->pf->next, 16);
+		long j;
+		if (i >= a->pf->n) break;
+		for (j = i; j < i + 16 && j < a->pf->n; ++j) a->pf->fn(a->pf->data, j, a->tid);
+	}
+	return 0;
+}
+
+static void parallel_for(int n_threads, void (*fn)(void*, long, int), void *data, long n)
+{
+	if (n_threads <= 1 || n < 32) { long i; for (i = 0; i < n; ++i) fn(data, i, 0); return; }
+	{
+		pfor_t pf = {fn, data, n, 0, n_threads};
+		pthread_t *tid = (pthread_t*)alloca((size_t)n_threads * sizeof(pthread_t));
+		pfor_arg_t *arg = (pfor_arg_t*)alloca((size_t)n_threads * sizeof(pfor_arg_t));
+		int i;
+		for (i = 0; i < n_threads; ++i) { arg[i].pf = &pf, arg[i].tid = i; pthread_create(&tid[i], 0, pfor_worker, &arg[i]); }
+		for (i = 0; i < n_threads; ++i) pthread_join(tid[i], 0);
+	}
+}
+
+/* ------------------------------------------------------------------ per-fragment state */
+
+typedef struct {
+	int n_segs, qlen_sum, rep_len, frag_gap, active, n_regs0, n_u, n_mini;
+	uint32_t hash;
+	int *qlens;           /* [n_segs] */
+	mm128_t *a;           /* chained anchors of the fragment (owned copy) */
+	uint64_t *u, *mini;
+	mm_reg1_t *regs0;
+	mm_seg_t *seg;        /* per-mate chains when n_segs > 1 */
+	mm_alnseg_t *aln;     /* [n_segs] */
+} frag_t;
+
+typedef struct {          /* one GPU's share of a mini-batch */
+	const mm_idx_t *mi;
+	const mm_mapopt_t *opt;
+	mmg_ctx_t *ctx;
+	mmg_idx_t *didx;
+	mmg_mapopt_t dopt;
+	int n_threads, f0, f1, s0; /* fragments [f0,f1); s0 = first read */
+	mm_bseq1_t *seq;
+	int *n_seg, *seg_off, *n_reg, *rep_len, *frag_gap;
+	mm_reg1_t **reg;
+	frag_t *fr;
+	mmg_chains_t ch;
+	int rc;
+} shard_t;
+
+static inline int mate_is_flipped(const mm_mapopt_t *opt, int n_segs, int j)
+{ /* map.c:468 */
+	return n_segs == 2 && ((j == 0 && (opt->pe_ori >> 1 & 1)) || (j == 1 && (opt->pe_ori & 1)));
+}
+
+static int chain_gap_ref(const mm_mapopt_t *opt, int qlen_sum)
+{ /* map.c:344-349 */
+	int g;
+	if (opt->max_gap_ref > 0) return opt->max_gap_ref;
+	if (opt->max_frag_len > 0) { g = opt->max_frag_len - qlen_sum; return g < opt->max_gap ? opt->max_gap : g; }
+	return opt->max_gap;
+}
+
+/* chains -> hits for fragment i of the shard (map.c:376-388, 390-400 up to the DP) */
+static void stage_hits(void *data, long i, int tid)
+{
+	shard_t *sh = (shard_t*)data;
+	const mm_mapopt_t *opt = sh->opt;
+	const mm_idx_t *mi = sh->mi;
+	const int f = sh->f0 + (int)i, off = sh->seg_off[f], ns = sh->n_seg[f];
+	frag_t *fr = &sh->fr[i];
+	const mmg_chains_t *ch = &sh->ch;
+	int j, is_sr = !!(opt->flag & MM_F_SR);
+	memset(fr, 0, sizeof(*fr));
+	fr->n_segs = ns;
+	fr->qlens = (int*)malloc((size_t)ns * sizeof(int));
+	for (j = 0; j < ns; ++j) {
+		sh->n_reg[off + j] = 0, sh->reg[off + j] = 0;
+		fr->qlens[j] = sh->seq[off + j].l_seq, fr->qlen_sum += fr->qlens[j];
+	}
+	if (fr->qlen_sum == 0 || ns <= 0 || ns > MM_MAX_SEG) return;
+	if (opt->max_qlen > 0 && fr->qlen_sum > opt->max_qlen) return;
+	for (j = 0; j < ns; ++j) /* host copy in mapping orientation, undone in stage_finish (map.c:467-469,489) */
+		if (mate_is_flipped(opt, ns, j)) mm_revcomp_bseq(&sh->seq[off + j]);
+	fr->hash = mm_frag_hash(sh->seq[off].name, fr->qlen_sum, opt->seed);
+	fr->frag_gap = chain_gap_ref(opt, fr->qlen_sum);
+	fr->rep_len = ch->rep_len[i];
+	fr->n_u = ch->n_u[i];
+	fr->n_mini = ch->n_mini[i];
+	if (fr->n_u > 0) {
+		const int n_a = ch->n_a[i];
+		fr->u = (uint64_t*)malloc((size_t)fr->n_u * 8);
+		memcpy(fr->u, ch->u + ch->u_off[i], (size_t)fr->n_u * 8);
+		fr->a = (mm128_t*)malloc((size_t)n_a * 16);
+		memcpy(fr->a, ch->a + ch->a_off[i], (size_t)n_a * 16);
+	}
+	fr->regs0 = mm_gen_regs(fr->hash, fr->qlen_sum, fr->n_u, fr->u, fr->a);
+	fr->n_regs0 = fr->n_u;
+	if (!(opt->flag & MM_F_ALL_CHAINS)) { /* chain_post, map.c:249-258 */
+		mm_set_parent(opt->mask_level, fr->n_regs0, fr->regs0, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL);
+		if (ns <= 1) mm_select_sub(opt->pri_ratio, mi->k * 2, opt->best_n, &fr->n_regs0, fr->regs0);
+		else mm_select_sub_multi(opt->pri_ratio, 0.2f, 0.7f, fr->frag_gap, mi->k * 2, opt->best_n, ns, fr->qlens, &fr->n_regs0, fr->regs0);
+		if (!(opt->flag & (MM_F_SPLICE|MM_F_SR|MM_F_NO_LJOIN))) mm_join_long(opt, fr->qlen_sum, &fr->n_regs0, fr->regs0, fr->a);
+	}
+	if (!is_sr) mm_est_err(mi, fr->qlen_sum, fr->n_regs0, fr->regs0, fr->a, fr->n_mini, ch->mini_pos + ch->mini_off[i]);
+	fr->aln = (mm_alnseg_t*)calloc(ns, sizeof(mm_alnseg_t));
+	if (ns == 1) {
+		sh->n_reg[off] = fr->n_regs0, sh->reg[off] = fr->regs0;
+		mm_aln_begin(&fr->aln[0], off - sh->s0, fr->qlens[0], sh->seq[off].seq, fr->n_regs0, fr->regs0, fr->a);
+	} else {
+		fr->seg = mm_seg_gen(fr->hash, ns, fr->qlens, fr->n_regs0, fr->regs0, &sh->n_reg[off], &sh->reg[off], fr->a);
+		free(fr->regs0); fr->regs0 = 0;
+		for (j = 0; j < ns; ++j) {
+			mm_set_parent(opt->mask_level, sh->n_reg[off + j], sh->reg[off + j], opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL);
+			mm_aln_begin(&fr->aln[j], off + j - sh->s0, fr->qlens[j], sh->seq[off + j].seq, sh->n_reg[off + j], sh->reg[off + j], fr->seg[j].a);
+		}
+	}
+	fr->active = (opt->flag & MM_F_CIGAR) ? 1 : 0;
+}
+
+/* one resumable pass over the regions of an active fragment (align_regs, map.c:260-270) */
+static void stage_align(void *data, long i, int tid)
+{
+	shard_t *sh = (shard_t*)data;
+	frag_t *fr = &sh->fr[i];
+	const mm_mapopt_t *opt = sh->opt;
+	int j, all_done = 1;
+	if (!fr->active) return;
+	for (j = 0; j < fr->n_segs; ++j) {
+		mm_alnseg_t *s = &fr->aln[j];
+		const int off = sh->seg_off[sh->f0 + i] + j;
+		if (s->finished) continue;
+		if (mm_aln_step(s, opt, sh->mi)) {
+			if (!(opt->flag & MM_F_ALL_CHAINS)) {
+				mm_set_parent(opt->mask_level, s->n_regs, s->regs, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL);
+				mm_select_sub(opt->pri_ratio, sh->mi->k * 2, opt->best_n, &s->n_regs, s->regs);
+				mm_set_sam_pri(s->n_regs, s->regs);
+			}
+			sh->n_reg[off] = s->n_regs, sh->reg[off] = s->regs;
+		} else all_done = 0;
+	}
+	if (all_done) fr->active = 0;
+}
+
+/* MAPQ, pairing, release, mate un-flip (map.c:392-406, 486-497) */
+static void stage_finish(void *data, long i, int tid)
+{
+	shard_t *sh = (shard_t*)data;
+	frag_t *fr = &sh->fr[i];
+	const mm_mapopt_t *opt = sh->opt;
+	const int f = sh->f0 + (int)i, off = sh->seg_off[f], ns = fr->n_segs, is_sr = !!(opt->flag & MM_F_SR);
+	int j, k, mapped = !(fr->qlen_sum == 0 || ns <= 0 || ns > MM_MAX_SEG || (opt->max_qlen > 0 && fr->qlen_sum > opt->max_qlen));
+	if (mapped) {
+		for (j = 0; j < ns; ++j) mm_set_mapq(sh->n_reg[off + j], sh->reg[off + j], opt->min_chain_score, opt->a, fr->rep_len, is_sr);
+		if (ns == 2 && opt->pe_ori >= 0 && (opt->flag & MM_F_CIGAR))
+			mm_pair(fr->frag_gap, opt->pe_bonus, opt->a * 2 + opt->b, opt->a, fr->qlens, &sh->n_reg[off], &sh->reg[off]);
+		for (j = 0; j < ns; ++j)
+			if (mate_is_flipped(opt, ns, j)) {
+				mm_revcomp_bseq(&sh->seq[off + j]);
+				for (k = 0; k < sh->n_reg[off + j]; ++k) {
+					mm_reg1_t *r = &sh->reg[off + j][k];
+					const int t = r->qs;
+					r->qs = fr->qlens[j] - r->qe, r->qe = fr->qlens[j] - t, r->rev = !r->rev;
+				}
+			}
+	}
+	for (j = 0; j < ns; ++j) sh->rep_len[off + j] = fr->rep_len, sh->frag_gap[off + j] = fr->frag_gap;
+	if (fr->aln) { for (j = 0; j < ns; ++j) mm_aln_end(&fr->aln[j]); free(fr->aln); }
+	if (fr->seg) mm_seg_free(ns, fr->seg);
+	free(fr->a); free(fr->u); free(fr->qlens);
+}
+
+static void shard_fail(shard_t *sh, const char *what)
+{
+	fprintf(stderr, "[ERROR] %s: %s\n", what, mmg_last_error());
+	sh->rc = -1;
+}
+
+/* map fragments [f0,f1) of a mini-batch on one GPU */
+static void *map_shard(void *data)
+{
+	shard_t *sh = (shard_t*)data;
+	const int nf = sh->f1 - sh->f0;
+	int i, j, n_seq = 0;
+	uint64_t n_bases = 0, o;
+	char *bases;
+	int32_t *n_seg, *seg_off, *seq_len;
+	uint64_t *seq_off;
+	mmg_batch_t b;
+	sh->rc = 0;
+	if (nf <= 0) return 0;
+	sh->s0 = sh->seg_off[sh->f0];
+	for (i = sh->f0; i < sh->f1; ++i) n_seq += sh->n_seg[i];
+	for (i = 0; i < n_seq; ++i) n_bases += sh->seq[sh->s0 + i].l_seq;
+	bases = (char*)malloc(n_bases + 1);
+	n_seg = (int32_t*)malloc((size_t)nf * 4), seg_off = (int32_t*)malloc((size_t)nf * 4);
+	seq_len = (int32_t*)malloc((size_t)(n_seq + 1) * 4), seq_off = (uint64_t*)malloc((size_t)(n_seq + 1) * 8);
+	for (i = 0, o = 0; i < n_seq; ++i) {
+		const mm_bseq1_t *t = &sh->seq[sh->s0 + i];
+		seq_len[i] = t->l_seq, seq_off[i] = o;
+		memcpy(bases + o, t->seq, t->l_seq);
+		o += t->l_seq;
+	}
+	for (i = 0; i < nf; ++i) n_seg[i] = sh->n_seg[sh->f0 + i], seg_off[i] = sh->seg_off[sh->f0 + i] - sh->s0;
+	b.n_frag = nf, b.n_seq = n_seq, b.n_seg = n_seg, b.seg_off = seg_off, b.seq_len = seq_len, b.seq_off = seq_off, b.bases = bases, b.n_bases = n_bases;
+	if (mmg_seed_chain_batch(sh->ctx, sh->didx, &sh->dopt, &b, &sh->ch) != MMG_OK) shard_fail(sh, "seed/chain stage failed");
+	free(bases); free(n_seg); free(seg_off); free(seq_len); free(seq_off);
+	if (sh->rc) return 0;
+
+	sh->fr = (frag_t*)calloc(nf, sizeof(frag_t));
+	parallel_for(sh->n_threads, stage_hits, sh, nf);
+	if (sh->opt->flag & MM_F_CIGAR) {
+		mmg_ksw_job_t *jobs = 0; mmg_ksw_res_t *res = 0;
+		size_t m_jobs = 0;
+		for (;;) { /* DP rounds */
+			size_t n_jobs = 0;
+			const uint32_t *cig = 0;
+			int n_active = 0;
+			parallel_for(sh->n_threads, stage_align, sh, nf);
+			for (i = 0; i < nf; ++i) {
+				frag_t *fr = &sh->fr[i];
+				if (!fr->active) continue;
+				++n_active;
+				for (j = 0; j < fr->n_segs; ++j) {
+					mm_dpcache_t *c = &fr->aln[j].cache;
+					for (; c->n_sent < c->n; ++c->n_sent) {
+						if (n_jobs == m_jobs) {
+							m_jobs = m_jobs ? m_jobs << 1 : 1 << 16;
+							jobs = (mmg_ksw_job_t*)realloc(jobs, m_jobs * sizeof(*jobs));
+							res = (mmg_ksw_res_t*)realloc(res, m_jobs * sizeof(*res));
+						}
+						jobs[n_jobs++] = c->a[c->n_sent].job;
+					}
+				}
+			}
+			if (n_active == 0) break;
+			if (n_jobs == 0) { fprintf(stderr, "[ERROR] alignment made no progress\n"); sh->rc = -1; break; }
+			if (mmg_ksw_batch(sh->ctx, sh->didx, &sh->dopt, (int)n_jobs, jobs, res, &cig, 0, 0) != MMG_OK) { shard_fail(sh, "DP stage failed"); break; }
+			{ /* scatter results back in the same traversal order */
+				size_t k = 0;
+				for (i = 0; i < nf; ++i) {
+					frag_t *fr = &sh->fr[i];
+					if (!fr->active) continue;
+					for (j = 0; j < fr->n_segs; ++j) {
+						mm_dpcache_t *c = &fr->aln[j].cache;
+						int q;
+						for (q = 0; q < c->n; ++q) {
+							mm_dpjob_t *dj = &c->a[q];
+							if (dj->done) continue;
+							dj->ez = res[k].ez;
+							if (dj->ez.n_cigar > 0) {
+								dj->cigar = (uint32_t*)malloc((size_t)dj->ez.n_cigar * 4);
+								memcpy(dj->cigar, cig + res[k].cigar_off, (size_t)dj->ez.n_cigar * 4);
+							}
+							dj->done = 1;
+							++k;
+						}
+					}
+				}
+				assert(k == n_jobs);
+			}
+		}
+		free(jobs); free(res);
+	}
+	parallel_for(sh->n_threads, stage_finish, sh, nf);
+	free(sh->fr); sh->fr = 0;
+	return 0;
+}
+
+/* ------------------------------------------------------------------ the three-step pipeline */
+
+typedef struct {
+	int n_seq, n_frag;
+	mm_bseq1_t *seq;
+	int *n_reg, *seg_off, *n_seg, *rep_len, *frag_gap;
+	mm_reg1_t **reg;
+} step_t;
+
+typedef struct {
+	int mini_batch_size, n_processed, n_threads, n_fp;
+	const mm_mapopt_t *opt;
+	mm_bseq_file_t **fp;
+	const mm_idx_t *mi;
+	mm_str_t str;
+	int failed;
+} pipeline_t;
+
+static step_t *step_read(pipeline_t *p)
+{ /* map.c:561-589 */
+	const int with_qual = (!!(p->opt->flag & MM_F_OUT_SAM) && !(p->opt->flag & MM_F_NO_QUAL));
+	const int with_comment = !!(p->opt->flag & MM_F_COPY_COMMENT);
+	const int frag_mode = (p->n_fp > 1 || !!(p->opt->flag & MM_F_FRAG_MODE));
+	step_t *s = (step_t*)calloc(1, sizeof(step_t));
+	int i, j;
+	if (p->n_fp > 1) s->seq = mm_bseq_read_frag2(p->n_fp, p->fp, p->mini_batch_size, with_qual, with_comment, &s->n_seq);
+	else s->seq = mm_bseq_read3(p->fp[0], p->mini_batch_size, with_qual, with_comment, frag_mode, &s->n_seq);
+	if (s->seq == 0) { free(s); return 0; }
+	for (i = 0; i < s->n_seq; ++i) s->seq[i].rid = p->n_processed++;
+	s->n_reg = (int*)calloc(5 * (size_t)s->n_seq, sizeof(int));
+	s->seg_off = s->n_reg + s->n_seq, s->n_seg = s->seg_off + s->n_seq, s->rep_len = s->n_seg + s->n_seq, s->frag_gap = s->rep_len + s->n_seq;
+	s->reg = (mm_reg1_t**)calloc(s->n_seq, sizeof(mm_reg1_t*));
+	for (i = 1, j = 0; i <= s->n_seq; ++i)
+		if (i == s->n_seq || !frag_mode || !mm_qname_same(s->seq[i-1].name, s->seq[i].name)) {
+			s->n_seg[s->n_frag] = i - j;
+			s->seg_off[s->n_frag++] = j;
+			j = i;
+		}
+	return s;
+}
+
+static int step_map(pipeline_t *p, step_t *s)
+{
+	struct mm_idx_bucket_s *B = p->mi->B;
+	const int n_dev = B->n_dev;
+	shard_t *sh = (shard_t*)calloc(n_dev, sizeof(shard_t));
+	pthread_t *tid = (pthread_t*)calloc(n_dev, sizeof(pthread_t));
+	int d, f = 0, rc = 0;
+	int64_t tot = 0, acc = 0;
+	if (p->opt->flag & MM_F_INDEPEND_SEG) { fprintf(stderr, "[ERROR] --no-pairing is not supported by this build\n"); return -1; }
+	for (d = 0; d < s->n_seq; ++d) tot += s->seq[d].l_seq;
+	for (d = 0; d < n_dev; ++d) { /* contiguous fragment ranges balanced by bases; a fragment is never cut */
+		shard_t *h = &sh[d];
+		const int64_t goal = tot * (d + 1) / n_dev;
+		h->mi = p->mi, h->opt = p->opt, h->ctx = B->ctx[d], h->didx = B->didx[d];
+		mm_mapopt_to_dev(p->opt, &h->dopt);
+		h->n_threads = p->n_threads / n_dev > 0 ? p->n_threads / n_dev : 1;
+		h->seq = s->seq, h->n_seg = s->n_seg, h->seg_off = s->seg_off, h->n_reg = s->n_reg, h->rep_len = s->rep_len, h->frag_gap = s->frag_gap, h->reg = s->reg;
+		h->f0 = f;
+		while (f < s->n_frag && (acc < goal || d == n_dev - 1)) {
+			int j;
+			for (j = 0; j < s->n_seg[f]; ++j) acc += s->seq[s->seg_off[f] + j].l_seq;
+			++f;
+		}
+		h->f1 = f;
+	}
+	if (n_dev == 1) map_shard(&sh[0]);
+	else {
+		for (d = 0; d < n_dev; ++d) pthread_create(&tid[d], 0, map_shard, &sh[d]);
+		for (d = 0; d < n_dev; ++d) pthread_join(tid[d], 0);
+	}
+	for (d = 0; d < n_dev; ++d) if (sh[d].rc) rc = -1;
+	free(sh); free(tid);
+	return rc;
+}
+
+static void step_write(pipeline_t *p, step_t *s)
+{ /* map.c:594-650 (no --split-prefix) */
+	const mm_idx_t *mi = p->mi;
+	int i, j, k;
+	for (k = 0; k < s->n_frag; ++k) {
+		const int seg_st = s->seg_off[k], seg_en = s->seg_off[k] + s->n_seg[k];
+		for (i = seg_st; i < seg_en; ++i) {
+			mm_bseq1_t *t = &s->seq[i];
+			if (s->n_reg[i] > 0) {
+				for (j = 0; j < s->n_reg[i]; ++j) {
+					mm_reg1_t *r = &s->reg[i][j];
+					assert(!r->sam_pri || r->id == r->parent);
+					if ((p->opt->flag & MM_F_NO_PRINT_2ND) && r->id != r->parent) continue;
+					if (p->opt->flag & MM_F_OUT_SAM)
+						mm_write_sam3(&p->str, mi, t, i - seg_st, j, s->n_seg[k], &s->n_reg[seg_st], (const mm_reg1_t*const*)&s->reg[seg_st], (int)p->opt->flag, s->rep_len[i]);
+					else mm_write_paf3(&p->str, mi, t, r, (int)p->opt->flag, s->rep_len[i]);
+					mm_err_puts(p->str.s);
+				}
+			} else if ((p->opt->flag & MM_F_PAF_NO_HIT) || ((p->opt->flag & MM_F_OUT_SAM) && !(p->opt->flag & MM_F_SAM_HIT_ONLY))) {
+				if (p->opt->flag & MM_F_OUT_SAM)
+					mm_write_sam3(&p->str, mi, t, i - seg_st, -1, s->n_seg[k], &s->n_reg[seg_st], (const mm_reg1_t*const*)&s->reg[seg_st], (int)p->opt->flag, s->rep_len[i]);
+				else mm_write_paf3(&p->str, mi, t, 0, (int)p->opt->flag, s->rep_len[i]);
+				mm_err_puts(p->str.s);
+			}
+		}
+		for (i = seg_st; i < seg_en; ++i) {
+			for (j = 0; j < s->n_reg[i]; ++j) free(s->reg[i][j].p);
+			free(s->reg[i]);
+			free(s->seq[i].seq); free(s->seq[i].name);
+			if (s->seq[i].qual) free(s->seq[i].qual);
+			if (s->seq[i].comment) free(s->seq[i].comment);
+		}
+	}
+	if (mm_verbose >= 3)
+		fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", "worker_pipeline", realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), s->n_seq);
+	free(s->reg); free(s->n_reg); free(s->seq);
+	free(s);
+}
+
+/* Ordered hand-off between the three steps: one slot per edge, so that reading batch n+1, mapping batch n and
+ * writing batch n-1 overlap while records still leave in input order (kthread.c:97-159 gives the same guarantee). */
+typedef struct { pthread_mutex_t mu; pthread_cond_t cv; step_t *item; int has, closed; } slot_t;
+
+static void slot_init(slot_t *q) { pthread_mutex_init(&q->mu, 0); pthread_cond_init(&q->cv, 0); q->item = 0, q->has = q->closed = 0; }
+static void slot_put(slot_t *q, step_t *s)
+{
+	pthread_mutex_lock(&q->mu);
+	while (q->has) pthread_cond_wait(&q->cv, &q->mu);
+	q->item = s, q->has = 1;
+	pthread_cond_broadcast(&q->cv);
+	pthread_mutex_unlock(&q->mu);
+}
+static void slot_close(slot_t *q)
+{
+	pthread_mutex_lock(&q->mu);
+	while (q->has) pthread_cond_wait(&q->cv, &q->mu);
+	q->closed = 1;
+	pthread_cond_broadcast(&q->cv);
+	pthread_mutex_unlock(&q->mu);
+}
+static step_t *slot_get(slot_t *q)
+{
+	step_t *s = 0;
+	pthread_mutex_lock(&q->mu);
+	while (!q->has && !q->closed) pthread_cond_wait(&q->cv, &q->mu);
+	if (q->has) { s = q->item; q->has = 0; pthread_cond_broadcast(&q->cv); }
+	pthread_mutex_unlock(&q->mu);
+	return s;
+}
+
+typedef struct { pipeline_t *p; slot_t *in, *out; } stage_arg_t;
+
+static void *reader_main(void *a)
+{
+	stage_arg_t *g = (stage_arg_t*)a;
+	step_t *s;
+	while (!g->p->failed && (s = step_read(g->p)) != 0) slot_put(g->out, s);
+	slot_close(g->out);
+	return 0;
+}
+
+static void *writer_main(void *a)
+{
+	stage_arg_t *g = (stage_arg_t*)a;
+	step_t *s;
+	while ((s = slot_get(g->in)) != 0) step_write(g->p, s);
+	return 0;
+}
+
+int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_mapopt_t *opt, int n_threads)
+{
+	pipeline_t pl;
+	slot_t q_read, q_write;
+	stage_arg_t ra, wa;
+	pthread_t t_read, t_write;
+	step_t *s;
+	int i;
+	if (n_segs < 1) return -1;
+	if (idx == 0 || idx->B == 0 || idx->B->n_dev < 1) { fprintf(stderr, "[ERROR] the index is not resident on a GPU\n"); return -1; }
+	if (opt->split_prefix) { fprintf(stderr, "[ERROR] --split-prefix is not supported by this build (the index is a single part in HBM)\n"); return -1; }
+	memset(&pl, 0, sizeof(pl));
+	pl.n_fp = n_segs;
+	pl.fp = (mm_bseq_file_t**)calloc(n_segs, sizeof(mm_bseq_file_t*));
+	for (i = 0; i < n_segs; ++i)
+		if ((pl.fp[i] = mm_bseq_open(fn[i])) == 0) {
+			int j;
+			if (mm_verbose >= 1) fprintf(stderr, "ERROR: failed to open file '%s': %s\n", fn[i], strerror(errno));
+			for (j = 0; j < i; ++j) mm_bseq_close(pl.fp[j]);
+			free(pl.fp);
+			return -1;
+		}
+	pl.opt = opt, pl.mi = idx;
+	pl.n_threads = n_threads > 1 ? n_threads : 1;
+	pl.mini_batch_size = opt->mini_batch_size;
+	slot_init(&q_read); slot_init(&q_write);
+	ra.p = wa.p = &pl, ra.in = 0, ra.out = &q_read, wa.in = &q_write, wa.out = 0;
+	pthread_create(&t_read, 0, reader_main, &ra);
+	pthread_create(&t_write, 0, writer_main, &wa);
+	while ((s = slot_get(&q_read)) != 0) {
+		if (!pl.failed && step_map(&pl, s) != 0) pl.failed = 1;
+		if (pl.failed) { /* keep draining so the reader can finish; nothing more is written */
+			for (i = 0; i < s->n_seq; ++i) { free(s->seq[i].seq); free(s->seq[i].name); free(s->seq[i].qual); free(s->seq[i].comment); }
+			free(s->reg); free(s->n_reg); free(s->seq); free(s);
+			continue;
+		}
+		slot_put(&q_write, s);
+	}
+	slot_close(&q_write);
+	pthread_join(t_read, 0);
+	pthread_join(t_write, 0);
+	free(pl.str.s);
+	for (i = 0; i < pl.n_fp; ++i) mm_bseq_close(pl.fp[i]);
+	free(pl.fp);
+	if (pl.failed) { fprintf(stderr, "[ERROR] mapping failed; no CPU fallback exists\n"); exit(1); }
+	return 0;
+}
+
+int mm_map_file(const mm_idx_t *idx, const char *fn, const mm_mapopt_t *opt, int n_threads)
+{
+	return mm_map_file_frag(idx, 1, &fn, opt, n_threads);
+}
+
+/* ------------------------------------------------------------------ per-fragment API (a batch of one) */
+
+struct mm_tbuf_s { int rep_len, frag_gap; };
+mm_tbuf_t *mm_tbuf_init(void) { return (mm_tbuf_t*)calloc(1, sizeof(mm_tbuf_t)); }
+void mm_tbuf_destroy(mm_tbuf_t *b) { free(b); }
+
+void mm_map_frag(const mm_idx_t *mi, int n_segs, const int *qlens, const char **seqs, int *n_regs, mm_reg1_t **regs, mm_tbuf_t *b,
+                 const mm_mapopt_t *opt, const char *qname)
+{ /* map.c:272-424 */
+	shard_t sh;
+	mm_bseq1_t *seq;
+	int j, one_off = 0, n_seg = n_segs, rep[MM_MAX_SEG], gap[MM_MAX_SEG];
+	mm_mapopt_t o2;
+	for (j = 0; j < n_segs; ++j) n_regs[j] = 0, regs[j] = 0;
+	if (n_segs <= 0 || n_segs > MM_MAX_SEG) return;
+	if (mi == 0 || mi->B == 0 || mi->B->n_dev < 1) { fprintf(stderr, "[ERROR] the index is not resident on a GPU\n"); exit(1); }
+	seq = (mm_bseq1_t*)calloc(n_segs, sizeof(mm_bseq1_t));
+	for (j = 0; j < n_segs; ++j) {
+		seq[j].l_seq = qlens[j], seq[j].name = (char*)qname, seq[j].seq = (char*)malloc((size_t)qlens[j] + 1);
+		memcpy(seq[j].seq, seqs[j], qlens[j]); seq[j].seq[qlens[j]] = 0;
+	}
+	memset(&sh, 0, sizeof(sh));
+	/* worker_for flips the mates of a pair around this call (map.c:467-469,486-497); callers of the library API
+	 * pass sequences already in mapping orientation, so neither the host nor the device flips here.
+	 * pe_ori = 0 keeps `pe_ori >= 0` (pairing on, map.c:404) while naming no mate to flip. */
+	o2 = *opt;
+	if (o2.pe_ori > 0) o2.pe_ori = 0;
+	sh.mi = mi, sh.opt = &o2, sh.ctx = mi->B->ctx[0], sh.didx = mi->B->didx[0];
+	mm_mapopt_to_dev(&o2, &sh.dopt);
+	sh.n_threads = 1, sh.f0 = 0, sh.f1 = 1;
+	sh.seq = seq, sh.n_seg = &n_seg, sh.seg_off = &one_off, sh.n_reg = n_regs, sh.rep_len = rep, sh.frag_gap = gap, sh.reg = regs;
+	map_shard(&sh);
+	if (sh.rc) { fprintf(stderr, "[ERROR] mapping failed; no CPU fallback exists\n"); exit(1); }
+	if (b) b->rep_len = rep[0], b->frag_gap = gap[0];
+	for (j = 0; j < n_segs; ++j) free(seq[j].seq);
+	free(seq);
+}
+
+mm_reg1_t *mm_map(const mm_idx_t *mi, int qlen, const char *seq, int *n_regs, mm_tbuf_t *b, const mm_mapopt_t *opt, const char *qname)
+{
+	mm_reg1_t *regs;
+	mm_map_frag(mi, 1, &qlen, &seq, n_regs, &regs, b, opt, qname);
+	return regs;
+}

@@ -1,0 +1,133 @@
+/* mm2b_priv.h -- host-side internals of the B200 mapper (counterpart of the reference's mmpriv.h). */
+#ifndef MM2B_PRIV_H
+#define MM2B_PRIV_H
+#include <stdlib.h>
+#include <string.h>
+#include <assert.h>
+#include "minimap_b200.h"
+#include "mmg.h"
+
+#define MM_VERSION_B200 "2.17-r954-b200"
+
+#define MM_PARENT_UNSET   (-1)
+#define MM_PARENT_TMP_PRI (-2)
+
+#define MM_DBG_NO_KALLOC     0x1
+#define MM_DBG_PRINT_QNAME   0x2
+#define MM_DBG_PRINT_SEED    0x4
+#define MM_DBG_PRINT_ALN_SEQ 0x8
+
+#define MM_SEED_LONG_JOIN  (1ULL<<40)
+#define MM_SEED_IGNORE     (1ULL<<41)
+#define MM_SEED_TANDEM     (1ULL<<42)
+#define MM_SEED_SELF       (1ULL<<43)
+#define MM_SEED_SEG_SHIFT  48
+#define MM_SEED_SEG_MASK   (0xffULL<<(MM_SEED_SEG_SHIFT))
+
+#define KSW_NEG_INF (-0x40000000)
+#define KSW_EZ_SCORE_ONLY  0x01
+#define KSW_EZ_RIGHT       0x02
+#define KSW_EZ_APPROX_MAX  0x08
+#define KSW_EZ_EXTZ_ONLY   0x40
+#define KSW_EZ_REV_CIGAR   0x80
+
+static inline uint32_t mm_roundup32(uint32_t x) { --x; x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16; return ++x; }
+#define mm_seq4_get(s, i) ((s)[(i)>>3] >> (((i)&7)<<2) & 0xf)
+
+typedef struct { unsigned l, m; char *s; } mm_str_t;
+
+/* one sequence record (bseq.h:14-17) */
+typedef struct { int l_seq, rid; char *name, *seq, *qual, *comment; } mm_bseq1_t;
+typedef struct mm_bseq_file_s mm_bseq_file_t;
+
+/* per-segment chains after mm_seg_gen (mmpriv.h:46-50) */
+typedef struct { int n_u, n_a; uint64_t *u; mm128_t *a; } mm_seg_t;
+
+/* hidden part of mm_idx_t */
+struct mm_idx_bucket_s {
+	int n_dev;
+	int dev_id[16];
+	mmg_ctx_t *ctx[16];
+	mmg_idx_t *didx[16];
+	int32_t max_occ_cache_set; float max_occ_cache_f; int32_t max_occ_cache;
+};
+
+extern unsigned char seq_nt4_table[256];
+extern unsigned char seq_comp_table[256];
+
+/* misc.c */
+double cputime(void);
+double realtime(void);
+long peakrss(void);
+void mm_err_puts(const char *str);
+void radix_sort_128x(mm128_t *beg, mm128_t *end);
+void radix_sort_64(uint64_t *beg, uint64_t *end);
+
+/* seqio.c */
+mm_bseq_file_t *mm_bseq_open(const char *fn);
+void mm_bseq_close(mm_bseq_file_t *fp);
+mm_bseq1_t *mm_bseq_read3(mm_bseq_file_t *fp, int chunk_size, int with_qual, int with_comment, int frag_mode, int *n_);
+mm_bseq1_t *mm_bseq_read_frag2(int n_fp, mm_bseq_file_t **fp, int chunk_size, int with_qual, int with_comment, int *n_);
+int mm_bseq_eof(mm_bseq_file_t *fp);
+int mm_qname_len(const char *s);
+int mm_qname_same(const char *s1, const char *s2);
+void mm_revcomp_bseq(mm_bseq1_t *s);
+
+/* hits.c */
+uint32_t mm_frag_hash(const char *qname, int qlen_sum, int seed);
+mm_reg1_t *mm_gen_regs(uint32_t hash, int qlen, int n_u, uint64_t *u, mm128_t *a);
+void mm_split_reg(mm_reg1_t *r, mm_reg1_t *r2, int n, int qlen, mm128_t *a);
+void mm_sync_regs(int n_regs, mm_reg1_t *regs);
+int mm_squeeze_a(int n_regs, mm_reg1_t *regs, mm128_t *a);
+int mm_set_sam_pri(int n, mm_reg1_t *r);
+void mm_set_parent(float mask_level, int n, mm_reg1_t *r, int sub_diff, int hard_mask_level);
+void mm_select_sub(float pri_ratio, int min_diff, int best_n, int *n_, mm_reg1_t *r);
+void mm_select_sub_multi(float pri_ratio, float pri1, float pri2, int max_gap_ref, int min_diff, int best_n, int n_segs, const int *qlens, int *n_, mm_reg1_t *r);
+void mm_filter_regs(const mm_mapopt_t *opt, int qlen, int *n_regs, mm_reg1_t *regs);
+void mm_join_long(const mm_mapopt_t *opt, int qlen, int *n_regs, mm_reg1_t *regs, mm128_t *a);
+void mm_hit_sort(int *n_regs, mm_reg1_t *r);
+void mm_set_mapq(int n_regs, mm_reg1_t *regs, int min_chain_sc, int match_sc, int rep_len, int is_sr);
+void mm_est_err(const mm_idx_t *mi, int qlen, int n_regs, mm_reg1_t *regs, const mm128_t *a, int32_t n, const uint64_t *mini_pos);
+mm_seg_t *mm_seg_gen(uint32_t hash, int n_segs, const int *qlens, int n_regs0, const mm_reg1_t *regs0, int *n_regs, mm_reg1_t **regs, const mm128_t *a);
+void mm_seg_free(int n_segs, mm_seg_t *segs);
+void mm_pair(int max_gap_ref, int dp_bonus, int sub_diff, int match_sc, const int *qlens, int *n_regs, mm_reg1_t **regs);
+
+/* llsw.c: local alignment score used by the inversion test (ksw_ll_qinit + ksw_ll_i16, ksw2_ll_sse.c) */
+int mm_ll_i16(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat, int gapo, int gape, int *qe, int *te);
+
+/* aln.c: resumable alignment of one segment's regions; DP goes through a job cache */
+typedef struct {
+	mmg_ksw_job_t job;
+	mmg_extz_t ez;
+	uint32_t *cigar;   /* owned */
+	int done;
+} mm_dpjob_t;
+
+typedef struct {
+	int n, m, n_sent;  /* jobs [n_sent, n) have not been submitted yet */
+	mm_dpjob_t *a;
+} mm_dpcache_t;
+
+typedef struct {       /* alignment progress of one segment (mm_align_skeleton, align.c:857-913, made resumable) */
+	int seq_id, qlen, n_regs, i, n_a, started, finished, inv_wait;
+	const char *qstr;
+	uint8_t *qseq0[2];
+	mm_reg1_t *regs;
+	mm128_t *a;
+	mm_dpcache_t cache;
+} mm_alnseg_t;
+
+void mm_aln_begin(mm_alnseg_t *s, int seq_id, int qlen, const char *qstr, int n_regs, mm_reg1_t *regs, mm128_t *a);
+/* returns 1 when every region is aligned (regs/n_regs final, filtered and sorted), 0 when new DP jobs were queued */
+int mm_aln_step(mm_alnseg_t *s, const mm_mapopt_t *opt, const mm_idx_t *mi);
+void mm_aln_end(mm_alnseg_t *s);
+
+/* fmt.c */
+void mm_write_paf3(mm_str_t *s, const mm_idx_t *mi, const mm_bseq1_t *t, const mm_reg1_t *r, int opt_flag, int rep_len);
+void mm_write_sam3(mm_str_t *s, const mm_idx_t *mi, const mm_bseq1_t *t, int seg_idx, int reg_idx, int n_seg, const int *n_regss,
+                   const mm_reg1_t *const* regss, int opt_flag, int rep_len);
+
+/* mapper.c */
+void mm_mapopt_to_dev(const mm_mapopt_t *opt, mmg_mapopt_t *d);
+
+#endif
