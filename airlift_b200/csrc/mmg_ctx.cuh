@@ -77,11 +77,18 @@ struct ResidentBatch {
 	std::vector<uint64_t> q_off; // packed (8-base aligned) offset of each read
 };
 
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+
 struct mmg_ctx_s {
 	int dev = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	long launches = 0;
+	uint64_t h2d_bytes = 0, d2h_bytes = 0;
+	bool prof_on = false;
+	std::vector<ProfRec> prof;       // one record per launch since the last fetch
+	std::vector<cudaEvent_t> ev_pool;
+	cudaEvent_t prof_event() { if (ev_pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; } cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
 	ResidentBatch rb;
 	// device arenas (grown on demand, reused across batches)
 	DevBuf d_ascii, d_Q, d_seq_len, d_seq_off, d_q_off, d_flip, d_units, d_unit_cnt, d_unit_off, d_mv, d_m_n, d_m_val,
@@ -96,7 +103,14 @@ struct mmg_ctx_s {
 };
 
 #define MMG_LAUNCH(ctx, kern, grid, block, smem, ...) do { \
+	ProfRec pr_ = {#kern, nullptr, nullptr}; \
+	if ((ctx)->prof_on) { pr_.a = (ctx)->prof_event(); pr_.b = (ctx)->prof_event(); cudaEventRecord(pr_.a, (ctx)->stream); } \
 	kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); ++(ctx)->launches; \
+	if ((ctx)->prof_on) { cudaEventRecord(pr_.b, (ctx)->stream); (ctx)->prof.push_back(pr_); } \
 	cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { mmg_set_error("launch %s: %s", #kern, cudaGetErrorString(e_)); return MMG_ECUDA; } } while (0)
+
+// account a host<->device copy issued on the context's stream
+#define MMG_H2D(ctx, dst, src, n) do { (ctx)->h2d_bytes += (uint64_t)(n); MMG_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyHostToDevice, (ctx)->stream)); } while (0)
+#define MMG_D2H(ctx, dst, src, n) do { (ctx)->d2h_bytes += (uint64_t)(n); MMG_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyDeviceToHost, (ctx)->stream)); } while (0)
 
 static inline unsigned mmg_blocks(size_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }

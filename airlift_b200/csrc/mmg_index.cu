@@ -54,6 +54,8 @@ extern "C" void mmg_destroy(mmg_ctx_t *c)
 	PinBuf *pins[] = {&c->h_in, &c->h_meta, &c->h_out_meta, &c->h_out_u, &c->h_out_a, &c->h_out_mini, &c->h_k_jobs, &c->h_k_res, &c->h_k_cig};
 	for (PinBuf *b : pins) b->release();
 	for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	for (const ProfRec &r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+	for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -61,6 +63,34 @@ extern "C" void mmg_destroy(mmg_ctx_t *c)
 extern "C" int mmg_device(const mmg_ctx_t *c) { return c->dev; }
 extern "C" void *mmg_stream(const mmg_ctx_t *c) { return (void*)c->stream; }
 extern "C" long mmg_launch_count(mmg_ctx_t *c, int reset) { long n = c->launches; if (reset) c->launches = 0; return n; }
+
+extern "C" void mmg_copy_bytes(mmg_ctx_t *c, uint64_t *h2d, uint64_t *d2h, int reset)
+{
+	*h2d = c->h2d_bytes, *d2h = c->d2h_bytes;
+	if (reset) c->h2d_bytes = c->d2h_bytes = 0;
+}
+
+extern "C" void mmg_profile_enable(mmg_ctx_t *c, int on) { c->prof_on = on != 0; }
+
+// per-kernel device time since the last fetch, from CUDA events recorded around every launch on the ctx stream.
+// Fills up to max entries (name pointers are static strings); returns the number of distinct kernels.
+extern "C" int mmg_profile_fetch(mmg_ctx_t *c, int max, const char **names, double *ms, long *launches)
+{
+	cudaSetDevice(c->dev);
+	cudaStreamSynchronize(c->stream);
+	int n = 0;
+	for (const ProfRec &r : c->prof) {
+		float t = 0;
+		cudaEventElapsedTime(&t, r.a, r.b);
+		int i;
+		for (i = 0; i < n; ++i) if (names[i] == r.name || strcmp(names[i], r.name) == 0) break;
+		if (i == n) { if (n == max) { c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b); continue; } names[n] = r.name, ms[n] = 0, launches[n] = 0, ++n; }
+		ms[i] += t, launches[i] += 1;
+		c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b);
+	}
+	c->prof.clear();
+	return n;
+}
 
 // ------------------------------------------------------------------ kernels
 

@@ -256,7 +256,7 @@ static int ksw_launch(mmg_ctx_t *c, const uint32_t *d_Q, const uint32_t *d_S, co
 	MMG_TRY(c->k_cig_off.ensure((size_t)(n + 2) * 12));
 	MMG_TRY(c->h_k_jobs.ensure((size_t)(n + 1) * sizeof(KswJobDev)));
 	memcpy(c->h_k_jobs.p, jd.data(), (size_t)n * sizeof(KswJobDev));
-	MMG_CUDA(cudaMemcpyAsync(c->k_jobs.p, c->h_k_jobs.p, (size_t)n * sizeof(KswJobDev), cudaMemcpyHostToDevice, c->stream));
+	MMG_H2D(c, c->k_jobs.p, c->h_k_jobs.p, (size_t)n * sizeof(KswJobDev));
 	MMG_CUDA(cudaEventRecord(c->ev[0], c->stream));
 	MMG_LAUNCH(c, k_ksw, mmg_blocks(n, KSW_JOBS_PER_BLOCK), KSW_GROUP * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
 	           c->k_jobs.as<KswJobDev>(), n, sc, d_Q, d_S, c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(), c->k_cig.as<uint32_t>(),
@@ -274,7 +274,7 @@ static int ksw_launch(mmg_ctx_t *c, const uint32_t *d_Q, const uint32_t *d_S, co
 		++c->launches;
 	}
 	int64_t tot = 0;
-	MMG_CUDA(cudaMemcpyAsync(&tot, d_off + n, 8, cudaMemcpyDeviceToHost, c->stream));
+	MMG_D2H(c, &tot, d_off + n, 8);
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	MMG_TRY(c->k_cig_out.ensure((size_t)(tot + 1) * 4));
 	MMG_LAUNCH(c, k_cig_gather, mmg_blocks(n, 128), 128, 0, n, c->k_jobs.as<KswJobDev>(), c->k_res.as<KswEz>(), d_off, c->k_cig.as<uint32_t>(),
@@ -283,9 +283,9 @@ static int ksw_launch(mmg_ctx_t *c, const uint32_t *d_Q, const uint32_t *d_S, co
 	MMG_TRY(c->h_k_res.ensure((((size_t)(n + 1) * sizeof(KswEz) + 15) & ~(size_t)15) + (size_t)(n + 1) * 8));
 	KswEz *h_ez = c->h_k_res.as<KswEz>();
 	int64_t *h_off = reinterpret_cast<int64_t*>(c->h_k_res.as<uint8_t>() + (((size_t)(n + 1) * sizeof(KswEz) + 15) & ~(size_t)15));
-	MMG_CUDA(cudaMemcpyAsync(h_ez, c->k_res.p, (size_t)n * sizeof(KswEz), cudaMemcpyDeviceToHost, c->stream));
-	MMG_CUDA(cudaMemcpyAsync(h_off, d_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-	if (tot) MMG_CUDA(cudaMemcpyAsync(c->h_k_cig.p, c->k_cig_out.p, (size_t)tot * 4, cudaMemcpyDeviceToHost, c->stream));
+	MMG_D2H(c, h_ez, c->k_res.p, (size_t)n * sizeof(KswEz));
+	MMG_D2H(c, h_off, d_off, (size_t)(n + 1) * 8);
+	if (tot) MMG_D2H(c, c->h_k_cig.p, c->k_cig_out.p, (size_t)tot * 4);
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	for (int i = 0; i < n; ++i) {
 		memcpy(&res[i].ez, &h_ez[i], sizeof(KswEz));

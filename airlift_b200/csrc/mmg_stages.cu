@@ -246,15 +246,15 @@ extern "C" int mmg_batch_upload(mmg_ctx_t *c, const mmg_mapopt_t *opt, const mmg
 	MMG_TRY(c->d_frag_unit0.ensure((size_t)(b->n_frag + 1) * 4));
 	MMG_TRY(c->d_frag_qlen.ensure((size_t)(b->n_frag + 1) * 4));
 	MMG_TRY(c->d_misc.ensure((size_t)(b->n_frag + 1) * 4)); // n_seg
-	MMG_CUDA(cudaMemcpyAsync(c->d_ascii.p, c->h_in.p, b->n_bases, cudaMemcpyHostToDevice, c->stream));
-	MMG_CUDA(cudaMemcpyAsync(c->d_seq_len.p, b->seq_len, (size_t)b->n_seq * 4, cudaMemcpyHostToDevice, c->stream));
-	MMG_CUDA(cudaMemcpyAsync(c->d_seq_off.p, b->seq_off, (size_t)b->n_seq * 8, cudaMemcpyHostToDevice, c->stream));
-	MMG_CUDA(cudaMemcpyAsync(c->d_q_off.p, rb.q_off.data(), (size_t)(b->n_seq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-	MMG_CUDA(cudaMemcpyAsync(c->d_flip.p, flip.data(), (size_t)b->n_seq, cudaMemcpyHostToDevice, c->stream));
-	MMG_CUDA(cudaMemcpyAsync(c->d_units.p, units.data(), (size_t)rb.n_units * sizeof(SketchUnit), cudaMemcpyHostToDevice, c->stream));
-	MMG_CUDA(cudaMemcpyAsync(c->d_frag_unit0.p, rb.frag_unit0.data(), (size_t)(b->n_frag + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-	MMG_CUDA(cudaMemcpyAsync(c->d_frag_qlen.p, rb.frag_qlen.data(), (size_t)b->n_frag * 4, cudaMemcpyHostToDevice, c->stream));
-	MMG_CUDA(cudaMemcpyAsync(c->d_misc.p, b->n_seg, (size_t)b->n_frag * 4, cudaMemcpyHostToDevice, c->stream));
+	MMG_H2D(c, c->d_ascii.p, c->h_in.p, b->n_bases);
+	MMG_H2D(c, c->d_seq_len.p, b->seq_len, (size_t)b->n_seq * 4);
+	MMG_H2D(c, c->d_seq_off.p, b->seq_off, (size_t)b->n_seq * 8);
+	MMG_H2D(c, c->d_q_off.p, rb.q_off.data(), (size_t)(b->n_seq + 1) * 8);
+	MMG_H2D(c, c->d_flip.p, flip.data(), (size_t)b->n_seq);
+	MMG_H2D(c, c->d_units.p, units.data(), (size_t)rb.n_units * sizeof(SketchUnit));
+	MMG_H2D(c, c->d_frag_unit0.p, rb.frag_unit0.data(), (size_t)(b->n_frag + 1) * 4);
+	MMG_H2D(c, c->d_frag_qlen.p, rb.frag_qlen.data(), (size_t)b->n_frag * 4);
+	MMG_H2D(c, c->d_misc.p, b->n_seg, (size_t)b->n_frag * 4);
 	if (rb.q_words)
 		MMG_LAUNCH(c, k_encode_reads, mmg_blocks(rb.q_words, 256), 256, 0, c->d_ascii.as<uint8_t>(), c->d_seq_off.as<uint64_t>(),
 		           c->d_seq_len.as<int32_t>(), c->d_q_off.as<uint64_t>(), c->d_flip.as<uint8_t>(), b->n_seq, rb.q_words, c->d_Q.as<uint32_t>());
@@ -287,7 +287,7 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	           pb.na->as<int32_t>(), pb.rep->as<int32_t>(), pb.nmini->as<int32_t>(), want_mini ? pb.mini->as<uint64_t>() : nullptr);
 	MMG_TRY(scan_i32_to_i64(c, pb.na->as<int32_t>(), pb.aoff->as<int64_t>(), n_list + 1));
 	int64_t tot = 0;
-	MMG_CUDA(cudaMemcpyAsync(&tot, pb.aoff->as<int64_t>() + n_list, 8, cudaMemcpyDeviceToHost, c->stream));
+	MMG_D2H(c, &tot, pb.aoff->as<int64_t>() + n_list, 8);
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	*n_anchors = tot;
 	MMG_TRY(pb.a->ensure((size_t)(tot + 1) * 16));
@@ -346,7 +346,7 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 	int32_t *d_list = c->d_frag_list.as<int32_t>(), *d_src = d_list + nf;
 	MMG_CUDA(cudaMemsetAsync(d_src, 0xff, (size_t)nf * 4, c->stream));
 	if (opt->max_occ > opt->mid_occ) {
-		MMG_CUDA(cudaMemcpyAsync(hflag.data(), c->d_frag_flag.p, nf, cudaMemcpyDeviceToHost, c->stream));
+		MMG_D2H(c, hflag.data(), c->d_frag_flag.p, nf);
 		MMG_CUDA(cudaStreamSynchronize(c->stream));
 		for (int f = 0; f < nf; ++f) if (hflag[f]) list.push_back(f);
 	}
@@ -354,7 +354,7 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 	               &c->d2_stack, &c->d2_frag_nu, &c->d2_frag_nv};
 	const int n2 = (int)list.size();
 	if (n2) {
-		MMG_CUDA(cudaMemcpyAsync(d_list, list.data(), (size_t)n2 * 4, cudaMemcpyHostToDevice, c->stream));
+		MMG_H2D(c, d_list, list.data(), (size_t)n2 * 4);
 		MMG_TRY(run_pass(c, mi, opt, ft, d_list, n2, n_mv, opt->max_occ, p2, want_mini, nullptr, &n_anch2));
 		MMG_LAUNCH(c, k_merge_pass2, mmg_blocks(n2, 128), 128, 0, n2, d_list, c->d2_frag_nu.as<int32_t>(), c->d2_frag_nv.as<int32_t>(),
 		           c->d2_frag_rep.as<int32_t>(), c->d2_frag_nmini.as<int32_t>(), c->d_frag_nu.as<int32_t>(), c->d_frag_nv.as<int32_t>(),
@@ -368,9 +368,9 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 	MMG_TRY(scan_i32_to_i64(c, c->d_frag_nv.as<int32_t>(), c->d_voff.as<int64_t>(), nf + 1));
 	if (want_mini) MMG_TRY(scan_i32_to_i64(c, c->d_frag_nmini.as<int32_t>(), c->d_moff.as<int64_t>(), nf + 1));
 	int64_t tot[3] = {0, 0, 0};
-	MMG_CUDA(cudaMemcpyAsync(&tot[0], c->d_uoff.as<int64_t>() + nf, 8, cudaMemcpyDeviceToHost, c->stream));
-	MMG_CUDA(cudaMemcpyAsync(&tot[1], c->d_voff.as<int64_t>() + nf, 8, cudaMemcpyDeviceToHost, c->stream));
-	if (want_mini) MMG_CUDA(cudaMemcpyAsync(&tot[2], c->d_moff.as<int64_t>() + nf, 8, cudaMemcpyDeviceToHost, c->stream));
+	MMG_D2H(c, &tot[0], c->d_uoff.as<int64_t>() + nf, 8);
+	MMG_D2H(c, &tot[1], c->d_voff.as<int64_t>() + nf, 8);
+	if (want_mini) MMG_D2H(c, &tot[2], c->d_moff.as<int64_t>() + nf, 8);
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	MMG_TRY(c->d_out_u.ensure((size_t)(tot[0] + 1) * 8));
 	MMG_TRY(c->d_out_a.ensure((size_t)(tot[1] + 1) * 16));
@@ -383,7 +383,7 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 		           c->d_moff.as<int64_t>(), c->d_out_mini.as<uint64_t>());
 	MMG_CUDA(cudaEventRecord(c->ev[1], c->stream));
 	unsigned long long iters = 0;
-	MMG_CUDA(cudaMemcpyAsync(&iters, c->d_frag_iter.p, 8, cudaMemcpyDeviceToHost, c->stream));
+	MMG_D2H(c, &iters, c->d_frag_iter.p, 8);
 	out->n_minimizers = (uint64_t)n_mv, out->n_anchors = (uint64_t)(n_anch1 + n_anch2);
 	if (download) {
 		// meta: n_u | n_a | rep_len | n_mini | rechained (int32 each) then u_off | a_off | mini_off (uint64 each, nf+1)
@@ -394,17 +394,17 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 		MMG_TRY(c->h_out_mini.ensure((size_t)(tot[2] + 1) * 8));
 		int32_t *hi = c->h_out_meta.as<int32_t>();
 		uint64_t *ho = reinterpret_cast<uint64_t*>(c->h_out_meta.as<uint8_t>() + ((meta_i + 15) & ~(size_t)15));
-		MMG_CUDA(cudaMemcpyAsync(hi, c->d_frag_nu.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
-		MMG_CUDA(cudaMemcpyAsync(hi + nf, c->d_frag_nv.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
-		MMG_CUDA(cudaMemcpyAsync(hi + 2 * nf, c->d_frag_rep.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
-		MMG_CUDA(cudaMemcpyAsync(hi + 3 * nf, c->d_frag_nmini.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
-		MMG_CUDA(cudaMemcpyAsync(hi + 4 * nf, d_src, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
-		MMG_CUDA(cudaMemcpyAsync(ho, c->d_uoff.p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-		MMG_CUDA(cudaMemcpyAsync(ho + (nf + 1), c->d_voff.p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-		if (want_mini) MMG_CUDA(cudaMemcpyAsync(ho + 2 * (nf + 1), c->d_moff.p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-		if (tot[0]) MMG_CUDA(cudaMemcpyAsync(c->h_out_u.p, c->d_out_u.p, (size_t)tot[0] * 8, cudaMemcpyDeviceToHost, c->stream));
-		if (tot[1]) MMG_CUDA(cudaMemcpyAsync(c->h_out_a.p, c->d_out_a.p, (size_t)tot[1] * 16, cudaMemcpyDeviceToHost, c->stream));
-		if (tot[2]) MMG_CUDA(cudaMemcpyAsync(c->h_out_mini.p, c->d_out_mini.p, (size_t)tot[2] * 8, cudaMemcpyDeviceToHost, c->stream));
+		MMG_D2H(c, hi, c->d_frag_nu.p, (size_t)nf * 4);
+		MMG_D2H(c, hi + nf, c->d_frag_nv.p, (size_t)nf * 4);
+		MMG_D2H(c, hi + 2 * nf, c->d_frag_rep.p, (size_t)nf * 4);
+		MMG_D2H(c, hi + 3 * nf, c->d_frag_nmini.p, (size_t)nf * 4);
+		MMG_D2H(c, hi + 4 * nf, d_src, (size_t)nf * 4);
+		MMG_D2H(c, ho, c->d_uoff.p, (size_t)(nf + 1) * 8);
+		MMG_D2H(c, ho + (nf + 1), c->d_voff.p, (size_t)(nf + 1) * 8);
+		if (want_mini) MMG_D2H(c, ho + 2 * (nf + 1), c->d_moff.p, (size_t)(nf + 1) * 8);
+		if (tot[0]) MMG_D2H(c, c->h_out_u.p, c->d_out_u.p, (size_t)tot[0] * 8);
+		if (tot[1]) MMG_D2H(c, c->h_out_a.p, c->d_out_a.p, (size_t)tot[1] * 16);
+		if (tot[2]) MMG_D2H(c, c->h_out_mini.p, c->d_out_mini.p, (size_t)tot[2] * 8);
 		MMG_CUDA(cudaEventRecord(c->ev[2], c->stream));
 		MMG_CUDA(cudaStreamSynchronize(c->stream));
 		for (int f = 0; f < nf; ++f) hi[4 * nf + f] = hi[4 * nf + f] >= 0 ? 1 : 0; // src slot -> rechained flag
@@ -452,12 +452,12 @@ extern "C" int mmg_sketch(mmg_ctx_t *c, const char *str, int len, int w, int k, 
 		units.push_back(u);
 	}
 	MMG_TRY(c->d_units.ensure(units.size() * sizeof(SketchUnit)));
-	MMG_CUDA(cudaMemcpyAsync(c->d_units.p, units.data(), units.size() * sizeof(SketchUnit), cudaMemcpyHostToDevice, c->stream));
+	MMG_H2D(c, c->d_units.p, units.data(), units.size() * sizeof(SketchUnit));
 	int64_t n = 0;
 	MMG_TRY(mmg_run_sketch(c, c->d_Q.as<uint32_t>(), c->d_units.as<SketchUnit>(), (int)units.size(), w, k, is_hpc, c->d_unit_cnt, c->d_unit_off, c->d_mv, &n));
 	*n_out = (int)n;
 	const int64_t m = n < cap ? n : cap;
-	if (m > 0) MMG_CUDA(cudaMemcpyAsync(out, c->d_mv.p, (size_t)m * 16, cudaMemcpyDeviceToHost, c->stream));
+	if (m > 0) MMG_D2H(c, out, c->d_mv.p, (size_t)m * 16);
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	return MMG_OK;
 }

@@ -301,9 +301,11 @@ int main(int argc, char *argv[])
 					__func__, realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), mi->n_seq);
 		if (argc != optind + 1) mm_mapopt_update(&opt, mi);
 		if (mm_verbose >= 3) mm_idx_stat(mi);
+		if (getenv("MM2_B200_PROFILE")) mm_b200_profile(mi, 1);
 		if (!(opt.flag & MM_F_FRAG_MODE)) {
 			for (i = optind + 1; i < argc; ++i) mm_map_file(mi, argv[i], &opt, n_threads);
 		} else mm_map_file_frag(mi, argc - (optind + 1), (const char**)&argv[optind + 1], &opt, n_threads);
+		if (mm_verbose >= 4 || getenv("MM2_B200_PROFILE")) mm_b200_report(mi, stderr);
 		mm_idx_destroy(mi);
 	}
 	mm_idx_reader_close(idx_rdr);

@@ -14,6 +14,19 @@
 #include <pthread.h>
 #include "mm2b_priv.h"
 
+/* ------------------------------------------------------------------ work / time counters (for bench.py and -v4) */
+
+static mm_b200_stats_t g_stats;
+static pthread_mutex_t g_stats_mu = PTHREAD_MUTEX_INITIALIZER;
+
+void mm_b200_stats(mm_b200_stats_t *out, int reset)
+{
+	pthread_mutex_lock(&g_stats_mu);
+	if (out) *out = g_stats;
+	if (reset) memset(&g_stats, 0, sizeof(g_stats));
+	pthread_mutex_unlock(&g_stats_mu);
+}
+
 /* ------------------------------------------------------------------ a tiny parallel-for */
 
 typedef struct { void (*fn)(void*, long, int); void *data; long n; volatile long next; int n_threads; } pfor_t;
@@ -69,6 +82,7 @@ typedef struct {          /* one GPU's share of a mini-batch */
 	mm_reg1_t **reg;
 	frag_t *fr;
 	mmg_chains_t ch;
+	mm_b200_stats_t st;
 	int rc;
 } shard_t;
 
@@ -200,17 +214,18 @@ static void shard_fail(shard_t *sh, const char *what)
 	sh->rc = -1;
 }
 
-/* map fragments [f0,f1) of a mini-batch on one GPU */
-static void *map_shard(void *data)
+/* stage the reads of fragments [f0,f1) on the shard's GPU (H2D + 4-bit encode) */
+static void *shard_upload(void *data)
 {
 	shard_t *sh = (shard_t*)data;
 	const int nf = sh->f1 - sh->f0;
-	int i, j, n_seq = 0;
+	int i, n_seq = 0;
 	uint64_t n_bases = 0, o;
 	char *bases;
 	int32_t *n_seg, *seg_off, *seq_len;
 	uint64_t *seq_off;
 	mmg_batch_t b;
+	double t0 = realtime();
 	sh->rc = 0;
 	if (nf <= 0) return 0;
 	sh->s0 = sh->seg_off[sh->f0];
@@ -227,12 +242,30 @@ static void *map_shard(void *data)
 	}
 	for (i = 0; i < nf; ++i) n_seg[i] = sh->n_seg[sh->f0 + i], seg_off[i] = sh->seg_off[sh->f0 + i] - sh->s0;
 	b.n_frag = nf, b.n_seq = n_seq, b.n_seg = n_seg, b.seg_off = seg_off, b.seq_len = seq_len, b.seq_off = seq_off, b.bases = bases, b.n_bases = n_bases;
-	if (mmg_seed_chain_batch(sh->ctx, sh->didx, &sh->dopt, &b, &sh->ch) != MMG_OK) shard_fail(sh, "seed/chain stage failed");
+	if (mmg_batch_upload(sh->ctx, &sh->dopt, &b) != MMG_OK) shard_fail(sh, "read upload failed");
 	free(bases); free(n_seg); free(seg_off); free(seq_len); free(seq_off);
-	if (sh->rc) return 0;
+	sh->st.n_frag += nf, sh->st.n_reads += n_seq, sh->st.n_bases += n_bases;
+	sh->st.t_upload += realtime() - t0;
+	return 0;
+}
+
+/* map the fragments [f0,f1) whose reads are resident on the shard's GPU */
+static void *map_shard(void *data)
+{
+	shard_t *sh = (shard_t*)data;
+	const int nf = sh->f1 - sh->f0;
+	int i, j;
+	double t0, t1;
+	if (nf <= 0 || sh->rc) return 0;
+	t0 = realtime();
+	if (mmg_seed_chain_resident(sh->ctx, sh->didx, &sh->dopt, &sh->ch, 1) != MMG_OK) { shard_fail(sh, "seed/chain stage failed"); return 0; }
+	t1 = realtime();
+	sh->st.t_seedchain += t1 - t0, sh->st.t_seedchain_kernels += sh->ch.t_kernels_ms * 1e-3;
+	sh->st.n_minimizers += sh->ch.n_minimizers, sh->st.n_anchors += sh->ch.n_anchors, sh->st.n_chain_iter += sh->ch.n_chain_iter;
 
 	sh->fr = (frag_t*)calloc(nf, sizeof(frag_t));
 	parallel_for(sh->n_threads, stage_hits, sh, nf);
+	t0 = realtime(); sh->st.t_hits += t0 - t1;
 	if (sh->opt->flag & MM_F_CIGAR) {
 		mmg_ksw_job_t *jobs = 0; mmg_ksw_res_t *res = 0;
 		size_t m_jobs = 0;
@@ -240,6 +273,8 @@ static void *map_shard(void *data)
 			size_t n_jobs = 0;
 			const uint32_t *cig = 0;
 			int n_active = 0;
+			double ta = realtime(), tb, kms = 0;
+			uint64_t cells = 0;
 			parallel_for(sh->n_threads, stage_align, sh, nf);
 			for (i = 0; i < nf; ++i) {
 				frag_t *fr = &sh->fr[i];
@@ -257,9 +292,13 @@ static void *map_shard(void *data)
 					}
 				}
 			}
+			tb = realtime(); sh->st.t_align_host += tb - ta;
 			if (n_active == 0) break;
 			if (n_jobs == 0) { fprintf(stderr, "[ERROR] alignment made no progress\n"); sh->rc = -1; break; }
-			if (mmg_ksw_batch(sh->ctx, sh->didx, &sh->dopt, (int)n_jobs, jobs, res, &cig, 0, 0) != MMG_OK) { shard_fail(sh, "DP stage failed"); break; }
+			if (mmg_ksw_batch(sh->ctx, sh->didx, &sh->dopt, (int)n_jobs, jobs, res, &cig, &kms, &cells) != MMG_OK) { shard_fail(sh, "DP stage failed"); break; }
+			sh->st.t_ksw_total += realtime() - tb, sh->st.t_ksw_kernel += kms * 1e-3;
+			sh->st.n_dp_jobs += n_jobs, sh->st.n_dp_cells += cells, sh->st.n_dp_rounds += 1;
+			ta = realtime();
 			{ /* scatter results back in the same traversal order */
 				size_t k = 0;
 				for (i = 0; i < nf; ++i) {
@@ -283,10 +322,13 @@ static void *map_shard(void *data)
 				}
 				assert(k == n_jobs);
 			}
+			sh->st.t_align_host += realtime() - ta;
 		}
 		free(jobs); free(res);
 	}
+	t0 = realtime();
 	parallel_for(sh->n_threads, stage_finish, sh, nf);
+	sh->st.t_finish += realtime() - t0;
 	free(sh->fr); sh->fr = 0;
 	return 0;
 }
@@ -332,22 +374,24 @@ static step_t *step_read(pipeline_t *p)
 	return s;
 }
 
-static int step_map(pipeline_t *p, step_t *s)
+/* mode 0: upload + map; 1: upload only; 2: map the batch uploaded by an earlier mode-1 call */
+static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, step_t *s, int mode)
 {
-	struct mm_idx_bucket_s *B = p->mi->B;
+	struct mm_idx_bucket_s *B = mi->B;
 	const int n_dev = B->n_dev;
 	shard_t *sh = (shard_t*)calloc(n_dev, sizeof(shard_t));
 	pthread_t *tid = (pthread_t*)calloc(n_dev, sizeof(pthread_t));
-	int d, f = 0, rc = 0;
+	int d, f = 0, rc = 0, pass;
 	int64_t tot = 0, acc = 0;
-	if (p->opt->flag & MM_F_INDEPEND_SEG) { fprintf(stderr, "[ERROR] --no-pairing is not supported by this build\n"); return -1; }
+	const double t_start = realtime();
+	if (opt->flag & MM_F_INDEPEND_SEG) { fprintf(stderr, "[ERROR] --no-pairing is not supported by this build\n"); return -1; }
 	for (d = 0; d < s->n_seq; ++d) tot += s->seq[d].l_seq;
 	for (d = 0; d < n_dev; ++d) { /* contiguous fragment ranges balanced by bases; a fragment is never cut */
 		shard_t *h = &sh[d];
 		const int64_t goal = tot * (d + 1) / n_dev;
-		h->mi = p->mi, h->opt = p->opt, h->ctx = B->ctx[d], h->didx = B->didx[d];
-		mm_mapopt_to_dev(p->opt, &h->dopt);
-		h->n_threads = p->n_threads / n_dev > 0 ? p->n_threads / n_dev : 1;
+		h->mi = mi, h->opt = opt, h->ctx = B->ctx[d], h->didx = B->didx[d];
+		mm_mapopt_to_dev(opt, &h->dopt);
+		h->n_threads = n_threads / n_dev > 0 ? n_threads / n_dev : 1;
 		h->seq = s->seq, h->n_seg = s->n_seg, h->seg_off = s->seg_off, h->n_reg = s->n_reg, h->rep_len = s->rep_len, h->frag_gap = s->frag_gap, h->reg = s->reg;
 		h->f0 = f;
 		while (f < s->n_frag && (acc < goal || d == n_dev - 1)) {
@@ -356,16 +400,37 @@ static int step_map(pipeline_t *p, step_t *s)
 			++f;
 		}
 		h->f1 = f;
+		if (h->f1 > h->f0) h->s0 = s->seg_off[h->f0];
 	}
-	if (n_dev == 1) map_shard(&sh[0]);
-	else {
-		for (d = 0; d < n_dev; ++d) pthread_create(&tid[d], 0, map_shard, &sh[d]);
-		for (d = 0; d < n_dev; ++d) pthread_join(tid[d], 0);
+	for (pass = 0; pass < 2; ++pass) {
+		void *(*fn)(void*) = pass == 0 ? shard_upload : map_shard;
+		if ((pass == 0 && mode == 2) || (pass == 1 && mode == 1)) continue;
+		if (n_dev == 1) fn(&sh[0]);
+		else {
+			for (d = 0; d < n_dev; ++d) pthread_create(&tid[d], 0, fn, &sh[d]);
+			for (d = 0; d < n_dev; ++d) pthread_join(tid[d], 0);
+		}
 	}
-	for (d = 0; d < n_dev; ++d) if (sh[d].rc) rc = -1;
+	pthread_mutex_lock(&g_stats_mu);
+	for (d = 0; d < n_dev; ++d) {
+		const mm_b200_stats_t *t = &sh[d].st;
+		uint64_t h2d = 0, d2h = 0;
+		if (sh[d].rc) rc = -1;
+		mmg_copy_bytes(sh[d].ctx, &h2d, &d2h, 1);
+		g_stats.t_upload += t->t_upload, g_stats.t_seedchain += t->t_seedchain, g_stats.t_seedchain_kernels += t->t_seedchain_kernels;
+		g_stats.t_hits += t->t_hits, g_stats.t_align_host += t->t_align_host, g_stats.t_ksw_total += t->t_ksw_total;
+		g_stats.t_ksw_kernel += t->t_ksw_kernel, g_stats.t_finish += t->t_finish;
+		g_stats.n_frag += t->n_frag, g_stats.n_reads += t->n_reads, g_stats.n_bases += t->n_bases, g_stats.n_minimizers += t->n_minimizers;
+		g_stats.n_anchors += t->n_anchors, g_stats.n_chain_iter += t->n_chain_iter, g_stats.n_dp_jobs += t->n_dp_jobs;
+		g_stats.n_dp_cells += t->n_dp_cells, g_stats.n_dp_rounds += t->n_dp_rounds, g_stats.h2d_bytes += h2d, g_stats.d2h_bytes += d2h;
+	}
+	g_stats.t_total += realtime() - t_start;
+	pthread_mutex_unlock(&g_stats_mu);
 	free(sh); free(tid);
 	return rc;
 }
+
+static int step_map(pipeline_t *p, step_t *s) { return map_step(p->mi, p->opt, p->n_threads, s, 0); }
 
 static void step_write(pipeline_t *p, step_t *s)
 { /* map.c:594-650 (no --split-prefix) */
@@ -540,6 +605,7 @@ void mm_map_frag(const mm_idx_t *mi, int n_segs, const int *qlens, const char **
 	mm_mapopt_to_dev(&o2, &sh.dopt);
 	sh.n_threads = 1, sh.f0 = 0, sh.f1 = 1;
 	sh.seq = seq, sh.n_seg = &n_seg, sh.seg_off = &one_off, sh.n_reg = n_regs, sh.rep_len = rep, sh.frag_gap = gap, sh.reg = regs;
+	shard_upload(&sh);
 	map_shard(&sh);
 	if (sh.rc) { fprintf(stderr, "[ERROR] mapping failed; no CPU fallback exists\n"); exit(1); }
 	if (b) b->rep_len = rep[0], b->frag_gap = gap[0];
@@ -552,4 +618,145 @@ mm_reg1_t *mm_map(const mm_idx_t *mi, int qlen, const char *seq, int *n_regs, mm
 	mm_reg1_t *regs;
 	mm_map_frag(mi, 1, &qlen, &seq, n_regs, &regs, b, opt, qname);
 	return regs;
+}
+
+/* ------------------------------------------------------------------ batch API (what bench.py and embedders call) */
+
+struct mm_b200_reader_s { pipeline_t pl; };
+
+mm_b200_reader_t *mm_b200_open_reads(int n_fp, const char **fn)
+{
+	mm_b200_reader_t *r = (mm_b200_reader_t*)calloc(1, sizeof(*r));
+	int i;
+	r->pl.n_fp = n_fp;
+	r->pl.fp = (mm_bseq_file_t**)calloc(n_fp, sizeof(mm_bseq_file_t*));
+	for (i = 0; i < n_fp; ++i)
+		if ((r->pl.fp[i] = mm_bseq_open(fn[i])) == 0) {
+			int j;
+			for (j = 0; j < i; ++j) mm_bseq_close(r->pl.fp[j]);
+			free(r->pl.fp); free(r);
+			return 0;
+		}
+	return r;
+}
+
+void mm_b200_close_reads(mm_b200_reader_t *r)
+{
+	int i;
+	if (r == 0) return;
+	for (i = 0; i < r->pl.n_fp; ++i) mm_bseq_close(r->pl.fp[i]);
+	free(r->pl.fp); free(r->pl.str.s); free(r);
+}
+
+mm_b200_batch_t *mm_b200_read_batch(mm_b200_reader_t *r, const mm_mapopt_t *opt, int batch_bases)
+{
+	r->pl.opt = opt, r->pl.mini_batch_size = batch_bases;
+	return (mm_b200_batch_t*)step_read(&r->pl);
+}
+
+void mm_b200_batch_info(const mm_b200_batch_t *b, int *n_seq, int *n_frag, int64_t *n_bases)
+{
+	const step_t *s = (const step_t*)b;
+	int64_t t = 0;
+	int i;
+	for (i = 0; i < s->n_seq; ++i) t += s->seq[i].l_seq;
+	if (n_seq) *n_seq = s->n_seq;
+	if (n_frag) *n_frag = s->n_frag;
+	if (n_bases) *n_bases = t;
+}
+
+int mm_b200_map_batch(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, mm_b200_batch_t *b, int mode)
+{
+	return map_step(mi, opt, n_threads > 1 ? n_threads : 1, (step_t*)b, mode);
+}
+
+/* drop the hits of a mapped batch so that it can be mapped again */
+void mm_b200_reset_batch(mm_b200_batch_t *b)
+{
+	step_t *s = (step_t*)b;
+	int i, j;
+	for (i = 0; i < s->n_seq; ++i) {
+		for (j = 0; j < s->n_reg[i]; ++j) free(s->reg[i][j].p);
+		free(s->reg[i]);
+		s->reg[i] = 0, s->n_reg[i] = 0;
+	}
+}
+
+/* order-independent digest of the hits of a batch (coordinates, strand, MAPQ, CIGAR, scores) */
+uint64_t mm_b200_batch_digest(const mm_b200_batch_t *b, int64_t *n_hits)
+{
+	const step_t *s = (const step_t*)b;
+	uint64_t h = 1469598103934665603ULL;
+	int64_t n = 0;
+	int i, j;
+	uint32_t k;
+#define MIX(v) do { h ^= (uint64_t)(v); h *= 1099511628211ULL; } while (0)
+	for (i = 0; i < s->n_seq; ++i)
+		for (j = 0; j < s->n_reg[i]; ++j) {
+			const mm_reg1_t *r = &s->reg[i][j];
+			MIX(i); MIX(r->rid); MIX(r->rs); MIX(r->re); MIX(r->qs); MIX(r->qe); MIX(r->rev); MIX(r->mapq); MIX(r->score); MIX(r->parent == r->id);
+			if (r->p) { MIX(r->p->dp_max); MIX(r->p->dp_score); for (k = 0; k < r->p->n_cigar; ++k) MIX(r->p->cigar[k]); }
+			++n;
+		}
+#undef MIX
+	if (n_hits) *n_hits = n;
+	return h;
+}
+
+void mm_b200_write_batch(const mm_idx_t *mi, const mm_mapopt_t *opt, mm_b200_batch_t *b)
+{
+	pipeline_t pl;
+	memset(&pl, 0, sizeof(pl));
+	pl.opt = opt, pl.mi = mi;
+	step_write(&pl, (step_t*)b);
+	free(pl.str.s);
+}
+
+void mm_b200_free_batch(mm_b200_batch_t *b)
+{
+	step_t *s = (step_t*)b;
+	int i;
+	mm_b200_reset_batch(b);
+	for (i = 0; i < s->n_seq; ++i) { free(s->seq[i].seq); free(s->seq[i].name); free(s->seq[i].qual); free(s->seq[i].comment); }
+	free(s->reg); free(s->n_reg); free(s->seq); free(s);
+}
+
+mmg_ctx_t *mm_b200_ctx(const mm_idx_t *mi, int dev_slot) { return mi->B->ctx[dev_slot]; }
+int mm_b200_n_devices(const mm_idx_t *mi) { return mi->B->n_dev; }
+
+void mm_b200_profile(const mm_idx_t *mi, int enable)
+{
+	int d;
+	for (d = 0; d < mi->B->n_dev; ++d) mmg_profile_enable(mi->B->ctx[d], enable);
+}
+
+/* per-kernel device time and launch counts since profiling was enabled (device slot 0..n-1 summed) */
+int mm_b200_profile_fetch(const mm_idx_t *mi, int max, const char **names, double *ms, long *launches)
+{
+	int d, n = 0, i, j;
+	for (d = 0; d < mi->B->n_dev; ++d) {
+		const char *nm[64]; double t[64]; long l[64];
+		const int k = mmg_profile_fetch(mi->B->ctx[d], 64, nm, t, l);
+		for (i = 0; i < k; ++i) {
+			for (j = 0; j < n; ++j) if (strcmp(names[j], nm[i]) == 0) break;
+			if (j == n) { if (n == max) continue; names[n] = nm[i], ms[n] = 0, launches[n] = 0, ++n; }
+			ms[j] += t[i], launches[j] += l[i];
+		}
+	}
+	return n;
+}
+
+void mm_b200_report(const mm_idx_t *mi, FILE *fp)
+{
+	mm_b200_stats_t s;
+	const char *nm[64]; double t[64]; long l[64];
+	int i, n;
+	mm_b200_stats(&s, 0);
+	fprintf(fp, "[M::b200] batches: %.3f s total = upload %.3f + seed/chain %.3f (kernels %.3f) + hits %.3f + align host %.3f + DP %.3f (kernel %.3f) + finish %.3f\n",
+			s.t_total, s.t_upload, s.t_seedchain, s.t_seedchain_kernels, s.t_hits, s.t_align_host, s.t_ksw_total, s.t_ksw_kernel, s.t_finish);
+	fprintf(fp, "[M::b200] reads %lu, bases %lu, minimizers %lu, anchors %lu, chain iterations %lu, DP jobs %lu in %lu rounds, DP cells %lu, H2D %lu B, D2H %lu B\n",
+			(unsigned long)s.n_reads, (unsigned long)s.n_bases, (unsigned long)s.n_minimizers, (unsigned long)s.n_anchors, (unsigned long)s.n_chain_iter,
+			(unsigned long)s.n_dp_jobs, (unsigned long)s.n_dp_rounds, (unsigned long)s.n_dp_cells, (unsigned long)s.h2d_bytes, (unsigned long)s.d2h_bytes);
+	n = mm_b200_profile_fetch(mi, 64, nm, t, l);
+	for (i = 0; i < n; ++i) fprintf(fp, "[M::b200] kernel %-18s %8ld launches %10.3f ms\n", nm[i], l[i], t[i]);
 }

@@ -128,6 +128,7 @@ void mm_write_sam3(mm_str_t *s, const mm_idx_t *mi, const mm_bseq1_t *t, int seg
                    const mm_reg1_t *const* regss, int opt_flag, int rep_len);
 
 /* mapper.c */
+mmg_ctx_t *mm_b200_ctx(const mm_idx_t *mi, int dev_slot);
 void mm_mapopt_to_dev(const mm_mapopt_t *opt, mmg_mapopt_t *d);
 
 #endif

@@ -179,6 +179,31 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 
 /* B200 additions */
 int mm_b200_set_devices(int n_gpus, const int *dev_ids); /* before building the index; default: device 0 */
+
+/* Batch interface = the drop-in cut point of SURVEY.md §8b (worker_pipeline step 1, map.c:590-593): a mini-batch of
+ * fragments with HOST buffers in, malloc'd mm_reg1_t arrays out.  mode 0 maps (upload + all stages); modes 1 / 2 split
+ * that into "stage the reads in HBM" and "map the resident batch" so that device-resident throughput can be timed. */
+typedef struct mm_b200_reader_s mm_b200_reader_t;
+typedef struct mm_b200_batch_s mm_b200_batch_t;
+mm_b200_reader_t *mm_b200_open_reads(int n_fp, const char **fn);
+void mm_b200_close_reads(mm_b200_reader_t *r);
+mm_b200_batch_t *mm_b200_read_batch(mm_b200_reader_t *r, const mm_mapopt_t *opt, int batch_bases);
+void mm_b200_batch_info(const mm_b200_batch_t *b, int *n_seq, int *n_frag, int64_t *n_bases);
+int  mm_b200_map_batch(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, mm_b200_batch_t *b, int mode);
+void mm_b200_reset_batch(mm_b200_batch_t *b);
+uint64_t mm_b200_batch_digest(const mm_b200_batch_t *b, int64_t *n_hits);
+void mm_b200_write_batch(const mm_idx_t *mi, const mm_mapopt_t *opt, mm_b200_batch_t *b); /* prints and frees */
+void mm_b200_free_batch(mm_b200_batch_t *b);
+int  mm_b200_n_devices(const mm_idx_t *mi);
+
+typedef struct { /* accumulated over mm_b200_map_batch / mm_map_file_frag calls; seconds and counts */
+	double t_total, t_upload, t_seedchain, t_seedchain_kernels, t_hits, t_align_host, t_ksw_total, t_ksw_kernel, t_finish;
+	uint64_t n_frag, n_reads, n_bases, n_minimizers, n_anchors, n_chain_iter, n_dp_jobs, n_dp_cells, n_dp_rounds, h2d_bytes, d2h_bytes;
+} mm_b200_stats_t;
+void mm_b200_stats(mm_b200_stats_t *out, int reset);
+void mm_b200_profile(const mm_idx_t *mi, int enable);   /* CUDA-event timing of every kernel launch */
+int  mm_b200_profile_fetch(const mm_idx_t *mi, int max, const char **names, double *ms, long *launches);
+void mm_b200_report(const mm_idx_t *mi, FILE *fp);
 void mm_write_sam_hdr(const mm_idx_t *mi, const char *rg, const char *ver, int argc, char *argv[]);
 
 #ifdef __cplusplus

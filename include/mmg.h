@@ -43,6 +43,11 @@ int  mmg_device(const mmg_ctx_t *ctx);
 void *mmg_stream(const mmg_ctx_t *ctx);           /* the cudaStream_t every launch of this ctx uses */
 /* kernels launched by this context since the last call (for bench.py's gpu_launches) */
 long mmg_launch_count(mmg_ctx_t *ctx, int reset);
+/* bytes copied host->device / device->host on the ctx stream since the last reset */
+void mmg_copy_bytes(mmg_ctx_t *ctx, uint64_t *h2d, uint64_t *d2h, int reset);
+/* per-kernel device time (CUDA events around every launch of this ctx); names[] receives static strings */
+void mmg_profile_enable(mmg_ctx_t *ctx, int on);
+int  mmg_profile_fetch(mmg_ctx_t *ctx, int max, const char **names, double *ms, long *launches);
 
 /* ------------------------------------------------------------------ index */
 /* Build the index on the device from n_seq ASCII sequences (not NUL-terminated; lens[] given).
@@ -72,6 +77,9 @@ int  mmg_idx_export(const mmg_idx_t *idx, mmg_idx_image_t *img);
 int  mmg_idx_alloc_like(mmg_ctx_t *ctx, mmg_idx_image_t *img, mmg_idx_t **idx);
 /* replicate src (on its device) into a new index on ctx's device with a peer/NVLink copy */
 int  mmg_idx_clone_to(mmg_ctx_t *ctx, const mmg_idx_t *src, mmg_idx_t **dst);
+/* after the buffers of an mmg_idx_alloc_like() index were filled (e.g. by an NCCL broadcast) */
+int  mmg_idx_finalize(mmg_idx_t *idx);
+int64_t mmg_idx_n_singletons(const mmg_idx_t *idx);
 
 /* ----------------------------------------------------- per-kernel entry points */
 /* mm_sketch on the device.  Returns the count in *n_out; writes min(count, cap) entries. */
