@@ -1,0 +1,55 @@
+"""End-to-end parity: the B200 CLI vs the reference fork (Oracle B binary, oracle/_ref/minimap2_B, built from
+/root/reference by oracle/Makefile; the binary travels to the GPU box) on the same synthetic files.
+Every output line except @PG must be identical: position, strand, CIGAR, MAPQ, tags, flags."""
+import os
+import subprocess
+import pytest
+import _libs as L
+
+pytestmark = pytest.mark.gpu
+NEW = os.path.join(L.ROOT, "build", "minimap2-b200")
+SYN = os.path.join(L.ROOT, "build", "mmsynth")
+
+
+@pytest.fixture(scope="module")
+def data(tmp_path_factory):
+    if not (os.path.exists(L.REF_BIN_B) and os.path.exists(NEW) and os.path.exists(SYN)):
+        pytest.skip("needs oracle/_ref/minimap2_B, build/minimap2-b200 and build/mmsynth")
+    d = tmp_path_factory.mktemp("e2e")
+    subprocess.check_call([SYN, "ref", str(d / "ref.fa"), "3000000", "3", "42"])
+    subprocess.check_call([SYN, "sr", str(d / "ref.fa"), str(d / "r1.fq"), str(d / "r2.fq"), "30000", "44", "0.05"])
+    subprocess.check_call([SYN, "long", str(d / "ref.fa"), str(d / "long.fq"), "150", "45"])
+    # edge cases the reference handles: empty read, read shorter than k, all-N read, lower case, U bases
+    with open(d / "edge.fq", "w") as f:
+        f.write("@short\nACGTACGT\n+\nIIIIIIII\n@allN\n" + "N" * 150 + "\n+\n" + "I" * 150 + "\n")
+        ref = open(d / "ref.fa").read().split("\n")
+        s = "".join(ref[1:4])[:150]
+        f.write("@lower\n" + s.lower() + "\n+\n" + "I" * len(s) + "\n@rna\n" + s.replace("T", "U") + "\n+\n" + "I" * len(s) + "\n")
+    return d
+
+
+def _run(binary, args, cwd):
+    p = subprocess.run([binary] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr.decode()[-800:]
+    return [l for l in p.stdout.decode().split("\n") if not l.startswith("@PG")]
+
+
+@pytest.mark.parametrize("args", [
+    ["-x", "sr", "-t", "8", "ref.fa", "r1.fq", "r2.fq"],
+    ["-ax", "sr", "-t", "8", "ref.fa", "r1.fq", "r2.fq"],
+    ["-ax", "sr", "-t", "3", "-K", "2M", "ref.fa", "r1.fq", "r2.fq"],       # many mini-batches
+    ["-ax", "sr", "-t", "8", "ref.fa", "r1.fq"],                             # single-end through the frag path
+    ["-ax", "sr", "-t", "8", "--cs", "--MD", "-Y", "ref.fa", "r1.fq", "r2.fq"],
+    ["-ax", "sr", "-t", "8", "-f", "20,60", "ref.fa", "r1.fq", "r2.fq"],     # low occurrence cut-offs: re-chain path
+    ["-cx", "sr", "-t", "8", "--eqx", "ref.fa", "r2.fq"],
+    ["-ax", "sr", "-t", "4", "ref.fa", "edge.fq"],
+    ["-x", "map-ont", "-t", "8", "ref.fa", "long.fq"],
+    ["-ax", "map-ont", "-t", "8", "ref.fa", "long.fq"],
+    ["-cx", "map-ont", "-t", "8", "--cs=long", "ref.fa", "long.fq"],
+], ids=lambda a: " ".join(a[:-2]))
+def test_cli_identical_to_reference(data, args):
+    want = _run(L.REF_BIN_B, args, data)
+    got = _run(NEW, args, data)
+    assert len(want) == len(got)
+    for i, (a, b) in enumerate(zip(want, got)):
+        assert a == b, f"line {i}:\nref: {a[:300]}\nnew: {b[:300]}"
