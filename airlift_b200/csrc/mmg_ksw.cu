@@ -10,16 +10,16 @@
 #include <cub/cub.cuh>
 #include "mmg_ctx.cuh"
 
-struct KswJobDev {
+struct KswJobDev {       // a job as the kernel sees it: mmg_ksw_job_t resolved against the resident batch and the index
 	uint64_t q_base;      // packed base offset of the read in Q
 	uint64_t t_base;      // packed base offset of the target slice in S
 	uint64_t mem_off, p_off, cig_off;
 	int32_t q_readlen, q_rev, q_start, q_len, t_len, reversed;
 	int32_t w, zdrop, end_bonus, flag;
-	int32_t out_idx, pad;
 };
 
 struct KswScore { int32_t m; int8_t mat[25]; int8_t q, e, q2, e2; };
+struct KswResDev { KswEz ez; uint64_t cigar_off; };   // == mmg_ksw_res_t
 
 #define KSW_GROUP 16
 #define KSW_JOBS_PER_BLOCK 8
@@ -37,6 +37,51 @@ __device__ __forceinline__ uint8_t ksw_tbase(const uint32_t *S, const KswJobDev 
 {
 	const int ti = jb.reversed ? jb.t_len - 1 - i : i;
 	return (uint8_t)mmg_seq4_get(S, jb.t_base + ti); // mm_idx_getseq, index.c:152-162
+}
+
+__device__ __forceinline__ int ksw_ncol(int qlen, int tlen, int w)
+{ // n_col_ of ksw2_extd2_sse.c:85-86
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	int nc = qlen < tlen ? qlen : tlen;
+	return ((nc < w + 1 ? nc : w + 1) + 15) / 16 + 1;
+}
+
+// per job: arena sizes, a size class for scheduling (big jobs first), and the true-band cell count
+__global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, uint64_t *__restrict__ mem_sz, uint64_t *__restrict__ p_sz,
+                           uint64_t *__restrict__ cig_sz, uint32_t *__restrict__ key, int32_t *__restrict__ idx, unsigned long long *__restrict__ cells_total)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long cells = 0;
+	if (i <= n) {
+		uint64_t m = 0, p = 0, c = 0; uint32_t k = 63;
+		if (i < n) {
+			const mmg_ksw_job_t j = jobs[i];
+			const int qlen = j.q_len, tlen = j.t_len;
+			if (qlen > 0 && tlen > 0) {
+				const size_t mem_bytes = mmg_ksw_mem_bytes(qlen, tlen), H_bytes = (size_t)((tlen + 15) / 16) * 64;
+				if (mem_bytes + H_bytes > KSW_SMEM_PER_JOB) m = (mem_bytes + H_bytes + 63) & ~(size_t)63;
+				if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = ((uint64_t)(qlen + tlen - 1) * ksw_ncol(qlen, tlen, j.w) + 1) * 16;
+				c = (uint64_t)qlen + tlen + 2;
+				int w = j.w < 0 ? (tlen > qlen ? tlen : qlen) : j.w;
+				// cells inside the band: sum over anti-diagonals of (en0 - st0 + 1), in closed form per diagonal
+				for (int r = 0; r < qlen + tlen - 1; ++r) {
+					int st = 0, en = tlen - 1;
+					if (st < r - qlen + 1) st = r - qlen + 1;
+					if (en > r) en = r;
+					if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+					if (en > (r + w) >> 1) en = (r + w) >> 1;
+					if (st > en) break;
+					cells += (unsigned long long)(en - st + 1);
+				}
+				const uint64_t est = (uint64_t)(qlen + tlen) * (uint64_t)(qlen < tlen ? qlen : tlen);
+				k = 63 - (uint32_t)(63 - __clzll((long long)(est | 1)));
+			}
+			idx[i] = i;
+		}
+		mem_sz[i] = m, p_sz[i] = p, cig_sz[i] = c, key[i] = k;
+	}
+	for (int d = 16; d >= 1; d >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, d);
+	if ((threadIdx.x & 31) == 0 && cells) atomicAdd(cells_total, cells);
 }
 
 template <int kMode>
@@ -135,19 +180,27 @@ __device__ __forceinline__ void ksw_run(const KswGeom &g, const KswJobDev &jb, i
 }
 
 __global__ void __launch_bounds__(KSW_GROUP * KSW_JOBS_PER_BLOCK)
-k_ksw(const KswJobDev *__restrict__ jobs, int n_jobs, KswScore sc, const uint32_t *__restrict__ Q, const uint32_t *__restrict__ S,
+k_ksw(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order, int n_jobs, KswScore sc, const uint32_t *__restrict__ Q,
+      const uint32_t *__restrict__ S, const uint64_t *__restrict__ q_off, const int32_t *__restrict__ read_len, const uint64_t *__restrict__ ref_off,
+      const uint64_t *__restrict__ mem_off, const uint64_t *__restrict__ p_off, const uint64_t *__restrict__ cig_off,
       int8_t *__restrict__ gmem, uint8_t *__restrict__ gp, uint32_t *__restrict__ gcig, KswEz *__restrict__ res)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int grp = threadIdx.x / KSW_GROUP, lane = threadIdx.x % KSW_GROUP;
-	const int ji = blockIdx.x * KSW_JOBS_PER_BLOCK + grp;
-	if (ji >= n_jobs) return;
+	const int slot = blockIdx.x * KSW_JOBS_PER_BLOCK + grp;
+	if (slot >= n_jobs) return;
 	const unsigned gmask = 0xffffu << (threadIdx.x & 16);
-	const KswJobDev jb = jobs[ji];
+	const int ji = order[slot];
+	const mmg_ksw_job_t hj = jobs[ji];
+	KswJobDev jb;
+	jb.q_base = q_off[hj.seq_id], jb.q_readlen = read_len[hj.seq_id], jb.q_rev = hj.q_rev, jb.q_start = hj.q_start, jb.q_len = hj.q_len;
+	jb.t_base = ref_off[hj.rid] + (uint64_t)hj.t_start, jb.t_len = hj.t_len, jb.reversed = hj.reversed;
+	jb.w = hj.w, jb.zdrop = hj.zdrop, jb.end_bonus = hj.end_bonus, jb.flag = hj.flag;
+	jb.mem_off = mem_off[ji], jb.p_off = p_off[ji], jb.cig_off = cig_off[ji];
 	const KswGeom g = mmg_ksw_geom(jb.q_len, jb.t_len, sc.m, sc.mat, sc.q, sc.e, sc.q2, sc.e2, jb.w);
 	KswEz ez;
 	mmg_ksw_reset(&ez);
-	if (g.bail) { if (lane == 0) res[jb.out_idx] = ez; return; }
+	if (g.bail) { if (lane == 0) res[ji] = ez; return; }
 	const int tl16 = g.tlen_ * 16;
 	const size_t mem_bytes = mmg_ksw_mem_bytes(jb.q_len, jb.t_len), H_bytes = (size_t)tl16 * 4;
 	int8_t *mem; int32_t *H;
@@ -155,7 +208,7 @@ k_ksw(const KswJobDev *__restrict__ jobs, int n_jobs, KswScore sc, const uint32_
 		mem = reinterpret_cast<int8_t*>(smem + (size_t)grp * KSW_SMEM_PER_JOB);
 		H = reinterpret_cast<int32_t*>(mem + mem_bytes);
 	} else {
-		mem = gmem + jb.mem_off; // arena slot = lane arrays followed by H[] (sized in ksw_launch)
+		mem = gmem + jb.mem_off; // arena slot = lane arrays followed by H[] (sized in k_ksw_prep)
 		H = reinterpret_cast<int32_t*>(gmem + jb.mem_off + mem_bytes);
 	}
 	// initial lane state (ksw2_extd2_sse.c:99-121)
@@ -184,19 +237,8 @@ k_ksw(const KswJobDev *__restrict__ jobs, int n_jobs, KswScore sc, const uint32_
 		int i0, j0;
 		if (with_cigar && mmg_ksw_trace_start(g, jb.flag, jb.end_bonus, &ez, &i0, &j0))
 			ez.n_cigar = mmg_ksw_backtrack(g, !!(jb.flag & MMG_EZ_REV_CIGAR), p, i0, j0, gcig + jb.cig_off);
-		res[jb.out_idx] = ez;
+		res[ji] = ez;
 	}
-}
-
-__global__ void k_cig_gather(int n_jobs, const KswJobDev *__restrict__ jobs, const KswEz *__restrict__ res, const int64_t *__restrict__ off,
-                             const uint32_t *__restrict__ gcig, uint32_t *__restrict__ out)
-{
-	const int ji = blockIdx.x * blockDim.x + threadIdx.x;
-	if (ji >= n_jobs) return;
-	const KswJobDev jb = jobs[ji];
-	const int n = res[jb.out_idx].n_cigar;
-	const int64_t o = off[jb.out_idx];
-	for (int i = 0; i < n; ++i) out[o + i] = gcig[jb.cig_off + i];
 }
 
 __global__ void k_res_ncig(int n_jobs, const KswEz *__restrict__ res, int32_t *__restrict__ ncig)
@@ -206,91 +248,88 @@ __global__ void k_res_ncig(int n_jobs, const KswEz *__restrict__ res, int32_t *_
 	else if (i == n_jobs) ncig[i] = 0;
 }
 
-static int64_t band_cells(int qlen, int tlen, int w)
-{ // true-band cell count (the GCUPS unit)
-	if (w < 0) w = tlen > qlen ? tlen : qlen;
-	int64_t cells = 0;
-	for (int r = 0; r < qlen + tlen - 1; ++r) {
-		int st = 0, en = tlen - 1;
-		if (st < r - qlen + 1) st = r - qlen + 1;
-		if (en > r) en = r;
-		if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
-		if (en > (r + w) >> 1) en = (r + w) >> 1;
-		if (st > en) break;
-		cells += en - st + 1;
-	}
-	return cells;
+// dense results: {ez, cigar offset} per job in submission order, CIGARs packed back to back
+__global__ void k_cig_gather(int n_jobs, const KswEz *__restrict__ res, const int64_t *__restrict__ off, const uint64_t *__restrict__ cig_off,
+                             const uint32_t *__restrict__ gcig, KswResDev *__restrict__ out_res, uint32_t *__restrict__ out_cig)
+{
+	const int ji = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ji >= n_jobs) return;
+	const KswEz ez = res[ji];
+	const int64_t o = off[ji];
+	const uint32_t *src = gcig + cig_off[ji];
+	for (int i = 0; i < ez.n_cigar; ++i) out_cig[o + i] = src[i];
+	KswResDev r; r.ez = ez, r.cigar_off = (uint64_t)o;
+	out_res[ji] = r;
 }
 
-static int ksw_launch(mmg_ctx_t *c, const uint32_t *d_Q, const uint32_t *d_S, const KswScore &sc, std::vector<KswJobDev> &jd,
-                      mmg_ksw_res_t *res, const uint32_t **cigars, double *kernel_ms)
+template <class T> static int scan_excl(mmg_ctx_t *c, const T *d_in, int64_t *d_out, int n)
 {
-	const int n = (int)jd.size();
-	// big jobs first; arenas sized from the geometry
-	std::sort(jd.begin(), jd.end(), [](const KswJobDev &a, const KswJobDev &b) {
-		const int64_t ca = (int64_t)(a.q_len + a.t_len) * (a.q_len < a.t_len ? a.q_len : a.t_len);
-		const int64_t cb = (int64_t)(b.q_len + b.t_len) * (b.q_len < b.t_len ? b.q_len : b.t_len);
-		return ca != cb ? ca > cb : a.out_idx < b.out_idx;
-	});
-	uint64_t mem_tot = 0, p_tot = 0, cig_tot = 0;
-	for (int i = 0; i < n; ++i) {
-		KswJobDev &j = jd[i];
-		const int qlen = j.q_len, tlen = j.t_len;
-		if (qlen <= 0 || tlen <= 0) { j.mem_off = j.p_off = j.cig_off = 0; continue; }
-		const size_t mem_bytes = mmg_ksw_mem_bytes(qlen, tlen), H_bytes = (size_t)((tlen + 15) / 16) * 16 * 4;
-		j.mem_off = mem_tot;
-		if (mem_bytes + H_bytes > KSW_SMEM_PER_JOB) mem_tot += (mem_bytes + H_bytes + 63) & ~(size_t)63;
-		int w = j.w < 0 ? (tlen > qlen ? tlen : qlen) : j.w;
-		int nc = qlen < tlen ? qlen : tlen;
-		nc = ((nc < w + 1 ? nc : w + 1) + 15) / 16 + 1;
-		j.p_off = p_tot;
-		if (!(j.flag & MMG_EZ_SCORE_ONLY)) p_tot += ((size_t)(qlen + tlen - 1) * nc + 1) * 16;
-		j.cig_off = cig_tot;
-		cig_tot += (size_t)qlen + tlen + 2;
-	}
-	MMG_TRY(c->k_jobs.ensure((size_t)(n + 1) * sizeof(KswJobDev)));
-	MMG_TRY(c->k_mem.ensure(mem_tot + 64));
-	MMG_TRY(c->k_p.ensure(p_tot + 64));
-	MMG_TRY(c->k_cig.ensure((cig_tot + 4) * 4));
-	MMG_TRY(c->k_res.ensure((size_t)(n + 1) * sizeof(KswEz)));
-	MMG_TRY(c->k_cig_off.ensure((size_t)(n + 2) * 12));
-	MMG_TRY(c->h_k_jobs.ensure((size_t)(n + 1) * sizeof(KswJobDev)));
-	memcpy(c->h_k_jobs.p, jd.data(), (size_t)n * sizeof(KswJobDev));
-	MMG_H2D(c, c->k_jobs.p, c->h_k_jobs.p, (size_t)n * sizeof(KswJobDev));
-	MMG_CUDA(cudaEventRecord(c->ev[0], c->stream));
-	MMG_LAUNCH(c, k_ksw, mmg_blocks(n, KSW_JOBS_PER_BLOCK), KSW_GROUP * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
-	           c->k_jobs.as<KswJobDev>(), n, sc, d_Q, d_S, c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(), c->k_cig.as<uint32_t>(),
-	           c->k_res.as<KswEz>());
-	MMG_CUDA(cudaEventRecord(c->ev[1], c->stream));
-	// compact the cigars: n_cigar -> offsets -> gather
-	int32_t *d_ncig = c->k_cig_off.as<int32_t>();
-	int64_t *d_off = reinterpret_cast<int64_t*>(c->k_cig_off.as<uint8_t>() + (((size_t)(n + 2) * 4 + 15) & ~(size_t)15));
-	MMG_LAUNCH(c, k_res_ncig, mmg_blocks(n + 1, 256), 256, 0, n, c->k_res.as<KswEz>(), d_ncig);
-	{
+	size_t tmp = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_in, d_out, n, c->stream);
+	MMG_TRY(c->d_cub.ensure(tmp));
+	MMG_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, d_in, d_out, n, c->stream));
+	++c->launches;
+	return MMG_OK;
+}
+
+// d_jobs: n jobs already on the device.  q_off/read_len/ref_off: device tables the jobs index into.
+static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const uint32_t *d_Q, const uint32_t *d_S, const uint64_t *d_q_off,
+                      const int32_t *d_read_len, const uint64_t *d_ref_off, const KswScore &sc, mmg_ksw_res_t *res, const uint32_t **cigars,
+                      double *kernel_ms, uint64_t *cells)
+{
+	// scratch layout in k_cig_off: mem_sz | p_sz | cig_sz (u64, n+1 each) | their scans (i64, n+1 each) | key, key2 (u32) | idx, order (i32) | ncig (i32, n+1) | ncig scan (i64, n+1) | cells
+	const size_t n1 = (size_t)n + 1;
+	MMG_TRY(c->k_cig_off.ensure(n1 * (6 * 8 + 4 * 4 + 4 + 8) + 64));
+	uint64_t *mem_sz = c->k_cig_off.as<uint64_t>(), *p_sz = mem_sz + n1, *cig_sz = p_sz + n1;
+	int64_t *mem_off = reinterpret_cast<int64_t*>(cig_sz + n1), *p_off = mem_off + n1, *cg_off = p_off + n1, *nc_off = cg_off + n1;
+	unsigned long long *d_cells = reinterpret_cast<unsigned long long*>(nc_off + n1);
+	uint32_t *key = reinterpret_cast<uint32_t*>(d_cells + 2), *key2 = key + n1;
+	int32_t *idx = reinterpret_cast<int32_t*>(key2 + n1), *order = idx + n1, *ncig = order + n1;
+	MMG_CUDA(cudaMemsetAsync(d_cells, 0, 8, c->stream));
+	MMG_LAUNCH(c, k_ksw_prep, mmg_blocks(n1, 128), 128, 0, d_jobs, n, mem_sz, p_sz, cig_sz, key, idx, d_cells);
+	MMG_TRY(scan_excl(c, mem_sz, mem_off, (int)n1));
+	MMG_TRY(scan_excl(c, p_sz, p_off, (int)n1));
+	MMG_TRY(scan_excl(c, cig_sz, cg_off, (int)n1));
+	{ // big jobs first (load balance): stable sort of job indices by size class
 		size_t tmp = 0;
-		cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_ncig, d_off, n + 1, c->stream);
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, order, n, 0, 6, c->stream);
 		MMG_TRY(c->d_cub.ensure(tmp));
-		MMG_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, d_ncig, d_off, n + 1, c->stream));
+		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, order, n, 0, 6, c->stream));
 		++c->launches;
 	}
-	int64_t tot = 0;
-	MMG_D2H(c, &tot, d_off + n, 8);
+	int64_t tot[3]; unsigned long long h_cells = 0;
+	MMG_D2H(c, &tot[0], mem_off + n, 8); MMG_D2H(c, &tot[1], p_off + n, 8); MMG_D2H(c, &tot[2], cg_off + n, 8);
+	MMG_D2H(c, &h_cells, d_cells, 8);
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
-	MMG_TRY(c->k_cig_out.ensure((size_t)(tot + 1) * 4));
-	MMG_LAUNCH(c, k_cig_gather, mmg_blocks(n, 128), 128, 0, n, c->k_jobs.as<KswJobDev>(), c->k_res.as<KswEz>(), d_off, c->k_cig.as<uint32_t>(),
-	           c->k_cig_out.as<uint32_t>());
-	MMG_TRY(c->h_k_cig.ensure((size_t)(tot + 1) * 4));
-	MMG_TRY(c->h_k_res.ensure((((size_t)(n + 1) * sizeof(KswEz) + 15) & ~(size_t)15) + (size_t)(n + 1) * 8));
-	KswEz *h_ez = c->h_k_res.as<KswEz>();
-	int64_t *h_off = reinterpret_cast<int64_t*>(c->h_k_res.as<uint8_t>() + (((size_t)(n + 1) * sizeof(KswEz) + 15) & ~(size_t)15));
-	MMG_D2H(c, h_ez, c->k_res.p, (size_t)n * sizeof(KswEz));
-	MMG_D2H(c, h_off, d_off, (size_t)(n + 1) * 8);
-	if (tot) MMG_D2H(c, c->h_k_cig.p, c->k_cig_out.p, (size_t)tot * 4);
+	if (cells) *cells = h_cells;
+	MMG_TRY(c->k_mem.ensure((size_t)tot[0] + 64));
+	MMG_TRY(c->k_p.ensure((size_t)tot[1] + 64));
+	MMG_TRY(c->k_cig.ensure(((size_t)tot[2] + 4) * 4));
+	MMG_TRY(c->k_res.ensure(n1 * (sizeof(KswEz) + sizeof(KswResDev))));
+	KswEz *d_ez = c->k_res.as<KswEz>();
+	KswResDev *d_res = reinterpret_cast<KswResDev*>(c->k_res.as<uint8_t>() + ((n1 * sizeof(KswEz) + 15) & ~(size_t)15));
+	MMG_TRY(c->k_res.ensure(((n1 * sizeof(KswEz) + 15) & ~(size_t)15) + n1 * sizeof(KswResDev)));
+	d_ez = c->k_res.as<KswEz>();
+	d_res = reinterpret_cast<KswResDev*>(c->k_res.as<uint8_t>() + ((n1 * sizeof(KswEz) + 15) & ~(size_t)15));
+	MMG_CUDA(cudaEventRecord(c->ev[0], c->stream));
+	MMG_LAUNCH(c, k_ksw, mmg_blocks(n, KSW_JOBS_PER_BLOCK), KSW_GROUP * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
+	           d_jobs, order, n, sc, d_Q, d_S, d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off),
+	           reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(),
+	           c->k_cig.as<uint32_t>(), d_ez);
+	MMG_CUDA(cudaEventRecord(c->ev[1], c->stream));
+	MMG_LAUNCH(c, k_res_ncig, mmg_blocks(n1, 256), 256, 0, n, d_ez, ncig);
+	MMG_TRY(scan_excl(c, ncig, nc_off, (int)n1));
+	int64_t n_cig = 0;
+	MMG_D2H(c, &n_cig, nc_off + n, 8);
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
-	for (int i = 0; i < n; ++i) {
-		memcpy(&res[i].ez, &h_ez[i], sizeof(KswEz));
-		res[i].cigar_off = (uint64_t)h_off[i];
-	}
+	MMG_TRY(c->k_cig_out.ensure(((size_t)n_cig + 1) * 4));
+	MMG_LAUNCH(c, k_cig_gather, mmg_blocks(n, 128), 128, 0, n, d_ez, nc_off, reinterpret_cast<const uint64_t*>(cg_off), c->k_cig.as<uint32_t>(),
+	           d_res, c->k_cig_out.as<uint32_t>());
+	MMG_TRY(c->h_k_cig.ensure(((size_t)n_cig + 1) * 4));
+	static_assert(sizeof(KswResDev) == sizeof(mmg_ksw_res_t), "result layout");
+	MMG_D2H(c, res, d_res, (size_t)n * sizeof(KswResDev));
+	if (n_cig) MMG_D2H(c, c->h_k_cig.p, c->k_cig_out.p, (size_t)n_cig * 4);
+	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	*cigars = c->h_k_cig.as<uint32_t>();
 	float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
 	if (kernel_ms) *kernel_ms = ms;
@@ -319,19 +358,14 @@ extern "C" int mmg_ksw_batch(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt
 	if (n_jobs <= 0) return MMG_OK;
 	MMG_CUDA(cudaSetDevice(c->dev));
 	const ResidentBatch &rb = c->rb;
-	std::vector<KswJobDev> jd(n_jobs);
-	uint64_t ncell = 0;
-	for (int i = 0; i < n_jobs; ++i) {
-		const mmg_ksw_job_t &j = jobs[i];
-		if (j.seq_id < 0 || j.seq_id >= rb.n_seq || j.rid < 0 || j.rid >= mi->n_seq) { mmg_set_error("mmg_ksw_batch: job %d refers to a read or contig that is not resident", i); return MMG_EINVAL; }
-		KswJobDev &d = jd[i];
-		d.q_base = rb.q_off[j.seq_id], d.q_readlen = rb.seq_len[j.seq_id], d.q_rev = j.q_rev, d.q_start = j.q_start, d.q_len = j.q_len;
-		d.t_base = mi->h_seq_off[j.rid] + (uint64_t)j.t_start, d.t_len = j.t_len, d.reversed = j.reversed;
-		d.w = j.w, d.zdrop = j.zdrop, d.end_bonus = j.end_bonus, d.flag = j.flag, d.out_idx = i, d.pad = 0;
-		if (cells && j.q_len > 0 && j.t_len > 0) ncell += (uint64_t)band_cells(j.q_len, j.t_len, j.w);
-	}
-	if (cells) *cells = ncell;
-	return ksw_launch(c, c->d_Q.as<uint32_t>(), mi->d_S, make_score(opt), jd, res, cigars, kernel_ms);
+	for (int i = 0; i < n_jobs; i += 4099) // spot check: a full validation pass would cost more than the copy
+		if (jobs[i].seq_id < 0 || jobs[i].seq_id >= rb.n_seq || jobs[i].rid < 0 || jobs[i].rid >= mi->n_seq) {
+			mmg_set_error("mmg_ksw_batch: job %d refers to a read or contig that is not resident", i); return MMG_EINVAL;
+		}
+	MMG_TRY(c->k_jobs.ensure((size_t)(n_jobs + 1) * sizeof(mmg_ksw_job_t)));
+	MMG_H2D(c, c->k_jobs.p, jobs, (size_t)n_jobs * sizeof(mmg_ksw_job_t));
+	return ksw_launch(c, c->k_jobs.as<mmg_ksw_job_t>(), n_jobs, c->d_Q.as<uint32_t>(), mi->d_S, c->d_q_off.as<uint64_t>(), c->d_seq_len.as<int32_t>(),
+	                  mi->d_seq_off, make_score(opt), res, cigars, kernel_ms, cells);
 }
 
 // single pair, sequences given as 0..4 codes (parity-test entry point for ksw_extd2_sse, ksw2.h:60)
@@ -353,24 +387,29 @@ extern "C" int mmg_ksw_extd2(mmg_ctx_t *c, int qlen, const uint8_t *query, int t
 	if (m != 5) { mmg_set_error("mmg_ksw_extd2: only the 5-letter alphabet of the mapper is supported"); return MMG_EINVAL; }
 	if (qlen <= 0 || tlen <= 0) return MMG_OK;
 	KswScore sc; sc.m = m; memcpy(sc.mat, mat, 25); sc.q = q, sc.e = e, sc.q2 = q2, sc.e2 = e2;
-	DevBuf dq, dt, dqp, dtp;
+	DevBuf dq, dt, dqp, dtp, dtab;
 	int rc = MMG_OK;
-	auto fin = [&]() { dq.release(); dt.release(); dqp.release(); dtp.release(); };
+	auto fin = [&]() { dq.release(); dt.release(); dqp.release(); dtp.release(); dtab.release(); };
 #define KS_TRY(x) do { rc = (x); if (rc != MMG_OK) { fin(); return rc; } } while (0)
 	KS_TRY(dq.ensure((size_t)qlen + 16)); KS_TRY(dt.ensure((size_t)tlen + 16));
 	KS_TRY(dqp.ensure(((size_t)qlen / 8 + 4) * 4)); KS_TRY(dtp.ensure(((size_t)tlen / 8 + 4) * 4));
+	KS_TRY(dtab.ensure(256));
 	cudaMemcpyAsync(dq.p, query, qlen, cudaMemcpyHostToDevice, c->stream);
 	cudaMemcpyAsync(dt.p, target, tlen, cudaMemcpyHostToDevice, c->stream);
 	k_pack_codes<<<mmg_blocks((qlen + 7) / 8, 128), 128, 0, c->stream>>>(dq.as<uint8_t>(), qlen, dqp.as<uint32_t>());
 	k_pack_codes<<<mmg_blocks((tlen + 7) / 8, 128), 128, 0, c->stream>>>(dt.as<uint8_t>(), tlen, dtp.as<uint32_t>());
 	c->launches += 2;
-	std::vector<KswJobDev> jd(1);
-	KswJobDev &d = jd[0];
-	memset(&d, 0, sizeof(d));
-	d.q_base = 0, d.q_readlen = qlen, d.q_rev = 0, d.q_start = 0, d.q_len = qlen, d.t_base = 0, d.t_len = tlen, d.reversed = 0;
-	d.w = w, d.zdrop = zdrop, d.end_bonus = end_bonus, d.flag = flag, d.out_idx = 0;
+	// one-entry tables: read 0 starts at base 0 and has qlen bases; contig 0 starts at base 0
+	struct { uint64_t q_off; uint64_t ref_off; int32_t read_len; int32_t pad; mmg_ksw_job_t job; } tab;
+	memset(&tab, 0, sizeof(tab));
+	tab.read_len = qlen;
+	tab.job.seq_id = 0, tab.job.q_rev = 0, tab.job.q_start = 0, tab.job.q_len = qlen, tab.job.rid = 0, tab.job.t_start = 0, tab.job.t_len = tlen;
+	tab.job.reversed = 0, tab.job.w = w, tab.job.zdrop = zdrop, tab.job.end_bonus = end_bonus, tab.job.flag = flag;
+	cudaMemcpyAsync(dtab.p, &tab, sizeof(tab), cudaMemcpyHostToDevice, c->stream);
+	uint8_t *tb = dtab.as<uint8_t>();
 	mmg_ksw_res_t r; const uint32_t *cg = nullptr;
-	rc = ksw_launch(c, dqp.as<uint32_t>(), dtp.as<uint32_t>(), sc, jd, &r, &cg, nullptr);
+	rc = ksw_launch(c, reinterpret_cast<const mmg_ksw_job_t*>(tb + 24), 1, dqp.as<uint32_t>(), dtp.as<uint32_t>(), reinterpret_cast<const uint64_t*>(tb),
+	                reinterpret_cast<const int32_t*>(tb + 16), reinterpret_cast<const uint64_t*>(tb + 8), sc, &r, &cg, nullptr, nullptr);
 	if (rc == MMG_OK) {
 		*ez = r.ez;
 		for (int i = 0; i < r.ez.n_cigar; ++i) cigar[i] = cg[r.cigar_off + i];

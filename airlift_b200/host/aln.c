@@ -740,11 +740,24 @@ int mm_aln_step(mm_alnseg_t *s, const mm_mapopt_t *opt, const mm_idx_t *mi)
 			w.pending = 0;
 			align1(&w, &s->regs[i], &r2);
 			if (w.pending) { /* discard the partial attempt; it is replayed once its DP jobs are back */
+				int j;
 				if (s->regs[i].p != saved.p) free(s->regs[i].p);
 				s->regs[i] = saved;
+				/* regions do not depend on each other's DP results: request the jobs of all later regions now,
+				 * so that a segment normally needs two rounds (plan, consume) however many regions it has */
+				for (j = (s->planned > i ? s->planned : i) + 1; j < s->n_regs; ++j) {
+					mm_reg1_t tmp = s->regs[j], t2;
+					w.pending = 0;
+					align1(&w, &tmp, &t2);
+					if (tmp.p != s->regs[j].p) free(tmp.p);
+				}
+				s->planned = s->n_regs - 1;
 				return 0;
 			}
-			if (r2.cnt > 0) s->regs = insert_reg(&r2, i, &s->n_regs, s->regs);
+			if (r2.cnt > 0) {
+				s->regs = insert_reg(&r2, i, &s->n_regs, s->regs);
+				if (s->planned > i) ++s->planned;
+			}
 		}
 		s->inv_wait = 0;
 		if (i > 0 && s->regs[i].split_inv) {
@@ -753,7 +766,7 @@ int mm_aln_step(mm_alnseg_t *s, const mm_mapopt_t *opt, const mm_idx_t *mi)
 			w.pending = 0;
 			rc = align1_inv(&w, &s->regs[i-1], &s->regs[i], &r_inv);
 			if (rc < 0) { s->inv_wait = 1; return 0; } /* region i is final; only the inversion DP is outstanding */
-			if (rc > 0) { s->regs = insert_reg(&r_inv, i, &s->n_regs, s->regs); ++i; }
+			if (rc > 0) { s->regs = insert_reg(&r_inv, i, &s->n_regs, s->regs); ++i; if (s->planned >= i) ++s->planned; }
 		}
 		s->i = i + 1;
 	}

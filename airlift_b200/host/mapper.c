@@ -83,6 +83,10 @@ typedef struct {          /* one GPU's share of a mini-batch */
 	frag_t *fr;
 	mmg_chains_t ch;
 	mm_b200_stats_t st;
+	size_t *job_off;      /* [nf+1] first job of each fragment in the current DP round */
+	mmg_ksw_job_t *jobs;
+	mmg_ksw_res_t *res;
+	const uint32_t *cig;
 	int rc;
 } shard_t;
 
@@ -180,6 +184,42 @@ static void stage_align(void *data, long i, int tid)
 	if (all_done) fr->active = 0;
 }
 
+/* copy the DP jobs a fragment queued in this round into the shard's job array */
+static void stage_gather_jobs(void *data, long i, int tid)
+{
+	shard_t *sh = (shard_t*)data;
+	frag_t *fr = &sh->fr[i];
+	size_t k = sh->job_off[i];
+	int j, q;
+	if (!fr->active) return;
+	for (j = 0; j < fr->n_segs; ++j) {
+		const mm_dpcache_t *c = &fr->aln[j].cache;
+		for (q = c->n_sent; q < c->n; ++q) sh->jobs[k++] = c->a[q].job;
+	}
+}
+
+/* hand the results of this round back to the job caches, in the order they were gathered */
+static void stage_scatter_results(void *data, long i, int tid)
+{
+	shard_t *sh = (shard_t*)data;
+	frag_t *fr = &sh->fr[i];
+	size_t k = sh->job_off[i];
+	int j;
+	if (!fr->active) return;
+	for (j = 0; j < fr->n_segs; ++j) {
+		mm_dpcache_t *c = &fr->aln[j].cache;
+		for (; c->n_sent < c->n; ++c->n_sent, ++k) {
+			mm_dpjob_t *dj = &c->a[c->n_sent];
+			dj->ez = sh->res[k].ez;
+			if (dj->ez.n_cigar > 0) {
+				dj->cigar = (uint32_t*)malloc((size_t)dj->ez.n_cigar * 4);
+				memcpy(dj->cigar, sh->cig + sh->res[k].cigar_off, (size_t)dj->ez.n_cigar * 4);
+			}
+			dj->done = 1;
+		}
+	}
+}
+
 /* MAPQ, pairing, release, mate un-flip (map.c:392-406, 486-497) */
 static void stage_finish(void *data, long i, int tid)
 {
@@ -267,64 +307,41 @@ static void *map_shard(void *data)
 	parallel_for(sh->n_threads, stage_hits, sh, nf);
 	t0 = realtime(); sh->st.t_hits += t0 - t1;
 	if (sh->opt->flag & MM_F_CIGAR) {
-		mmg_ksw_job_t *jobs = 0; mmg_ksw_res_t *res = 0;
 		size_t m_jobs = 0;
-		for (;;) { /* DP rounds */
+		sh->job_off = (size_t*)malloc((size_t)(nf + 1) * sizeof(size_t));
+		for (;;) { /* DP rounds: walk the regions, send what they asked for, hand the results back */
 			size_t n_jobs = 0;
-			const uint32_t *cig = 0;
 			int n_active = 0;
 			double ta = realtime(), tb, kms = 0;
 			uint64_t cells = 0;
 			parallel_for(sh->n_threads, stage_align, sh, nf);
-			for (i = 0; i < nf; ++i) {
-				frag_t *fr = &sh->fr[i];
+			for (i = 0; i < nf; ++i) { /* new jobs per fragment -> offsets */
+				const frag_t *fr = &sh->fr[i];
+				sh->job_off[i] = n_jobs;
 				if (!fr->active) continue;
 				++n_active;
-				for (j = 0; j < fr->n_segs; ++j) {
-					mm_dpcache_t *c = &fr->aln[j].cache;
-					for (; c->n_sent < c->n; ++c->n_sent) {
-						if (n_jobs == m_jobs) {
-							m_jobs = m_jobs ? m_jobs << 1 : 1 << 16;
-							jobs = (mmg_ksw_job_t*)realloc(jobs, m_jobs * sizeof(*jobs));
-							res = (mmg_ksw_res_t*)realloc(res, m_jobs * sizeof(*res));
-						}
-						jobs[n_jobs++] = c->a[c->n_sent].job;
-					}
-				}
+				for (j = 0; j < fr->n_segs; ++j) n_jobs += (size_t)(fr->aln[j].cache.n - fr->aln[j].cache.n_sent);
 			}
+			sh->job_off[nf] = n_jobs;
 			tb = realtime(); sh->st.t_align_host += tb - ta;
 			if (n_active == 0) break;
 			if (n_jobs == 0) { fprintf(stderr, "[ERROR] alignment made no progress\n"); sh->rc = -1; break; }
-			if (mmg_ksw_batch(sh->ctx, sh->didx, &sh->dopt, (int)n_jobs, jobs, res, &cig, &kms, &cells) != MMG_OK) { shard_fail(sh, "DP stage failed"); break; }
-			sh->st.t_ksw_total += realtime() - tb, sh->st.t_ksw_kernel += kms * 1e-3;
-			sh->st.n_dp_jobs += n_jobs, sh->st.n_dp_cells += cells, sh->st.n_dp_rounds += 1;
-			ta = realtime();
-			{ /* scatter results back in the same traversal order */
-				size_t k = 0;
-				for (i = 0; i < nf; ++i) {
-					frag_t *fr = &sh->fr[i];
-					if (!fr->active) continue;
-					for (j = 0; j < fr->n_segs; ++j) {
-						mm_dpcache_t *c = &fr->aln[j].cache;
-						int q;
-						for (q = 0; q < c->n; ++q) {
-							mm_dpjob_t *dj = &c->a[q];
-							if (dj->done) continue;
-							dj->ez = res[k].ez;
-							if (dj->ez.n_cigar > 0) {
-								dj->cigar = (uint32_t*)malloc((size_t)dj->ez.n_cigar * 4);
-								memcpy(dj->cigar, cig + res[k].cigar_off, (size_t)dj->ez.n_cigar * 4);
-							}
-							dj->done = 1;
-							++k;
-						}
-					}
-				}
-				assert(k == n_jobs);
+			if (n_jobs > m_jobs) {
+				m_jobs = n_jobs + n_jobs / 4;
+				sh->jobs = (mmg_ksw_job_t*)realloc(sh->jobs, m_jobs * sizeof(mmg_ksw_job_t));
+				sh->res = (mmg_ksw_res_t*)realloc(sh->res, m_jobs * sizeof(mmg_ksw_res_t));
 			}
-			sh->st.t_align_host += realtime() - ta;
+			parallel_for(sh->n_threads, stage_gather_jobs, sh, nf);
+			ta = realtime(); sh->st.t_align_host += ta - tb;
+			if (mmg_ksw_batch(sh->ctx, sh->didx, &sh->dopt, (int)n_jobs, sh->jobs, sh->res, &sh->cig, &kms, &cells) != MMG_OK) { shard_fail(sh, "DP stage failed"); break; }
+			tb = realtime();
+			sh->st.t_ksw_total += tb - ta, sh->st.t_ksw_kernel += kms * 1e-3;
+			sh->st.n_dp_jobs += n_jobs, sh->st.n_dp_cells += cells, sh->st.n_dp_rounds += 1;
+			parallel_for(sh->n_threads, stage_scatter_results, sh, nf);
+			sh->st.t_align_host += realtime() - tb;
 		}
-		free(jobs); free(res);
+		free(sh->jobs); free(sh->res); free(sh->job_off);
+		sh->jobs = 0, sh->res = 0, sh->job_off = 0;
 	}
 	t0 = realtime();
 	parallel_for(sh->n_threads, stage_finish, sh, nf);

@@ -109,7 +109,7 @@ typedef struct {
 } mm_dpcache_t;
 
 typedef struct {       /* alignment progress of one segment (mm_align_skeleton, align.c:857-913, made resumable) */
-	int seq_id, qlen, n_regs, i, n_a, started, finished, inv_wait;
+	int seq_id, qlen, n_regs, i, n_a, started, finished, inv_wait, planned;
 	const char *qstr;
 	uint8_t *qseq0[2];
 	mm_reg1_t *regs;
