@@ -101,12 +101,137 @@ __device__ __forceinline__ ChainParams mmg_chain_params(const ChainOptDev &o, in
 	return P;
 }
 
-// K3: mm_chain_dp per fragment (chain.c:22-162), then the re-chain test of map.c:353-366
-__global__ void k_chain(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
+// ---- K3, warp-cooperative form -------------------------------------------------------------------------
+// mm_chain_dp's fill (chain.c:45-85) cannot look back further than max_dist_x on the reference, so the sorted anchor array
+// of a fragment falls apart into independent SEGMENTS wherever a[i].x > a[i-1].x + max_dist_x (the `st` pointer of
+// chain.c:51 would jump to i).  Segments are filled by one warp each; a fragment drawn from a 3 000-copy repeat becomes
+// thousands of parallel work items instead of one 10^5-step serial loop.
+
+__device__ __forceinline__ int frag_of_anchor(const int64_t *aoff, int n_list, int64_t g)
+{ // last li with aoff[li] <= g
+	int lo = 0, hi = n_list - 1;
+	while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (aoff[mid] <= g) lo = mid; else hi = mid - 1; }
+	return lo;
+}
+
+// flag the first anchor of every segment; zero the t[] array of chain.c:39
+__global__ void k_chain_heads(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
+                              const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, const mm128 *__restrict__ a, int64_t n_total,
+                              uint8_t *__restrict__ head, int32_t *__restrict__ work)
+{
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n_total) return;
+	const int li = frag_of_anchor(aoff, n_list, g);
+	const int64_t ao = aoff[li], i = g - ao, n = na[li];
+	uint8_t h = 0;
+	if (i < n) {
+		const int f = list ? list[li] : li;
+		const ChainParams P = mmg_chain_params(co, ft.qlen[f], n_seg[f]);
+		h = (i == 0 || a[g].x > a[g - 1].x + (uint64_t)P.max_dist_x) ? 1 : 0;
+		work[ao * 4 + 2 * n + i] = 0; // t[i]
+	}
+	head[g] = h;
+}
+
+// avg_qspan = (float)sum_qspan / n per fragment (chain.c:41-42): one warp per fragment
+__global__ void k_chain_avgspan(int n_list, const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, const mm128 *__restrict__ a, float *__restrict__ avg)
+{
+	const int li = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (li >= n_list) return;
+	const int64_t ao = aoff[li]; const int n = na[li];
+	unsigned long long sum = 0;
+	for (int i = lane; i < n; i += 32) sum += a[ao + i].y >> 32 & 0xff;
+	for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+	if (lane == 0) avg[li] = n > 0 ? (float)sum / (float)(int64_t)n : 0.f;
+}
+
+// one warp per segment: lanes evaluate 32 predecessors at a time; the order-dependent parts of the inner loop
+// (strict-max winner, n_skip counter, early break, t[] marks; chain.c:53-82) are resolved from ballots so that the
+// result is the sequential one
+__global__ void __launch_bounds__(128)
+k_chain_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
+             const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, const mm128 *__restrict__ a, int32_t *__restrict__ work,
+             const float *__restrict__ avg, const int64_t *__restrict__ seg_start, const int32_t *__restrict__ n_seg_total,
+             int32_t *__restrict__ next_seg, unsigned long long *__restrict__ iter_total)
+{
+	const int lane = threadIdx.x & 31;
+	const int n_segments = *n_seg_total;
+	unsigned long long iters = 0;
+	for (;;) {
+		int sidx = 0;
+		if (lane == 0) sidx = atomicAdd(next_seg, 1);
+		sidx = __shfl_sync(0xffffffffu, sidx, 0);
+		if (sidx >= n_segments) break;
+		const int64_t g0 = seg_start[sidx];
+		const int li = frag_of_anchor(aoff, n_list, g0);
+		const int f = list ? list[li] : li;
+		const int64_t ao = aoff[li];
+		const int n = na[li];
+		const int64_t frag_end = ao + n;
+		int64_t g1 = frag_end;
+		if (sidx + 1 < n_segments) { const int64_t nx = seg_start[sidx + 1]; if (nx < frag_end) g1 = nx; }
+		const ChainParams P = mmg_chain_params(co, ft.qlen[f], n_seg[f]);
+		const float avg_qspan = avg[li];
+		const mm128 *A = a + ao;
+		int32_t *F = work + ao * 4, *Pp = F + n, *T = Pp + n, *V = T + n;
+		const int s = (int)(g0 - ao), e = (int)(g1 - ao);
+		int st = s;
+		for (int i = s; i < e; ++i) {
+			const mm128 ai = A[i];
+			const uint64_t ri = ai.x;
+			const int32_t qi = (int32_t)ai.y, q_span = (int32_t)(ai.y >> 32 & 0xff);
+			const int32_t sidi = (int32_t)((ai.y & MMG_SEED_SEG_MASK) >> MMG_SEED_SEG_SHIFT);
+			int32_t max_f = q_span, max_j = -1, n_skip = 0;
+			while (st < i && ri > A[st].x + (uint64_t)P.max_dist_x) ++st;
+			if (i - st > P.max_iter) st = i - P.max_iter;
+			bool done = false;
+			for (int jhi = i - 1; jhi >= st && !done; jhi -= 32) {
+				const int j = jhi - lane;
+				bool valid = j >= st;
+				int32_t sc = 0, pj = -1;
+				if (valid) {
+					const mm128 aj = A[j];
+					valid = mmg_chain_score(P, ri, qi, q_span, sidi, aj, avg_qspan, &sc);
+					if (valid) { sc += F[j]; pj = Pp[j]; if (pj >= 0) T[pj] = i; }
+				}
+				__syncwarp();
+				const bool tmark = valid && T[j] == i;
+				int32_t incl = valid ? sc : INT32_MIN; // running max over lanes 0..lane = predecessors visited so far
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) { const int32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d && o > incl) incl = o; }
+				int32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+				excl = (lane == 0 || excl < max_f) ? max_f : excl; // best score before this lane, counting what earlier chunks found
+				const bool win = valid && sc > excl;
+				const unsigned wmask = __ballot_sync(0xffffffffu, win), mmask = __ballot_sync(0xffffffffu, tmark && !win);
+				unsigned ev = wmask | mmask;
+				int brk = -1;
+				while (ev) {
+					const int b = __ffs((int)ev) - 1;
+					ev &= ev - 1;
+					if (wmask >> b & 1) { if (n_skip > 0) --n_skip; }
+					else if (++n_skip > P.max_skip) { brk = b; break; }
+				}
+				const unsigned lim = brk >= 0 ? (brk == 31 ? 0xffffffffu : ((2u << brk) - 1u)) : 0xffffffffu;
+				const unsigned w2 = wmask & lim;
+				if (w2) { const int last = 31 - __clz((int)w2); max_f = __shfl_sync(0xffffffffu, sc, last); max_j = jhi - last; }
+				if (brk >= 0) { done = true; iters += (unsigned)(brk + 1); }
+				else iters += (unsigned)((jhi - st + 1) < 32 ? (jhi - st + 1) : 32);
+			}
+			if (lane == 0) {
+				F[i] = max_f, Pp[i] = max_j;
+				V[i] = (max_j >= 0 && V[max_j] > max_f) ? V[max_j] : max_f; // chain.c:84
+			}
+			__syncwarp();
+		}
+	}
+	if (lane == 0 && iters) atomicAdd(iter_total, iters);
+}
+
+// K3 tail: everything after the fill (chain.c:87-160) per fragment, then the re-chain test of map.c:353-366
+__global__ void k_chain_tail(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
                         const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
                         uint64_t *__restrict__ u, mm128 *__restrict__ bb, RsFrame *__restrict__ stack, int32_t *__restrict__ nu_out,
-                        int32_t *__restrict__ nv_out, const int32_t *__restrict__ rep, int rechain_enabled, uint8_t *__restrict__ flag_out,
-                        unsigned long long *__restrict__ iter_total)
+                        int32_t *__restrict__ nv_out, const int32_t *__restrict__ rep, int rechain_enabled, uint8_t *__restrict__ flag_out)
 {
 	const int li = blockIdx.x * blockDim.x + threadIdx.x;
 	if (li >= n_list) return;
@@ -118,8 +243,6 @@ __global__ void k_chain(FragTab ft, const int32_t *__restrict__ list, int n_list
 		const ChainParams P = mmg_chain_params(co, ft.qlen[f], segs);
 		int32_t *fp = work + ao * 4;
 		mm128 *A = a + ao;
-		const uint64_t it = mmg_chain_fill_seq(P, n, A, fp, fp + n, fp + 2 * n, fp + 3 * n);
-		atomicAdd(iter_total, (unsigned long long)it);
 		n_u = mmg_chain_backtrack(P, n, A, fp, fp + n, fp + 2 * n, fp + 3 * n, u + ao * 2, bb + ao, stack + ao / 65 + 2 * (int64_t)li, &n_v);
 	}
 	nu_out[li] = n_u, nv_out[li] = (int32_t)n_v;
@@ -303,10 +426,33 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	co.bw = opt->bw, co.max_gap = opt->max_gap, co.max_gap_ref = opt->max_gap_ref, co.max_frag_len = opt->max_frag_len;
 	co.max_skip = opt->max_chain_skip, co.max_iter = opt->max_chain_iter, co.min_cnt = opt->min_cnt, co.min_sc = opt->min_chain_score;
 	co.is_cdna = !!(opt->flag & MMG_F_SPLICE), co.is_sr = !!(opt->flag & MMG_F_SR);
-	MMG_LAUNCH(c, k_chain, mmg_blocks(n_list, 64), 64, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+	if (tot > 0) {
+		// segments: head flags -> compacted start indices
+		MMG_TRY(c->d_seg_head.ensure((size_t)tot + 16));
+		MMG_TRY(c->d_seg_start.ensure(((size_t)tot + 2) * 8 + 64));
+		MMG_TRY(c->d_seg_avg.ensure((size_t)(n_list + 1) * 4));
+		int64_t *seg_start = c->d_seg_start.as<int64_t>();
+		int32_t *d_nseg = reinterpret_cast<int32_t*>(seg_start + tot + 1), *d_next = d_nseg + 1;
+		MMG_CUDA(cudaMemsetAsync(d_nseg, 0, 8, c->stream));
+		MMG_LAUNCH(c, k_chain_heads, mmg_blocks(tot, 256), 256, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+		           pb.na->as<int32_t>(), pb.a->as<mm128>(), tot, c->d_seg_head.as<uint8_t>(), pb.work->as<int32_t>());
+		MMG_LAUNCH(c, k_chain_avgspan, mmg_blocks((size_t)n_list * 32, 128), 128, 0, n_list, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(),
+		           pb.a->as<mm128>(), c->d_seg_avg.as<float>());
+		{
+			size_t tmp = 0;
+			cub::CountingInputIterator<int64_t> it(0);
+			cub::DeviceSelect::Flagged(nullptr, tmp, it, c->d_seg_head.as<uint8_t>(), seg_start, d_nseg, tot, c->stream);
+			MMG_TRY(c->d_cub.ensure(tmp));
+			MMG_CUDA(cub::DeviceSelect::Flagged(c->d_cub.p, tmp, it, c->d_seg_head.as<uint8_t>(), seg_start, d_nseg, tot, c->stream));
+			++c->launches;
+		}
+		// persistent warps pull segments from a counter: 148 SMs x 16 warps x 4 CTAs in flight
+		MMG_LAUNCH(c, k_chain_fill, 148 * 8, 128, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(),
+		           pb.a->as<mm128>(), pb.work->as<int32_t>(), c->d_seg_avg.as<float>(), seg_start, d_nseg, d_next, c->d_frag_iter.as<unsigned long long>());
+	}
+	MMG_LAUNCH(c, k_chain_tail, mmg_blocks(n_list, 64), 64, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
 	           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
-	           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), pb.rep->as<int32_t>(), opt->max_occ > opt->mid_occ ? 1 : 0, d_flag,
-	           c->d_frag_iter.as<unsigned long long>());
+	           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), pb.rep->as<int32_t>(), opt->max_occ > opt->mid_occ ? 1 : 0, d_flag);
 	return MMG_OK;
 }
 
