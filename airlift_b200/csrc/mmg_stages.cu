@@ -128,7 +128,7 @@ __global__ void k_chain_heads(FragTab ft, const int32_t *__restrict__ list, int 
 		const int f = list ? list[li] : li;
 		const ChainParams P = mmg_chain_params(co, ft.qlen[f], n_seg[f]);
 		h = (i == 0 || a[g].x > a[g - 1].x + (uint64_t)P.max_dist_x) ? 1 : 0;
-		work[ao * 4 + 2 * n + i] = 0; // t[i]
+		work[ao * 8 + 2 * n + i] = 0; // t[i]
 	}
 	head[g] = h;
 }
@@ -173,7 +173,7 @@ k_chain_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const int
 		const ChainParams P = mmg_chain_params(co, ft.qlen[f], n_seg[f]);
 		const float avg_qspan = avg[li];
 		const mm128 *A = a + ao;
-		int32_t *F = work + ao * 4, *Pp = F + n, *T = Pp + n, *V = T + n;
+		int32_t *F = work + ao * 8, *Pp = F + n, *T = Pp + n, *V = T + n;
 		const int s = (int)(g0 - ao), e = (int)(g1 - ao);
 		int st = s;
 		for (int i = s; i < e; ++i) {
@@ -227,38 +227,135 @@ k_chain_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const int
 	if (lane == 0 && iters) atomicAdd(iter_total, iters);
 }
 
-// K3 tail: everything after the fill (chain.c:87-160) per fragment, then the re-chain test of map.c:353-366
-__global__ void k_chain_tail(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
-                        const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
-                        uint64_t *__restrict__ u, mm128 *__restrict__ bb, RsFrame *__restrict__ stack, int32_t *__restrict__ nu_out,
-                        int32_t *__restrict__ nv_out, const int32_t *__restrict__ rep, int rechain_enabled, uint8_t *__restrict__ flag_out)
+// K3 tail, one warp per fragment: chain ends and peaks, ranking by peak score, backtracking, output order
+// (chain.c:87-160).  The sequential backtrack marks anchors as used chain by chain in rank order; the same
+// ownership is obtained in parallel as "the lowest rank whose path passes through the anchor" (atomicMin while
+// walking), after which every chain counts the anchors it owns.  Work arrays: f|p|t|v (4n int32) followed by room
+// for the chain-order array w (n mm128); u has 2n entries; b has n.
+__global__ void __launch_bounds__(128)
+k_chain_tail_warp(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
+                  const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
+                  uint64_t *__restrict__ u, mm128 *__restrict__ bb, RsFrame *__restrict__ stack, int32_t *__restrict__ nu_out,
+                  int32_t *__restrict__ nv_out, const int32_t *__restrict__ rep, int rechain_enabled, uint8_t *__restrict__ flag_out)
 {
-	const int li = blockIdx.x * blockDim.x + threadIdx.x;
+	const int li = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
 	if (li >= n_list) return;
+	const unsigned FULL = 0xffffffffu;
 	const int f = list ? list[li] : li;
-	const int64_t ao = aoff[li], n = na[li];
-	const int segs = n_seg[f];
-	int n_u = 0; int64_t n_v = 0;
+	const int64_t ao = aoff[li];
+	const int n = na[li], segs = n_seg[f];
+	int n_u = 0, n_v = 0;
+	mm128 *A = a + ao, *B = bb + ao;
+	uint64_t *U0 = u + ao * 2, *U1 = U0 + n;
 	if (n > 0) {
 		const ChainParams P = mmg_chain_params(co, ft.qlen[f], segs);
-		int32_t *fp = work + ao * 4;
-		mm128 *A = a + ao;
-		n_u = mmg_chain_backtrack(P, n, A, fp, fp + n, fp + 2 * n, fp + 3 * n, u + ao * 2, bb + ao, stack + ao / 65 + 2 * (int64_t)li, &n_v);
+		int32_t *F = work + ao * 8, *Pp = F + n, *T = Pp + n, *V = T + n;
+		mm128 *W = reinterpret_cast<mm128*>(F + 4 * (int64_t)n);
+		// 1. chain ends: anchors nobody extends (chain.c:88-90)
+		for (int i = lane; i < n; i += 32) T[i] = 0;
+		__syncwarp();
+		for (int i = lane; i < n; i += 32) { const int pj = Pp[i]; if (pj >= 0) T[pj] = 1; }
+		__syncwarp();
+		// 2. for every end with a good enough peak, the anchor where the score peaks (chain.c:99-106)
+		for (int i0 = 0; i0 < n; i0 += 32) {
+			const int i = i0 + lane;
+			const bool is_end = i < n && T[i] == 0 && V[i] >= P.min_sc;
+			uint64_t val = 0;
+			if (is_end) {
+				int j = i;
+				while (j >= 0 && F[j] < V[j]) j = Pp[j];
+				if (j < 0) j = i;
+				val = (uint64_t)F[j] << 32 | (uint32_t)j;
+			}
+			const unsigned m = __ballot_sync(FULL, is_end);
+			if (is_end) U1[n_u + __popc(m & ((1u << lane) - 1u))] = val;
+			n_u += __popc(m);
+		}
+		__syncwarp();
+		if (n_u > 0) {
+			// 3. rank by (peak score, anchor) descending (chain.c:107-111); equal values are duplicates
+			for (int e = lane; e < n_u; e += 32) {
+				const uint64_t x = U1[e];
+				int r = 0;
+				for (int k = 0; k < n_u; ++k) { const uint64_t y = U1[k]; r += (y > x || (y == x && k < e)) ? 1 : 0; }
+				U0[r] = x;
+			}
+			// 4. ownership: lowest rank whose walk passes through the anchor
+			for (int i = lane; i < n; i += 32) T[i] = 0x7fffffff;
+			__syncwarp();
+			for (int k = lane; k < n_u; k += 32) {
+				int j = (int32_t)U0[k];
+				while (j >= 0) { const int old = atomicMin(&T[j], k); if (old < k) break; j = Pp[j]; }
+			}
+			__syncwarp();
+			// 5. what each chain keeps (chain.c:115-129): its peak, then the anchors it owns; V[k] = kept count or 0
+			for (int k = lane; k < n_u; k += 32) {
+				const int j0 = (int32_t)U0[k];
+				const int32_t sc = (int32_t)(U0[k] >> 32);
+				int cnt = 1, j = Pp[j0];
+				while (j >= 0 && T[j] == k) ++cnt, j = Pp[j];
+				bool keep; int32_t score;
+				if (j < 0) keep = cnt >= P.min_cnt, score = sc;
+				else keep = (sc - F[j] >= P.min_sc) && cnt >= P.min_cnt, score = sc - F[j];
+				U1[k] = keep ? ((uint64_t)(uint32_t)score << 32 | (uint32_t)cnt) : 0; // per rank; compacted below
+			}
+			__syncwarp();
+			// 6. kept chains in rank order -> b[] (anchors ascending inside a chain), compacted u, chain-order keys w
+			int n_keep = 0;
+			for (int k0 = 0; k0 < n_u; k0 += 32) {
+				const int k = k0 + lane;
+				const uint64_t uk = k < n_u ? U1[k] : 0;
+				const int cnt = (int32_t)(uint32_t)uk;
+				int incl = cnt;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+				const unsigned m = __ballot_sync(FULL, cnt > 0);
+				if (cnt > 0) {
+					const int off = n_v + incl - cnt, kk = n_keep + __popc(m & ((1u << lane) - 1u));
+					int j = (int32_t)U0[k];
+					for (int q = cnt - 1; q >= 0; --q) { B[off + q] = A[j]; j = Pp[j]; }
+					V[kk] = off; // start of chain kk in b[]
+					W[kk].y = (uint64_t)off << 32 | (uint32_t)kk;
+				}
+				__syncwarp();
+				if (cnt > 0) U1[n_keep + __popc(m & ((1u << lane) - 1u))] = uk; // compaction never overtakes unread entries: kk <= k
+				n_v += __shfl_sync(FULL, incl, 31);
+				n_keep += __popc(m);
+				__syncwarp();
+			}
+			n_u = n_keep;
+			for (int kk = lane; kk < n_u; kk += 32) W[kk].x = B[V[kk]].x;
+			__syncwarp();
+			// 7. order chains by the position of their first anchor, klib radix semantics (chain.c:150)
+			if (lane == 0) mmg_rs_sort_exact(W, (int64_t)n_u, stack + ao / 65 + 2 * (int64_t)li, KeyX());
+			__syncwarp();
+			// 8. write chains back to a[] in that order (chain.c:152-159)
+			int dst = 0;
+			for (int i = 0; i < n_u; ++i) {
+				const uint64_t wy = W[i].y;
+				const int jj = (int32_t)(uint32_t)wy, src = (int)(wy >> 32);
+				const uint64_t uk = U1[jj];
+				const int nn = (int32_t)(uint32_t)uk;
+				for (int q = lane; q < nn; q += 32) A[dst + q] = B[src + q];
+				if (lane == 0) U0[i] = uk;
+				dst += nn;
+			}
+			__syncwarp();
+		}
 	}
-	nu_out[li] = n_u, nv_out[li] = (int32_t)n_v;
+	if (lane != 0) return;
+	nu_out[li] = n_u, nv_out[li] = n_v;
 	if (flag_out) {
 		uint8_t rechain = 0;
 		if (rechain_enabled && rep[li] > 0) {
 			if (n_u > 0) { // does the best chain span every segment? (map.c:355-365)
-				const uint64_t *U = u + ao * 2;
-				const mm128 *A = a + ao;
 				int n_chained = 1, max = 0, max_i = -1, max_off = -1, off = 0;
 				for (int i = 0; i < n_u; ++i) {
-					if (max < (int)(U[i] >> 32)) max = (int)(U[i] >> 32), max_i = i, max_off = off;
-					off += (int32_t)U[i];
+					if (max < (int)(U0[i] >> 32)) max = (int)(U0[i] >> 32), max_i = i, max_off = off;
+					off += (int32_t)U0[i];
 				}
 				if (max_i >= 0)
-					for (int i = 1; i < (int32_t)U[max_i]; ++i)
+					for (int i = 1; i < (int32_t)U0[max_i]; ++i)
 						if ((A[max_off + i].y & MMG_SEED_SEG_MASK) != (A[max_off + i - 1].y & MMG_SEED_SEG_MASK)) ++n_chained;
 				if (n_chained < segs) rechain = 1;
 			} else rechain = 1;
@@ -414,7 +511,7 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	*n_anchors = tot;
 	MMG_TRY(pb.a->ensure((size_t)(tot + 1) * 16));
-	MMG_TRY(pb.work->ensure((size_t)(tot + 1) * 16));
+	MMG_TRY(pb.work->ensure((size_t)(tot + 1) * 32)); // f|p|t|v then the chain-order array
 	MMG_TRY(pb.u->ensure((size_t)(tot + 1) * 16));
 	MMG_TRY(pb.b->ensure((size_t)(tot + 1) * 16));
 	MMG_TRY(pb.stack->ensure((size_t)(tot / 65 + 2 * (size_t)n_list + 4) * sizeof(RsFrame)));
@@ -450,7 +547,7 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		MMG_LAUNCH(c, k_chain_fill, 148 * 8, 128, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(),
 		           pb.a->as<mm128>(), pb.work->as<int32_t>(), c->d_seg_avg.as<float>(), seg_start, d_nseg, d_next, c->d_frag_iter.as<unsigned long long>());
 	}
-	MMG_LAUNCH(c, k_chain_tail, mmg_blocks(n_list, 64), 64, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+	MMG_LAUNCH(c, k_chain_tail_warp, mmg_blocks((size_t)n_list * 32, 128), 128, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
 	           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
 	           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), pb.rep->as<int32_t>(), opt->max_occ > opt->mid_occ ? 1 : 0, d_flag);
 	return MMG_OK;
