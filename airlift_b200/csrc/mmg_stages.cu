@@ -54,10 +54,17 @@ struct FragTab {  // per-fragment tables of the resident batch
 	const int32_t *qlen;       // [n_frag] summed segment lengths
 };
 
+__device__ __forceinline__ int frag_of_anchor(const int64_t *aoff, int n_list, int64_t g)
+{ // last li with aoff[li] <= g
+	int lo = 0, hi = n_list - 1;
+	while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (aoff[mid] <= g) lo = mid; else hi = mid - 1; }
+	return lo;
+}
+
 // K2b: collect_matches bookkeeping per fragment (map.c:90-123)
 __global__ void k_plan(FragTab ft, const int32_t *__restrict__ list, int n_list, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
                        int max_occ, int32_t *__restrict__ na, int32_t *__restrict__ rep, int32_t *__restrict__ nmini,
-                       uint64_t *__restrict__ mini /* may be null */)
+                       uint64_t *__restrict__ mini /* may be null */, uint8_t *__restrict__ replay /* may be null */)
 {
 	const int li = blockIdx.x * blockDim.x + threadIdx.x;
 	if (li >= n_list) return;
@@ -66,15 +73,85 @@ __global__ void k_plan(FragTab ft, const int32_t *__restrict__ list, int n_list,
 	int r, nm;
 	const int64_t n_a = mmg_frag_plan(mv + b, m_n + b, (int)(e - b), max_occ, &r, &nm, mini ? mini + b : nullptr);
 	na[li] = (int32_t)n_a, rep[li] = r, nmini[li] = nm;
+	if (replay) {
+		// Positions of different minimizers are disjoint, so two heap entries can only tie when two kept query minimizers
+		// carry the same hash (tandem k-mers, overlapping mates).  Only those fragments need the heap replayed.
+		const int m = (int)(e - b);
+		uint8_t dup = m > 256 ? 1 : 0;
+		for (int i = 0; i < m && !dup; ++i) {
+			if (m_n[b + i] <= 0 || m_n[b + i] >= max_occ) continue;
+			const uint64_t h = mv[b + i].x >> 8;
+			for (int j = i + 1; j < m; ++j)
+				if (mv[b + j].x >> 8 == h && m_n[b + j] > 0 && m_n[b + j] < max_occ) { dup = 1; break; }
+		}
+		replay[li] = dup;
+	}
+}
+
+// K2c, sort form (fragments without repeated hashes): every planned anchor slot finds its (minimizer, hit), and emits the
+// heap's pop key (strand class, reference position incl. strand bit) with the anchor's y as payload
+__global__ void k_expand(FragTab ft, const int32_t *__restrict__ list, int n_list, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
+                         const uint64_t *__restrict__ m_val, const uint64_t *__restrict__ pos, int max_occ, int64_t flag,
+                         const int64_t *__restrict__ aoff, const uint8_t *__restrict__ replay, int64_t n_total,
+                         uint64_t *__restrict__ key, uint64_t *__restrict__ val, int32_t *__restrict__ n_skipped)
+{
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n_total) return;
+	const int li = frag_of_anchor(aoff, n_list, g);
+	if (replay[li]) return; // segment of length zero in the sort
+	const int f = list ? list[li] : li;
+	const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]];
+	int64_t i = g - aoff[li];
+	int m = 0;
+	for (; b + m < e; ++m) {
+		const int n = m_n[b + m];
+		if (n <= 0 || n >= max_occ) continue;
+		if (i < n) break;
+		i -= n;
+	}
+	const mm128 mz = mv[b + m];
+	const uint64_t r = mmg_hit_pos(pos, m_n[b + m], m_val[b + m], (uint32_t)i);
+	if (mmg_skip_seed(flag, r, (uint32_t)mz.y)) { key[g] = MMG_NONE, val[g] = 0; atomicAdd(&n_skipped[li], 1); return; }
+	const mm128 an = mmg_make_anchor(r, mz, mmg_is_tandem(mv + b, (int)(e - b), m), ft.qlen[f]);
+	key[g] = (an.x & (1ULL << 63)) | r; // r < 2^63
+	val[g] = an.y;
+}
+
+__global__ void k_sort_segments(int n_list, const int64_t *__restrict__ aoff, const uint8_t *__restrict__ replay, int64_t *__restrict__ seg_b, int64_t *__restrict__ seg_e)
+{
+	const int li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= n_list) return;
+	seg_b[li] = aoff[li];
+	seg_e[li] = replay[li] ? aoff[li] : aoff[li + 1];
+}
+
+__global__ void k_emit_sorted(int n_list, const int64_t *__restrict__ aoff, const uint8_t *__restrict__ replay, int64_t n_total,
+                              const uint64_t *__restrict__ key, const uint64_t *__restrict__ val, const int32_t *__restrict__ n_skipped,
+                              int32_t *__restrict__ na, mm128 *__restrict__ a)
+{
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n_total) return;
+	const int li = frag_of_anchor(aoff, n_list, g);
+	if (replay[li]) return;
+	const uint64_t k = key[g];
+	if (g == aoff[li]) na[li] = (int32_t)(aoff[li + 1] - aoff[li]) - n_skipped[li];
+	if (k == MMG_NONE) return;
+	const uint64_t r = k & ~(1ULL << 63);
+	mm128 an;
+	an.x = (k & (1ULL << 63)) | (r & 0xffffffff00000000ULL) | ((uint32_t)r >> 1);
+	an.y = val[g];
+	a[g] = an;
 }
 
 // K2c: anchors per fragment, in the reference's order (map.c:149-247)
 __global__ void k_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
                        const uint64_t *__restrict__ m_val, const uint64_t *__restrict__ pos, int max_occ, int64_t flag,
-                       const int64_t *__restrict__ aoff, int32_t *__restrict__ na, mm128 *__restrict__ a, mm128 *__restrict__ heap, RsFrame *__restrict__ stack)
+                       const int64_t *__restrict__ aoff, int32_t *__restrict__ na, mm128 *__restrict__ a, mm128 *__restrict__ heap, RsFrame *__restrict__ stack,
+                       const uint8_t *__restrict__ replay /* null: every fragment */)
 {
 	const int li = blockIdx.x * blockDim.x + threadIdx.x;
 	if (li >= n_list) return;
+	if (replay && !replay[li]) return;
 	const int f = list ? list[li] : li;
 	const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]];
 	const int64_t ao = aoff[li];
@@ -106,13 +183,6 @@ __device__ __forceinline__ ChainParams mmg_chain_params(const ChainOptDev &o, in
 // of a fragment falls apart into independent SEGMENTS wherever a[i].x > a[i-1].x + max_dist_x (the `st` pointer of
 // chain.c:51 would jump to i).  Segments are filled by one warp each; a fragment drawn from a 3 000-copy repeat becomes
 // thousands of parallel work items instead of one 10^5-step serial loop.
-
-__device__ __forceinline__ int frag_of_anchor(const int64_t *aoff, int n_list, int64_t g)
-{ // last li with aoff[li] <= g
-	int lo = 0, hi = n_list - 1;
-	while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (aoff[mid] <= g) lo = mid; else hi = mid - 1; }
-	return lo;
-}
 
 // flag the first anchor of every segment; zero the t[] array of chain.c:39
 __global__ void k_chain_heads(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
@@ -499,12 +569,15 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	MMG_TRY(pb.nu->ensure((size_t)(n_list + 1) * 4));
 	MMG_TRY(pb.nv->ensure((size_t)(n_list + 1) * 4));
 	if (want_mini) MMG_TRY(pb.mini->ensure((size_t)(n_mv + 1) * 8));
+	const bool heap_path = (opt->flag & MMG_F_HEAP_SORT) != 0;
+	MMG_TRY(c->d_replay.ensure((size_t)n_list + 16));
 	MMG_CUDA(cudaMemsetAsync(pb.na->p, 0, (size_t)(n_list + 1) * 4, c->stream));
 	MMG_CUDA(cudaMemsetAsync(pb.nu->p, 0, (size_t)(n_list + 1) * 4, c->stream)); // slot n_list must read 0 for the scans
 	MMG_CUDA(cudaMemsetAsync(pb.nv->p, 0, (size_t)(n_list + 1) * 4, c->stream));
 	MMG_CUDA(cudaMemsetAsync(pb.nmini->p, 0, (size_t)(n_list + 1) * 4, c->stream));
 	MMG_LAUNCH(c, k_plan, mmg_blocks(n_list, 128), 128, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), max_occ,
-	           pb.na->as<int32_t>(), pb.rep->as<int32_t>(), pb.nmini->as<int32_t>(), want_mini ? pb.mini->as<uint64_t>() : nullptr);
+	           pb.na->as<int32_t>(), pb.rep->as<int32_t>(), pb.nmini->as<int32_t>(), want_mini ? pb.mini->as<uint64_t>() : nullptr,
+	           heap_path ? c->d_replay.as<uint8_t>() : nullptr);
 	MMG_TRY(scan_i32_to_i64(c, pb.na->as<int32_t>(), pb.aoff->as<int64_t>(), n_list + 1));
 	int64_t tot = 0;
 	MMG_D2H(c, &tot, pb.aoff->as<int64_t>() + n_list, 8);
@@ -516,9 +589,31 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	MMG_TRY(pb.b->ensure((size_t)(tot + 1) * 16));
 	MMG_TRY(pb.stack->ensure((size_t)(tot / 65 + 2 * (size_t)n_list + 4) * sizeof(RsFrame)));
 	MMG_TRY(c->d_heap.ensure((size_t)(n_mv + 1) * 16));
+	if (heap_path && tot > 0) {
+		// fragments whose heap keys are all distinct: the merged order is simply the sorted order -> segmented sort
+		MMG_TRY(c->d_skey.ensure(((size_t)tot + 1) * 16)); MMG_TRY(c->d_sval.ensure(((size_t)tot + 1) * 16));
+		MMG_TRY(c->d_sseg.ensure(((size_t)n_list + 1) * 20 + 64));
+		uint64_t *k0 = c->d_skey.as<uint64_t>(), *k1 = k0 + tot + 1, *v0 = c->d_sval.as<uint64_t>(), *v1 = v0 + tot + 1;
+		int64_t *seg_b = c->d_sseg.as<int64_t>(), *seg_e = seg_b + n_list + 1;
+		int32_t *n_skipped = reinterpret_cast<int32_t*>(seg_e + n_list + 1);
+		MMG_CUDA(cudaMemsetAsync(n_skipped, 0, (size_t)n_list * 4, c->stream));
+		MMG_LAUNCH(c, k_expand, mmg_blocks(tot, 256), 256, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
+		           mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), tot, k0, v0, n_skipped);
+		MMG_LAUNCH(c, k_sort_segments, mmg_blocks(n_list, 256), 256, 0, n_list, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), seg_b, seg_e);
+		{
+			size_t tmp = 0;
+			cub::DeviceSegmentedSort::SortPairs(nullptr, tmp, k0, k1, v0, v1, tot, n_list, seg_b, seg_e, c->stream);
+			MMG_TRY(c->d_cub.ensure(tmp));
+			MMG_CUDA(cub::DeviceSegmentedSort::SortPairs(c->d_cub.p, tmp, k0, k1, v0, v1, tot, n_list, seg_b, seg_e, c->stream));
+			++c->launches;
+		}
+		MMG_LAUNCH(c, k_emit_sorted, mmg_blocks(tot, 256), 256, 0, n_list, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), tot, k1, v1, n_skipped,
+		           pb.na->as<int32_t>(), pb.a->as<mm128>());
+	}
+	// literal replay: the heap merge for fragments with repeated hashes; fill + klib radix sort for the non-heap presets
 	MMG_LAUNCH(c, k_fill, mmg_blocks(n_list, 64), 64, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
 	           mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>(), c->d_heap.as<mm128>(),
-	           pb.stack->as<RsFrame>());
+	           pb.stack->as<RsFrame>(), heap_path ? c->d_replay.as<uint8_t>() : nullptr);
 	ChainOptDev co;
 	co.bw = opt->bw, co.max_gap = opt->max_gap, co.max_gap_ref = opt->max_gap_ref, co.max_frag_len = opt->max_frag_len;
 	co.max_skip = opt->max_chain_skip, co.max_iter = opt->max_chain_iter, co.min_cnt = opt->min_cnt, co.min_sc = opt->min_chain_score;
