@@ -69,7 +69,7 @@ static int dp_request(walk_t *w, int q_rev, int q_start, int q_len, int rid, int
 		ez->cigar = j->cigar;
 		return 1;
 	}
-	if (c->n == c->m) { c->m = c->m ? c->m << 1 : 8; c->a = (mm_dpjob_t*)realloc(c->a, (size_t)c->m * sizeof(mm_dpjob_t)); }
+	if (c->n == c->m) { const size_t old = (size_t)c->m * sizeof(mm_dpjob_t); c->m = c->m ? c->m << 1 : 8; c->a = (mm_dpjob_t*)mm_arealloc(c->a, old, (size_t)c->m * sizeof(mm_dpjob_t)); }
 	j = &c->a[c->n++];
 	memset(j, 0, sizeof(*j));
 	j->job.seq_id = w->seg->seq_id, j->job.q_rev = q_rev, j->job.q_start = q_start, j->job.q_len = q_len;
@@ -293,14 +293,14 @@ static int test_zdrop(const walk_t *w, const uint8_t *qseq, const uint8_t *tseq,
 #undef TRACK
 	q_len = pos[1][1] - pos[1][0], t_len = pos[0][1] - pos[0][0];
 	if (!(opt->flag & (MM_F_SPLICE|MM_F_SR|MM_F_FOR_ONLY|MM_F_REV_ONLY)) && max_zdrop > opt->zdrop_inv && q_len < opt->max_gap && t_len < opt->max_gap) {
-		uint8_t *qseq2 = (uint8_t*)malloc(q_len > 0 ? q_len : 1);
+		uint8_t *qseq2 = (uint8_t*)mm_amalloc(q_len > 0 ? q_len : 1);
 		int q_off, t_off;
 		for (i = 0; i < q_len; ++i) {
 			const int c = qseq[pos[1][1] - i - 1];
 			qseq2[i] = c >= 4 ? 4 : 3 - c;
 		}
 		score = mm_ll_i16(q_len, qseq2, t_len, tseq + pos[0][0], 5, w->mat, opt->q, opt->e, &q_off, &t_off);
-		free(qseq2);
+		mm_afree(qseq2);
 		if (score >= opt->min_chain_score * opt->a && score >= opt->min_dp_max) return 2; /* looks like an inversion */
 	}
 	return max_zdrop > opt->zdrop ? 1 : 0;
@@ -336,7 +336,7 @@ static int *long_gaps(int as1, int cnt1, const mm128_t *a, int min_gap, int *n_)
 	*n_ = 0;
 	for (i = 1; i < cnt1; ++i) { const int gap = GAP_AT(a + as1, i); if (gap < -min_gap || gap > min_gap) ++n; }
 	if (n <= 1) return 0;
-	K = (int*)malloc((size_t)n * sizeof(int));
+	K = (int*)mm_amalloc((size_t)n * sizeof(int));
 	for (i = 1, n = 0; i < cnt1; ++i) { const int gap = GAP_AT(a + as1, i); if (gap < -min_gap || gap > min_gap) K[n++] = i; }
 	*n_ = n;
 	return K;
@@ -370,7 +370,7 @@ static void filter_bad_seeds(int as1, int cnt1, mm128_t *a, int min_gap, int dif
 		}
 		if (max_diff > diff_thres && max_diff > max) max = max_diff, max_st = k, max_en = max_diff_l;
 	}
-	free(K);
+	mm_afree(K);
 }
 
 static void filter_bad_seeds_alt(int as1, int cnt1, mm128_t *a, int min_gap, int max_ext)
@@ -403,7 +403,7 @@ static void filter_bad_seeds_alt(int as1, int cnt1, mm128_t *a, int min_gap, int
 		}
 		k = l;
 	}
-	free(K);
+	mm_afree(K);
 }
 
 static void fix_bad_ends(const mm_reg1_t *r, const mm128_t *a, int bw, int min_match, int32_t *as, int32_t *cnt)
@@ -565,7 +565,7 @@ static void align1(walk_t *w, mm_reg1_t *r, mm_reg1_t *r2)
 		if (qe0 - r->qe > max_ext) qe0 = r->qe + max_ext;
 	}
 	assert(re0 > rs0);
-	tseq = (uint8_t*)malloc((size_t)(re0 - rs0));
+	tseq = (uint8_t*)mm_amalloc((size_t)(re0 - rs0));
 
 	if (qs > 0 && rs > 0) { /* left extension: both slices reversed, gaps right-aligned, CIGAR reversed (align.c:690-705) */
 		dp_request(w, rev, qs0, qs - qs0, rid, rs0, rs - rs0, 1, bw, opt->end_bonus, r->split_inv ? opt->zdrop_inv : opt->zdrop,
@@ -590,18 +590,38 @@ static void align1(walk_t *w, mm_reg1_t *r, mm_reg1_t *r2)
 			const uint8_t *qseq = &qseq0[rev][qs];
 			uint32_t one_op;
 			if (a[as1 + i].y & MM_SEED_LONG_JOIN) bw1 = qe - qs > re - rs ? qe - qs : re - rs;
-			mm_idx_getseq(mi, rid, rs, re, tseq);
 			if (is_sr) { /* short reads: no DP between the ends of the stretch; N scores +e2 (align.c:724-731) */
+				mm_fillmemo_t *fm = 0;
+				int q;
 				assert(qe - qs == re - rs);
 				ez_reset(&ez);
-				for (j = 0, ez.score = 0; j < qe - qs; ++j) {
-					if (qseq[j] >= 4 || tseq[j] >= 4) ez.score += opt->e2;
-					else ez.score += qseq[j] == tseq[j] ? opt->a : -opt->b;
+				for (q = 0; q < sg->n_fill; ++q) /* a region is walked twice (request DP, consume DP): score its stretch once */
+					if (sg->fill[q].rev == rev && sg->fill[q].rid == rid && sg->fill[q].rs == rs && sg->fill[q].qs == qs && sg->fill[q].len == qe - qs) { fm = &sg->fill[q]; break; }
+				if (fm == 0) {
+					mm_idx_getseq(mi, rid, rs, re, tseq);
+					for (j = 0, ez.score = 0; j < qe - qs; ++j) {
+						if (qseq[j] >= 4 || tseq[j] >= 4) ez.score += opt->e2;
+						else ez.score += qseq[j] == tseq[j] ? opt->a : -opt->b;
+					}
+					one_op = (uint32_t)(qe - qs) << 4 | 0;
+					zdrop_code = test_zdrop(w, qseq, tseq, 1, &one_op);
+					if (sg->n_fill == sg->m_fill) {
+						const size_t old_b = (size_t)sg->m_fill * sizeof(mm_fillmemo_t);
+						sg->m_fill = sg->m_fill ? sg->m_fill << 1 : 4;
+						sg->fill = (mm_fillmemo_t*)mm_arealloc(sg->fill, old_b, (size_t)sg->m_fill * sizeof(mm_fillmemo_t));
+					}
+					fm = &sg->fill[sg->n_fill++];
+					fm->rev = rev, fm->rid = rid, fm->rs = rs, fm->qs = qs, fm->len = qe - qs, fm->score = ez.score, fm->zdrop_code = zdrop_code;
 				}
+				ez.score = fm->score, zdrop_code = fm->zdrop_code;
 				one_op = (uint32_t)(qe - qs) << 4 | 0;
 				ez.cigar = &one_op, ez.n_cigar = 1;
-			} else dp_request(w, rev, qs, qe - qs, rid, rs, re - rs, 0, bw1, -1, opt->zdrop, KSW_EZ_APPROX_MAX, &ez);
-			if ((zdrop_code = test_zdrop(w, qseq, tseq, ez.n_cigar, ez.cigar)) != 0) /* second, exact pass */
+			} else {
+				mm_idx_getseq(mi, rid, rs, re, tseq);
+				dp_request(w, rev, qs, qe - qs, rid, rs, re - rs, 0, bw1, -1, opt->zdrop, KSW_EZ_APPROX_MAX, &ez);
+				zdrop_code = test_zdrop(w, qseq, tseq, ez.n_cigar, ez.cigar);
+			}
+			if (zdrop_code != 0) /* second, exact pass */
 				dp_request(w, rev, qs, qe - qs, rid, rs, re - rs, 0, bw1, -1, zdrop_code == 2 ? opt->zdrop_inv : opt->zdrop, 0, &ez);
 			if (ez.n_cigar > 0) append_cigar(r, ez.n_cigar, ez.cigar);
 			if (ez.zdropped) { /* cut the region here; the rest becomes r2 (align.c:741-754) */
@@ -631,7 +651,7 @@ static void align1(walk_t *w, mm_reg1_t *r, mm_reg1_t *r2)
 		re1 = re + (ez.reach_end ? ez.mqe_t + 1 : ez.max_t + 1);
 		qe1 = qe + (ez.reach_end ? qe0 - qe : ez.max_q + 1);
 	}
-	if (w->pending) { free(tseq); return; } /* the caller throws this attempt away */
+	if (w->pending) { mm_afree(tseq); return; } /* the caller throws this attempt away */
 	assert(qe1 <= qlen);
 
 	r->rs = rs1, r->re = re1;
@@ -643,7 +663,7 @@ static void align1(walk_t *w, mm_reg1_t *r, mm_reg1_t *r2)
 		update_extra(r, &qseq0[r->rev][qs1], tseq, w->mat, opt->q, opt->e, opt->flag & MM_F_EQX);
 		if (rev && r->p->trans_strand) r->p->trans_strand ^= 3;
 	}
-	free(tseq);
+	mm_afree(tseq);
 }
 
 /* ---- inversion rescue between two pieces of a z-drop split (align.c:790-845) */
@@ -669,7 +689,7 @@ static int align1_inv(walk_t *w, const mm_reg1_t *r1, const mm_reg1_t *r2, mm_re
 	if (ql < opt->min_chain_score || ql > opt->max_gap) return 0;
 	if (tl < opt->min_chain_score || tl > opt->max_gap) return 0;
 
-	tseq = (uint8_t*)malloc((size_t)tl * 2 + (size_t)ql);
+	tseq = (uint8_t*)mm_amalloc((size_t)tl * 2 + (size_t)ql);
 	trev = tseq + tl, qrev = trev + tl;
 	mm_idx_getseq(mi, r1->rid, r1->re, r2->rs, tseq);
 	q_rev = r1->rev ? 0 : 1, q_base = r1->rev ? r2->qe : qlen - r2->qs; /* the opposite strand of the gap (align.c:810) */
@@ -694,7 +714,7 @@ static int align1_inv(walk_t *w, const mm_reg1_t *r1, const mm_reg1_t *r2, mm_re
 	update_extra(r_inv, &qseq[q_off], &tseq[t_off], w->mat, opt->q, opt->e, opt->flag & MM_F_EQX);
 	ret = 1;
 done:
-	free(tseq);
+	mm_afree(tseq);
 	return ret;
 }
 
@@ -724,7 +744,7 @@ int mm_aln_step(mm_alnseg_t *s, const mm_mapopt_t *opt, const mm_idx_t *mi)
 	w.seg = s, w.opt = opt, w.mi = mi, w.pending = 0;
 	gen_simple_mat(w.mat, opt->a, opt->b, opt->sc_ambi);
 	if (!s->started) { /* encode both strands of the query, compact the anchors (align.c:864-873) */
-		s->qseq0[0] = (uint8_t*)malloc((size_t)(s->qlen > 0 ? s->qlen : 1) * 2);
+		s->qseq0[0] = (uint8_t*)mm_amalloc((size_t)(s->qlen > 0 ? s->qlen : 1) * 2);
 		s->qseq0[1] = s->qseq0[0] + s->qlen;
 		for (i = 0; i < s->qlen; ++i) {
 			s->qseq0[0][i] = seq_nt4_table[(uint8_t)s->qstr[i]];
@@ -770,7 +790,7 @@ int mm_aln_step(mm_alnseg_t *s, const mm_mapopt_t *opt, const mm_idx_t *mi)
 		}
 		s->i = i + 1;
 	}
-	free(s->qseq0[0]); s->qseq0[0] = s->qseq0[1] = 0;
+	mm_afree(s->qseq0[0]); s->qseq0[0] = s->qseq0[1] = 0;
 	mm_filter_regs(opt, s->qlen, &s->n_regs, s->regs);
 	mm_hit_sort(&s->n_regs, s->regs);
 	s->finished = 1;
@@ -780,9 +800,9 @@ int mm_aln_step(mm_alnseg_t *s, const mm_mapopt_t *opt, const mm_idx_t *mi)
 void mm_aln_end(mm_alnseg_t *s)
 {
 	int i;
-	for (i = 0; i < s->cache.n; ++i) free(s->cache.a[i].cigar);
-	free(s->cache.a);
-	free(s->qseq0[0]);
+	for (i = 0; i < s->cache.n; ++i) mm_afree(s->cache.a[i].cigar);
+	mm_afree(s->cache.a);
+	mm_afree(s->qseq0[0]);
 	memset(&s->cache, 0, sizeof(s->cache));
 	s->qseq0[0] = s->qseq0[1] = 0;
 }

@@ -68,7 +68,7 @@ mm_reg1_t *mm_gen_regs(uint32_t hash, int qlen, int n_u, uint64_t *u, mm128_t *a
 	mm_reg1_t *r;
 	int i, k;
 	if (n_u == 0) return 0;
-	z = (mm128_t*)malloc((size_t)n_u * 16);
+	z = (mm128_t*)mm_amalloc((size_t)n_u * 16);
 	for (i = k = 0; i < n_u; ++i) { /* order: chain score, ties broken by a salted hash of the first anchor */
 		const uint32_t h = (uint32_t)mix64((mix64(a[k].x) + mix64(a[k].y)) ^ hash);
 		z[i].x = u[i] ^ h;
@@ -87,7 +87,7 @@ mm_reg1_t *mm_gen_regs(uint32_t hash, int qlen, int n_u, uint64_t *u, mm128_t *a
 		ri->div = -1.0f;
 		reg_set_coor(ri, qlen, a);
 	}
-	free(z);
+	mm_afree(z);
 	return r;
 }
 
@@ -112,8 +112,8 @@ void mm_set_parent(float mask_level, int n, mm_reg1_t *r, int sub_diff, int hard
 	uint64_t *cov;
 	if (n <= 0) return;
 	for (i = 0; i < n; ++i) r[i].id = i;
-	cov = (uint64_t*)malloc((size_t)n * sizeof(uint64_t));
-	w = (int*)malloc((size_t)n * sizeof(int));
+	cov = (uint64_t*)mm_amalloc((size_t)n * sizeof(uint64_t));
+	w = (int*)mm_amalloc((size_t)n * sizeof(int));
 	w[0] = 0, r[0].parent = 0;
 	for (i = 1, k = 1; i < n; ++i) {
 		mm_reg1_t *ri = &r[i];
@@ -163,7 +163,7 @@ void mm_set_parent(float mask_level, int n, mm_reg1_t *r, int sub_diff, int hard
 new_primary:
 		if (j == k) w[k++] = i, ri->parent = i, ri->n_sub = 0;
 	}
-	free(cov); free(w);
+	mm_afree(cov); mm_afree(w);
 }
 
 void mm_hit_sort(int *n_regs, mm_reg1_t *r)
@@ -172,8 +172,8 @@ void mm_hit_sort(int *n_regs, mm_reg1_t *r)
 	mm128_t *aux;
 	mm_reg1_t *t;
 	if (n <= 1) return;
-	aux = (mm128_t*)malloc((size_t)n * 16);
-	t = (mm_reg1_t*)malloc((size_t)n * sizeof(mm_reg1_t));
+	aux = (mm128_t*)mm_amalloc((size_t)n * 16);
+	t = (mm_reg1_t*)mm_amalloc((size_t)n * sizeof(mm_reg1_t));
 	for (i = n_aux = 0; i < n; ++i) {
 		if (r[i].inv || r[i].cnt > 0) {
 			if (r[i].p) aux[n_aux].x = (uint64_t)r[i].p->dp_max << 32 | r[i].hash, has_cigar = 1;
@@ -186,7 +186,7 @@ void mm_hit_sort(int *n_regs, mm_reg1_t *r)
 	for (i = n_aux - 1; i >= 0; --i) t[n_aux - 1 - i] = r[aux[i].y];
 	memcpy(r, t, sizeof(mm_reg1_t) * n_aux);
 	*n_regs = n_aux;
-	free(aux); free(t);
+	mm_afree(aux); mm_afree(t);
 }
 
 int mm_set_sam_pri(int n, mm_reg1_t *r)
@@ -205,7 +205,7 @@ void mm_sync_regs(int n_regs, mm_reg1_t *regs)
 	if (n_regs <= 0) return;
 	for (i = 0; i < n_regs; ++i) max_id = max_id > regs[i].id ? max_id : regs[i].id;
 	n_map = max_id + 1;
-	map = (int*)malloc((size_t)(n_map > 0 ? n_map : 1) * sizeof(int));
+	map = (int*)mm_amalloc((size_t)(n_map > 0 ? n_map : 1) * sizeof(int));
 	for (i = 0; i < n_map; ++i) map[i] = -1;
 	for (i = 0; i < n_regs; ++i) if (regs[i].id >= 0) map[regs[i].id] = i;
 	for (i = 0; i < n_regs; ++i) {
@@ -215,7 +215,7 @@ void mm_sync_regs(int n_regs, mm_reg1_t *regs)
 		else if (r->parent >= 0 && map[r->parent] >= 0) r->parent = map[r->parent];
 		else r->parent = MM_PARENT_UNSET;
 	}
-	free(map);
+	mm_afree(map);
 	mm_set_sam_pri(n_regs, regs);
 }
 
@@ -289,7 +289,7 @@ void mm_filter_regs(const mm_mapopt_t *opt, int qlen, int *n_regs, mm_reg1_t *re
 int mm_squeeze_a(int n_regs, mm_reg1_t *regs, mm128_t *a)
 { /* hit.c:278-296: compact a[] to the anchors still referenced, in order of `as` */
 	int i, as = 0;
-	uint64_t *aux = (uint64_t*)malloc((size_t)(n_regs > 0 ? n_regs : 1) * 8);
+	uint64_t *aux = (uint64_t*)mm_amalloc((size_t)(n_regs > 0 ? n_regs : 1) * 8);
 	for (i = 0; i < n_regs; ++i) aux[i] = (uint64_t)regs[i].as << 32 | (uint32_t)i;
 	radix_sort_64(aux, aux + n_regs);
 	for (i = 0; i < n_regs; ++i) {
@@ -300,7 +300,7 @@ int mm_squeeze_a(int n_regs, mm_reg1_t *regs, mm128_t *a)
 		}
 		as += r->cnt;
 	}
-	free(aux);
+	mm_afree(aux);
 	return as;
 }
 
@@ -310,7 +310,7 @@ void mm_join_long(const mm_mapopt_t *opt, int qlen, int *n_regs_, mm_reg1_t *reg
 	uint64_t *aux;
 	if (n_regs < 2) return;
 	mm_squeeze_a(n_regs, regs, a);
-	aux = (uint64_t*)malloc((size_t)n_regs * 8);
+	aux = (uint64_t*)mm_amalloc((size_t)n_regs * 8);
 	for (i = n_aux = 0; i < n_regs; ++i)
 		if (regs[i].parent == i || regs[i].parent < 0) aux[n_aux++] = (uint64_t)regs[i].as << 32 | (uint32_t)i;
 	radix_sort_64(aux, aux + n_aux);
@@ -338,7 +338,7 @@ void mm_join_long(const mm_mapopt_t *opt, int qlen, int *n_regs_, mm_reg1_t *reg
 		r1->parent = r0->id;
 		++n_drop;
 	}
-	free(aux);
+	mm_afree(aux);
 	if (n_drop > 0) {
 		for (i = 0; i < n_regs; ++i) { /* re-point secondaries of a dropped chain to the surviving one */
 			mm_reg1_t *r = &regs[i];
@@ -358,9 +358,9 @@ mm_seg_t *mm_seg_gen(uint32_t hash, int n_segs, const int *qlens, int n_regs0, c
 	assert(n_segs <= MM_MAX_SEG);
 	for (s = 1, acc_qlen[0] = 0; s < n_segs; ++s) acc_qlen[s] = acc_qlen[s-1] + qlens[s-1];
 	qlen_sum = acc_qlen[n_segs - 1] + qlens[n_segs - 1];
-	seg = (mm_seg_t*)calloc(n_segs, sizeof(mm_seg_t));
+	seg = (mm_seg_t*)mm_acalloc(n_segs, sizeof(mm_seg_t));
 	for (s = 0; s < n_segs; ++s) {
-		seg[s].u = (uint64_t*)malloc((size_t)(n_regs0 > 0 ? n_regs0 : 1) * 8);
+		seg[s].u = (uint64_t*)mm_amalloc((size_t)(n_regs0 > 0 ? n_regs0 : 1) * 8);
 		for (i = 0; i < n_regs0; ++i) seg[s].u[i] = (uint64_t)regs0[i].score << 32;
 	}
 	for (i = 0; i < n_regs0; ++i)
@@ -372,7 +372,7 @@ mm_seg_t *mm_seg_gen(uint32_t hash, int n_segs, const int *qlens, int n_regs0, c
 		mm_seg_t *sr = &seg[s];
 		for (i = 0, sr->n_u = 0; i < n_regs0; ++i)
 			if ((int32_t)sr->u[i] != 0) sr->u[sr->n_u++] = sr->u[i];
-		sr->a = (mm128_t*)malloc((size_t)(sr->n_a > 0 ? sr->n_a : 1) * sizeof(mm128_t));
+		sr->a = (mm128_t*)mm_amalloc((size_t)(sr->n_a > 0 ? sr->n_a : 1) * sizeof(mm128_t));
 		sr->n_a = 0;
 	}
 	for (i = 0; i < n_regs0; ++i)
@@ -393,8 +393,8 @@ mm_seg_t *mm_seg_gen(uint32_t hash, int n_segs, const int *qlens, int n_regs0, c
 void mm_seg_free(int n_segs, mm_seg_t *segs)
 {
 	int i;
-	for (i = 0; i < n_segs; ++i) { free(segs[i].u); free(segs[i].a); }
-	free(segs);
+	for (i = 0; i < n_segs; ++i) { mm_afree(segs[i].u); mm_afree(segs[i].a); }
+	mm_afree(segs);
 }
 
 static void set_inv_mapq(int n_regs, mm_reg1_t *regs)
@@ -404,7 +404,7 @@ static void set_inv_mapq(int n_regs, mm_reg1_t *regs)
 	if (n_regs < 3) return;
 	for (i = 0; i < n_regs; ++i) if (regs[i].inv) break;
 	if (i == n_regs) return;
-	aux = (mm128_t*)malloc((size_t)n_regs * 16);
+	aux = (mm128_t*)mm_amalloc((size_t)n_regs * 16);
 	for (i = n_aux = 0; i < n_regs; ++i)
 		if (regs[i].parent == i || regs[i].parent < 0)
 			aux[n_aux].y = i, aux[n_aux++].x = (uint64_t)regs[i].rid << 32 | (uint32_t)regs[i].rs;
@@ -416,7 +416,7 @@ static void set_inv_mapq(int n_regs, mm_reg1_t *regs)
 			inv->mapq = l->mapq < r->mapq ? l->mapq : r->mapq;
 		}
 	}
-	free(aux);
+	mm_afree(aux);
 }
 
 void mm_set_mapq(int n_regs, mm_reg1_t *regs, int min_chain_sc, int match_sc, int rep_len, int is_sr)
@@ -522,7 +522,7 @@ void mm_pair(int max_gap_ref, int pe_bonus, int sub_diff, int match_sc, const in
 	int64_t max;
 	pair_elem_t *a;
 	uint64_t *sc = 0; size_t n_sc = 0, m_sc = 0;
-	a = (pair_elem_t*)malloc((size_t)(n_regs[0] + n_regs[1] + 1) * sizeof(pair_elem_t));
+	a = (pair_elem_t*)mm_amalloc((size_t)(n_regs[0] + n_regs[1] + 1) * sizeof(pair_elem_t));
 	for (s = n = 0, dp_thres = 0; s < 2; ++s) {
 		int best = 0;
 		for (i = 0; i < n_regs[s]; ++i) {
@@ -533,12 +533,12 @@ void mm_pair(int max_gap_ref, int pe_bonus, int sub_diff, int match_sc, const in
 		}
 		dp_thres += best;
 	}
-	if (segs != 3) { free(a); return; } /* only one mate mapped */
+	if (segs != 3) { mm_afree(a); return; } /* only one mate mapped */
 	dp_thres -= pe_bonus;
 	if (dp_thres < 0) dp_thres = 0;
 	sort_pairs(a, a + n);
 	max = -1, max_idx[0] = max_idx[1] = -1, last[0] = last[1] = -1;
-	m_sc = (size_t)n; sc = (uint64_t*)malloc((m_sc ? m_sc : 1) * 8); /* kv_resize(n) then kv_push growth */
+	m_sc = (size_t)n; sc = (uint64_t*)mm_amalloc((m_sc ? m_sc : 1) * 8); /* kv_resize(n) then kv_push growth */
 	for (i = 0; i < n; ++i) {
 		if (a[i].key & 1) { /* a mate that closes a pair: scan back over candidate openers on the same strand */
 			mm_reg1_t *q, *r;
@@ -553,7 +553,7 @@ void mm_pair(int max_gap_ref, int pe_bonus, int sub_diff, int match_sc, const in
 				if (r->p->dp_max + q->p->dp_max < dp_thres) continue;
 				score = (int64_t)(r->p->dp_max + q->p->dp_max) << 32 | (r->hash + q->hash);
 				if (score > max) max = score, max_idx[a[j].s] = j, max_idx[a[i].s] = i;
-				if (n_sc == m_sc) { m_sc = m_sc ? m_sc << 1 : 2; sc = (uint64_t*)realloc(sc, m_sc * 8); }
+				if (n_sc == m_sc) { const size_t old = m_sc * 8; m_sc = m_sc ? m_sc << 1 : 2; sc = (uint64_t*)mm_arealloc(sc, old, m_sc * 8); }
 				sc[n_sc++] = (uint64_t)score;
 			}
 		} else last[a[i].rev] = i;
@@ -593,7 +593,7 @@ void mm_pair(int max_gap_ref, int pe_bonus, int sub_diff, int match_sc, const in
 			if (r[1]->mapq < 1) r[1]->mapq = 1;
 		}
 	}
-	free(a); free(sc);
+	mm_afree(a); mm_afree(sc);
 	set_pe_thru(qlens, n_regs, regs);
 }
 

@@ -68,6 +68,7 @@ typedef struct {
 	mm_reg1_t *regs0;
 	mm_seg_t *seg;        /* per-mate chains when n_segs > 1 */
 	mm_alnseg_t *aln;     /* [n_segs] */
+	mm_arena_t arena;     /* everything above lives here */
 } frag_t;
 
 typedef struct {          /* one GPU's share of a mini-batch */
@@ -114,8 +115,9 @@ static void stage_hits(void *data, long i, int tid)
 	const mmg_chains_t *ch = &sh->ch;
 	int j, is_sr = !!(opt->flag & MM_F_SR);
 	memset(fr, 0, sizeof(*fr));
+	mm_tls_arena = &fr->arena;
 	fr->n_segs = ns;
-	fr->qlens = (int*)malloc((size_t)ns * sizeof(int));
+	fr->qlens = (int*)mm_amalloc((size_t)ns * sizeof(int));
 	for (j = 0; j < ns; ++j) {
 		sh->n_reg[off + j] = 0, sh->reg[off + j] = 0;
 		fr->qlens[j] = sh->seq[off + j].l_seq, fr->qlen_sum += fr->qlens[j];
@@ -131,9 +133,9 @@ static void stage_hits(void *data, long i, int tid)
 	fr->n_mini = ch->n_mini[i];
 	if (fr->n_u > 0) {
 		const int n_a = ch->n_a[i];
-		fr->u = (uint64_t*)malloc((size_t)fr->n_u * 8);
+		fr->u = (uint64_t*)mm_amalloc((size_t)fr->n_u * 8);
 		memcpy(fr->u, ch->u + ch->u_off[i], (size_t)fr->n_u * 8);
-		fr->a = (mm128_t*)malloc((size_t)n_a * 16);
+		fr->a = (mm128_t*)mm_amalloc((size_t)n_a * 16);
 		memcpy(fr->a, ch->a + ch->a_off[i], (size_t)n_a * 16);
 	}
 	fr->regs0 = mm_gen_regs(fr->hash, fr->qlen_sum, fr->n_u, fr->u, fr->a);
@@ -145,7 +147,7 @@ static void stage_hits(void *data, long i, int tid)
 		if (!(opt->flag & (MM_F_SPLICE|MM_F_SR|MM_F_NO_LJOIN))) mm_join_long(opt, fr->qlen_sum, &fr->n_regs0, fr->regs0, fr->a);
 	}
 	if (!is_sr) mm_est_err(mi, fr->qlen_sum, fr->n_regs0, fr->regs0, fr->a, fr->n_mini, ch->mini_pos + ch->mini_off[i]);
-	fr->aln = (mm_alnseg_t*)calloc(ns, sizeof(mm_alnseg_t));
+	fr->aln = (mm_alnseg_t*)mm_acalloc(ns, sizeof(mm_alnseg_t));
 	if (ns == 1) {
 		sh->n_reg[off] = fr->n_regs0, sh->reg[off] = fr->regs0;
 		mm_aln_begin(&fr->aln[0], off - sh->s0, fr->qlens[0], sh->seq[off].seq, fr->n_regs0, fr->regs0, fr->a);
@@ -158,6 +160,7 @@ static void stage_hits(void *data, long i, int tid)
 		}
 	}
 	fr->active = (opt->flag & MM_F_CIGAR) ? 1 : 0;
+	mm_tls_arena = 0;
 }
 
 /* one resumable pass over the regions of an active fragment (align_regs, map.c:260-270) */
@@ -168,6 +171,7 @@ static void stage_align(void *data, long i, int tid)
 	const mm_mapopt_t *opt = sh->opt;
 	int j, all_done = 1;
 	if (!fr->active) return;
+	mm_tls_arena = &fr->arena;
 	for (j = 0; j < fr->n_segs; ++j) {
 		mm_alnseg_t *s = &fr->aln[j];
 		const int off = sh->seg_off[sh->f0 + i] + j;
@@ -182,6 +186,7 @@ static void stage_align(void *data, long i, int tid)
 		} else all_done = 0;
 	}
 	if (all_done) fr->active = 0;
+	mm_tls_arena = 0;
 }
 
 /* copy the DP jobs a fragment queued in this round into the shard's job array */
@@ -206,13 +211,14 @@ static void stage_scatter_results(void *data, long i, int tid)
 	size_t k = sh->job_off[i];
 	int j;
 	if (!fr->active) return;
+	mm_tls_arena = &fr->arena;
 	for (j = 0; j < fr->n_segs; ++j) {
 		mm_dpcache_t *c = &fr->aln[j].cache;
 		for (; c->n_sent < c->n; ++c->n_sent, ++k) {
 			mm_dpjob_t *dj = &c->a[c->n_sent];
 			dj->ez = sh->res[k].ez;
 			if (dj->ez.n_cigar > 0) {
-				dj->cigar = (uint32_t*)malloc((size_t)dj->ez.n_cigar * 4);
+				dj->cigar = (uint32_t*)mm_amalloc((size_t)dj->ez.n_cigar * 4);
 				memcpy(dj->cigar, sh->cig + sh->res[k].cigar_off, (size_t)dj->ez.n_cigar * 4);
 			}
 			dj->done = 1;
@@ -227,7 +233,9 @@ static void stage_finish(void *data, long i, int tid)
 	frag_t *fr = &sh->fr[i];
 	const mm_mapopt_t *opt = sh->opt;
 	const int f = sh->f0 + (int)i, off = sh->seg_off[f], ns = fr->n_segs, is_sr = !!(opt->flag & MM_F_SR);
-	int j, k, mapped = !(fr->qlen_sum == 0 || ns <= 0 || ns > MM_MAX_SEG || (opt->max_qlen > 0 && fr->qlen_sum > opt->max_qlen));
+	int j, k, mapped;
+	mm_tls_arena = &fr->arena;
+	mapped = !(fr->qlen_sum == 0 || ns <= 0 || ns > MM_MAX_SEG || (opt->max_qlen > 0 && fr->qlen_sum > opt->max_qlen));
 	if (mapped) {
 		for (j = 0; j < ns; ++j) mm_set_mapq(sh->n_reg[off + j], sh->reg[off + j], opt->min_chain_score, opt->a, fr->rep_len, is_sr);
 		if (ns == 2 && opt->pe_ori >= 0 && (opt->flag & MM_F_CIGAR))
@@ -243,9 +251,8 @@ static void stage_finish(void *data, long i, int tid)
 			}
 	}
 	for (j = 0; j < ns; ++j) sh->rep_len[off + j] = fr->rep_len, sh->frag_gap[off + j] = fr->frag_gap;
-	if (fr->aln) { for (j = 0; j < ns; ++j) mm_aln_end(&fr->aln[j]); free(fr->aln); }
-	if (fr->seg) mm_seg_free(ns, fr->seg);
-	free(fr->a); free(fr->u); free(fr->qlens);
+	mm_arena_release(&fr->arena); /* anchors, chains, per-mate copies, DP cache, temporaries: gone in one sweep */
+	mm_tls_arena = 0;
 }
 
 static void shard_fail(shard_t *sh, const char *what)

@@ -104,3 +104,56 @@ void NAME(T *beg, T *end) \
 #define KEY_ID(v) (v)
 RADIX_IMPL(radix_sort_128x, mm128_t, KEY_X)
 RADIX_IMPL(radix_sort_64, uint64_t, KEY_ID)
+
+/* ---- per-fragment arena (see mm2b_priv.h) */
+
+__thread mm_arena_t *mm_tls_arena = 0;
+
+void *mm_amalloc(size_t n)
+{
+	mm_arena_t *a = mm_tls_arena;
+	mm_arena_chunk_t *c;
+	if (a == 0) return malloc(n);
+	n = (n + 15) & ~(size_t)15;
+	c = a->head;
+	if (c == 0 || c->used + n > c->cap) {
+		size_t cap = n > 8192 - sizeof(mm_arena_chunk_t) - 16 ? n : 8192 - sizeof(mm_arena_chunk_t) - 16;
+		mm_arena_chunk_t *nc = (mm_arena_chunk_t*)malloc(sizeof(mm_arena_chunk_t) + 16 + cap);
+		nc->cap = cap, nc->used = 0;
+		if (c && n > 4096) { nc->next = c->next; c->next = nc; c = nc; } /* a big block gets its own chunk; keep filling the current one */
+		else { nc->next = c; a->head = nc; c = nc; }
+	}
+	{
+		char *base = (char*)(((size_t)(c + 1) + 15) & ~(size_t)15);
+		void *r = base + c->used;
+		c->used += n;
+		return r;
+	}
+}
+
+void *mm_acalloc(size_t n, size_t sz)
+{
+	void *p;
+	if (mm_tls_arena == 0) return calloc(n, sz);
+	p = mm_amalloc(n * sz);
+	memset(p, 0, n * sz);
+	return p;
+}
+
+void *mm_arealloc(void *p, size_t old_bytes, size_t new_bytes)
+{
+	void *q;
+	if (mm_tls_arena == 0) return realloc(p, new_bytes);
+	q = mm_amalloc(new_bytes);
+	if (p && old_bytes) memcpy(q, p, old_bytes < new_bytes ? old_bytes : new_bytes);
+	return q;
+}
+
+void mm_afree(void *p) { if (mm_tls_arena == 0) free(p); }
+
+void mm_arena_release(mm_arena_t *a)
+{
+	mm_arena_chunk_t *c = a->head, *n;
+	for (; c; c = n) { n = c->next; free(c); }
+	a->head = 0;
+}

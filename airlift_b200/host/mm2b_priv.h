@@ -55,6 +55,18 @@ struct mm_idx_bucket_s {
 extern unsigned char seq_nt4_table[256];
 extern unsigned char seq_comp_table[256];
 
+/* misc.c: per-fragment bump arena.  Everything whose lifetime ends with the fragment (work arrays, per-mate anchor
+ * copies, the DP job cache, temporaries) is carved from it; the stage functions select it through a thread-local
+ * pointer.  API-visible blocks (mm_reg1_t arrays, mm_extra_t) stay on malloc because callers free() them. */
+typedef struct mm_arena_chunk_s { struct mm_arena_chunk_s *next; size_t cap, used; } mm_arena_chunk_t;
+typedef struct { mm_arena_chunk_t *head; } mm_arena_t;
+extern __thread mm_arena_t *mm_tls_arena;
+void *mm_amalloc(size_t n);
+void *mm_acalloc(size_t n, size_t sz);
+void *mm_arealloc(void *p, size_t old_bytes, size_t new_bytes);
+void mm_afree(void *p);
+void mm_arena_release(mm_arena_t *a);
+
 /* misc.c */
 double cputime(void);
 double realtime(void);
@@ -108,6 +120,8 @@ typedef struct {
 	mm_dpjob_t *a;
 } mm_dpcache_t;
 
+typedef struct { int rev, rid, rs, qs, len, score, zdrop_code; } mm_fillmemo_t; /* ungapped stretch already scored */
+
 typedef struct {       /* alignment progress of one segment (mm_align_skeleton, align.c:857-913, made resumable) */
 	int seq_id, qlen, n_regs, i, n_a, started, finished, inv_wait, planned;
 	const char *qstr;
@@ -115,6 +129,8 @@ typedef struct {       /* alignment progress of one segment (mm_align_skeleton, 
 	mm_reg1_t *regs;
 	mm128_t *a;
 	mm_dpcache_t cache;
+	int n_fill, m_fill;
+	mm_fillmemo_t *fill;
 } mm_alnseg_t;
 
 void mm_aln_begin(mm_alnseg_t *s, int seq_id, int qlen, const char *qstr, int n_regs, mm_reg1_t *regs, mm128_t *a);
