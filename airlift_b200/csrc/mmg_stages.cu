@@ -484,6 +484,22 @@ static int scan_i32_to_i64(mmg_ctx_t *c, const int32_t *d_in, int64_t *d_out, in
 	return MMG_OK;
 }
 
+extern "C" void *mmg_staging(mmg_ctx_t *c, size_t bytes)
+{ // pinned host buffer owned by the ctx; valid until the next mmg_staging / mmg_batch_upload of another size
+	cudaSetDevice(c->dev);
+	if (c->h_in.ensure(bytes + 64) != MMG_OK) return nullptr;
+	return c->h_in.p;
+}
+
+extern "C" int mmg_job_buffers(mmg_ctx_t *c, size_t n_jobs, mmg_ksw_job_t **jobs, mmg_ksw_res_t **res)
+{ // page-locked, owned by the ctx, grown on demand and kept across batches (allocating pinned memory is slow)
+	cudaSetDevice(c->dev);
+	MMG_TRY(c->h_k_jobs.ensure((n_jobs + 1) * sizeof(mmg_ksw_job_t)));
+	MMG_TRY(c->h_k_res.ensure((n_jobs + 1) * sizeof(mmg_ksw_res_t)));
+	*jobs = c->h_k_jobs.as<mmg_ksw_job_t>(), *res = c->h_k_res.as<mmg_ksw_res_t>();
+	return MMG_OK;
+}
+
 extern "C" int mmg_batch_upload(mmg_ctx_t *c, const mmg_mapopt_t *opt, const mmg_batch_t *b)
 {
 	MMG_CUDA(cudaSetDevice(c->dev));
@@ -524,8 +540,10 @@ extern "C" int mmg_batch_upload(mmg_ctx_t *c, const mmg_mapopt_t *opt, const mmg
 
 	// stage everything through one pinned buffer so that the copies are truly asynchronous
 	const size_t sz_bases = (b->n_bases + 15) & ~(size_t)15;
-	MMG_TRY(c->h_in.ensure(sz_bases + 64));
-	memcpy(c->h_in.p, b->bases, b->n_bases);
+	if ((const void*)b->bases != c->h_in.p) { // callers that filled mmg_staging() skip this copy
+		MMG_TRY(c->h_in.ensure(sz_bases + 64));
+		memcpy(c->h_in.p, b->bases, b->n_bases);
+	}
 	MMG_TRY(c->d_ascii.ensure(sz_bases + 64));
 	MMG_TRY(c->d_Q.ensure((rb.q_words + 8) * 4));
 	MMG_TRY(c->d_seq_len.ensure((size_t)(b->n_seq + 1) * 4));

@@ -88,6 +88,8 @@ typedef struct {          /* one GPU's share of a mini-batch */
 	mmg_ksw_job_t *jobs;
 	mmg_ksw_res_t *res;
 	const uint32_t *cig;
+	char *stage_dst; const uint64_t *stage_off;
+	size_t m_jobs;
 	int rc;
 } shard_t;
 
@@ -261,6 +263,13 @@ static void shard_fail(shard_t *sh, const char *what)
 	sh->rc = -1;
 }
 
+static void stage_copy_read(void *data, long i, int tid)
+{
+	shard_t *sh = (shard_t*)data;
+	const mm_bseq1_t *t = &sh->seq[sh->s0 + i];
+	memcpy(sh->stage_dst + sh->stage_off[i], t->seq, t->l_seq);
+}
+
 /* stage the reads of fragments [f0,f1) on the shard's GPU (H2D + 4-bit encode) */
 static void *shard_upload(void *data)
 {
@@ -278,19 +287,20 @@ static void *shard_upload(void *data)
 	sh->s0 = sh->seg_off[sh->f0];
 	for (i = sh->f0; i < sh->f1; ++i) n_seq += sh->n_seg[i];
 	for (i = 0; i < n_seq; ++i) n_bases += sh->seq[sh->s0 + i].l_seq;
-	bases = (char*)malloc(n_bases + 1);
+	bases = (char*)mmg_staging(sh->ctx, n_bases + 1);
+	if (bases == 0) { shard_fail(sh, "cannot allocate the staging buffer"); return 0; }
 	n_seg = (int32_t*)malloc((size_t)nf * 4), seg_off = (int32_t*)malloc((size_t)nf * 4);
 	seq_len = (int32_t*)malloc((size_t)(n_seq + 1) * 4), seq_off = (uint64_t*)malloc((size_t)(n_seq + 1) * 8);
 	for (i = 0, o = 0; i < n_seq; ++i) {
-		const mm_bseq1_t *t = &sh->seq[sh->s0 + i];
-		seq_len[i] = t->l_seq, seq_off[i] = o;
-		memcpy(bases + o, t->seq, t->l_seq);
-		o += t->l_seq;
+		seq_len[i] = sh->seq[sh->s0 + i].l_seq, seq_off[i] = o;
+		o += seq_len[i];
 	}
+	sh->stage_dst = bases, sh->stage_off = seq_off;
+	parallel_for(sh->n_threads, stage_copy_read, sh, n_seq);
 	for (i = 0; i < nf; ++i) n_seg[i] = sh->n_seg[sh->f0 + i], seg_off[i] = sh->seg_off[sh->f0 + i] - sh->s0;
 	b.n_frag = nf, b.n_seq = n_seq, b.n_seg = n_seg, b.seg_off = seg_off, b.seq_len = seq_len, b.seq_off = seq_off, b.bases = bases, b.n_bases = n_bases;
 	if (mmg_batch_upload(sh->ctx, &sh->dopt, &b) != MMG_OK) shard_fail(sh, "read upload failed");
-	free(bases); free(n_seg); free(seg_off); free(seq_len); free(seq_off);
+	free(n_seg); free(seg_off); free(seq_len); free(seq_off);
 	sh->st.n_frag += nf, sh->st.n_reads += n_seq, sh->st.n_bases += n_bases;
 	sh->st.t_upload += realtime() - t0;
 	return 0;
@@ -333,10 +343,9 @@ static void *map_shard(void *data)
 			tb = realtime(); sh->st.t_align_host += tb - ta;
 			if (n_active == 0) break;
 			if (n_jobs == 0) { fprintf(stderr, "[ERROR] alignment made no progress\n"); sh->rc = -1; break; }
-			if (n_jobs > m_jobs) {
+			if (n_jobs > m_jobs) { /* page-locked arrays kept by the ctx: they cross PCIe every round */
 				m_jobs = n_jobs + n_jobs / 4;
-				sh->jobs = (mmg_ksw_job_t*)realloc(sh->jobs, m_jobs * sizeof(mmg_ksw_job_t));
-				sh->res = (mmg_ksw_res_t*)realloc(sh->res, m_jobs * sizeof(mmg_ksw_res_t));
+				if (mmg_job_buffers(sh->ctx, m_jobs, &sh->jobs, &sh->res) != MMG_OK) { shard_fail(sh, "cannot allocate page-locked job arrays"); break; }
 			}
 			parallel_for(sh->n_threads, stage_gather_jobs, sh, nf);
 			ta = realtime(); sh->st.t_align_host += ta - tb;
@@ -347,7 +356,7 @@ static void *map_shard(void *data)
 			parallel_for(sh->n_threads, stage_scatter_results, sh, nf);
 			sh->st.t_align_host += realtime() - tb;
 		}
-		free(sh->jobs); free(sh->res); free(sh->job_off);
+		free(sh->job_off);
 		sh->jobs = 0, sh->res = 0, sh->job_off = 0;
 	}
 	t0 = realtime();
@@ -398,11 +407,13 @@ static step_t *step_read(pipeline_t *p)
 	return s;
 }
 
+static void *shard_both(void *data) { shard_upload(data); return map_shard(data); }
+
 /* mode 0: upload + map; 1: upload only; 2: map the batch uploaded by an earlier mode-1 call */
 static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, step_t *s, int mode)
 {
 	struct mm_idx_bucket_s *B = mi->B;
-	const int n_dev = B->n_dev;
+	const int n_dev = B->n_dev * B->lanes; /* shards: `lanes` per GPU, each with its own stream */
 	shard_t *sh = (shard_t*)calloc(n_dev, sizeof(shard_t));
 	pthread_t *tid = (pthread_t*)calloc(n_dev, sizeof(pthread_t));
 	int d, f = 0, rc = 0, pass;
@@ -413,9 +424,9 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 	for (d = 0; d < n_dev; ++d) { /* contiguous fragment ranges balanced by bases; a fragment is never cut */
 		shard_t *h = &sh[d];
 		const int64_t goal = tot * (d + 1) / n_dev;
-		h->mi = mi, h->opt = opt, h->ctx = B->ctx[d], h->didx = B->didx[d];
+		h->mi = mi, h->opt = opt, h->ctx = B->ctx[d], h->didx = B->didx[d / B->lanes];
 		mm_mapopt_to_dev(opt, &h->dopt);
-		h->n_threads = n_threads / n_dev > 0 ? n_threads / n_dev : 1;
+		h->n_threads = (n_threads + n_dev - 1) / n_dev > 0 ? (n_threads + n_dev - 1) / n_dev : 1;
 		h->seq = s->seq, h->n_seg = s->n_seg, h->seg_off = s->seg_off, h->n_reg = s->n_reg, h->rep_len = s->rep_len, h->frag_gap = s->frag_gap, h->reg = s->reg;
 		h->f0 = f;
 		while (f < s->n_frag && (acc < goal || d == n_dev - 1)) {
@@ -427,8 +438,8 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		if (h->f1 > h->f0) h->s0 = s->seg_off[h->f0];
 	}
 	for (pass = 0; pass < 2; ++pass) {
-		void *(*fn)(void*) = pass == 0 ? shard_upload : map_shard;
-		if ((pass == 0 && mode == 2) || (pass == 1 && mode == 1)) continue;
+		void *(*fn)(void*) = mode == 0 ? shard_both : pass == 0 ? shard_upload : map_shard;
+		if ((pass == 0 && mode == 2) || (pass == 1 && mode == 1) || (pass == 1 && mode == 0)) continue;
 		if (n_dev == 1) fn(&sh[0]);
 		else {
 			for (d = 0; d < n_dev; ++d) pthread_create(&tid[d], 0, fn, &sh[d]);
@@ -751,14 +762,14 @@ int mm_b200_n_devices(const mm_idx_t *mi) { return mi->B->n_dev; }
 void mm_b200_profile(const mm_idx_t *mi, int enable)
 {
 	int d;
-	for (d = 0; d < mi->B->n_dev; ++d) mmg_profile_enable(mi->B->ctx[d], enable);
+	for (d = 0; d < mi->B->n_dev * mi->B->lanes; ++d) mmg_profile_enable(mi->B->ctx[d], enable);
 }
 
 /* per-kernel device time and launch counts since profiling was enabled (device slot 0..n-1 summed) */
 int mm_b200_profile_fetch(const mm_idx_t *mi, int max, const char **names, double *ms, long *launches)
 {
 	int d, n = 0, i, j;
-	for (d = 0; d < mi->B->n_dev; ++d) {
+	for (d = 0; d < mi->B->n_dev * mi->B->lanes; ++d) {
 		const char *nm[64]; double t[64]; long l[64];
 		const int k = mmg_profile_fetch(mi->B->ctx[d], 64, nm, t, l);
 		for (i = 0; i < k; ++i) {
@@ -783,4 +794,12 @@ void mm_b200_report(const mm_idx_t *mi, FILE *fp)
 			(unsigned long)s.n_dp_jobs, (unsigned long)s.n_dp_rounds, (unsigned long)s.n_dp_cells, (unsigned long)s.h2d_bytes, (unsigned long)s.d2h_bytes);
 	n = mm_b200_profile_fetch(mi, 64, nm, t, l);
 	for (i = 0; i < n; ++i) fprintf(fp, "[M::b200] kernel %-18s %8ld launches %10.3f ms\n", nm[i], l[i], t[i]);
+}
+
+long mm_b200_launch_count(const mm_idx_t *mi, int reset)
+{
+	long n = 0;
+	int d;
+	for (d = 0; d < mi->B->n_dev * mi->B->lanes; ++d) n += mmg_launch_count(mi->B->ctx[d], reset);
+	return n;
 }

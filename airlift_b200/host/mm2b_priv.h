@@ -44,10 +44,11 @@ typedef struct mm_bseq_file_s mm_bseq_file_t;
 typedef struct { int n_u, n_a; uint64_t *u; mm128_t *a; } mm_seg_t;
 
 /* hidden part of mm_idx_t */
+#define MM_B200_MAX_LANES 4  /* a batch is cut in `lanes` shards per GPU (own stream each) so that one shard's host work overlaps another's kernels */
 struct mm_idx_bucket_s {
-	int n_dev;
+	int n_dev, lanes;
 	int dev_id[16];
-	mmg_ctx_t *ctx[16];
+	mmg_ctx_t *ctx[16 * MM_B200_MAX_LANES]; /* ctx[d * lanes + lane]: own stream and arenas, same device */
 	mmg_idx_t *didx[16];
 	int32_t max_occ_cache_set; float max_occ_cache_f; int32_t max_occ_cache;
 };

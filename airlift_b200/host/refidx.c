@@ -6,7 +6,14 @@
 #include <unistd.h>
 #include "mm2b_priv.h"
 
-static int g_n_dev = 1, g_dev[16] = {0};
+static int g_n_dev = 1, g_dev[16] = {0}, g_lanes = 1;
+
+int mm_b200_set_lanes(int lanes)
+{
+	if (lanes < 1 || lanes > MM_B200_MAX_LANES) return -1;
+	g_lanes = lanes;
+	return 0;
+}
 
 int mm_b200_set_devices(int n_gpus, const int *dev_ids)
 {
@@ -40,13 +47,16 @@ static mm_idx_t *idx_from_seqs(int w, int k, int b, int flag, int n, char **seq,
 		sum += len[i];
 	}
 	B->n_dev = g_n_dev;
+	B->lanes = g_lanes;
 	for (d = 0; d < g_n_dev; ++d) {
+		int l;
 		B->dev_id[d] = g_dev[d];
-		if (mmg_init(g_dev[d], &B->ctx[d]) != MMG_OK) die_gpu("cannot initialise the GPU");
+		for (l = 0; l < B->lanes; ++l)
+			if (mmg_init(g_dev[d], &B->ctx[d * B->lanes + l]) != MMG_OK) die_gpu("cannot initialise the GPU");
 	}
 	if (mmg_idx_build(B->ctx[0], w, k, !!(flag & MM_I_HPC), n, (const char *const*)seq, len, &B->didx[0]) != MMG_OK) die_gpu("index construction failed");
 	for (d = 1; d < g_n_dev; ++d) /* replicate over NVLink; nothing else ever crosses GPUs */
-		if (mmg_idx_clone_to(B->ctx[d], B->didx[0], &B->didx[d]) != MMG_OK) die_gpu("index replication failed");
+		if (mmg_idx_clone_to(B->ctx[d * B->lanes], B->didx[0], &B->didx[d]) != MMG_OK) die_gpu("index replication failed");
 	/* the host keeps the packed sequence: CIGAR post-processing and cs/MD read it (index.c:152-162) */
 	mi->S = (uint32_t*)calloc((sum + 7) / 8 + 1, 4);
 	if (mmg_idx_copy_S(B->didx[0], mi->S) != MMG_OK) die_gpu("cannot fetch the packed reference");
@@ -59,7 +69,8 @@ void mm_idx_destroy(mm_idx_t *mi)
 	int d;
 	if (mi == 0) return;
 	if (mi->B) {
-		for (d = 0; d < mi->B->n_dev; ++d) { mmg_idx_free(mi->B->didx[d]); mmg_destroy(mi->B->ctx[d]); }
+		for (d = 0; d < mi->B->n_dev; ++d) mmg_idx_free(mi->B->didx[d]);
+		for (d = 0; d < mi->B->n_dev * mi->B->lanes; ++d) mmg_destroy(mi->B->ctx[d]);
 		free(mi->B);
 	}
 	for (i = 0; i < mi->n_seq; ++i) free(mi->seq[i].name);

@@ -93,8 +93,8 @@ def load_lib():
     L.mm_b200_ctx.argtypes = [C.c_void_p, C.c_int]
     L.mmg_stream.restype = C.c_void_p
     L.mmg_stream.argtypes = [C.c_void_p]
-    L.mmg_launch_count.restype = C.c_long
-    L.mmg_launch_count.argtypes = [C.c_void_p, C.c_int]
+    L.mm_b200_launch_count.restype = C.c_long
+    L.mm_b200_launch_count.argtypes = [C.c_void_p, C.c_int]
     return L
 
 
@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=1, help="shards (streams) per GPU a batch is cut into")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -249,6 +250,7 @@ def main():
     L = load_lib()
     dev = (C.c_int * 1)(local_rank)
     L.mm_b200_set_devices(1, dev)
+    L.mm_b200_set_lanes(args.lanes)
     ipt, opt = IdxOpt(), MapOptFull()
     L.mm_set_opt(None, C.byref(ipt), C.byref(opt))
     L.mm_set_opt(b"sr", C.byref(ipt), C.byref(opt))
@@ -295,7 +297,7 @@ def main():
             L.mm_b200_batch_info(b, C.byref(ns), None, None)
             n_reads += ns.value
         L.mm_b200_stats(None, 1)
-        L.mmg_launch_count(ctx, 1)
+        L.mm_b200_launch_count(mi, 1)
         L.mm_b200_profile(mi, 1)
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -332,7 +334,7 @@ def main():
         nk = L.mm_b200_profile_fetch(mi, 64, names, ms, ln)
         prof = {names[i].decode(): (ms[i], ln[i]) for i in range(nk)}
         L.mm_b200_profile(mi, 0)
-        launches = L.mmg_launch_count(ctx, 0)
+        launches = L.mm_b200_launch_count(mi, 0)
         digest = 0
         for b in batches:
             digest ^= L.mm_b200_batch_digest(b, None)

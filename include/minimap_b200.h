@@ -179,6 +179,7 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 
 /* B200 additions */
 int mm_b200_set_devices(int n_gpus, const int *dev_ids); /* before building the index; default: device 0 */
+int mm_b200_set_lanes(int lanes); /* shards (streams) per GPU a batch is cut into, 1..4; before building the index */
 
 /* Batch interface = the drop-in cut point of SURVEY.md §8b (worker_pipeline step 1, map.c:590-593): a mini-batch of
  * fragments with HOST buffers in, malloc'd mm_reg1_t arrays out.  mode 0 maps (upload + all stages); modes 1 / 2 split
@@ -204,6 +205,7 @@ void mm_b200_stats(mm_b200_stats_t *out, int reset);
 void mm_b200_profile(const mm_idx_t *mi, int enable);   /* CUDA-event timing of every kernel launch */
 int  mm_b200_profile_fetch(const mm_idx_t *mi, int max, const char **names, double *ms, long *launches);
 void mm_b200_report(const mm_idx_t *mi, FILE *fp);
+long mm_b200_launch_count(const mm_idx_t *mi, int reset); /* kernels launched on all streams of all GPUs */
 void mm_write_sam_hdr(const mm_idx_t *mi, const char *rg, const char *ver, int argc, char *argv[]);
 
 #ifdef __cplusplus

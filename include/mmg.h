@@ -146,6 +146,10 @@ int  mmg_seed_chain_batch(mmg_ctx_t *ctx, const mmg_idx_t *idx, const mmg_mapopt
                           mmg_chains_t *out);
 /* same, split so that a caller can time device-resident work separately */
 int  mmg_batch_upload(mmg_ctx_t *ctx, const mmg_mapopt_t *opt, const mmg_batch_t *batch);
+/* pinned staging buffer of the ctx: fill it with the concatenated reads and pass it as batch->bases to skip one host copy */
+void *mmg_staging(mmg_ctx_t *ctx, size_t bytes);
+/* page-locked job / result arrays owned by the ctx (kept across batches) for mmg_ksw_batch; plain malloc'd arrays work too, slower */
+
 int  mmg_seed_chain_resident(mmg_ctx_t *ctx, const mmg_idx_t *idx, const mmg_mapopt_t *opt, mmg_chains_t *out, int download);
 
 typedef struct {            /* one DP job against the resident batch and index (align.c:313 call sites) */
@@ -165,6 +169,7 @@ typedef struct {
 /* run n_jobs DP jobs; res[] (n_jobs) is caller-allocated; *cigars points to a ctx-owned HOST array */
 int  mmg_ksw_batch(mmg_ctx_t *ctx, const mmg_idx_t *idx, const mmg_mapopt_t *opt, int n_jobs, const mmg_ksw_job_t *jobs,
                    mmg_ksw_res_t *res, const uint32_t **cigars, double *kernel_ms, uint64_t *cells);
+int  mmg_job_buffers(mmg_ctx_t *ctx, size_t n_jobs, mmg_ksw_job_t **jobs, mmg_ksw_res_t **res);
 
 #ifdef __cplusplus
 }
