@@ -506,3 +506,9 @@ extern "C" int64_t mmg_idx_n_singletons(const mmg_idx_t *mi)
 	cudaFree(d);
 	return (int64_t)h;
 }
+
+extern "C" int mmg_memcpy_d2d(void *dst, const void *src, size_t bytes)
+{ // same-device copy helper for callers that stage index buffers through their own tensors
+	MMG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+	return MMG_OK;
+}

@@ -202,3 +202,59 @@ mm_idx_t *mm_idx_reader_read(mm_idx_reader_t *r, int n_threads)
 	mi->index = r->n_parts++;
 	return mi;
 }
+
+/* ---- index replication across processes (one process per GPU): rank 0 builds, the others receive the flat
+ * device image through a collective the caller runs (bench.py: NCCL broadcast over NVLink) */
+
+int mm_b200_idx_image(const mm_idx_t *mi, mmg_idx_image_t *img) { return mmg_idx_export(mi->B->didx[0], img); }
+
+/* names/lengths come from the FASTA (cheap); the minimizer table, positions and packed sequence are allocated
+ * uninitialised on the GPU with the shape given by `shape`; their device pointers are returned in `ptrs` */
+mm_idx_t *mm_b200_idx_alloc(const char *fn, const mm_idxopt_t *opt, const mmg_idx_image_t *shape, mmg_idx_image_t *ptrs)
+{
+	mm_bseq_file_t *fp = mm_bseq_open(fn);
+	mm_idx_t *mi;
+	struct mm_idx_bucket_s *B;
+	int n_seq, i, d = 0, b = opt->bucket_bits;
+	uint64_t sum = 0;
+	if (fp == 0) return 0;
+	mi = (mm_idx_t*)calloc(1, sizeof(mm_idx_t));
+	B = (struct mm_idx_bucket_s*)calloc(1, sizeof(*B));
+	if (opt->k * 2 < b) b = opt->k * 2;
+	mi->w = opt->w < 1 ? 1 : opt->w, mi->k = opt->k, mi->b = b, mi->flag = opt->flag, mi->B = B;
+	mi->seq = (mm_idx_seq_t*)calloc(shape->n_seq > 0 ? shape->n_seq : 1, sizeof(mm_idx_seq_t));
+	while (d < shape->n_seq) {
+		mm_bseq1_t *s = mm_bseq_read3(fp, 1 << 28, 0, 0, 0, &n_seq);
+		if (s == 0) break;
+		for (i = 0; i < n_seq && d < shape->n_seq; ++i, ++d) {
+			mi->seq[d].name = s[i].name, mi->seq[d].len = (uint32_t)s[i].l_seq, mi->seq[d].offset = sum;
+			sum += (uint64_t)s[i].l_seq;
+			free(s[i].seq);
+		}
+		for (; i < n_seq; ++i) { free(s[i].seq); free(s[i].name); }
+		free(s);
+	}
+	mm_bseq_close(fp);
+	mi->n_seq = d;
+	if (d != shape->n_seq || sum != shape->total_len) {
+		fprintf(stderr, "[ERROR] '%s' does not match the index being received (%d sequences, %lu bases expected)\n", fn, shape->n_seq, (unsigned long)shape->total_len);
+		exit(1);
+	}
+	B->n_dev = 1, B->lanes = g_lanes, B->dev_id[0] = g_dev[0];
+	for (i = 0; i < B->lanes; ++i)
+		if (mmg_init(g_dev[0], &B->ctx[i]) != MMG_OK) die_gpu("cannot initialise the GPU");
+	*ptrs = *shape;
+	if (mmg_idx_alloc_like(B->ctx[0], ptrs, &B->didx[0]) != MMG_OK) die_gpu("cannot allocate the index replica");
+	return mi;
+}
+
+int mm_b200_idx_finalize(mm_idx_t *mi)
+{
+	uint64_t sum = 0;
+	uint32_t i;
+	for (i = 0; i < mi->n_seq; ++i) sum += mi->seq[i].len;
+	if (mmg_idx_finalize(mi->B->didx[0]) != MMG_OK) die_gpu("index replica");
+	mi->S = (uint32_t*)calloc((sum + 7) / 8 + 1, 4);
+	if (mmg_idx_copy_S(mi->B->didx[0], mi->S) != MMG_OK) die_gpu("cannot fetch the packed reference");
+	return 0;
+}

@@ -89,6 +89,11 @@ def load_lib():
     L.mm_b200_stats.argtypes = [C.POINTER(Stats), C.c_int]
     L.mm_b200_profile.argtypes = [C.c_void_p, C.c_int]
     L.mm_b200_profile_fetch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_long)]
+    L.mm_b200_idx_image.argtypes = [C.c_void_p, C.c_void_p]
+    L.mm_b200_idx_alloc.restype = C.c_void_p
+    L.mm_b200_idx_alloc.argtypes = [C.c_char_p, C.POINTER(IdxOpt), C.c_void_p, C.c_void_p]
+    L.mm_b200_idx_finalize.argtypes = [C.c_void_p]
+    L.mmg_memcpy_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.mm_b200_ctx.restype = C.c_void_p
     L.mm_b200_ctx.argtypes = [C.c_void_p, C.c_int]
     L.mmg_stream.restype = C.c_void_p
@@ -255,12 +260,31 @@ def main():
     L.mm_set_opt(None, C.byref(ipt), C.byref(opt))
     L.mm_set_opt(b"sr", C.byref(ipt), C.byref(opt))
     opt.flag |= 0x004 | 0x008  # -a: MM_F_CIGAR | MM_F_OUT_SAM
-    rd = L.mm_idx_reader_open(fa.encode(), C.byref(ipt), None)
     t0 = time.time()
-    mi = L.mm_idx_reader_read(rd, 3)
+    bcast_bytes = 0
+    if world == 1 or rank == 0:
+        rd = L.mm_idx_reader_open(fa.encode(), C.byref(ipt), None)
+        mi = L.mm_idx_reader_read(rd, 3)
+        L.mm_idx_reader_close(rd)
+        L.mm_mapopt_update(C.byref(opt), mi)
+    if world > 1:
+        # the index is built once (rank 0) and replicated: one NCCL broadcast per buffer over NVLink/NVSwitch;
+        # nothing else is ever exchanged between ranks
+        from airlift_b200 import dist as D
+        img = D.IdxImage()
+        if rank == 0:
+            assert L.mm_b200_idx_image(mi, C.byref(img)) == 0
+        shape = D.broadcast_object((img.shape_tuple(), opt.mid_occ) if rank == 0 else None)
+        if rank != 0:
+            shp = D.IdxImage.from_shape(shape[0])
+            img = D.IdxImage()
+            mi = L.mm_b200_idx_alloc(fa.encode(), C.byref(ipt), C.byref(shp), C.byref(img))
+            opt.mid_occ = shape[1]
+        bcast_bytes = D.broadcast_buffers(L, img, torch.device("cuda", local_rank), src=0)
+        if rank != 0:
+            L.mm_b200_idx_finalize(mi)
+        torch.cuda.synchronize()
     t_index = time.time() - t0
-    L.mm_idx_reader_close(rd)
-    L.mm_mapopt_update(C.byref(opt), mi)
     n_threads = args.threads or max(1, (os.cpu_count() or 1) // world)
     ctx = L.mm_b200_ctx(mi, 0)
     stream = torch.cuda.ExternalStream(L.mmg_stream(ctx), device=torch.device("cuda", local_rank))
@@ -395,7 +419,7 @@ def main():
             "host_s_per_step": {"seed_chain_call": st_res.t_seedchain / args.steps, "hits": st_res.t_hits / args.steps,
                                 "align_host": st_res.t_align_host / args.steps, "dp_call": st_res.t_ksw_total / args.steps,
                                 "finish": st_res.t_finish / args.steps, "dp_rounds": st_res.n_dp_rounds / args.steps},
-            "host_threads": n_threads, "index_build_s": t_index, "clocks": clocks_res,
+            "host_threads": n_threads, "index_build_s": t_index, "index_broadcast_bytes": bcast_bytes, "clocks": clocks_res,
         }
     # ---- CPU baseline next to it (rank 0, N=1 only): the reference fork on a bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):

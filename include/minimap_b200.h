@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <sys/types.h>
+#include "mmg.h"
 
 /* mapping flags (minimap.h:8-38) */
 #define MM_F_NO_DIAG       0x001
@@ -179,6 +180,11 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 
 /* B200 additions */
 int mm_b200_set_devices(int n_gpus, const int *dev_ids); /* before building the index; default: device 0 */
+/* one process per GPU: rank 0 builds the index, exports its flat device image (mm_b200_idx_image), the other ranks allocate
+ * the same shape (mm_b200_idx_alloc), a collective fills the five buffers, mm_b200_idx_finalize completes the replica */
+int mm_b200_idx_image(const mm_idx_t *mi, mmg_idx_image_t *img);
+mm_idx_t *mm_b200_idx_alloc(const char *fasta, const mm_idxopt_t *opt, const mmg_idx_image_t *shape, mmg_idx_image_t *ptrs);
+int mm_b200_idx_finalize(mm_idx_t *mi);
 int mm_b200_set_lanes(int lanes); /* shards (streams) per GPU a batch is cut into, 1..4; before building the index */
 
 /* Batch interface = the drop-in cut point of SURVEY.md §8b (worker_pipeline step 1, map.c:590-593): a mini-batch of

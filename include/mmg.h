@@ -80,6 +80,7 @@ int  mmg_idx_clone_to(mmg_ctx_t *ctx, const mmg_idx_t *src, mmg_idx_t **dst);
 /* after the buffers of an mmg_idx_alloc_like() index were filled (e.g. by an NCCL broadcast) */
 int  mmg_idx_finalize(mmg_idx_t *idx);
 int64_t mmg_idx_n_singletons(const mmg_idx_t *idx);
+int  mmg_memcpy_d2d(void *dst, const void *src, size_t bytes);
 
 /* ----------------------------------------------------- per-kernel entry points */
 /* mm_sketch on the device.  Returns the count in *n_out; writes min(count, cap) entries. */
