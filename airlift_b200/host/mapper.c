@@ -35,12 +35,15 @@ typedef struct { pfor_t *pf; int tid; } pfor_arg_t;
 static void *pfor_worker(void *p)
 {
 	pfor_arg_t *a = (pfor_arg_t*)p;
+	mm_tls_pool = mm_pool_acquire(); /* arena chunks recycled without locks while this worker lives */
 	for (;;) {
 		const long i = __sync_fetch_and_add(&a->pf->next, 16);
 		long j;
 		if (i >= a->pf->n) break;
 		for (j = i; j < i + 16 && j < a->pf->n; ++j) a->pf->fn(a->pf->data, j, a->tid);
 	}
+	mm_pool_release(mm_tls_pool);
+	mm_tls_pool = 0;
 	return 0;
 }
 

@@ -2,6 +2,7 @@
 #include <stdio.h>
 #include <sys/resource.h>
 #include <sys/time.h>
+#include <pthread.h>
 #include "mm2b_priv.h"
 
 int mm_verbose = 1;
@@ -109,6 +110,47 @@ RADIX_IMPL(radix_sort_64, uint64_t, KEY_ID)
 
 __thread mm_arena_t *mm_tls_arena = 0;
 
+/* Standard-size chunks are recycled instead of going back to malloc (with short-lived worker threads glibc grows and
+ * trims its per-thread heaps with mprotect() on every batch).  Each worker thread borrows a private pool for its
+ * lifetime, so the hot path takes no lock; pools themselves live in a mutex-protected free list. */
+#define ARENA_STD_CAP (16384 - sizeof(mm_arena_chunk_t) - 16)
+#define ARENA_FIRST_CAP (3072 - sizeof(mm_arena_chunk_t) - 16) /* most short-read fragments fit their whole state in this */
+#define POOL_MAX_CHUNKS 8192
+struct mm_chunk_pool_s { struct mm_chunk_pool_s *next; mm_arena_chunk_t *chunks, *small; int n, n_small; };
+__thread mm_chunk_pool_t *mm_tls_pool = 0;
+static mm_chunk_pool_t *g_pools = 0;
+static pthread_mutex_t g_pools_mu = PTHREAD_MUTEX_INITIALIZER;
+
+mm_chunk_pool_t *mm_pool_acquire(void)
+{
+	mm_chunk_pool_t *p;
+	pthread_mutex_lock(&g_pools_mu);
+	if ((p = g_pools) != 0) g_pools = p->next;
+	pthread_mutex_unlock(&g_pools_mu);
+	if (p == 0) p = (mm_chunk_pool_t*)calloc(1, sizeof(*p));
+	p->next = 0;
+	return p;
+}
+
+void mm_pool_release(mm_chunk_pool_t *p)
+{
+	if (p == 0) return;
+	pthread_mutex_lock(&g_pools_mu);
+	p->next = g_pools, g_pools = p;
+	pthread_mutex_unlock(&g_pools_mu);
+}
+
+static mm_arena_chunk_t *chunk_get(size_t cap)
+{
+	mm_arena_chunk_t *c = 0;
+	mm_chunk_pool_t *p = mm_tls_pool;
+	if (cap == ARENA_STD_CAP && p && p->chunks) c = p->chunks, p->chunks = c->next, --p->n;
+	else if (cap == ARENA_FIRST_CAP && p && p->small) c = p->small, p->small = c->next, --p->n_small;
+	if (c == 0) c = (mm_arena_chunk_t*)malloc(sizeof(mm_arena_chunk_t) + 16 + cap);
+	c->cap = cap, c->used = 0, c->next = 0;
+	return c;
+}
+
 void *mm_amalloc(size_t n)
 {
 	mm_arena_t *a = mm_tls_arena;
@@ -117,10 +159,8 @@ void *mm_amalloc(size_t n)
 	n = (n + 15) & ~(size_t)15;
 	c = a->head;
 	if (c == 0 || c->used + n > c->cap) {
-		size_t cap = n > 8192 - sizeof(mm_arena_chunk_t) - 16 ? n : 8192 - sizeof(mm_arena_chunk_t) - 16;
-		mm_arena_chunk_t *nc = (mm_arena_chunk_t*)malloc(sizeof(mm_arena_chunk_t) + 16 + cap);
-		nc->cap = cap, nc->used = 0;
-		if (c && n > 4096) { nc->next = c->next; c->next = nc; c = nc; } /* a big block gets its own chunk; keep filling the current one */
+		mm_arena_chunk_t *nc = chunk_get(c == 0 && n <= ARENA_FIRST_CAP ? ARENA_FIRST_CAP : n > ARENA_STD_CAP ? n : ARENA_STD_CAP);
+		if (c && n > ARENA_STD_CAP / 2) { nc->next = c->next; c->next = nc; c = nc; } /* a big block gets its own chunk; keep filling the current one */
 		else { nc->next = c; a->head = nc; c = nc; }
 	}
 	{
@@ -154,6 +194,12 @@ void mm_afree(void *p) { if (mm_tls_arena == 0) free(p); }
 void mm_arena_release(mm_arena_t *a)
 {
 	mm_arena_chunk_t *c = a->head, *n;
-	for (; c; c = n) { n = c->next; free(c); }
+	mm_chunk_pool_t *p = mm_tls_pool;
+	for (; c; c = n) {
+		n = c->next;
+		if (p && c->cap == ARENA_STD_CAP && p->n < POOL_MAX_CHUNKS) c->next = p->chunks, p->chunks = c, ++p->n;
+		else if (p && c->cap == ARENA_FIRST_CAP && p->n_small < 4 * POOL_MAX_CHUNKS) c->next = p->small, p->small = c, ++p->n_small;
+		else free(c);
+	}
 	a->head = 0;
 }

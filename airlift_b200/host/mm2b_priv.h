@@ -67,6 +67,10 @@ void *mm_acalloc(size_t n, size_t sz);
 void *mm_arealloc(void *p, size_t old_bytes, size_t new_bytes);
 void mm_afree(void *p);
 void mm_arena_release(mm_arena_t *a);
+typedef struct mm_chunk_pool_s mm_chunk_pool_t;
+extern __thread mm_chunk_pool_t *mm_tls_pool;
+mm_chunk_pool_t *mm_pool_acquire(void);
+void mm_pool_release(mm_chunk_pool_t *p);
 
 /* misc.c */
 double cputime(void);
