@@ -733,6 +733,97 @@ MMG_HD bool mmg_ksw_trace_start(const KswGeom &g, int flag, int end_bonus, KswEz
 	return false;
 }
 
+// ksw_extd2 for one job walked by ONE thread: the 16 int8 lanes of each SSE block are visited in order with the
+// previous lane's old x/v/x2 carried in registers, so the result is the reference's lane for lane (same widened band,
+// stale lanes, spill of the score chunk into sf[], exact-max tie order).  `mem` holds u|v|x|y|x2|y2|s|sf|qr as laid out
+// by mmg_ksw_mem_bytes(); the caller has filled sf[] (target, zero padded) and qr[] (reversed query, zero padded).
+// This is the form used for the short-read job mix (hundreds of thousands of tiny DPs): one job per thread.
+template <int kMode>
+MMG_HDN inline void mmg_ksw_scalar_run(const KswGeom &g, int flag, int zdrop, int8_t *mem, int32_t *H, uint8_t *p, KswEz &ez)
+{
+	const int tl16 = g.tlen_ * 16, qlen = g.qlen, tlen = g.tlen;
+	int8_t *u = mem, *v = u + tl16, *x = v + tl16, *y = x + tl16, *x2 = y + tl16, *y2 = x2 + tl16, *s = y2 + tl16;
+	const uint8_t *sf = reinterpret_cast<const uint8_t*>(s + tl16), *qr = sf + tl16;
+	const bool approx = (flag & MMG_EZ_APPROX_MAX) != 0;
+	const int8_t n1 = (int8_t)(-g.q - g.e), n2 = (int8_t)(-g.q2 - g.e2);
+	for (int i = 0; i < tl16; ++i) { u[i] = v[i] = x[i] = y[i] = n1; x2[i] = y2[i] = n2; s[i] = 0; H[i] = MMG_KSW_NEG_INF; }
+	int last_st = -1, last_en = -1;
+	int32_t H0 = 0, last_H0_t = 0;
+	for (int r = 0; r < qlen + tlen - 1; ++r) {
+		int st0, en0;
+		if (!mmg_ksw_band(g, r, &st0, &en0)) { ez.zdropped = 1; break; }
+		const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
+		int8_t x1, x21, v1;
+		if (st > 0) {
+			if (st - 1 >= last_st && st - 1 <= last_en) x1 = x[st - 1], x21 = x2[st - 1], v1 = v[st - 1];
+			else x1 = n1, x21 = n2, v1 = n1;
+		} else x1 = n1, x21 = n2, v1 = (int8_t)mmg_ksw_first_col(g, r);
+		if (en >= r) y[r] = n1, y2[r] = n2, u[r] = (int8_t)mmg_ksw_first_col(g, r);
+		{
+			const uint8_t *qrr = qr + (qlen - 1 - r);
+			for (int t = st0; t <= en0; t += 16)
+				for (int l = 0; l < 16; ++l) s[t + l] = mmg_ksw_score(g, sf[t + l], qrr[t + l]);
+		}
+		for (int blk = st / 16; blk <= en / 16; ++blk) {
+			const int base = blk * 16;
+			uint8_t *pr = kMode ? p + ((size_t)r * g.n_col_ + (blk - st / 16)) * 16 : nullptr;
+#pragma unroll 4
+			for (int l = 0; l < 16; ++l) {
+				const int i = base + l;
+				const int8_t xo = x[i], vo = v[i], x2o = x2[i];
+				const KswCell c = mmg_ksw_cell<kMode>(g, s[i], x1, v1, u[i], y[i], x21, y2[i]);
+				u[i] = c.u, v[i] = c.v, x[i] = c.x, y[i] = c.y, x2[i] = c.x2, y2[i] = c.y2;
+				if (kMode) pr[l] = c.d;
+				x1 = xo, v1 = vo, x21 = x2o;
+			}
+		}
+		if (!approx) {
+			int32_t max_H, max_t, H_en0;
+			if (r > 0) {
+				H_en0 = en0 > 0 ? H[en0 - 1] + u[en0] : H[en0] + v[en0];
+				int32_t bh = H_en0, bt = en0; uint32_t br = 0;
+				for (int t = st0; t < en0; ++t) {
+					const int32_t h = H[t] + v[t];
+					H[t] = h;
+					const uint32_t rk = mmg_ksw_max_rank(t, st0, en0);
+					if (h > bh || (h == bh && rk < br)) bh = h, bt = t, br = rk;
+				}
+				H[en0] = H_en0;
+				max_H = bh, max_t = bt;
+			} else { H_en0 = v[0] - g.qe_pre; H[0] = H_en0; max_H = H_en0, max_t = 0; }
+			if (en0 == tlen - 1 && H_en0 > ez.mte) ez.mte = H_en0, ez.mte_q = r - en;
+			if (r - st0 == qlen - 1) { const int32_t hs = H[st0]; if (hs > ez.mqe) ez.mqe = hs, ez.mqe_t = st0; }
+			if (mmg_ksw_zdrop(&ez, max_H, r, max_t, zdrop, g.e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H[tlen - 1];
+		} else {
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					const int32_t d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+					if (d0 > d1) H0 += d0; else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += v[last_H0_t];
+				else ++last_H0_t, H0 += u[last_H0_t];
+			} else H0 = v[0] - g.qe_pre, last_H0_t = 0;
+			if ((flag & MMG_EZ_APPROX_DROP) && mmg_ksw_zdrop(&ez, H0, r, last_H0_t, zdrop, g.e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
+		}
+		last_st = st, last_en = en;
+	}
+}
+
+MMG_HDN inline void mmg_ksw_scalar(const KswGeom &g, int flag, int zdrop, int end_bonus, int8_t *mem, int32_t *H, uint8_t *p, KswEz *ez_out, uint32_t *cigar)
+{
+	KswEz ez;
+	mmg_ksw_reset(&ez);
+	const bool with_cigar = !(flag & MMG_EZ_SCORE_ONLY);
+	if (!with_cigar) mmg_ksw_scalar_run<0>(g, flag, zdrop, mem, H, p, ez);
+	else if (!(flag & MMG_EZ_RIGHT)) mmg_ksw_scalar_run<1>(g, flag, zdrop, mem, H, p, ez);
+	else mmg_ksw_scalar_run<2>(g, flag, zdrop, mem, H, p, ez);
+	int i0, j0;
+	if (with_cigar && mmg_ksw_trace_start(g, flag, end_bonus, &ez, &i0, &j0))
+		ez.n_cigar = mmg_ksw_backtrack(g, !!(flag & MMG_EZ_REV_CIGAR), p, i0, j0, cigar);
+	*ez_out = ez;
+}
+
 // bytes of lane memory for one job, laid out as the reference does (ksw2_extd2_sse.c:99-102):
 // u | v | x | y | x2 | y2 | s | sf | qr (+16 spare), all tlen_*16 except qr
 MMG_HD size_t mmg_ksw_mem_bytes(int qlen, int tlen) { return ((size_t)((tlen + 15) / 16) * 8 + (size_t)((qlen + 15) / 16) + 1) * 16; }
