@@ -63,7 +63,7 @@ static void parallel_for(int n_threads, void (*fn)(void*, long, int), void *data
 /* ------------------------------------------------------------------ per-fragment state */
 
 typedef struct {
-	int n_segs, qlen_sum, rep_len, frag_gap, active, n_regs0, n_u, n_mini;
+	int n_segs, qlen_sum, rep_len, frag_gap, active, finished, n_regs0, n_u, n_mini;
 	uint32_t hash;
 	int *qlens;           /* [n_segs] */
 	mm128_t *a;           /* chained anchors of the fragment (owned copy) */
@@ -108,6 +108,9 @@ static int chain_gap_ref(const mm_mapopt_t *opt, int qlen_sum)
 	if (opt->max_frag_len > 0) { g = opt->max_frag_len - qlen_sum; return g < opt->max_gap ? opt->max_gap : g; }
 	return opt->max_gap;
 }
+
+static void stage_align(void *data, long i, int tid);
+static void stage_finish(void *data, long i, int tid);
 
 /* chains -> hits for fragment i of the shard (map.c:376-388, 390-400 up to the DP) */
 static void stage_hits(void *data, long i, int tid)
@@ -166,6 +169,7 @@ static void stage_hits(void *data, long i, int tid)
 	}
 	fr->active = (opt->flag & MM_F_CIGAR) ? 1 : 0;
 	mm_tls_arena = 0;
+	if (fr->active) stage_align(data, i, tid); /* first walk (requests the DP jobs) while the fragment is still in cache */
 }
 
 /* one resumable pass over the regions of an active fragment (align_regs, map.c:260-270) */
@@ -192,6 +196,7 @@ static void stage_align(void *data, long i, int tid)
 	}
 	if (all_done) fr->active = 0;
 	mm_tls_arena = 0;
+	if (all_done) stage_finish(data, i, tid); /* MAPQ, pairing, release: same thread, same cache lines */
 }
 
 /* copy the DP jobs a fragment queued in this round into the shard's job array */
@@ -239,6 +244,8 @@ static void stage_finish(void *data, long i, int tid)
 	const mm_mapopt_t *opt = sh->opt;
 	const int f = sh->f0 + (int)i, off = sh->seg_off[f], ns = fr->n_segs, is_sr = !!(opt->flag & MM_F_SR);
 	int j, k, mapped;
+	if (fr->finished) return;
+	fr->finished = 1;
 	mm_tls_arena = &fr->arena;
 	mapped = !(fr->qlen_sum == 0 || ns <= 0 || ns > MM_MAX_SEG || (opt->max_qlen > 0 && fr->qlen_sum > opt->max_qlen));
 	if (mapped) {
@@ -328,13 +335,14 @@ static void *map_shard(void *data)
 	t0 = realtime(); sh->st.t_hits += t0 - t1;
 	if (sh->opt->flag & MM_F_CIGAR) {
 		size_t m_jobs = 0;
+		int round = 0;
 		sh->job_off = (size_t*)malloc((size_t)(nf + 1) * sizeof(size_t));
 		for (;;) { /* DP rounds: walk the regions, send what they asked for, hand the results back */
 			size_t n_jobs = 0;
 			int n_active = 0;
 			double ta = realtime(), tb, kms = 0;
 			uint64_t cells = 0;
-			parallel_for(sh->n_threads, stage_align, sh, nf);
+			if (round++ > 0) parallel_for(sh->n_threads, stage_align, sh, nf);
 			for (i = 0; i < nf; ++i) { /* new jobs per fragment -> offsets */
 				const frag_t *fr = &sh->fr[i];
 				sh->job_off[i] = n_jobs;
