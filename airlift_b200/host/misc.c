@@ -114,8 +114,8 @@ __thread mm_arena_t *mm_tls_arena = 0;
  * trims its per-thread heaps with mprotect() on every batch).  Each worker thread borrows a private pool for its
  * lifetime, so the hot path takes no lock; pools themselves live in a mutex-protected free list. */
 #define ARENA_STD_CAP (16384 - sizeof(mm_arena_chunk_t) - 16)
-#define ARENA_FIRST_CAP (3072 - sizeof(mm_arena_chunk_t) - 16) /* most short-read fragments fit their whole state in this */
-#define POOL_MAX_CHUNKS 8192
+#define ARENA_FIRST_CAP (8192 - sizeof(mm_arena_chunk_t) - 16) /* most short-read fragments fit their whole state in this */
+#define POOL_MAX_CHUNKS (1 << 20)
 struct mm_chunk_pool_s { struct mm_chunk_pool_s *next; mm_arena_chunk_t *chunks, *small; int n, n_small; };
 __thread mm_chunk_pool_t *mm_tls_pool = 0;
 static mm_chunk_pool_t *g_pools = 0;
