@@ -87,6 +87,7 @@ typedef struct {          /* one GPU's share of a mini-batch */
 	frag_t *fr;
 	mmg_chains_t ch;
 	mm_b200_stats_t st;
+	pthread_mutex_t *gpu_token; /* held during device stages when the GPU is shared by several shards */
 	size_t *job_off;      /* [nf+1] first job of each fragment in the current DP round */
 	mmg_ksw_job_t *jobs;
 	mmg_ksw_res_t *res;
@@ -325,7 +326,10 @@ static void *map_shard(void *data)
 	double t0, t1;
 	if (nf <= 0 || sh->rc) return 0;
 	t0 = realtime();
-	if (mmg_seed_chain_resident(sh->ctx, sh->didx, &sh->dopt, &sh->ch, 1) != MMG_OK) { shard_fail(sh, "seed/chain stage failed"); return 0; }
+	if (sh->gpu_token) pthread_mutex_lock(sh->gpu_token);
+	i = mmg_seed_chain_resident(sh->ctx, sh->didx, &sh->dopt, &sh->ch, 1);
+	if (sh->gpu_token) pthread_mutex_unlock(sh->gpu_token);
+	if (i != MMG_OK) { shard_fail(sh, "seed/chain stage failed"); return 0; }
 	t1 = realtime();
 	sh->st.t_seedchain += t1 - t0, sh->st.t_seedchain_kernels += sh->ch.t_kernels_ms * 1e-3;
 	sh->st.n_minimizers += sh->ch.n_minimizers, sh->st.n_anchors += sh->ch.n_anchors, sh->st.n_chain_iter += sh->ch.n_chain_iter;
@@ -360,7 +364,10 @@ static void *map_shard(void *data)
 			}
 			parallel_for(sh->n_threads, stage_gather_jobs, sh, nf);
 			ta = realtime(); sh->st.t_align_host += ta - tb;
-			if (mmg_ksw_batch(sh->ctx, sh->didx, &sh->dopt, (int)n_jobs, sh->jobs, sh->res, &sh->cig, &kms, &cells) != MMG_OK) { shard_fail(sh, "DP stage failed"); break; }
+			if (sh->gpu_token) pthread_mutex_lock(sh->gpu_token);
+			j = mmg_ksw_batch(sh->ctx, sh->didx, &sh->dopt, (int)n_jobs, sh->jobs, sh->res, &sh->cig, &kms, &cells);
+			if (sh->gpu_token) pthread_mutex_unlock(sh->gpu_token);
+			if (j != MMG_OK) { shard_fail(sh, "DP stage failed"); break; }
 			tb = realtime();
 			sh->st.t_ksw_total += tb - ta, sh->st.t_ksw_kernel += kms * 1e-3;
 			sh->st.n_dp_jobs += n_jobs, sh->st.n_dp_cells += cells, sh->st.n_dp_rounds += 1;
@@ -437,7 +444,9 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		const int64_t goal = tot * (d + 1) / n_dev;
 		h->mi = mi, h->opt = opt, h->ctx = B->ctx[d], h->didx = B->didx[d / B->lanes];
 		mm_mapopt_to_dev(opt, &h->dopt);
-		h->n_threads = (n_threads + n_dev - 1) / n_dev > 0 ? (n_threads + n_dev - 1) / n_dev : 1;
+		/* lanes of one GPU alternate between device and host stages, so each may use that GPU's whole share of host threads */
+		h->n_threads = n_threads / B->n_dev > 0 ? n_threads / B->n_dev : 1;
+		h->gpu_token = B->lanes > 1 ? &B->gpu_token[d / B->lanes] : 0;
 		h->seq = s->seq, h->n_seg = s->n_seg, h->seg_off = s->seg_off, h->n_reg = s->n_reg, h->rep_len = s->rep_len, h->frag_gap = s->frag_gap, h->reg = s->reg;
 		h->f0 = f;
 		while (f < s->n_frag && (acc < goal || d == n_dev - 1)) {

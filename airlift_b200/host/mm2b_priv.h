@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <assert.h>
+#include <pthread.h>
 #include "minimap_b200.h"
 #include "mmg.h"
 
@@ -50,6 +51,7 @@ struct mm_idx_bucket_s {
 	int dev_id[16];
 	mmg_ctx_t *ctx[16 * MM_B200_MAX_LANES]; /* ctx[d * lanes + lane]: own stream and arenas, same device */
 	mmg_idx_t *didx[16];
+	pthread_mutex_t gpu_token[16]; /* with lanes > 1: one shard per GPU runs device stages at a time, the others do their host stages */
 	int32_t max_occ_cache_set; float max_occ_cache_f; int32_t max_occ_cache;
 };
 

@@ -6,7 +6,7 @@
 #include <unistd.h>
 #include "mm2b_priv.h"
 
-static int g_n_dev = 1, g_dev[16] = {0}, g_lanes = 1;
+static int g_n_dev = 1, g_dev[16] = {0}, g_lanes = 2;
 
 int mm_b200_set_lanes(int lanes)
 {
@@ -50,6 +50,7 @@ static mm_idx_t *idx_from_seqs(int w, int k, int b, int flag, int n, char **seq,
 	B->lanes = g_lanes;
 	for (d = 0; d < g_n_dev; ++d) {
 		int l;
+		pthread_mutex_init(&B->gpu_token[d], 0);
 		B->dev_id[d] = g_dev[d];
 		for (l = 0; l < B->lanes; ++l)
 			if (mmg_init(g_dev[d], &B->ctx[d * B->lanes + l]) != MMG_OK) die_gpu("cannot initialise the GPU");
@@ -241,6 +242,7 @@ mm_idx_t *mm_b200_idx_alloc(const char *fn, const mm_idxopt_t *opt, const mmg_id
 		exit(1);
 	}
 	B->n_dev = 1, B->lanes = g_lanes, B->dev_id[0] = g_dev[0];
+	pthread_mutex_init(&B->gpu_token[0], 0);
 	for (i = 0; i < B->lanes; ++i)
 		if (mmg_init(g_dev[0], &B->ctx[i]) != MMG_OK) die_gpu("cannot initialise the GPU");
 	*ptrs = *shape;
