@@ -824,6 +824,224 @@ MMG_HDN inline void mmg_ksw_scalar(const KswGeom &g, int flag, int zdrop, int en
 	*ez_out = ez;
 }
 
+// ---- K4 fast form: jobs whose band never binds ------------------------------------------------------------------
+// When [st0,en0] is the whole anti-diagonal for every r (ksw2_extd2_sse.c:124-139 with a band that never clips), no valid
+// cell ever reads one of the stale out-of-band lanes of the SSE program (every predecessor is itself a valid cell or one of
+// the explicitly initialised first-row/first-column values), the traceback never leaves the matrix, and the exact-max scan
+// only sees valid cells.  The result is then the plain difference-form DP, so one thread can sweep each anti-diagonal over
+// exactly its valid cells.  Per-cell state (u,v,x,y,x2,y2 and a 16-bit H) is one 64-bit word in a circular window of
+// min(qlen,tlen)+1 slots; element i of every per-job array sits at [i*stride] so that the threads of a CTA interleave.
+MMG_HD bool mmg_ksw_band_clips(const KswGeom &g, int r)
+{
+	int st = 0, en = g.tlen - 1;
+	if (st < r - g.qlen + 1) st = r - g.qlen + 1;
+	if (en > r) en = r;
+	return st < ((r - g.w + 1) >> 1) || en > ((r + g.w) >> 1);
+}
+
+MMG_HD int mmg_ksw_fast_pw(int qlen, int tlen) { return ((qlen < tlen ? qlen : tlen) + 3) & ~3; } // traceback row width
+MMG_HD size_t mmg_ksw_fast_p_bytes(int qlen, int tlen) { return ((size_t)(qlen + tlen - 1) * mmg_ksw_fast_pw(qlen, tlen) + 15) & ~(size_t)15; }
+// limits of the fast form's packed max key (score << 11 | preference): scores stay far below 2^20 and an anti-diagonal
+// has at most 1024 cells
+MMG_HD bool mmg_ksw_fast_ok(const KswGeom &g)
+{
+	int m = g.sc_mch > -g.sc_mis ? g.sc_mch : -g.sc_mis;
+	if (m < -g.sc_N) m = -g.sc_N;
+	if (m < g.q + g.e) m = g.q + g.e;
+	if (m < g.q2 + g.e2) m = g.q2 + g.e2;
+	return (int64_t)(g.qlen + g.tlen + 2) * m < 500000 && (g.qlen < g.tlen ? g.qlen : g.tlen) <= 1023;
+}
+
+#ifndef MMG_KSW_RANGE   // the emulation harness defines this to prove that no value of a valid cell leaves the int8 range
+#define MMG_KSW_RANGE(v) ((void)0)
+#endif
+
+struct KswCell32 { int32_t u, v, x, y, x2, y2; uint32_t d; };
+
+// mmg_ksw_cell in 32-bit registers: identical as long as nothing wraps, which holds for valid cells (checked by the
+// emulation tests through MMG_KSW_RANGE; ksw2's scoring constraints, options.c:171-180, are what guarantee it)
+template <int kMode>
+MMG_HD KswCell32 mmg_ksw_cell32(const KswGeom &g, int32_t z, int32_t xt1, int32_t vt1, int32_t ut, int32_t yt, int32_t x2t1, int32_t y2t)
+{
+	KswCell32 c;
+	int32_t a = xt1 + vt1, b = yt + ut, a2 = x2t1 + vt1, b2 = y2t + ut, tmp;
+	uint32_t d = 0;
+	MMG_KSW_RANGE(a); MMG_KSW_RANGE(b); MMG_KSW_RANGE(a2); MMG_KSW_RANGE(b2);
+	if (kMode == 0) {
+		z = z > a ? z : a; z = z > b ? z : b; z = z > a2 ? z : a2; z = z > b2 ? z : b2;
+	} else if (kMode == 1) {
+		d = a > z ? 1 : 0;   z = z > a ? z : a;
+		d = b > z ? 2 : d;   z = z > b ? z : b;
+		d = a2 > z ? 3 : d;  z = z > a2 ? z : a2;
+		d = b2 > z ? 4 : d;  z = z > b2 ? z : b2;
+	} else {
+		d = z > a ? 0 : 1;   z = z > a ? z : a;
+		d = z > b ? d : 2;   z = z > b ? z : b;
+		d = z > a2 ? d : 3;  z = z > a2 ? z : a2;
+		d = z > b2 ? d : 4;  z = z > b2 ? z : b2;
+	}
+	z = z < g.sc_mch ? z : g.sc_mch;
+	c.u = z - vt1;
+	c.v = z - ut;
+	tmp = z - g.q;  a -= tmp;  b -= tmp;
+	MMG_KSW_RANGE(tmp);
+	tmp = z - g.q2; a2 -= tmp; b2 -= tmp;
+	MMG_KSW_RANGE(tmp); MMG_KSW_RANGE(c.u); MMG_KSW_RANGE(c.v); MMG_KSW_RANGE(a); MMG_KSW_RANGE(b); MMG_KSW_RANGE(a2); MMG_KSW_RANGE(b2);
+	const int32_t qe = g.q + g.e, qe2 = g.q2 + g.e2;
+	if (kMode != 2) {
+		c.x  = (a  > 0 ? a  : 0) - qe;  if (kMode && a  > 0) d |= 0x08;
+		c.y  = (b  > 0 ? b  : 0) - qe;  if (kMode && b  > 0) d |= 0x10;
+		c.x2 = (a2 > 0 ? a2 : 0) - qe2; if (kMode && a2 > 0) d |= 0x20;
+		c.y2 = (b2 > 0 ? b2 : 0) - qe2; if (kMode && b2 > 0) d |= 0x40;
+	} else {
+		c.x  = (a  < 0 ? 0 : a)  - qe;  if (!(a  < 0)) d |= 0x08;
+		c.y  = (b  < 0 ? 0 : b)  - qe;  if (!(b  < 0)) d |= 0x10;
+		c.x2 = (a2 < 0 ? 0 : a2) - qe2; if (!(a2 < 0)) d |= 0x20;
+		c.y2 = (b2 < 0 ? 0 : b2) - qe2; if (!(b2 < 0)) d |= 0x40;
+	}
+	MMG_KSW_RANGE(c.x); MMG_KSW_RANGE(c.y); MMG_KSW_RANGE(c.x2); MMG_KSW_RANGE(c.y2);
+	c.d = d;
+	return c;
+}
+
+// state word of a cell: u | v<<8 | x<<16 | y<<24 | x2<<32 | y2<<40 | target base<<48
+#define MMG_KSW_PACK6(u, v, x, y, x2, y2) ((uint64_t)((uint32_t)((u) & 0xff) | (uint32_t)((v) & 0xff) << 8 | (uint32_t)((x) & 0xff) << 16 | (uint32_t)(y) << 24) | \
+	(uint64_t)((uint32_t)((x2) & 0xff) | (uint32_t)((y2) & 0xff) << 8) << 32)
+#define MMG_KSW_TB_MASK 0x00ff000000000000ULL
+
+template <int kMode>
+MMG_HDN inline void mmg_ksw_fast_run(const KswGeom &g, int flag, int zdrop, uint64_t *S, const uint8_t *tb, const uint8_t *qb, int stride,
+                                     uint32_t *p /* rows of mmg_ksw_fast_pw() bytes */, KswEz &ez)
+{
+	const int qlen = g.qlen, tlen = g.tlen;
+	const int W = (qlen < tlen ? qlen : tlen) + 1, PWw = mmg_ksw_fast_pw(qlen, tlen) >> 2;
+	const bool approx = (flag & MMG_EZ_APPROX_MAX) != 0;
+	const int32_t n1 = -g.q - g.e, n2 = -g.q2 - g.e2;
+	uint64_t *const S_end = S + (size_t)W * stride;
+	uint64_t *sp_st = S;      // window slot of cell st0
+	int32_t Hst = 0;          // H of cell st0 of the previous anti-diagonal
+	int32_t H0 = 0, last_H0_t = 0;
+	for (int r = 0; r < qlen + tlen - 1; ++r) {
+		const int st0 = r - qlen + 1 > 0 ? r - qlen + 1 : 0, en0 = r < tlen - 1 ? r : tlen - 1, n = en0 - st0 + 1;
+		const int32_t fc = mmg_ksw_first_col(g, r);
+		int32_t cx, cv, cx2; // x, v, x2 of cell t-1 on the previous anti-diagonal
+		if (st0 == 0) cx = n1, cx2 = n2, cv = fc;
+		else {
+			const uint64_t w = *(sp_st == S ? S_end - stride : sp_st - stride);
+			cv = (int8_t)(w >> 8), cx = (int8_t)(w >> 16), cx2 = (int8_t)(w >> 32);
+		}
+		if (r < tlen) { // the cell entering on the first row: boundary u/y/y2 (ksw2_extd2_sse.c:152-156) and its target base
+			uint64_t *sn = sp_st + (size_t)(n - 1) * stride;
+			if (sn >= S_end) sn -= (size_t)W * stride;
+			*sn = MMG_KSW_PACK6(fc, n1, n1, n1, n2, n2) | (uint64_t)tb[(size_t)r * stride] << 48;
+		}
+		uint64_t *sp = sp_st;
+		const uint8_t *qp = qb + (size_t)(r - st0) * stride;
+		// exact max: E_k = H(r,st0+k) - H(r,st0) + u_0 accumulates from u - v of neighbouring cells; key = E<<11 | preference
+		int32_t E = 0, best = INT32_MIN;
+		const int en1k = (n - 1) / 4 * 4;
+		uint32_t pw = 0;
+		uint32_t *prow = p + (size_t)r * PWw;
+		int32_t v_last = 0;
+		for (int k = 0; k < n; ++k) {
+			const uint64_t w = *sp;
+			const int32_t ou = (int8_t)w, ov = (int8_t)(w >> 8), ox = (int8_t)(w >> 16), oy = (int8_t)(w >> 24), ox2 = (int8_t)(w >> 32), oy2 = (int8_t)(w >> 40);
+			const uint32_t tbase = (uint32_t)(w >> 48) & 0xff, qbase = *qp;
+			int32_t s = tbase == qbase ? g.sc_mch : g.sc_mis;
+			if ((tbase | qbase) & 4) s = g.sc_N; // codes are 0..4: either one is N
+			const KswCell32 c = mmg_ksw_cell32<kMode>(g, s, cx, cv, ou, oy, cx2, oy2);
+			*sp = MMG_KSW_PACK6(c.u, c.v, c.x, c.y, c.x2, c.y2) | (w & MMG_KSW_TB_MASK);
+			cx = ox, cv = ov, cx2 = ox2;
+			if (kMode) {
+				pw = pw >> 8 | c.d << 24;
+				if ((k & 3) == 3) prow[k >> 2] = pw;
+			}
+			E += c.u;
+			{
+				const int32_t rk = k < en1k ? ((k & 3) << 8 | k >> 2) : (4 << 8 | (k - en1k));
+				const int32_t key = E * 2048 + (2046 - rk);
+				best = best > key ? best : key;
+			}
+			E -= c.v; v_last = c.v;
+			sp += stride; if (sp == S_end) sp = S;
+			qp -= stride;
+		}
+		if (kMode && (n & 3)) prow[n >> 2] = pw >> ((4 - (n & 3)) << 3);
+		if (!approx) {
+			const uint64_t w0 = *sp_st;
+			const int32_t u0 = (int8_t)w0, v0 = (int8_t)(w0 >> 8);
+			const int32_t H_st0 = r == 0 ? v0 - g.qe_pre : Hst + (st0 > 0 ? u0 : v0);
+			const int32_t off = H_st0 - u0, H_en0 = off + E + v_last;
+			int32_t bh, bt;
+			{ // the cell en0 wins every tie (ksw2_extd2_sse.c:319-349 starts from it)
+				const int32_t key = (E + v_last) * 2048 + 2047;
+				best = best > key ? best : key;
+				const int32_t low = best & 2047;
+				bh = ((best - low) >> 11) + off; // exact: best - low is a multiple of 2048
+				if (low == 2047) bt = en0;
+				else { const int32_t rk = 2046 - low; bt = (rk >> 8) == 4 ? st0 + en1k + (rk & 255) : st0 + ((rk & 255) << 2) + (rk >> 8); }
+			}
+			Hst = H_st0;
+			if (en0 == tlen - 1 && H_en0 > ez.mte) ez.mte = H_en0, ez.mte_q = r - ((en0 + 16) / 16 * 16 - 1); // the widened end (ksw2_extd2_sse.c:352)
+			if (r - st0 == qlen - 1 && H_st0 > ez.mqe) ez.mqe = H_st0, ez.mqe_t = st0;
+			if (mmg_ksw_zdrop(&ez, bh, r, bt, zdrop, g.e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H_en0;
+		} else { // ksw2_extd2_sse.c:359-375, reading the cells just written
+#define MMG_FAST_AT(t_) S[(size_t)(((int)((sp_st - S) / stride) + ((t_) - st0)) % W) * stride]
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					const int32_t d0 = (int8_t)(MMG_FAST_AT(last_H0_t) >> 8), d1 = (int8_t)MMG_FAST_AT(last_H0_t + 1);
+					if (d0 > d1) H0 += d0; else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += (int8_t)(MMG_FAST_AT(last_H0_t) >> 8);
+				else { ++last_H0_t; H0 += (int8_t)MMG_FAST_AT(last_H0_t); }
+			} else H0 = (int8_t)(S[0] >> 8) - g.qe_pre, last_H0_t = 0;
+#undef MMG_FAST_AT
+			if ((flag & MMG_EZ_APPROX_DROP) && mmg_ksw_zdrop(&ez, H0, r, last_H0_t, zdrop, g.e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
+		}
+		if (r + 2 - qlen > 0) { sp_st += stride; if (sp_st == S_end) sp_st = S; } // st0 of the next anti-diagonal is one further
+	}
+}
+
+MMG_HDN inline int mmg_ksw_backtrack_fast(const KswGeom &g, int is_rev, const uint8_t *p, int i0, int j0, uint32_t *cigar)
+{ // ksw_backtrack (ksw2.h:119-151) over the fast form's rows; the walk cannot leave the band, so no forced states
+	int n = 0, i = i0, j = j0, state = 0;
+	const int pw = mmg_ksw_fast_pw(g.qlen, g.tlen);
+#define MMG_PUSH(op, len) do { if (n == 0 || (uint32_t)(op) != (cigar[n - 1] & 0xf)) cigar[n++] = (uint32_t)(len) << 4 | (uint32_t)(op); else cigar[n - 1] += (uint32_t)(len) << 4; } while (0)
+	while (i >= 0 && j >= 0) {
+		const int r = i + j, st0 = r - g.qlen + 1 > 0 ? r - g.qlen + 1 : 0;
+		const uint32_t tmp = p[(size_t)r * pw + i - st0];
+		if (state == 0) state = tmp & 7;
+		else if (!(tmp >> (state + 2) & 1)) state = 0;
+		if (state == 0) state = tmp & 7;
+		if (state == 0) { MMG_PUSH(0, 1); --i, --j; }
+		else if (state == 1 || state == 3) { MMG_PUSH(2, 1); --i; }
+		else { MMG_PUSH(1, 1); --j; }
+	}
+	if (i >= 0) MMG_PUSH(2, i + 1);
+	if (j >= 0) MMG_PUSH(1, j + 1);
+#undef MMG_PUSH
+	if (!is_rev)
+		for (int k = 0; k < n >> 1; ++k) { uint32_t t = cigar[k]; cigar[k] = cigar[n - 1 - k]; cigar[n - 1 - k] = t; }
+	return n;
+}
+
+// one job, one thread: S/tb/qb as described above (tb[t], qb[j] already filled), p = this job's traceback rows
+MMG_HDN inline void mmg_ksw_fast(const KswGeom &g, int flag, int zdrop, int end_bonus, uint64_t *S, const uint8_t *tb, const uint8_t *qb, int stride,
+                                 uint32_t *p, KswEz *ez_out, uint32_t *cigar)
+{
+	KswEz ez;
+	mmg_ksw_reset(&ez);
+	const bool with_cigar = !(flag & MMG_EZ_SCORE_ONLY);
+	if (!with_cigar) mmg_ksw_fast_run<0>(g, flag, zdrop, S, tb, qb, stride, p, ez);
+	else if (!(flag & MMG_EZ_RIGHT)) mmg_ksw_fast_run<1>(g, flag, zdrop, S, tb, qb, stride, p, ez);
+	else mmg_ksw_fast_run<2>(g, flag, zdrop, S, tb, qb, stride, p, ez);
+	int i0, j0;
+	if (with_cigar && mmg_ksw_trace_start(g, flag, end_bonus, &ez, &i0, &j0))
+		ez.n_cigar = mmg_ksw_backtrack_fast(g, !!(flag & MMG_EZ_REV_CIGAR), reinterpret_cast<const uint8_t*>(p), i0, j0, cigar);
+	*ez_out = ez;
+}
+
 // bytes of lane memory for one job, laid out as the reference does (ksw2_extd2_sse.c:99-102):
 // u | v | x | y | x2 | y2 | s | sf | qr (+16 spare), all tlen_*16 except qr
 MMG_HD size_t mmg_ksw_mem_bytes(int qlen, int tlen) { return ((size_t)((tlen + 15) / 16) * 8 + (size_t)((qlen + 15) / 16) + 1) * 16; }

@@ -46,39 +46,66 @@ __device__ __forceinline__ int ksw_ncol(int qlen, int tlen, int w)
 	return ((nc < w + 1 ? nc : w + 1) + 15) / 16 + 1;
 }
 
-// per job: arena sizes, a size class for scheduling (big jobs first), and the true-band cell count
-__global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, uint64_t *__restrict__ mem_sz, uint64_t *__restrict__ p_sz,
-                           uint64_t *__restrict__ cig_sz, uint32_t *__restrict__ key, int32_t *__restrict__ idx, unsigned long long *__restrict__ cells_total)
+// Fast-form size classes: a job whose band never clips runs one-thread-per-job (k_ksw_tpj) in the first class it fits:
+// min(qlen,tlen) <= mc (depth of the circular state window), tlen <= tc, qlen <= qc; nt = threads (jobs) per CTA.
+#define KSW_N_FAST 3
+#define KSW_CLS_LITERAL KSW_N_FAST
+struct KswFastClass { int32_t mc, tc, qc, nt; };
+struct KswFastTab { KswFastClass c[KSW_N_FAST]; };
+static inline size_t ksw_fast_smem(const KswFastClass &k) { return (size_t)k.nt * ((size_t)(k.mc + 1) * 8 + (size_t)k.tc + (size_t)k.qc); }
+
+// per job: arena sizes, the scheduling key (form and size class, then shape so that the threads of a warp walk the same
+// loops), and the true-band cell count
+__global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, KswScore sc, KswFastTab ft, uint64_t *__restrict__ mem_sz,
+                           uint64_t *__restrict__ p_sz, uint64_t *__restrict__ cig_sz, uint32_t *__restrict__ key, int32_t *__restrict__ idx,
+                           unsigned long long *__restrict__ cells_total, uint32_t *__restrict__ cls_count)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned long long cells = 0;
+	int cls = -1;
 	if (i <= n) {
-		uint64_t m = 0, p = 0, c = 0; uint32_t k = 63;
+		uint64_t m = 0, p = 0, c = 0; uint32_t k = (uint32_t)KSW_CLS_LITERAL << 28 | 63u;
 		if (i < n) {
 			const mmg_ksw_job_t j = jobs[i];
 			const int qlen = j.q_len, tlen = j.t_len;
+			cls = KSW_CLS_LITERAL;
 			if (qlen > 0 && tlen > 0) {
-				const size_t mem_bytes = mmg_ksw_mem_bytes(qlen, tlen), H_bytes = (size_t)((tlen + 15) / 16) * 64;
-				if (mem_bytes + H_bytes > KSW_SMEM_PER_JOB) m = (mem_bytes + H_bytes + 63) & ~(size_t)63;
-				if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = ((uint64_t)(qlen + tlen - 1) * ksw_ncol(qlen, tlen, j.w) + 1) * 16;
-				c = (uint64_t)qlen + tlen + 2;
-				int w = j.w < 0 ? (tlen > qlen ? tlen : qlen) : j.w;
-				// cells inside the band: sum over anti-diagonals of (en0 - st0 + 1), in closed form per diagonal
+				const KswGeom g = mmg_ksw_geom(qlen, tlen, sc.m, sc.mat, sc.q, sc.e, sc.q2, sc.e2, j.w);
+				bool clips = false;
+				// cells inside the band: sum over anti-diagonals of (en0 - st0 + 1)
 				for (int r = 0; r < qlen + tlen - 1; ++r) {
-					int st = 0, en = tlen - 1;
-					if (st < r - qlen + 1) st = r - qlen + 1;
-					if (en > r) en = r;
-					if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
-					if (en > (r + w) >> 1) en = (r + w) >> 1;
-					if (st > en) break;
+					int st, en;
+					clips |= mmg_ksw_band_clips(g, r);
+					if (!mmg_ksw_band(g, r, &st, &en)) break;
 					cells += (unsigned long long)(en - st + 1);
 				}
-				const uint64_t est = (uint64_t)(qlen + tlen) * (uint64_t)(qlen < tlen ? qlen : tlen);
-				k = 63 - (uint32_t)(63 - __clzll((long long)(est | 1)));
+				if (!g.bail && !clips && mmg_ksw_fast_ok(g)) {
+					const int mn = qlen < tlen ? qlen : tlen;
+					for (int q = KSW_N_FAST - 1; q >= 0; --q)
+						if (mn <= ft.c[q].mc && tlen <= ft.c[q].tc && qlen <= ft.c[q].qc) cls = q;
+				}
+				c = (uint64_t)qlen + tlen + 2;
+				if (cls == KSW_CLS_LITERAL) {
+					const size_t mem_bytes = mmg_ksw_mem_bytes(qlen, tlen), H_bytes = (size_t)((tlen + 15) / 16) * 64;
+					if (mem_bytes + H_bytes > KSW_SMEM_PER_JOB) m = (mem_bytes + H_bytes + 63) & ~(size_t)63;
+					if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = ((uint64_t)(qlen + tlen - 1) * ksw_ncol(qlen, tlen, j.w) + 1) * 16;
+					const uint64_t est = (uint64_t)(qlen + tlen) * (uint64_t)(qlen < tlen ? qlen : tlen);
+					k = (uint32_t)KSW_CLS_LITERAL << 28 | (63u - (uint32_t)(63 - __clzll((long long)(est | 1)))); // big jobs first
+				} else {
+					if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = mmg_ksw_fast_p_bytes(qlen, tlen);
+					const uint32_t mode = (j.flag & MMG_EZ_SCORE_ONLY) ? 0u : (j.flag & MMG_EZ_RIGHT) ? 2u : 1u;
+					k = (uint32_t)cls << 28 | mode << 26 | (uint32_t)(1023 - tlen) << 10 | (uint32_t)(1023 - qlen);
+				}
 			}
 			idx[i] = i;
 		}
 		mem_sz[i] = m, p_sz[i] = p, cig_sz[i] = c, key[i] = k;
+	}
+	for (int q = 0; q <= KSW_N_FAST; ++q) {
+		const unsigned b = __ballot_sync(0xffffffffu, cls == q);
+		unsigned long long cq = cls == q ? cells : 0;
+		for (int d = 16; d >= 1; d >>= 1) cq += __shfl_xor_sync(0xffffffffu, cq, d);
+		if ((threadIdx.x & 31) == 0 && b) { atomicAdd(&cls_count[q], (uint32_t)__popc(b)); atomicAdd(&cells_total[1 + q], cq); }
 	}
 	for (int d = 16; d >= 1; d >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, d);
 	if ((threadIdx.x & 31) == 0 && cells) atomicAdd(cells_total, cells);
@@ -241,6 +268,58 @@ k_ksw(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order,
 	}
 }
 
+// K4, fast form: one thread per job whose band never clips (mmg_ksw_fast, mmg_core.h).  The threads of a CTA interleave
+// their per-job arrays in shared memory ([element][thread]): a warp's accesses fall on consecutive banks.
+__global__ void __launch_bounds__(128)
+k_ksw_tpj(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order, int n_jobs, KswScore sc, KswFastClass fc,
+          const uint32_t *__restrict__ Q, const uint32_t *__restrict__ S, const uint64_t *__restrict__ q_off, const int32_t *__restrict__ read_len,
+          const uint64_t *__restrict__ ref_off, const uint64_t *__restrict__ p_off, const uint64_t *__restrict__ cig_off,
+          uint8_t *__restrict__ gp, uint32_t *__restrict__ gcig, KswEz *__restrict__ res)
+{
+	extern __shared__ __align__(16) uint8_t smem[];
+	const int NT = blockDim.x, tid = threadIdx.x;
+	const int slot = blockIdx.x * NT + tid;
+	if (slot >= n_jobs) return;
+	uint64_t *st = reinterpret_cast<uint64_t*>(smem) + tid;
+	uint8_t *tb = smem + (size_t)(fc.mc + 1) * NT * 8 + tid, *qb = tb + (size_t)fc.tc * NT;
+	const int ji = order[slot];
+	const mmg_ksw_job_t hj = jobs[ji];
+	const int qlen = hj.q_len, tlen = hj.t_len;
+	const KswGeom g = mmg_ksw_geom(qlen, tlen, sc.m, sc.mat, sc.q, sc.e, sc.q2, sc.e2, hj.w);
+	{ // target slice of S (mm_idx_getseq, index.c:152-162), reversed for left extensions (align.c:694-695)
+		const uint64_t a0 = ref_off[hj.rid] + (uint64_t)hj.t_start, a1 = a0 + (uint64_t)tlen;
+		for (uint64_t wa = a0 >> 3; wa <= (a1 - 1) >> 3; ++wa) {
+			const uint32_t word = S[wa];
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				const uint64_t a = wa * 8 + k;
+				if (a >= a0 && a < a1) { const int i = (int)(a - a0); tb[(size_t)(hj.reversed ? tlen - 1 - i : i) * NT] = (uint8_t)(word >> (4 * k) & 0xf); }
+			}
+		}
+	}
+	{ // query slice of qseq0[q_rev] (align.c:865-870)
+		const uint64_t qbase = q_off[hj.seq_id];
+		const int rl = read_len[hj.seq_id];
+		const int lo = hj.q_rev ? rl - hj.q_start - qlen : hj.q_start, hi = lo + qlen;
+		for (int wp = lo >> 3; wp <= (hi - 1) >> 3; ++wp) {
+			const uint32_t word = Q[(qbase >> 3) + wp]; // reads start on 8-base boundaries
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				const int pos = wp * 8 + k;
+				if (pos >= lo && pos < hi) {
+					const int c = (int)(word >> (4 * k) & 0xf);
+					const int idx = hj.q_rev ? rl - 1 - pos : pos;
+					const int j = hj.reversed ? hj.q_start + qlen - 1 - idx : idx - hj.q_start;
+					qb[(size_t)j * NT] = (uint8_t)(hj.q_rev ? (c < 4 ? 3 - c : 4) : c);
+				}
+			}
+		}
+	}
+	KswEz ez;
+	mmg_ksw_fast(g, hj.flag, hj.zdrop, hj.end_bonus, st, tb, qb, NT, reinterpret_cast<uint32_t*>(gp + p_off[ji]), &ez, gcig + cig_off[ji]);
+	res[ji] = ez;
+}
+
 __global__ void k_res_ncig(int n_jobs, const KswEz *__restrict__ res, int32_t *__restrict__ ncig)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,45 +356,71 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
                       const int32_t *d_read_len, const uint64_t *d_ref_off, const KswScore &sc, mmg_ksw_res_t *res, const uint32_t **cigars,
                       double *kernel_ms, uint64_t *cells)
 {
-	// scratch layout in k_cig_off: mem_sz | p_sz | cig_sz (u64, n+1 each) | their scans (i64, n+1 each) | key, key2 (u32) | idx, order (i32) | ncig (i32, n+1) | ncig scan (i64, n+1) | cells
+	// scratch layout in k_cig_off: mem_sz | p_sz | cig_sz (u64, n+1 each) | their scans (i64, n+1 each) | ncig scan (i64, n+1) | cells, class counts |
+	// key, key2 (u32) | idx, order (i32) | ncig (i32, n+1)
 	const size_t n1 = (size_t)n + 1;
-	MMG_TRY(c->k_cig_off.ensure(n1 * (6 * 8 + 4 * 4 + 4 + 8) + 64));
+	MMG_TRY(c->k_cig_off.ensure(n1 * (7 * 8 + 5 * 4) + 256));
 	uint64_t *mem_sz = c->k_cig_off.as<uint64_t>(), *p_sz = mem_sz + n1, *cig_sz = p_sz + n1;
 	int64_t *mem_off = reinterpret_cast<int64_t*>(cig_sz + n1), *p_off = mem_off + n1, *cg_off = p_off + n1, *nc_off = cg_off + n1;
 	unsigned long long *d_cells = reinterpret_cast<unsigned long long*>(nc_off + n1);
-	uint32_t *key = reinterpret_cast<uint32_t*>(d_cells + 2), *key2 = key + n1;
+	uint32_t *d_cls = reinterpret_cast<uint32_t*>(d_cells + 6); // d_cells: total, then per class; d_cls: KSW_N_FAST + 1 job counters
+	uint32_t *key = d_cls + 8, *key2 = key + n1;
 	int32_t *idx = reinterpret_cast<int32_t*>(key2 + n1), *order = idx + n1, *ncig = order + n1;
-	MMG_CUDA(cudaMemsetAsync(d_cells, 0, 8, c->stream));
-	MMG_LAUNCH(c, k_ksw_prep, mmg_blocks(n1, 128), 128, 0, d_jobs, n, mem_sz, p_sz, cig_sz, key, idx, d_cells);
+	static const KswFastTab ftab = {{{24, 56, 56, 128}, {48, 104, 104, 128}, {80, 160, 160, 64}}};
+	MMG_CUDA(cudaMemsetAsync(d_cells, 0, 48 + 32, c->stream));
+	MMG_LAUNCH(c, k_ksw_prep, mmg_blocks(n1, 128), 128, 0, d_jobs, n, sc, ftab, mem_sz, p_sz, cig_sz, key, idx, d_cells, d_cls);
 	MMG_TRY(scan_excl(c, mem_sz, mem_off, (int)n1));
 	MMG_TRY(scan_excl(c, p_sz, p_off, (int)n1));
 	MMG_TRY(scan_excl(c, cig_sz, cg_off, (int)n1));
-	{ // big jobs first (load balance): stable sort of job indices by size class
+	{ // stable sort of job indices by scheduling key
 		size_t tmp = 0;
-		cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, order, n, 0, 6, c->stream);
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, order, n, 0, 30, c->stream);
 		MMG_TRY(c->d_cub.ensure(tmp));
-		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, order, n, 0, 6, c->stream));
+		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, order, n, 0, 30, c->stream));
 		++c->launches;
 	}
-	int64_t tot[3]; unsigned long long h_cells = 0;
+	int64_t tot[3]; unsigned long long h_cells = 0; uint32_t h_cls[KSW_N_FAST + 1];
 	MMG_D2H(c, &tot[0], mem_off + n, 8); MMG_D2H(c, &tot[1], p_off + n, 8); MMG_D2H(c, &tot[2], cg_off + n, 8);
-	MMG_D2H(c, &h_cells, d_cells, 8);
+	MMG_D2H(c, &h_cells, d_cells, 8); MMG_D2H(c, h_cls, d_cls, sizeof(h_cls));
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	if (cells) *cells = h_cells;
+	if (getenv("MMG_KSW_DEBUG")) {
+		unsigned long long hc[KSW_N_FAST + 1];
+		cudaMemcpy(hc, d_cells + 1, sizeof(hc), cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[mmg_ksw] %d jobs, %llu cells:", n, h_cells);
+		for (int q = 0; q <= KSW_N_FAST; ++q) fprintf(stderr, " class %d: %u jobs %llu cells;", q, h_cls[q], hc[q]);
+		fprintf(stderr, " p %ld B, mem %ld B\n", (long)tot[1], (long)tot[0]);
+	}
 	MMG_TRY(c->k_mem.ensure((size_t)tot[0] + 64));
 	MMG_TRY(c->k_p.ensure((size_t)tot[1] + 64));
 	MMG_TRY(c->k_cig.ensure(((size_t)tot[2] + 4) * 4));
-	MMG_TRY(c->k_res.ensure(n1 * (sizeof(KswEz) + sizeof(KswResDev))));
+	MMG_TRY(c->k_res.ensure(((n1 * sizeof(KswEz) + 15) & ~(size_t)15) + n1 * sizeof(KswResDev)));
 	KswEz *d_ez = c->k_res.as<KswEz>();
 	KswResDev *d_res = reinterpret_cast<KswResDev*>(c->k_res.as<uint8_t>() + ((n1 * sizeof(KswEz) + 15) & ~(size_t)15));
-	MMG_TRY(c->k_res.ensure(((n1 * sizeof(KswEz) + 15) & ~(size_t)15) + n1 * sizeof(KswResDev)));
-	d_ez = c->k_res.as<KswEz>();
-	d_res = reinterpret_cast<KswResDev*>(c->k_res.as<uint8_t>() + ((n1 * sizeof(KswEz) + 15) & ~(size_t)15));
 	MMG_CUDA(cudaEventRecord(c->ev[0], c->stream));
-	MMG_LAUNCH(c, k_ksw, mmg_blocks(n, KSW_JOBS_PER_BLOCK), KSW_GROUP * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
-	           d_jobs, order, n, sc, d_Q, d_S, d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off),
-	           reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(),
-	           c->k_cig.as<uint32_t>(), d_ez);
+	{
+		static bool attr_set[16] = {false};
+		if (c->dev < 16 && !attr_set[c->dev]) {
+			size_t mx = 0;
+			for (int q = 0; q < KSW_N_FAST; ++q) mx = std::max(mx, ksw_fast_smem(ftab.c[q]));
+			MMG_CUDA(cudaFuncSetAttribute(k_ksw_tpj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+			attr_set[c->dev] = true;
+		}
+	}
+	uint32_t first = 0;
+	for (int q = 0; q < KSW_N_FAST; ++q) { // fast-form classes, then the literal 16-lane form for everything else
+		const uint32_t nq = h_cls[q];
+		if (nq)
+			MMG_LAUNCH(c, k_ksw_tpj, mmg_blocks(nq, ftab.c[q].nt), ftab.c[q].nt, ksw_fast_smem(ftab.c[q]), d_jobs, order + first, (int)nq, sc, ftab.c[q],
+			           d_Q, d_S, d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off),
+			           c->k_p.as<uint8_t>(), c->k_cig.as<uint32_t>(), d_ez);
+		first += nq;
+	}
+	if (h_cls[KSW_CLS_LITERAL])
+		MMG_LAUNCH(c, k_ksw, mmg_blocks(h_cls[KSW_CLS_LITERAL], KSW_JOBS_PER_BLOCK), KSW_GROUP * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
+		           d_jobs, order + first, (int)h_cls[KSW_CLS_LITERAL], sc, d_Q, d_S, d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off),
+		           reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(),
+		           c->k_cig.as<uint32_t>(), d_ez);
 	MMG_CUDA(cudaEventRecord(c->ev[1], c->stream));
 	MMG_LAUNCH(c, k_res_ncig, mmg_blocks(n1, 256), 256, 0, n, d_ez, ncig);
 	MMG_TRY(scan_excl(c, ncig, nc_off, (int)n1));

@@ -4,6 +4,8 @@
 #include <vector>
 #include <cstring>
 #include <cstdlib>
+static long g_ksw_range_viol; // values of valid cells that left the int8 range (must stay 0: the fast form computes in 32 bits)
+#define MMG_KSW_RANGE(v) do { if ((v) < -128 || (v) > 127) ++g_ksw_range_viol; } while (0)
 #include "mmg_core.h"
 
 extern "C" {
@@ -104,6 +106,26 @@ int emu_ksw(int qlen, const uint8_t *query, int tlen, const uint8_t *target, con
 	for (int i = 0; i < qlen; ++i) qr[i] = query[qlen - 1 - i];
 	mmg_ksw_scalar(g, flag, zdrop, end_bonus, mem.data(), H.data(), p.data(), ez_out, cigar);
 	return 0;
+}
+
+// the fast form (band never clips): returns -1 when the job does not qualify
+int emu_ksw_fast(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int q, int e, int q2, int e2, int w,
+                 int zdrop, int end_bonus, int flag, int stride, KswEz *ez_out, uint32_t *cigar)
+{
+	KswGeom g = mmg_ksw_geom(qlen, tlen, 5, mat, q, e, q2, e2, w);
+	KswEz ez; mmg_ksw_reset(&ez);
+	if (g.bail) { *ez_out = ez; return 0; }
+	for (int r = 0; r < qlen + tlen - 1; ++r) if (mmg_ksw_band_clips(g, r)) return -1;
+	if (!mmg_ksw_fast_ok(g)) return -1;
+	const int W = (qlen < tlen ? qlen : tlen) + 1;
+	std::vector<uint64_t> S((size_t)W * stride, 0x5a5a5a5a5a5a5a5aULL); // garbage: the fast form must never read an unwritten slot
+	std::vector<uint8_t> tb((size_t)tlen * stride, 9), qb((size_t)qlen * stride, 9);
+	std::vector<uint32_t> p(mmg_ksw_fast_p_bytes(qlen, tlen) / 4 + 4, 0xa5a5a5a5u);
+	for (int i = 0; i < tlen; ++i) tb[(size_t)i * stride] = target[i];
+	for (int i = 0; i < qlen; ++i) qb[(size_t)i * stride] = query[i];
+	const long viol0 = g_ksw_range_viol;
+	mmg_ksw_fast(g, flag, zdrop, end_bonus, S.data(), tb.data(), qb.data(), stride, p.data(), ez_out, cigar);
+	return g_ksw_range_viol != viol0 ? -2 : 0;
 }
 
 }

@@ -34,6 +34,8 @@ def emu():
     E.emu_rs_sort_128x.argtypes = [C.c_void_p, C.c_int64]
     E.emu_ksw.restype = C.c_int
     E.emu_ksw.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.POINTER(Ez), C.c_void_p]
+    E.emu_ksw_fast.restype = C.c_int
+    E.emu_ksw_fast.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.POINTER(Ez), C.c_void_p]
     return E
 
 
@@ -142,3 +144,40 @@ def test_ksw_pieces(emu, preset):
                     a["cigar"] = []
                 assert a == b, (len(q), len(t), fl, w)
         n += 1
+
+
+def emu_ksw_fast(E, q, t, mat, pen, w, zd, eb, fl, stride):
+    ez = Ez()
+    cig = np.zeros(len(q) + len(t) + 4, dtype=np.uint32)
+    q = np.ascontiguousarray(q, dtype=np.uint8); t = np.ascontiguousarray(t, dtype=np.uint8)
+    rc = E.emu_ksw_fast(len(q), q.ctypes.data, len(t), t.ctypes.data, mat.ctypes.data, *pen, w, zd, eb, fl, stride, C.byref(ez), cig.ctypes.data)
+    assert rc != -2, "a valid cell left the int8 range: the 32-bit cell would differ from the reference's int8 lanes"
+    if rc < 0:
+        return None
+    return dict(max=ez.max, zdropped=ez.zdropped, max_q=ez.max_q, max_t=ez.max_t, mqe=ez.mqe, mqe_t=ez.mqe_t, mte=ez.mte,
+                mte_q=ez.mte_q, score=ez.score, reach_end=ez.reach_end, cigar=cig[:ez.n_cigar].tolist())
+
+
+@pytest.mark.parametrize("preset", ["sr", "ont"])
+def test_ksw_fast_form(emu, preset):
+    """The thread-per-job form used when the band never clips equals ksw_extd2 bit for bit (all flags, incl. w=-1)."""
+    from test_oracle_vs_ref import _ksw_cases
+    rng = np.random.default_rng(777)
+    if preset == "sr":
+        mat, pen, bw, zd, eb = L.simple_mat(2, 8, 1), (12, 2, 24, 1), 151, 100, 10
+    else:
+        mat, pen, bw, zd, eb = L.simple_mat(2, 4, 1), (4, 2, 24, 1), 751, 400, -1
+    n_fast = n_skip = 0
+    for q, t in _ksw_cases(rng, 240):
+        for fl in [0xC2, 0x40, 0x08, 0x18, 0x00, 0x01, 0x02, 0x80]:
+            for w in [bw, -1]:
+                b = emu_ksw_fast(emu, q, t, mat, pen, w, zd, eb if fl & 0x40 else -1, fl, 1 + (n_fast % 3))
+                if b is None:
+                    n_skip += 1
+                    continue
+                a = L.orc_ksw(q, t, mat, *pen, w, zd, eb if fl & 0x40 else -1, fl)
+                if fl & 0x01:
+                    a["cigar"] = []
+                assert a == b, (len(q), len(t), fl, w)
+                n_fast += 1
+    assert n_fast > 1500 and (preset != "sr" or n_skip > 0)
