@@ -297,6 +297,31 @@ k_chain_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const int
 	if (lane == 0 && iters) atomicAdd(iter_total, iters);
 }
 
+// Warp-cooperative bitonic sort of a[0,n) in global/shared memory for ANY n: every compare-exchange is oriented the same
+// way (the first step of each merge mirrors the block, partner = i ^ (k-1)), so the virtual elements beyond n act as
+// "already last" padding and are never touched.  before(x, y) = x must precede y.
+template <class T, class Before>
+__device__ __forceinline__ void warp_bitonic(T *a, int n, int lane, Before before)
+{
+	int N = 2; while (N < n) N <<= 1;
+	for (int k = 2; k <= N; k <<= 1) {
+		for (int i = lane; i < n; i += 32) {
+			const int l = i ^ (k - 1);
+			if (l > i && l < n) { const T x = a[i], y = a[l]; if (before(y, x)) a[i] = y, a[l] = x; }
+		}
+		__syncwarp();
+		for (int j = k >> 2; j > 0; j >>= 1) {
+			for (int i = lane; i < n; i += 32) {
+				const int l = i ^ j;
+				if (l > i && l < n) { const T x = a[i], y = a[l]; if (before(y, x)) a[i] = y, a[l] = x; }
+			}
+			__syncwarp();
+		}
+	}
+}
+struct U64Desc { __device__ bool operator()(uint64_t x, uint64_t y) const { return x > y; } };
+struct M128ByX { __device__ bool operator()(const mm128 &x, const mm128 &y) const { return x.x < y.x; } };
+
 // K3 tail, one warp per fragment: chain ends and peaks, ranking by peak score, backtracking, output order
 // (chain.c:87-160).  The sequential backtrack marks anchors as used chain by chain in rank order; the same
 // ownership is obtained in parallel as "the lowest rank whose path passes through the anchor" (atomicMin while
@@ -344,11 +369,16 @@ k_chain_tail_warp(FragTab ft, const int32_t *__restrict__ list, int n_list, cons
 		__syncwarp();
 		if (n_u > 0) {
 			// 3. rank by (peak score, anchor) descending (chain.c:107-111); equal values are duplicates
-			for (int e = lane; e < n_u; e += 32) {
-				const uint64_t x = U1[e];
-				int r = 0;
-				for (int k = 0; k < n_u; ++k) { const uint64_t y = U1[k]; r += (y > x || (y == x && k < e)) ? 1 : 0; }
-				U0[r] = x;
+			if (n_u <= 64) {
+				for (int e = lane; e < n_u; e += 32) {
+					const uint64_t x = U1[e];
+					int r = 0;
+					for (int k = 0; k < n_u; ++k) { const uint64_t y = U1[k]; r += (y > x || (y == x && k < e)) ? 1 : 0; }
+					U0[r] = x;
+				}
+			} else {
+				warp_bitonic(U1, n_u, lane, U64Desc());
+				for (int e = lane; e < n_u; e += 32) U0[e] = U1[e];
 			}
 			// 4. ownership: lowest rank whose walk passes through the anchor
 			for (int i = lane; i < n; i += 32) T[i] = 0x7fffffff;
@@ -397,18 +427,36 @@ k_chain_tail_warp(FragTab ft, const int32_t *__restrict__ list, int n_list, cons
 			for (int kk = lane; kk < n_u; kk += 32) W[kk].x = B[V[kk]].x;
 			__syncwarp();
 			// 7. order chains by the position of their first anchor, klib radix semantics (chain.c:150)
-			if (lane == 0) mmg_rs_sort_exact(W, (int64_t)n_u, stack + ao / 65 + 2 * (int64_t)li, KeyX());
+			// With distinct keys the sorted order is unique, so a parallel sort gives klib's result; only equal keys (two chains
+			// starting on anchors with the same reference position) need the in-place MSD radix sort replayed literally.
+			if (n_u <= 64) {
+				if (lane == 0) mmg_rs_sort_exact(W, (int64_t)n_u, stack + ao / 65 + 2 * (int64_t)li, KeyX());
+			} else {
+				warp_bitonic(W, n_u, lane, M128ByX());
+				bool tie = false;
+				for (int kk = lane + 1; kk < n_u; kk += 32) tie |= W[kk].x == W[kk - 1].x;
+				if (__any_sync(FULL, tie)) {
+					for (int kk = lane; kk < n_u; kk += 32) { const int off = V[kk]; W[kk].x = B[off].x; W[kk].y = (uint64_t)off << 32 | (uint32_t)kk; }
+					__syncwarp();
+					if (lane == 0) mmg_rs_sort_exact(W, (int64_t)n_u, stack + ao / 65 + 2 * (int64_t)li, KeyX());
+				}
+			}
 			__syncwarp();
-			// 8. write chains back to a[] in that order (chain.c:152-159)
+			// 8. write chains back to a[] in that order (chain.c:152-159): 32 chains at a time, offsets from a warp scan
 			int dst = 0;
-			for (int i = 0; i < n_u; ++i) {
-				const uint64_t wy = W[i].y;
-				const int jj = (int32_t)(uint32_t)wy, src = (int)(wy >> 32);
-				const uint64_t uk = U1[jj];
+			for (int i0 = 0; i0 < n_u; i0 += 32) {
+				const int i = i0 + lane;
+				uint64_t uk = 0; int src = 0;
+				if (i < n_u) { const uint64_t wy = W[i].y; uk = U1[(int32_t)(uint32_t)wy]; src = (int)(wy >> 32); }
 				const int nn = (int32_t)(uint32_t)uk;
-				for (int q = lane; q < nn; q += 32) A[dst + q] = B[src + q];
-				if (lane == 0) U0[i] = uk;
-				dst += nn;
+				int incl = nn;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+				const int off = dst + incl - nn;
+				for (int q = 0; q < nn; ++q) A[off + q] = B[src + q];
+				dst += __shfl_sync(FULL, incl, 31);
+				__syncwarp();
+				if (i < n_u) U0[i] = uk; // U1 = U0 + n: the compacted values are not overwritten
 			}
 			__syncwarp();
 		}

@@ -35,15 +35,13 @@ typedef struct { pfor_t *pf; int tid; } pfor_arg_t;
 static void *pfor_worker(void *p)
 {
 	pfor_arg_t *a = (pfor_arg_t*)p;
-	mm_tls_pool = mm_pool_acquire(); /* arena chunks recycled without locks while this worker lives */
 	for (;;) {
 		const long i = __sync_fetch_and_add(&a->pf->next, 16);
 		long j;
 		if (i >= a->pf->n) break;
 		for (j = i; j < i + 16 && j < a->pf->n; ++j) a->pf->fn(a->pf->data, j, a->tid);
 	}
-	mm_pool_release(mm_tls_pool);
-	mm_tls_pool = 0;
+	mm_arena_thread_done(); /* what is left of this worker's arena block goes to the next worker */
 	return 0;
 }
 
@@ -71,7 +69,6 @@ typedef struct {
 	mm_reg1_t *regs0;
 	mm_seg_t *seg;        /* per-mate chains when n_segs > 1 */
 	mm_alnseg_t *aln;     /* [n_segs] */
-	mm_arena_t arena;     /* everything above lives here */
 } frag_t;
 
 typedef struct {          /* one GPU's share of a mini-batch */
@@ -87,6 +84,7 @@ typedef struct {          /* one GPU's share of a mini-batch */
 	frag_t *fr;
 	mmg_chains_t ch;
 	mm_b200_stats_t st;
+	mm_arena_t arena;     /* per-fragment state of this shard: anchors, chains, per-mate copies, DP cache, temporaries */
 	pthread_mutex_t *gpu_token; /* held during device stages when the GPU is shared by several shards */
 	size_t *job_off;      /* [nf+1] first job of each fragment in the current DP round */
 	mmg_ksw_job_t *jobs;
@@ -124,7 +122,7 @@ static void stage_hits(void *data, long i, int tid)
 	const mmg_chains_t *ch = &sh->ch;
 	int j, is_sr = !!(opt->flag & MM_F_SR);
 	memset(fr, 0, sizeof(*fr));
-	mm_tls_arena = &fr->arena;
+	mm_tls_arena = &sh->arena;
 	fr->n_segs = ns;
 	fr->qlens = (int*)mm_amalloc((size_t)ns * sizeof(int));
 	for (j = 0; j < ns; ++j) {
@@ -181,7 +179,7 @@ static void stage_align(void *data, long i, int tid)
 	const mm_mapopt_t *opt = sh->opt;
 	int j, all_done = 1;
 	if (!fr->active) return;
-	mm_tls_arena = &fr->arena;
+	mm_tls_arena = &sh->arena;
 	for (j = 0; j < fr->n_segs; ++j) {
 		mm_alnseg_t *s = &fr->aln[j];
 		const int off = sh->seg_off[sh->f0 + i] + j;
@@ -222,7 +220,7 @@ static void stage_scatter_results(void *data, long i, int tid)
 	size_t k = sh->job_off[i];
 	int j;
 	if (!fr->active) return;
-	mm_tls_arena = &fr->arena;
+	mm_tls_arena = &sh->arena;
 	for (j = 0; j < fr->n_segs; ++j) {
 		mm_dpcache_t *c = &fr->aln[j].cache;
 		for (; c->n_sent < c->n; ++c->n_sent, ++k) {
@@ -247,7 +245,7 @@ static void stage_finish(void *data, long i, int tid)
 	int j, k, mapped;
 	if (fr->finished) return;
 	fr->finished = 1;
-	mm_tls_arena = &fr->arena;
+	mm_tls_arena = &sh->arena;
 	mapped = !(fr->qlen_sum == 0 || ns <= 0 || ns > MM_MAX_SEG || (opt->max_qlen > 0 && fr->qlen_sum > opt->max_qlen));
 	if (mapped) {
 		for (j = 0; j < ns; ++j) mm_set_mapq(sh->n_reg[off + j], sh->reg[off + j], opt->min_chain_score, opt->a, fr->rep_len, is_sr);
@@ -264,7 +262,6 @@ static void stage_finish(void *data, long i, int tid)
 			}
 	}
 	for (j = 0; j < ns; ++j) sh->rep_len[off + j] = fr->rep_len, sh->frag_gap[off + j] = fr->frag_gap;
-	mm_arena_release(&fr->arena); /* anchors, chains, per-mate copies, DP cache, temporaries: gone in one sweep */
 	mm_tls_arena = 0;
 }
 
@@ -381,6 +378,7 @@ static void *map_shard(void *data)
 	parallel_for(sh->n_threads, stage_finish, sh, nf);
 	sh->st.t_finish += realtime() - t0;
 	free(sh->fr); sh->fr = 0;
+	mm_arena_release(&sh->arena); /* gone in one sweep */
 	return 0;
 }
 
@@ -437,6 +435,7 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 	int d, f = 0, rc = 0, pass;
 	int64_t tot = 0, acc = 0;
 	const double t_start = realtime();
+	mm_b200_tune_malloc();
 	if (opt->flag & MM_F_INDEPEND_SEG) { fprintf(stderr, "[ERROR] --no-pairing is not supported by this build\n"); return -1; }
 	for (d = 0; d < s->n_seq; ++d) tot += s->seq[d].l_seq;
 	for (d = 0; d < n_dev; ++d) { /* contiguous fragment ranges balanced by bases; a fragment is never cut */
@@ -444,6 +443,7 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		const int64_t goal = tot * (d + 1) / n_dev;
 		h->mi = mi, h->opt = opt, h->ctx = B->ctx[d], h->didx = B->didx[d / B->lanes];
 		mm_mapopt_to_dev(opt, &h->dopt);
+		mm_arena_init(&h->arena);
 		/* lanes of one GPU alternate between device and host stages, so each may use that GPU's whole share of host threads */
 		h->n_threads = n_threads / B->n_dev > 0 ? n_threads / B->n_dev : 1;
 		h->gpu_token = B->lanes > 1 ? &B->gpu_token[d / B->lanes] : 0;
@@ -651,6 +651,7 @@ void mm_map_frag(const mm_idx_t *mi, int n_segs, const int *qlens, const char **
 		memcpy(seq[j].seq, seqs[j], qlens[j]); seq[j].seq[qlens[j]] = 0;
 	}
 	memset(&sh, 0, sizeof(sh));
+	mm_arena_init(&sh.arena);
 	/* worker_for flips the mates of a pair around this call (map.c:467-469,486-497); callers of the library API
 	 * pass sequences already in mapping orientation, so neither the host nor the device flips here.
 	 * pe_ori = 0 keeps `pe_ori >= 0` (pairing on, map.c:404) while naming no mate to flip. */

@@ -106,69 +106,83 @@ void NAME(T *beg, T *end) \
 RADIX_IMPL(radix_sort_128x, mm128_t, KEY_X)
 RADIX_IMPL(radix_sort_64, uint64_t, KEY_ID)
 
-/* ---- per-fragment arena (see mm2b_priv.h) */
+/* ---- shard-lifetime bump arena (see mm2b_priv.h) */
 
 __thread mm_arena_t *mm_tls_arena = 0;
 
-/* Standard-size chunks are recycled instead of going back to malloc (with short-lived worker threads glibc grows and
- * trims its per-thread heaps with mprotect() on every batch).  Each worker thread borrows a private pool for its
- * lifetime, so the hot path takes no lock; pools themselves live in a mutex-protected free list. */
-#define ARENA_STD_CAP (16384 - sizeof(mm_arena_chunk_t) - 16)
-#define ARENA_FIRST_CAP (8192 - sizeof(mm_arena_chunk_t) - 16) /* most short-read fragments fit their whole state in this */
-#define POOL_MAX_CHUNKS (1 << 20)
-struct mm_chunk_pool_s { struct mm_chunk_pool_s *next; mm_arena_chunk_t *chunks, *small; int n, n_small; };
-__thread mm_chunk_pool_t *mm_tls_pool = 0;
-static mm_chunk_pool_t *g_pools = 0;
-static pthread_mutex_t g_pools_mu = PTHREAD_MUTEX_INITIALIZER;
+/* Memory is carved from 256 KB blocks that are recycled through a global free list, so a mini-batch takes no trip to
+ * malloc for its working state (short-lived worker threads otherwise make glibc grow and trim its per-thread heaps with
+ * mprotect() all the time: that was 40 % of the host time).  A worker bumps inside its own block without locks; the block
+ * it leaves half full when it exits is handed to the next worker of the same shard. */
+#define ABLOCK_BYTES ((size_t)256 << 10)
+#define ABLOCK_CAP (ABLOCK_BYTES - 32)          /* usable bytes after the 32-byte header slot */
+#define ABLOCK_KEEP_MAX ((size_t)16 << 30)      /* blocks kept for reuse */
+static mm_ablock_t *g_free_blocks = 0;
+static size_t g_free_bytes = 0;
+static pthread_mutex_t g_blocks_mu = PTHREAD_MUTEX_INITIALIZER;
+static uint64_t g_arena_gen = 0;
+static __thread struct { mm_arena_t *owner; uint64_t gen; char *cur, *end; } tls_bump;
 
-mm_chunk_pool_t *mm_pool_acquire(void)
+void mm_arena_init(mm_arena_t *a)
 {
-	mm_chunk_pool_t *p;
-	pthread_mutex_lock(&g_pools_mu);
-	if ((p = g_pools) != 0) g_pools = p->next;
-	pthread_mutex_unlock(&g_pools_mu);
-	if (p == 0) p = (mm_chunk_pool_t*)calloc(1, sizeof(*p));
-	p->next = 0;
-	return p;
+	memset(a, 0, sizeof(*a));
+	pthread_mutex_init(&a->mu, 0);
+	a->gen = __sync_add_and_fetch(&g_arena_gen, 1);
 }
 
-void mm_pool_release(mm_chunk_pool_t *p)
-{
-	if (p == 0) return;
-	pthread_mutex_lock(&g_pools_mu);
-	p->next = g_pools, g_pools = p;
-	pthread_mutex_unlock(&g_pools_mu);
-}
-
-static mm_arena_chunk_t *chunk_get(size_t cap)
-{
-	mm_arena_chunk_t *c = 0;
-	mm_chunk_pool_t *p = mm_tls_pool;
-	if (cap == ARENA_STD_CAP && p && p->chunks) c = p->chunks, p->chunks = c->next, --p->n;
-	else if (cap == ARENA_FIRST_CAP && p && p->small) c = p->small, p->small = c->next, --p->n_small;
-	if (c == 0) c = (mm_arena_chunk_t*)malloc(sizeof(mm_arena_chunk_t) + 16 + cap);
-	c->cap = cap, c->used = 0, c->next = 0;
-	return c;
+static mm_ablock_t *block_new(mm_arena_t *a, size_t cap)
+{ /* a standard block from the free list (or the system), or a dedicated one for a large request; registered with the arena */
+	mm_ablock_t *b = 0;
+	if (cap == ABLOCK_CAP) {
+		pthread_mutex_lock(&g_blocks_mu);
+		if ((b = g_free_blocks) != 0) g_free_blocks = b->next, g_free_bytes -= ABLOCK_BYTES;
+		pthread_mutex_unlock(&g_blocks_mu);
+	}
+	if (b == 0) b = (mm_ablock_t*)malloc(32 + cap);
+	b->cap = cap;
+	pthread_mutex_lock(&a->mu);
+	b->next = a->blocks, a->blocks = b;
+	pthread_mutex_unlock(&a->mu);
+	return b;
 }
 
 void *mm_amalloc(size_t n)
 {
 	mm_arena_t *a = mm_tls_arena;
-	mm_arena_chunk_t *c;
 	if (a == 0) return malloc(n);
 	n = (n + 15) & ~(size_t)15;
-	c = a->head;
-	if (c == 0 || c->used + n > c->cap) {
-		mm_arena_chunk_t *nc = chunk_get(c == 0 && n <= ARENA_FIRST_CAP ? ARENA_FIRST_CAP : n > ARENA_STD_CAP ? n : ARENA_STD_CAP);
-		if (c && n > ARENA_STD_CAP / 2) { nc->next = c->next; c->next = nc; c = nc; } /* a big block gets its own chunk; keep filling the current one */
-		else { nc->next = c; a->head = nc; c = nc; }
+	if (tls_bump.owner != a || tls_bump.gen != a->gen) tls_bump.owner = a, tls_bump.gen = a->gen, tls_bump.cur = tls_bump.end = 0;
+	if (tls_bump.cur + n > tls_bump.end) {
+		if (n > ABLOCK_CAP / 4) return (char*)block_new(a, n) + 32; /* own block; the current one keeps filling */
+		pthread_mutex_lock(&a->mu); /* a block another worker left behind? */
+		if (a->n_partial > 0 && a->partial[a->n_partial - 1].end - a->partial[a->n_partial - 1].cur >= (long)n) {
+			--a->n_partial;
+			tls_bump.cur = a->partial[a->n_partial].cur, tls_bump.end = a->partial[a->n_partial].end;
+			pthread_mutex_unlock(&a->mu);
+		} else {
+			mm_ablock_t *b;
+			pthread_mutex_unlock(&a->mu);
+			b = block_new(a, ABLOCK_CAP);
+			tls_bump.cur = (char*)b + 32, tls_bump.end = tls_bump.cur + ABLOCK_CAP;
+		}
 	}
 	{
-		char *base = (char*)(((size_t)(c + 1) + 15) & ~(size_t)15);
-		void *r = base + c->used;
-		c->used += n;
+		void *r = tls_bump.cur;
+		tls_bump.cur += n;
 		return r;
 	}
+}
+
+/* a worker thread is about to exit: pass on what is left of its block */
+void mm_arena_thread_done(void)
+{
+	mm_arena_t *a = tls_bump.owner;
+	if (a && tls_bump.end - tls_bump.cur >= 4096 && tls_bump.gen == a->gen) {
+		pthread_mutex_lock(&a->mu);
+		if (a->n_partial < MM_ARENA_MAX_PARTIAL) a->partial[a->n_partial].cur = tls_bump.cur, a->partial[a->n_partial].end = tls_bump.end, ++a->n_partial;
+		pthread_mutex_unlock(&a->mu);
+	}
+	tls_bump.owner = 0, tls_bump.cur = tls_bump.end = 0;
 }
 
 void *mm_acalloc(size_t n, size_t sz)
@@ -191,15 +205,37 @@ void *mm_arealloc(void *p, size_t old_bytes, size_t new_bytes)
 
 void mm_afree(void *p) { if (mm_tls_arena == 0) free(p); }
 
+/* the shard is done: every block goes back to the free list in one sweep */
 void mm_arena_release(mm_arena_t *a)
 {
-	mm_arena_chunk_t *c = a->head, *n;
-	mm_chunk_pool_t *p = mm_tls_pool;
-	for (; c; c = n) {
-		n = c->next;
-		if (p && c->cap == ARENA_STD_CAP && p->n < POOL_MAX_CHUNKS) c->next = p->chunks, p->chunks = c, ++p->n;
-		else if (p && c->cap == ARENA_FIRST_CAP && p->n_small < 4 * POOL_MAX_CHUNKS) c->next = p->small, p->small = c, ++p->n_small;
-		else free(c);
+	mm_ablock_t *b = a->blocks, *n, *keep = 0, *keep_tail = 0;
+	size_t n_keep = 0;
+	for (; b; b = n) {
+		n = b->next;
+		if (b->cap == ABLOCK_CAP) { b->next = keep; if (keep == 0) keep_tail = b; keep = b; ++n_keep; }
+		else free(b);
 	}
-	a->head = 0;
+	if (keep) {
+		pthread_mutex_lock(&g_blocks_mu);
+		if (g_free_bytes + n_keep * ABLOCK_BYTES <= ABLOCK_KEEP_MAX) {
+			keep_tail->next = g_free_blocks, g_free_blocks = keep, g_free_bytes += n_keep * ABLOCK_BYTES;
+			keep = 0;
+		}
+		pthread_mutex_unlock(&g_blocks_mu);
+		for (b = keep; b; b = n) { n = b->next; free(b); }
+	}
+	a->blocks = 0, a->n_partial = 0;
+	a->gen = __sync_add_and_fetch(&g_arena_gen, 1);
+	if (tls_bump.owner == a) tls_bump.owner = 0, tls_bump.cur = tls_bump.end = 0;
+}
+
+/* glibc: keep freed memory instead of trimming and re-growing the heaps on every mini-batch */
+#include <malloc.h>
+void mm_b200_tune_malloc(void)
+{
+	static int done = 0;
+	if (__sync_lock_test_and_set(&done, 1)) return;
+	mallopt(M_TRIM_THRESHOLD, 1 << 30);
+	mallopt(M_TOP_PAD, 64 << 20);
+	mallopt(M_MMAP_THRESHOLD, 32 << 20);
 }

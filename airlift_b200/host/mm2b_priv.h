@@ -58,21 +58,28 @@ struct mm_idx_bucket_s {
 extern unsigned char seq_nt4_table[256];
 extern unsigned char seq_comp_table[256];
 
-/* misc.c: per-fragment bump arena.  Everything whose lifetime ends with the fragment (work arrays, per-mate anchor
- * copies, the DP job cache, temporaries) is carved from it; the stage functions select it through a thread-local
- * pointer.  API-visible blocks (mm_reg1_t arrays, mm_extra_t) stay on malloc because callers free() them. */
-typedef struct mm_arena_chunk_s { struct mm_arena_chunk_s *next; size_t cap, used; } mm_arena_chunk_t;
-typedef struct { mm_arena_chunk_t *head; } mm_arena_t;
+/* misc.c: shard-lifetime bump arena.  Everything whose lifetime ends with the mini-batch shard (work arrays, per-mate
+ * anchor copies, the DP job cache, temporaries) is carved from recycled 256 KB blocks; the stage functions select the
+ * shard's arena through a thread-local pointer.  API-visible blocks (mm_reg1_t arrays, mm_extra_t) stay on malloc because
+ * callers free() them. */
+#define MM_ARENA_MAX_PARTIAL 64
+typedef struct mm_ablock_s { struct mm_ablock_s *next; size_t cap; } mm_ablock_t;
+typedef struct {
+	mm_ablock_t *blocks;      /* every block handed out for this arena */
+	pthread_mutex_t mu;
+	uint64_t gen;             /* changes on release, so a stale thread-local bump pointer is never reused */
+	int n_partial;
+	struct { char *cur, *end; } partial[MM_ARENA_MAX_PARTIAL]; /* blocks that exited workers left half full */
+} mm_arena_t;
 extern __thread mm_arena_t *mm_tls_arena;
+void mm_arena_init(mm_arena_t *a);
 void *mm_amalloc(size_t n);
 void *mm_acalloc(size_t n, size_t sz);
 void *mm_arealloc(void *p, size_t old_bytes, size_t new_bytes);
 void mm_afree(void *p);
+void mm_arena_thread_done(void);
 void mm_arena_release(mm_arena_t *a);
-typedef struct mm_chunk_pool_s mm_chunk_pool_t;
-extern __thread mm_chunk_pool_t *mm_tls_pool;
-mm_chunk_pool_t *mm_pool_acquire(void);
-void mm_pool_release(mm_chunk_pool_t *p);
+void mm_b200_tune_malloc(void);
 
 /* misc.c */
 double cputime(void);
