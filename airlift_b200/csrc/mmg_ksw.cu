@@ -379,16 +379,16 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, order, n, 0, 30, c->stream));
 		++c->launches;
 	}
-	int64_t tot[3]; unsigned long long h_cells = 0; uint32_t h_cls[KSW_N_FAST + 1];
+	int64_t tot[3]; unsigned long long h_cells[2 + KSW_N_FAST]; uint32_t h_cls[KSW_N_FAST + 1];
 	MMG_D2H(c, &tot[0], mem_off + n, 8); MMG_D2H(c, &tot[1], p_off + n, 8); MMG_D2H(c, &tot[2], cg_off + n, 8);
-	MMG_D2H(c, &h_cells, d_cells, 8); MMG_D2H(c, h_cls, d_cls, sizeof(h_cls));
+	MMG_D2H(c, h_cells, d_cells, sizeof(h_cells)); MMG_D2H(c, h_cls, d_cls, sizeof(h_cls));
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
-	if (cells) *cells = h_cells;
+	if (cells) *cells = h_cells[0];
+	c->k_last_jobs_literal = h_cls[KSW_CLS_LITERAL], c->k_last_cells_literal = h_cells[1 + KSW_CLS_LITERAL];
+	c->k_last_jobs_fast = (uint64_t)n - h_cls[KSW_CLS_LITERAL], c->k_last_cells_fast = h_cells[0] - h_cells[1 + KSW_CLS_LITERAL];
 	if (getenv("MMG_KSW_DEBUG")) {
-		unsigned long long hc[KSW_N_FAST + 1];
-		cudaMemcpy(hc, d_cells + 1, sizeof(hc), cudaMemcpyDeviceToHost);
-		fprintf(stderr, "[mmg_ksw] %d jobs, %llu cells:", n, h_cells);
-		for (int q = 0; q <= KSW_N_FAST; ++q) fprintf(stderr, " class %d: %u jobs %llu cells;", q, h_cls[q], hc[q]);
+		fprintf(stderr, "[mmg_ksw] %d jobs, %llu cells:", n, h_cells[0]);
+		for (int q = 0; q <= KSW_N_FAST; ++q) fprintf(stderr, " class %d: %u jobs %llu cells;", q, h_cls[q], h_cells[1 + q]);
 		fprintf(stderr, " p %ld B, mem %ld B\n", (long)tot[1], (long)tot[0]);
 	}
 	MMG_TRY(c->k_mem.ensure((size_t)tot[0] + 64));
@@ -452,6 +452,14 @@ static KswScore make_score(const mmg_mapopt_t *opt)
 	for (int j = 0; j < 5; ++j) sc.mat[20 + j] = (int8_t)amb;
 	sc.q = (int8_t)opt->q, sc.e = (int8_t)opt->e, sc.q2 = (int8_t)opt->q2, sc.e2 = (int8_t)opt->e2;
 	return sc;
+}
+
+extern "C" void mmg_ksw_last_split(const mmg_ctx_t *c, uint64_t *jobs_fast, uint64_t *cells_fast, uint64_t *jobs_literal, uint64_t *cells_literal)
+{ // how the last mmg_ksw_batch() divided its jobs between the thread-per-job fast form and the literal 16-lane form
+	if (jobs_fast) *jobs_fast = c->k_last_jobs_fast;
+	if (cells_fast) *cells_fast = c->k_last_cells_fast;
+	if (jobs_literal) *jobs_literal = c->k_last_jobs_literal;
+	if (cells_literal) *cells_literal = c->k_last_cells_literal;
 }
 
 extern "C" int mmg_ksw_batch(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, int n_jobs, const mmg_ksw_job_t *jobs,

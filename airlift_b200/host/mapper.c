@@ -368,6 +368,7 @@ static void *map_shard(void *data)
 			tb = realtime();
 			sh->st.t_ksw_total += tb - ta, sh->st.t_ksw_kernel += kms * 1e-3;
 			sh->st.n_dp_jobs += n_jobs, sh->st.n_dp_cells += cells, sh->st.n_dp_rounds += 1;
+			{ uint64_t jf = 0, cf = 0; mmg_ksw_last_split(sh->ctx, &jf, &cf, 0, 0); sh->st.n_dp_jobs_fast += jf, sh->st.n_dp_cells_fast += cf; }
 			parallel_for(sh->n_threads, stage_scatter_results, sh, nf);
 			sh->st.t_align_host += realtime() - tb;
 		}
@@ -478,20 +479,46 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		g_stats.n_frag += t->n_frag, g_stats.n_reads += t->n_reads, g_stats.n_bases += t->n_bases, g_stats.n_minimizers += t->n_minimizers;
 		g_stats.n_anchors += t->n_anchors, g_stats.n_chain_iter += t->n_chain_iter, g_stats.n_dp_jobs += t->n_dp_jobs;
 		g_stats.n_dp_cells += t->n_dp_cells, g_stats.n_dp_rounds += t->n_dp_rounds, g_stats.h2d_bytes += h2d, g_stats.d2h_bytes += d2h;
+		g_stats.n_dp_jobs_fast += t->n_dp_jobs_fast, g_stats.n_dp_cells_fast += t->n_dp_cells_fast;
 	}
 	g_stats.t_total += realtime() - t_start;
 	pthread_mutex_unlock(&g_stats_mu);
+	if (getenv("MM2_B200_TRACE")) /* per-batch stage times of every shard */
+		for (d = 0; d < n_dev; ++d) {
+			const mm_b200_stats_t *t = &sh[d].st;
+			fprintf(stderr, "[T::map_step] at %.3f: %.3f s, shard %d: %d frags, upload %.3f seed/chain %.3f (kernels %.3f) hits %.3f align %.3f dp %.3f (kernel %.3f) finish %.3f\n",
+					realtime() - mm_realtime0, realtime() - t_start, d, sh[d].f1 - sh[d].f0, t->t_upload, t->t_seedchain, t->t_seedchain_kernels, t->t_hits, t->t_align_host, t->t_ksw_total, t->t_ksw_kernel, t->t_finish);
+		}
 	free(sh); free(tid);
 	return rc;
 }
 
 static int step_map(pipeline_t *p, step_t *s) { return map_step(p->mi, p->opt, p->n_threads, s, 0); }
 
-static void step_write(pipeline_t *p, step_t *s)
-{ /* map.c:594-650 (no --split-prefix) */
+/* Step 2 (map.c:594-650, no --split-prefix).  Records are formatted by the worker threads, one output buffer per block of
+ * fragments, and the buffers leave through stdout in input order: the bytes are those of one puts() per record. */
+typedef struct { pipeline_t *p; step_t *s; int frags_per_chunk; char **buf; size_t *len; } write_job_t;
+
+static inline void out_append(char **o, size_t *ol, size_t *om, const char *rec, size_t l)
+{
+	if (*ol + l + 1 > *om) { *om = (*ol + l + 1) * 2 > (1 << 20) ? (*ol + l + 1) * 2 : (1 << 20); *o = (char*)realloc(*o, *om); }
+	memcpy(*o + *ol, rec, l);
+	(*o)[*ol + l] = '\n';
+	*ol += l + 1;
+}
+
+static void write_chunk(void *data, long c, int tid)
+{
+	write_job_t *w = (write_job_t*)data;
+	pipeline_t *p = w->p;
+	step_t *s = w->s;
 	const mm_idx_t *mi = p->mi;
+	const int k0 = (int)c * w->frags_per_chunk, k1 = k0 + w->frags_per_chunk < s->n_frag ? k0 + w->frags_per_chunk : s->n_frag;
+	mm_str_t str = {0, 0, 0};
+	char *o = 0;
+	size_t ol = 0, om = 0;
 	int i, j, k;
-	for (k = 0; k < s->n_frag; ++k) {
+	for (k = k0; k < k1; ++k) {
 		const int seg_st = s->seg_off[k], seg_en = s->seg_off[k] + s->n_seg[k];
 		for (i = seg_st; i < seg_en; ++i) {
 			mm_bseq1_t *t = &s->seq[i];
@@ -501,25 +528,44 @@ static void step_write(pipeline_t *p, step_t *s)
 					assert(!r->sam_pri || r->id == r->parent);
 					if ((p->opt->flag & MM_F_NO_PRINT_2ND) && r->id != r->parent) continue;
 					if (p->opt->flag & MM_F_OUT_SAM)
-						mm_write_sam3(&p->str, mi, t, i - seg_st, j, s->n_seg[k], &s->n_reg[seg_st], (const mm_reg1_t*const*)&s->reg[seg_st], (int)p->opt->flag, s->rep_len[i]);
-					else mm_write_paf3(&p->str, mi, t, r, (int)p->opt->flag, s->rep_len[i]);
-					mm_err_puts(p->str.s);
+						mm_write_sam3(&str, mi, t, i - seg_st, j, s->n_seg[k], &s->n_reg[seg_st], (const mm_reg1_t*const*)&s->reg[seg_st], (int)p->opt->flag, s->rep_len[i]);
+					else mm_write_paf3(&str, mi, t, r, (int)p->opt->flag, s->rep_len[i]);
+					out_append(&o, &ol, &om, str.s, str.l);
 				}
 			} else if ((p->opt->flag & MM_F_PAF_NO_HIT) || ((p->opt->flag & MM_F_OUT_SAM) && !(p->opt->flag & MM_F_SAM_HIT_ONLY))) {
 				if (p->opt->flag & MM_F_OUT_SAM)
-					mm_write_sam3(&p->str, mi, t, i - seg_st, -1, s->n_seg[k], &s->n_reg[seg_st], (const mm_reg1_t*const*)&s->reg[seg_st], (int)p->opt->flag, s->rep_len[i]);
-				else mm_write_paf3(&p->str, mi, t, 0, (int)p->opt->flag, s->rep_len[i]);
-				mm_err_puts(p->str.s);
+					mm_write_sam3(&str, mi, t, i - seg_st, -1, s->n_seg[k], &s->n_reg[seg_st], (const mm_reg1_t*const*)&s->reg[seg_st], (int)p->opt->flag, s->rep_len[i]);
+				else mm_write_paf3(&str, mi, t, 0, (int)p->opt->flag, s->rep_len[i]);
+				out_append(&o, &ol, &om, str.s, str.l);
 			}
 		}
 		for (i = seg_st; i < seg_en; ++i) {
 			for (j = 0; j < s->n_reg[i]; ++j) free(s->reg[i][j].p);
 			free(s->reg[i]);
-			free(s->seq[i].seq); free(s->seq[i].name);
-			if (s->seq[i].qual) free(s->seq[i].qual);
-			if (s->seq[i].comment) free(s->seq[i].comment);
+			mm_bseq_free1(&s->seq[i], 1);
 		}
 	}
+	free(str.s);
+	w->buf[c] = o, w->len[c] = ol;
+}
+
+static void step_write(pipeline_t *p, step_t *s)
+{
+	write_job_t w;
+	const int fpc = 256, n_chunks = (s->n_frag + fpc - 1) / fpc;
+	int c;
+	w.p = p, w.s = s, w.frags_per_chunk = fpc;
+	w.buf = (char**)calloc(n_chunks > 0 ? n_chunks : 1, sizeof(char*));
+	w.len = (size_t*)calloc(n_chunks > 0 ? n_chunks : 1, sizeof(size_t));
+	parallel_for(p->n_threads, write_chunk, &w, n_chunks);
+	for (c = 0; c < n_chunks; ++c) {
+		if (w.len[c] && fwrite(w.buf[c], 1, w.len[c], stdout) != w.len[c]) { /* a short write is fatal (misc.c:123-131) */
+			perror("[ERROR] failed to write the results");
+			exit(EXIT_FAILURE);
+		}
+		free(w.buf[c]);
+	}
+	free(w.buf); free(w.len);
 	if (mm_verbose >= 3)
 		fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", "worker_pipeline", realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), s->n_seq);
 	free(s->reg); free(s->n_reg); free(s->seq);
@@ -563,7 +609,13 @@ static void *reader_main(void *a)
 {
 	stage_arg_t *g = (stage_arg_t*)a;
 	step_t *s;
-	while (!g->p->failed && (s = step_read(g->p)) != 0) slot_put(g->out, s);
+	const int trace = getenv("MM2_B200_TRACE") != 0;
+	double t0 = realtime();
+	while (!g->p->failed && (s = step_read(g->p)) != 0) {
+		if (trace) fprintf(stderr, "[T::read] at %.3f: %d reads parsed in %.3f s\n", realtime() - mm_realtime0, s->n_seq, realtime() - t0);
+		slot_put(g->out, s);
+		t0 = realtime();
+	}
 	slot_close(g->out);
 	return 0;
 }
@@ -572,7 +624,12 @@ static void *writer_main(void *a)
 {
 	stage_arg_t *g = (stage_arg_t*)a;
 	step_t *s;
-	while ((s = slot_get(g->in)) != 0) step_write(g->p, s);
+	while ((s = slot_get(g->in)) != 0) {
+		const double t0 = realtime();
+		const int n = s->n_seq;
+		step_write(g->p, s);
+		if (getenv("MM2_B200_TRACE")) fprintf(stderr, "[T::write] at %.3f: %d reads written in %.3f s\n", realtime() - mm_realtime0, n, realtime() - t0);
+	}
 	return 0;
 }
 
@@ -598,6 +655,7 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 			free(pl.fp);
 			return -1;
 		}
+	for (i = 0; i < n_segs; ++i) mm_bseq_set_readahead(pl.fp[i], 1); /* parse each file ahead in its own thread */
 	pl.opt = opt, pl.mi = idx;
 	pl.n_threads = n_threads > 1 ? n_threads : 1;
 	pl.mini_batch_size = opt->mini_batch_size;
@@ -608,7 +666,7 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 	while ((s = slot_get(&q_read)) != 0) {
 		if (!pl.failed && step_map(&pl, s) != 0) pl.failed = 1;
 		if (pl.failed) { /* keep draining so the reader can finish; nothing more is written */
-			for (i = 0; i < s->n_seq; ++i) { free(s->seq[i].seq); free(s->seq[i].name); free(s->seq[i].qual); free(s->seq[i].comment); }
+			for (i = 0; i < s->n_seq; ++i) mm_bseq_free1(&s->seq[i], 1);
 			free(s->reg); free(s->n_reg); free(s->seq); free(s);
 			continue;
 		}
@@ -693,6 +751,7 @@ mm_b200_reader_t *mm_b200_open_reads(int n_fp, const char **fn)
 			free(r->pl.fp); free(r);
 			return 0;
 		}
+	for (i = 0; i < n_fp; ++i) mm_bseq_set_readahead(r->pl.fp[i], 1);
 	return r;
 }
 
@@ -773,7 +832,7 @@ void mm_b200_free_batch(mm_b200_batch_t *b)
 	step_t *s = (step_t*)b;
 	int i;
 	mm_b200_reset_batch(b);
-	for (i = 0; i < s->n_seq; ++i) { free(s->seq[i].seq); free(s->seq[i].name); free(s->seq[i].qual); free(s->seq[i].comment); }
+	for (i = 0; i < s->n_seq; ++i) mm_bseq_free1(&s->seq[i], 1);
 	free(s->reg); free(s->n_reg); free(s->seq); free(s);
 }
 

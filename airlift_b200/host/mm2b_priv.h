@@ -95,6 +95,8 @@ void mm_bseq_close(mm_bseq_file_t *fp);
 mm_bseq1_t *mm_bseq_read3(mm_bseq_file_t *fp, int chunk_size, int with_qual, int with_comment, int frag_mode, int *n_);
 mm_bseq1_t *mm_bseq_read_frag2(int n_fp, mm_bseq_file_t **fp, int chunk_size, int with_qual, int with_comment, int *n_);
 int mm_bseq_eof(mm_bseq_file_t *fp);
+void mm_bseq_set_readahead(mm_bseq_file_t *fp, int packed);
+void mm_bseq_free1(mm_bseq1_t *s, int packed);
 int mm_qname_len(const char *s);
 int mm_qname_same(const char *s1, const char *s2);
 void mm_revcomp_bseq(mm_bseq1_t *s);

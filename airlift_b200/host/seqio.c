@@ -5,6 +5,7 @@
 #include <zlib.h>
 #include <stdio.h>
 #include <ctype.h>
+#include <pthread.h>
 #include "mm2b_priv.h"
 
 #define IO_BUF (256 * 1024)
@@ -18,11 +19,28 @@ typedef struct {
 
 typedef struct { mm_str_t name, comment, seq, qual; int last_char; } record_t;
 
+/* Query files are parsed by a read-ahead thread per file (mm_bseq_set_readahead): blocks of records travel through a
+ * small ring, so that the two mate files of a paired run are parsed concurrently and ahead of the mapper. */
+#define RA_BLOCK 4096
+#define RA_RING 8
+typedef struct { mm_bseq1_t *a; int n, ret; } ra_block_t; /* ret: what ended the block (>= 0: more follow; -1: end of file; -2: bad record) */
+
 struct mm_bseq_file_s {
 	gzstream_t st;
 	record_t rec;
 	mm_bseq1_t pending; /* a record read ahead while completing a pair (bseq.c:100-110) */
+	int packed;         /* records are one malloc block owned by `name` (seq/qual/comment point inside it) */
+	int ra_on, ra_started, ra_stop, ra_with_qual, ra_with_comment;
+	pthread_t ra_thread;
+	pthread_mutex_t ra_mu;
+	pthread_cond_t ra_cv;
+	ra_block_t ring[RA_RING];
+	uint64_t ra_head, ra_tail; /* blocks [head, tail) are ready */
+	ra_block_t cur;            /* block being consumed */
+	int cur_i, ra_final;       /* ra_final: the status that ended the stream, once the consumer has seen it */
 };
+
+static int next_bseq(mm_bseq_file_t *fp, mm_bseq1_t *out, int with_qual, int with_comment);
 
 static inline int st_fill(gzstream_t *s)
 {
@@ -110,12 +128,33 @@ mm_bseq_file_t *mm_bseq_open(const char *fn)
 	fp = (mm_bseq_file_t*)calloc(1, sizeof(*fp));
 	fp->st.fp = f;
 	fp->st.buf = (unsigned char*)malloc(IO_BUF);
+	pthread_mutex_init(&fp->ra_mu, 0);
+	pthread_cond_init(&fp->ra_cv, 0);
 	return fp;
 }
 
 void mm_bseq_close(mm_bseq_file_t *fp)
 {
 	if (fp == 0) return;
+	if (fp->ra_started) { /* stop the read-ahead thread and drop what it had queued */
+		int i;
+		pthread_mutex_lock(&fp->ra_mu);
+		fp->ra_stop = 1;
+		pthread_cond_broadcast(&fp->ra_cv);
+		pthread_mutex_unlock(&fp->ra_mu);
+		for (;;) { /* keep draining so that a producer blocked on a full ring can finish */
+			mm_bseq1_t t;
+			if (next_bseq(fp, &t, fp->ra_with_qual, fp->ra_with_comment) < 0) break;
+			mm_bseq_free1(&t, fp->packed);
+		}
+		pthread_join(fp->ra_thread, 0);
+		while (fp->ra_head < fp->ra_tail) {
+			ra_block_t *b = &fp->ring[fp->ra_head++ % RA_RING];
+			for (i = 0; i < b->n; ++i) mm_bseq_free1(&b->a[i], fp->packed);
+			free(b->a);
+		}
+	}
+	if (fp->pending.seq) mm_bseq_free1(&fp->pending, fp->packed);
 	free(fp->rec.name.s); free(fp->rec.comment.s); free(fp->rec.seq.s); free(fp->rec.qual.s);
 	free(fp->st.buf);
 	gzclose(fp->st.fp);
@@ -124,28 +163,132 @@ void mm_bseq_close(mm_bseq_file_t *fp)
 
 int mm_bseq_eof(mm_bseq_file_t *fp)
 {
+	if (fp->ra_on) return fp->ra_final < 0 && fp->pending.seq == 0;
 	return fp->st.eof && fp->st.beg >= fp->st.end && fp->pending.seq == 0;
 }
 
-static char *dup_str(const mm_str_t *s)
-{
-	char *t = (char*)malloc(s->l + 1);
-	memcpy(t, s->s, s->l); t[s->l] = 0;
-	return t;
+static inline void fix_u(char *q, int l)
+{ /* U -> T, u -> t (bseq.c:72-74) */
+	int i;
+	for (i = 0; i < l; ++i) q[i] -= ((q[i] | 0x20) == 'u');
 }
 
-static void record_to_bseq(const record_t *r, mm_bseq1_t *s, int with_qual, int with_comment)
+/* one record from its four pieces; packed: a single block [name\0 seq\0 qual\0 comment\0] owned by `name` */
+static void make_bseq(mm_bseq1_t *s, int packed, const char *name, int l_name, const char *seq, int l_seq, const char *qual, int l_qual,
+                      const char *comment, int l_comment)
 {
-	int i;
-	if (r->name.l == 0) fprintf(stderr, "[WARNING]\033[1;31m empty sequence name in the input.\033[0m\n");
-	s->name = dup_str(&r->name);
-	s->seq = dup_str(&r->seq);
-	for (i = 0; i < (int)r->seq.l; ++i) /* U -> T, u -> t (bseq.c:72-74) */
-		if (s->seq[i] == 'u' || s->seq[i] == 'U') --s->seq[i];
-	s->qual = with_qual && r->qual.l ? dup_str(&r->qual) : 0;
-	s->comment = with_comment && r->comment.l ? dup_str(&r->comment) : 0;
-	s->l_seq = (int)r->seq.l;
+	if (l_name == 0) fprintf(stderr, "[WARNING]\033[1;31m empty sequence name in the input.\033[0m\n");
+	if (packed) {
+		char *b = (char*)malloc((size_t)l_name + l_seq + (qual ? l_qual + 1 : 0) + (comment ? l_comment + 1 : 0) + 2);
+		s->name = b; memcpy(b, name, l_name); b[l_name] = 0; b += l_name + 1;
+		s->seq = b; memcpy(b, seq, l_seq); b[l_seq] = 0; b += l_seq + 1;
+		s->qual = 0, s->comment = 0;
+		if (qual) { s->qual = b; memcpy(b, qual, l_qual); b[l_qual] = 0; b += l_qual + 1; }
+		if (comment) { s->comment = b; memcpy(b, comment, l_comment); b[l_comment] = 0; }
+	} else {
+		s->name = (char*)malloc((size_t)l_name + 1); memcpy(s->name, name, l_name); s->name[l_name] = 0;
+		s->seq = (char*)malloc((size_t)l_seq + 1); memcpy(s->seq, seq, l_seq); s->seq[l_seq] = 0;
+		s->qual = 0, s->comment = 0;
+		if (qual) { s->qual = (char*)malloc((size_t)l_qual + 1); memcpy(s->qual, qual, l_qual); s->qual[l_qual] = 0; }
+		if (comment) { s->comment = (char*)malloc((size_t)l_comment + 1); memcpy(s->comment, comment, l_comment); s->comment[l_comment] = 0; }
+	}
+	fix_u(s->seq, l_seq);
+	s->l_seq = l_seq;
 	s->rid = 0;
+}
+
+static void record_to_bseq(const record_t *r, mm_bseq1_t *s, int packed, int with_qual, int with_comment)
+{
+	make_bseq(s, packed, r->name.s, (int)r->name.l, r->seq.s, (int)r->seq.l, with_qual && r->qual.l ? r->qual.s : 0, (int)r->qual.l,
+	          with_comment && r->comment.l ? r->comment.s : 0, (int)r->comment.l);
+}
+
+/* The common case, a four-line FASTQ record lying entirely inside the inflate window, is cut out with four memchr()
+ * calls; anything else (FASTA, wrapped lines, '\r', a record straddling the window, ...) takes the general parser above,
+ * which defines the behaviour.  Returns 1 if a record was produced, 0 if the general parser must be used. */
+static int fastq_fast_path(mm_bseq_file_t *fp, mm_bseq1_t *out, int with_qual, int with_comment)
+{
+	gzstream_t *st = &fp->st;
+	const unsigned char *b = st->buf, *e = st->buf + st->end, *p0 = st->buf + st->beg, *p1, *p2, *p3, *p4, *ws;
+	int l_name, l_seq;
+	if (fp->rec.last_char != 0 || p0 >= e || *p0 != '@') return 0;
+	if ((p1 = (const unsigned char*)memchr(p0, '\n', e - p0)) == 0) return 0;
+	if ((p2 = (const unsigned char*)memchr(p1 + 1, '\n', e - (p1 + 1))) == 0) return 0;
+	if (p2 + 1 >= e || p2[1] != '+') return 0;
+	if ((p3 = (const unsigned char*)memchr(p2 + 1, '\n', e - (p2 + 1))) == 0) return 0;
+	if ((p4 = (const unsigned char*)memchr(p3 + 1, '\n', e - (p3 + 1))) == 0) return 0;
+	l_seq = (int)(p2 - p1 - 1);
+	if (l_seq <= 0 || p4 - p3 - 1 != l_seq) return 0;
+	if (p1[-1] == '\r' || p2[-1] == '\r' || p4[-1] == '\r') return 0;
+	if (p4 + 1 < e && p4[1] != '@') return 0;                 /* not followed by a record start: leave it to the general parser */
+	if (p4 + 1 >= e && !st->eof) return 0;                     /* cannot see what follows */
+	if (memchr(p1 + 1, '>', l_seq) || memchr(p1 + 1, '@', l_seq) || memchr(p1 + 1, '+', l_seq)) return 0;
+	for (ws = p0 + 1; ws < p1; ++ws) if (isspace(*ws)) break; /* name ends at the first white space; the rest of the line is the comment */
+	l_name = (int)(ws - (p0 + 1));
+	make_bseq(out, fp->packed, (const char*)p0 + 1, l_name, (const char*)p1 + 1, l_seq, with_qual ? (const char*)p3 + 1 : 0, l_seq,
+	          with_comment && ws < p1 && p1 - ws - 1 > 0 ? (const char*)ws + 1 : 0, ws < p1 ? (int)(p1 - ws - 1) : 0);
+	st->beg = (int)(p4 + 1 - b);
+	return 1;
+}
+
+/* next record straight from the file: >= 0 sequence length (record in *out); -1 end of file; -2 bad record */
+static int next_direct(mm_bseq_file_t *fp, mm_bseq1_t *out, int with_qual, int with_comment)
+{
+	int ret;
+	if (fp->st.beg >= fp->st.end && !fp->st.eof && fp->rec.last_char == 0) st_fill(&fp->st);
+	if (fastq_fast_path(fp, out, with_qual, with_comment)) return out->l_seq;
+	ret = read_record(&fp->st, &fp->rec);
+	if (ret >= 0) record_to_bseq(&fp->rec, out, fp->packed, with_qual, with_comment);
+	return ret;
+}
+
+static void *ra_main(void *arg)
+{
+	mm_bseq_file_t *fp = (mm_bseq_file_t*)arg;
+	for (;;) {
+		ra_block_t blk;
+		blk.a = (mm_bseq1_t*)malloc(RA_BLOCK * sizeof(mm_bseq1_t)), blk.n = 0, blk.ret = 0;
+		while (blk.n < RA_BLOCK && (blk.ret = next_direct(fp, &blk.a[blk.n], fp->ra_with_qual, fp->ra_with_comment)) >= 0) ++blk.n;
+		pthread_mutex_lock(&fp->ra_mu);
+		while (fp->ra_tail - fp->ra_head == RA_RING && !fp->ra_stop) pthread_cond_wait(&fp->ra_cv, &fp->ra_mu);
+		fp->ring[fp->ra_tail % RA_RING] = blk; ++fp->ra_tail;
+		pthread_cond_broadcast(&fp->ra_cv);
+		pthread_mutex_unlock(&fp->ra_mu);
+		if (blk.ret < 0 || fp->ra_stop) break;
+	}
+	return 0;
+}
+
+/* next record of the file, through the read-ahead ring when it is enabled */
+static int next_bseq(mm_bseq_file_t *fp, mm_bseq1_t *out, int with_qual, int with_comment)
+{
+	if (!fp->ra_on) return next_direct(fp, out, with_qual, with_comment);
+	if (!fp->ra_started) {
+		fp->ra_with_qual = with_qual, fp->ra_with_comment = with_comment, fp->ra_started = 1;
+		pthread_create(&fp->ra_thread, 0, ra_main, fp);
+	}
+	for (;;) {
+		if (fp->cur_i < fp->cur.n) { *out = fp->cur.a[fp->cur_i++]; return out->l_seq; }
+		if (fp->cur.a) { free(fp->cur.a); fp->cur.a = 0; fp->cur.n = fp->cur_i = 0; if (fp->cur.ret < 0) fp->ra_final = fp->cur.ret; }
+		if (fp->ra_final < 0) return fp->ra_final;
+		pthread_mutex_lock(&fp->ra_mu);
+		while (fp->ra_tail == fp->ra_head) pthread_cond_wait(&fp->ra_cv, &fp->ra_mu);
+		fp->cur = fp->ring[fp->ra_head % RA_RING]; ++fp->ra_head; fp->cur_i = 0;
+		pthread_cond_broadcast(&fp->ra_cv);
+		pthread_mutex_unlock(&fp->ra_mu);
+	}
+}
+
+void mm_bseq_set_readahead(mm_bseq_file_t *fp, int packed)
+{ /* query files: parse ahead in a thread of its own; `packed` records are single blocks released with mm_bseq_free1() */
+	fp->ra_on = 1, fp->packed = packed;
+}
+
+void mm_bseq_free1(mm_bseq1_t *s, int packed)
+{
+	if (packed) free(s->name);
+	else { free(s->seq); free(s->name); free(s->qual); free(s->comment); }
+	s->seq = s->name = s->qual = s->comment = 0;
 }
 
 typedef struct { int n, m; mm_bseq1_t *a; } bseq_v;
@@ -192,14 +335,14 @@ mm_bseq1_t *mm_bseq_read3(mm_bseq_file_t *fp, int chunk_size, int with_qual, int
 		size = fp->pending.l_seq;
 		memset(&fp->pending, 0, sizeof(mm_bseq1_t));
 	}
-	while ((ret = read_record(&fp->st, &fp->rec)) >= 0) {
-		mm_bseq1_t *s = vec_next(&a);
-		record_to_bseq(&fp->rec, s, with_qual, with_comment);
-		size += s->l_seq;
+	for (;;) {
+		mm_bseq1_t t;
+		if ((ret = next_bseq(fp, &t, with_qual, with_comment)) < 0) break;
+		*vec_next(&a) = t;
+		size += t.l_seq;
 		if (size >= chunk_size) {
 			if (frag_mode && a.a[a.n-1].l_seq < CHECK_PAIR_THRES) { /* never split a pair across batches */
-				while (read_record(&fp->st, &fp->rec) >= 0) {
-					record_to_bseq(&fp->rec, &fp->pending, with_qual, with_comment);
+				while (next_bseq(fp, &fp->pending, with_qual, with_comment) >= 0) {
 					if (mm_qname_same(fp->pending.name, a.a[a.n-1].name)) {
 						*vec_next(&a) = fp->pending;
 						memset(&fp->pending, 0, sizeof(mm_bseq1_t));
@@ -223,17 +366,18 @@ mm_bseq1_t *mm_bseq_read_frag2(int n_fp, mm_bseq_file_t **fp, int chunk_size, in
 	if (n_fp < 1) return 0;
 	for (;;) {
 		int n_read = 0;
-		for (i = 0; i < n_fp; ++i)
-			if (read_record(&fp[i]->st, &fp[i]->rec) >= 0) ++n_read;
+		mm_bseq1_t t[MM_MAX_SEG];
+		for (i = 0; i < n_fp && i < MM_MAX_SEG; ++i)
+			if (next_bseq(fp[i], &t[i], with_qual, with_comment) >= 0) ++n_read; else memset(&t[i], 0, sizeof(t[i]));
 		if (n_read < n_fp) {
 			if (n_read > 0)
 				fprintf(stderr, "[W::%s]\033[1;31m query files have different number of records; extra records skipped.\033[0m\n", __func__);
+			for (i = 0; i < n_fp && i < MM_MAX_SEG; ++i) if (t[i].seq) mm_bseq_free1(&t[i], fp[i]->packed);
 			break;
 		}
 		for (i = 0; i < n_fp; ++i) {
-			mm_bseq1_t *s = vec_next(&a);
-			record_to_bseq(&fp[i]->rec, s, with_qual, with_comment);
-			size += s->l_seq;
+			*vec_next(&a) = t[i];
+			size += t[i].l_seq;
 		}
 		if (size >= chunk_size) break;
 	}

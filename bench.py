@@ -30,6 +30,10 @@ sys.path.insert(0, ROOT)
 LIB = os.path.join(ROOT, "airlift_b200", "libmm2b200.so")
 SYNTH = os.path.join(ROOT, "build", "mmsynth")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "minimap2_B")
+CLI_BIN = os.path.join(ROOT, "build", "minimap2-b200")
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "traffic_r01.json")   # dram bytes per launch from the committed ncu --set full captures
+# integer-pipe roofline of K4: 148 SMs x 128 lanes x 1.965 GHz lane-ops/s over ~30 lane-ops per DP cell (one cell per lane-op)
+K4_INT_ROOFLINE_GCUPS = 148 * 128 * 1.965 / 30.0
 
 GENOME_BP = 100_000_000
 N_CONTIGS = 6
@@ -59,7 +63,7 @@ class Stats(C.Structure):  # mm_b200_stats_t
     _fields_ = [(n, C.c_double) for n in ("t_total", "t_upload", "t_seedchain", "t_seedchain_kernels", "t_hits", "t_align_host",
                                           "t_ksw_total", "t_ksw_kernel", "t_finish")] + \
                [(n, C.c_uint64) for n in ("n_frag", "n_reads", "n_bases", "n_minimizers", "n_anchors", "n_chain_iter", "n_dp_jobs",
-                                          "n_dp_cells", "n_dp_rounds", "h2d_bytes", "d2h_bytes")]
+                                          "n_dp_cells", "n_dp_rounds", "h2d_bytes", "d2h_bytes", "n_dp_jobs_fast", "n_dp_cells_fast")]
 
 
 def load_lib():
@@ -221,6 +225,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the whole-CLI (parse + map + SAM) timing at N=1")
     ap.add_argument("--lanes", type=int, default=2, help="shards (streams) per GPU a batch is cut into")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -391,21 +396,36 @@ def main():
         dom = max(prof_res.items(), key=lambda kv: kv[1][0]) if prof_res else ("none", (0.0, 0))
         dname, (dms, dn) = dom
         step_dev_ms = sum(v[0] for v in prof_res.values())
-        # algorithmic HBM bytes of each kernel over the timed region ("Kernels and rooflines")
+        # algorithmic HBM bytes of each kernel over the timed region (bytes per unit x units from the live counters)
         nmv, nanch, cells, jobs = st_res.n_minimizers, st_res.n_anchors, st_res.n_dp_cells, st_res.n_dp_jobs
+        cells_fast, jobs_fast = st_res.n_dp_cells_fast, st_res.n_dp_jobs_fast
         algo = {
             "k_sketch_count": st_res.n_bases * 0.5, "k_sketch_fill": st_res.n_bases * 0.5 + nmv * 16,
-            "k_lookup": nmv * (16 + 16 + 12), "k_fill": nmv * 28 + nanch * (8 + 16),
-            "k_chain": nanch * (16 + 16 + 16 + 16), "k_ksw": cells * 1.0 + jobs * 64, "k_encode_reads": st_res.n_bases * 1.5,
+            "k_lookup": nmv * (16 + 16 + 12), "k_fill": nmv * 28 + nanch * (8 + 16), "k_expand": nmv * 28 + nanch * (8 + 16),
+            "k_chain_fill": nanch * (16 + 16), "k_chain_tail_warp": nanch * (16 + 16 + 16 + 16),
+            "k_ksw": (cells - cells_fast) * 1.0 + (jobs - jobs_fast) * 64, "k_ksw_tpj": cells_fast * 1.0 + jobs_fast * 64,
+            "k_encode_reads": st_res.n_bases * 1.5,
         }
         a_bytes = algo.get(dname, 0.0)
         achieved = a_bytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
+        traffic = None
+        if os.path.exists(TRAFFIC_JSON):
+            traffic = _json.load(open(TRAFFIC_JSON)).get(dname, {}).get("dram_bytes_per_launch")
         roof = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "launches": dn, "avg_launch_ms": dms / dn if dn else None,
+                "traffic": traffic, "peak_source": peak_src, "launches": dn, "avg_launch_ms": dms / dn if dn else None,
+                "algorithmic_bytes_per_launch": a_bytes / dn if dn else None,
                 "share_of_kernel_time": dms / step_dev_ms if step_dev_ms else None,
-                "note": "latency/integer-bound stage: see ksw_gcups and DESIGN.md for the integer-pipe roofline"}
-        ksw_ms = prof_res.get("k_ksw", (0.0, 0))[0]
+                "note": "the chaining and DP kernels are integer/latency-bound, not HBM-bound: their HBM fraction is small by construction; "
+                        "see k4 (GCUPS against the integer-pipe roofline) and DESIGN.md section 4"}
+        ksw_lit_ms = prof_res.get("k_ksw", (0.0, 0))[0]
+        ksw_fast_ms = prof_res.get("k_ksw_tpj", (0.0, 0))[0]
+        ksw_ms = ksw_lit_ms + ksw_fast_ms
         lookup_ms = prof_res.get("k_lookup", (0.0, 0))[0]
+        gc = lambda c, ms: c / (ms * 1e-3) / 1e9 if ms else None
+        k4 = {"gcups": gc(cells, ksw_ms), "gcups_fast_form": gc(cells_fast, ksw_fast_ms), "gcups_literal_form": gc(cells - cells_fast, ksw_lit_ms),
+              "cells_per_step": cells / args.steps, "fast_form_cell_share": cells_fast / cells if cells else None,
+              "int_roofline_gcups": K4_INT_ROOFLINE_GCUPS, "frac": (gc(cells, ksw_ms) or 0.0) / K4_INT_ROOFLINE_GCUPS,
+              "roofline_def": "148 SMs x 128 int lanes x 1.965 GHz / 30 lane-ops per cell (SURVEY.md 8d, one cell per lane-op)"}
         out = {
             "metric": METRIC, "value": reads_res / secs_res, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs_res * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -413,7 +433,7 @@ def main():
             "e2e": {"value": reads_e2e / secs_e2e, "unit": "reads/s", "h2d_bytes_per_step": st_e2e.h2d_bytes // args.steps,
                     "d2h_bytes_per_step": st_e2e.d2h_bytes // args.steps, "ms_per_step": secs_e2e * 1e3 / args.steps},
             "gpu_launches": int(launches_res), "roofline": roof,
-            "ksw_gcups": cells / (ksw_ms * 1e-3) / 1e9 if ksw_ms else None,
+            "ksw_gcups": k4["gcups"], "k4": k4,
             "seed_lookup_gbs": algo["k_lookup"] / (lookup_ms * 1e-3) / 1e9 if lookup_ms else None,
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof_res.items(), key=lambda kv: -kv[1][0])},
             "host_s_per_step": {"seed_chain_call": st_res.t_seedchain / args.steps, "hits": st_res.t_hits / args.steps,
@@ -432,6 +452,18 @@ def main():
                                    "sample": f"{n_pairs} pairs (2x150) of the same workload, mapping phase only, -t {cores}"}
         except Exception as e:  # noqa
             out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+    if rank == 0 and world == 1 and not args.no_cli and os.path.exists(CLI_BIN):
+        # the whole drop-in binary (FASTQ parse + all stages + SAM on stdout), timed exactly like the reference arm
+        n_pairs = 4_000_000
+        c1, c2 = make_reads(d, fa, n_pairs, 45, f"sr_cli_{n_pairs}")
+        try:
+            t = ref_mapping_phase([CLI_BIN, "-ax", "sr", "-t", str(os.cpu_count() or 1), "-K", "150M", fa, c1, c2])
+            out["cli"] = {"value": 2 * n_pairs / t, "unit": "reads/s", "sample": f"{n_pairs} pairs, build/minimap2-b200 -ax sr -t {os.cpu_count()} -K 150M, "
+                          "mapping phase (after the index is built) incl. FASTQ parsing, first-batch buffer growth and SAM output"}
+        except Exception as e:  # noqa
+            out["cli"] = {"value": None, "unit": "reads/s", "sample": f"failed: {e}"}
+    if rank == 0 and "cpu_baseline" in out:
+        pass
     elif rank == 0:
         out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "reference",
                                "sample": "measured at N=1 only" if world > 1 else "oracle/_ref/minimap2_B not built"}

@@ -205,7 +205,7 @@ int  mm_b200_n_devices(const mm_idx_t *mi);
 
 typedef struct { /* accumulated over mm_b200_map_batch / mm_map_file_frag calls; seconds and counts */
 	double t_total, t_upload, t_seedchain, t_seedchain_kernels, t_hits, t_align_host, t_ksw_total, t_ksw_kernel, t_finish;
-	uint64_t n_frag, n_reads, n_bases, n_minimizers, n_anchors, n_chain_iter, n_dp_jobs, n_dp_cells, n_dp_rounds, h2d_bytes, d2h_bytes;
+	uint64_t n_frag, n_reads, n_bases, n_minimizers, n_anchors, n_chain_iter, n_dp_jobs, n_dp_cells, n_dp_rounds, h2d_bytes, d2h_bytes, n_dp_jobs_fast, n_dp_cells_fast;
 } mm_b200_stats_t;
 void mm_b200_stats(mm_b200_stats_t *out, int reset);
 void mm_b200_profile(const mm_idx_t *mi, int enable);   /* CUDA-event timing of every kernel launch */

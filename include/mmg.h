@@ -170,6 +170,8 @@ typedef struct {
 /* run n_jobs DP jobs; res[] (n_jobs) is caller-allocated; *cigars points to a ctx-owned HOST array */
 int  mmg_ksw_batch(mmg_ctx_t *ctx, const mmg_idx_t *idx, const mmg_mapopt_t *opt, int n_jobs, const mmg_ksw_job_t *jobs,
                    mmg_ksw_res_t *res, const uint32_t **cigars, double *kernel_ms, uint64_t *cells);
+/* jobs and true-band cells the last mmg_ksw_batch() ran in the thread-per-job fast form (band never clips) and in the literal 16-lane form */
+void mmg_ksw_last_split(const mmg_ctx_t *ctx, uint64_t *jobs_fast, uint64_t *cells_fast, uint64_t *jobs_literal, uint64_t *cells_literal);
 int  mmg_job_buffers(mmg_ctx_t *ctx, size_t n_jobs, mmg_ksw_job_t **jobs, mmg_ksw_res_t **res);
 
 #ifdef __cplusplus
