@@ -139,11 +139,9 @@ static void stage_hits(void *data, long i, int tid)
 	fr->n_u = ch->n_u[i];
 	fr->n_mini = ch->n_mini[i];
 	if (fr->n_u > 0) {
-		const int n_a = ch->n_a[i];
-		fr->u = (uint64_t*)mm_amalloc((size_t)fr->n_u * 8);
-		memcpy(fr->u, ch->u + ch->u_off[i], (size_t)fr->n_u * 8);
-		fr->a = (mm128_t*)mm_amalloc((size_t)n_a * 16);
-		memcpy(fr->a, ch->a + ch->a_off[i], (size_t)n_a * 16);
+		/* used in place: the fragment's slice of the ctx's pinned download stays untouched until this shard's next batch */
+		fr->u = (uint64_t*)(ch->u + ch->u_off[i]);
+		fr->a = (mm128_t*)(ch->a + ch->a_off[i]);
 	}
 	fr->regs0 = mm_gen_regs(fr->hash, fr->qlen_sum, fr->n_u, fr->u, fr->a);
 	fr->n_regs0 = fr->n_u;
