@@ -8,7 +8,7 @@ CFLAGS   := -O2 -g -Wall -fPIC -ffp-contract=off -Iinclude -Iairlift_b200/host
 BUILD    := build
 CSRC     := airlift_b200/csrc
 HOST     := airlift_b200/host
-CUOBJ    := $(BUILD)/mmg_index.o $(BUILD)/mmg_stages.o $(BUILD)/mmg_ksw.o
+CUOBJ    := $(BUILD)/mmg_index.o $(BUILD)/mmg_stages.o $(BUILD)/mmg_ksw.o $(BUILD)/mmg_post.o
 HOSTSRC  := $(wildcard $(HOST)/*.c)
 HOSTOBJ  := $(patsubst $(HOST)/%.c,$(BUILD)/host_%.o,$(filter-out $(HOST)/main.c,$(HOSTSRC)))
 LIB      := airlift_b200/libmm2b200.so
@@ -23,6 +23,8 @@ emu: $(BUILD)/libmmg_emu.so
 
 $(BUILD):
 	mkdir -p $(BUILD)
+
+$(BUILD)/mmg_post.o: $(HOST)/hits.c $(HOST)/aln.c $(HOST)/llsw.c $(HOST)/mm2b_priv.h include/minimap_b200.h
 
 $(BUILD)/%.o: $(CSRC)/%.cu $(CSRC)/mmg_core.h $(CSRC)/mmg_ctx.cuh include/mmg.h | $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; false)

@@ -354,7 +354,7 @@ template <class T> static int scan_excl(mmg_ctx_t *c, const T *d_in, int64_t *d_
 // d_jobs: n jobs already on the device.  q_off/read_len/ref_off: device tables the jobs index into.
 static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const uint32_t *d_Q, const uint32_t *d_S, const uint64_t *d_q_off,
                       const int32_t *d_read_len, const uint64_t *d_ref_off, const KswScore &sc, mmg_ksw_res_t *res, const uint32_t **cigars,
-                      double *kernel_ms, uint64_t *cells)
+                      double *kernel_ms, uint64_t *cells, bool to_host = true)
 {
 	// scratch layout in k_cig_off: mem_sz | p_sz | cig_sz (u64, n+1 each) | their scans (i64, n+1 each) | ncig scan (i64, n+1) | cells, class counts |
 	// key, key2 (u32) | idx, order (i32) | ncig (i32, n+1)
@@ -430,12 +430,18 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 	MMG_TRY(c->k_cig_out.ensure(((size_t)n_cig + 1) * 4));
 	MMG_LAUNCH(c, k_cig_gather, mmg_blocks(n, 128), 128, 0, n, d_ez, nc_off, reinterpret_cast<const uint64_t*>(cg_off), c->k_cig.as<uint32_t>(),
 	           d_res, c->k_cig_out.as<uint32_t>());
-	MMG_TRY(c->h_k_cig.ensure(((size_t)n_cig + 1) * 4));
 	static_assert(sizeof(KswResDev) == sizeof(mmg_ksw_res_t), "result layout");
-	MMG_D2H(c, res, d_res, (size_t)n * sizeof(KswResDev));
-	if (n_cig) MMG_D2H(c, c->h_k_cig.p, c->k_cig_out.p, (size_t)n_cig * 4);
-	MMG_CUDA(cudaStreamSynchronize(c->stream));
-	*cigars = c->h_k_cig.as<uint32_t>();
+	if (to_host) {
+		MMG_TRY(c->h_k_cig.ensure(((size_t)n_cig + 1) * 4));
+		MMG_D2H(c, res, d_res, (size_t)n * sizeof(KswResDev));
+		if (n_cig) MMG_D2H(c, c->h_k_cig.p, c->k_cig_out.p, (size_t)n_cig * 4);
+		MMG_CUDA(cudaStreamSynchronize(c->stream));
+		*cigars = c->h_k_cig.as<uint32_t>();
+	} else { // results stay on the device: {ez, cigar offset} per job and the packed CIGARs
+		c->k_last_res = d_res;
+		*cigars = c->k_cig_out.as<uint32_t>();
+		MMG_CUDA(cudaStreamSynchronize(c->stream));
+	}
 	float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
 	if (kernel_ms) *kernel_ms = ms;
 	return MMG_OK;
@@ -452,6 +458,20 @@ static KswScore make_score(const mmg_mapopt_t *opt)
 	for (int j = 0; j < 5; ++j) sc.mat[20 + j] = (int8_t)amb;
 	sc.q = (int8_t)opt->q, sc.e = (int8_t)opt->e, sc.q2 = (int8_t)opt->q2, sc.e2 = (int8_t)opt->e2;
 	return sc;
+}
+
+// DP jobs that are already on the device, results left on the device (mmg_post.cu)
+int mmg_ksw_device(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, int n_jobs, const mmg_ksw_job_t *d_jobs, const void **d_res,
+                   const uint32_t **d_cigars, double *kernel_ms, uint64_t *cells)
+{
+	*d_res = nullptr, *d_cigars = nullptr;
+	if (kernel_ms) *kernel_ms = 0;
+	if (cells) *cells = 0;
+	if (n_jobs <= 0) return MMG_OK;
+	MMG_TRY(ksw_launch(c, d_jobs, n_jobs, c->d_Q.as<uint32_t>(), mi->d_S, c->d_q_off.as<uint64_t>(), c->d_seq_len.as<int32_t>(), mi->d_seq_off, make_score(opt),
+	                   nullptr, d_cigars, kernel_ms, cells, false));
+	*d_res = c->k_last_res;
+	return MMG_OK;
 }
 
 extern "C" void mmg_ksw_last_split(const mmg_ctx_t *c, uint64_t *jobs_fast, uint64_t *cells_fast, uint64_t *jobs_literal, uint64_t *cells_literal)

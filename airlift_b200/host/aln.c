@@ -26,14 +26,14 @@ typedef struct {
 	int8_t mat[25];
 } walk_t;
 
-static void ez_reset(ez_t *ez)
+MM_FN static void ez_reset(ez_t *ez)
 {
 	ez->max_q = ez->max_t = ez->mqe_t = -1;
 	ez->max = 0, ez->score = ez->mqe = KSW_NEG_INF;
 	ez->n_cigar = 0, ez->zdropped = 0, ez->reach_end = 0, ez->cigar = 0;
 }
 
-static void gen_simple_mat(int8_t *mat, int a, int b, int sc_ambi)
+MM_FN static void gen_simple_mat(int8_t *mat, int a, int b, int sc_ambi)
 { /* align.c:9-22, m = 5 */
 	int i, j;
 	a = a < 0 ? -a : a, b = b > 0 ? -b : b, sc_ambi = sc_ambi > 0 ? -sc_ambi : sc_ambi;
@@ -46,7 +46,7 @@ static void gen_simple_mat(int8_t *mat, int a, int b, int sc_ambi)
 
 /* ---- DP through the cache (replaces mm_align_pair, align.c:313-339) */
 
-static int dp_request(walk_t *w, int q_rev, int q_start, int q_len, int rid, int t_start, int t_len, int reversed,
+MM_FN static int dp_request(walk_t *w, int q_rev, int q_start, int q_len, int rid, int t_start, int t_len, int reversed,
                       int bw, int end_bonus, int zdrop, int flag, ez_t *ez)
 {
 	mm_dpcache_t *c = &w->seg->cache;
@@ -81,7 +81,7 @@ static int dp_request(walk_t *w, int q_rev, int q_start, int q_len, int rid, int
 
 /* ---- CIGAR bookkeeping */
 
-static void append_cigar(mm_reg1_t *r, uint32_t n_cigar, const uint32_t *cigar)
+MM_FN static void append_cigar(mm_reg1_t *r, uint32_t n_cigar, const uint32_t *cigar)
 { /* align.c:288-311 */
 	mm_extra_t *p;
 	if (n_cigar == 0) return;
@@ -106,7 +106,7 @@ static void append_cigar(mm_reg1_t *r, uint32_t n_cigar, const uint32_t *cigar)
 	}
 }
 
-static void fix_cigar(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq, int *qshift, int *tshift)
+MM_FN static void fix_cigar(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq, int *qshift, int *tshift)
 { /* align.c:91-167: left-align indels, collapse I/D runs, drop zero-length ops and a leading I/D */
 	mm_extra_t *p = r->p;
 	int32_t toff = 0, qoff = 0, to_shrink = 0;
@@ -172,7 +172,7 @@ static void fix_cigar(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq, in
 	}
 }
 
-static void cigar_to_eqx(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq)
+MM_FN static void cigar_to_eqx(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq)
 { /* align.c:169-238: M -> =/X */
 	uint32_t n_EQX = 0, k, l, m, cap, toff = 0, qoff = 0, n_M = 0;
 	mm_extra_t *p;
@@ -222,7 +222,7 @@ static void cigar_to_eqx(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq)
 	r->p = p;
 }
 
-static void update_extra(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq, const int8_t *mat, int8_t q, int8_t e, int is_eqx)
+MM_FN static void update_extra(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq, const int8_t *mat, int8_t q, int8_t e, int is_eqx)
 { /* align.c:240-286: final CIGAR clean-up, then blen/mlen/n_ambi and the local-style dp_max */
 	uint32_t k, l;
 	int32_t s = 0, max = 0, qshift, tshift, toff = 0, qoff = 0;
@@ -262,7 +262,7 @@ static void update_extra(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq,
 
 /* ---- z-drop re-test on a finished gap fill (align.c:32-89) */
 
-static int test_zdrop(const walk_t *w, const uint8_t *qseq, const uint8_t *tseq, uint32_t n_cigar, const uint32_t *cigar)
+MM_FN static int test_zdrop(const walk_t *w, const uint8_t *qseq, const uint8_t *tseq, uint32_t n_cigar, const uint32_t *cigar)
 {
 	const mm_mapopt_t *opt = w->opt;
 	uint32_t k;
@@ -308,7 +308,7 @@ static int test_zdrop(const walk_t *w, const uint8_t *qseq, const uint8_t *tseq,
 
 /* ---- which anchors bound the DP (align.c:341-521) */
 
-static void adjust_minier(const mm_idx_t *mi, uint8_t *const qseq0[2], const mm128_t *a, int32_t *r, int32_t *q)
+MM_FN static void adjust_minier(const mm_idx_t *mi, uint8_t *const qseq0[2], const mm128_t *a, int32_t *r, int32_t *q)
 { /* align.c:341-365 */
 	if (mi->flag & MM_I_HPC) {
 		const uint8_t *qseq = qseq0[a->x >> 63];
@@ -330,7 +330,7 @@ static void adjust_minier(const mm_idx_t *mi, uint8_t *const qseq0[2], const mm1
 
 #define GAP_AT(a, i) (((int32_t)(a)[i].y - (int32_t)(a)[(i) - 1].y) - ((int32_t)(a)[i].x - (int32_t)(a)[(i) - 1].x))
 
-static int *long_gaps(int as1, int cnt1, const mm128_t *a, int min_gap, int *n_)
+MM_FN static int *long_gaps(int as1, int cnt1, const mm128_t *a, int min_gap, int *n_)
 { /* align.c:367-384: anchor indices after which the diagonal moves by more than min_gap */
 	int i, n = 0, *K;
 	*n_ = 0;
@@ -342,7 +342,7 @@ static int *long_gaps(int as1, int cnt1, const mm128_t *a, int min_gap, int *n_)
 	return K;
 }
 
-static void filter_bad_seeds(int as1, int cnt1, mm128_t *a, int min_gap, int diff_thres, int max_ext_len, int max_ext_cnt)
+MM_FN static void filter_bad_seeds(int as1, int cnt1, mm128_t *a, int min_gap, int diff_thres, int max_ext_len, int max_ext_cnt)
 { /* align.c:386-421: ignore seeds between an insertion and a compensating deletion */
 	int max_st = -1, max_en = -1, n, i, k, max = 0, *K;
 	mm128_t *b = a + as1;
@@ -373,7 +373,7 @@ static void filter_bad_seeds(int as1, int cnt1, mm128_t *a, int min_gap, int dif
 	mm_afree(K);
 }
 
-static void filter_bad_seeds_alt(int as1, int cnt1, mm128_t *a, int min_gap, int max_ext)
+MM_FN static void filter_bad_seeds_alt(int as1, int cnt1, mm128_t *a, int min_gap, int max_ext)
 { /* align.c:423-457: merge nearby long gaps into one long-join DP */
 	int n, k, *K;
 	mm128_t *b = a + as1;
@@ -406,7 +406,7 @@ static void filter_bad_seeds_alt(int as1, int cnt1, mm128_t *a, int min_gap, int
 	mm_afree(K);
 }
 
-static void fix_bad_ends(const mm_reg1_t *r, const mm128_t *a, int bw, int min_match, int32_t *as, int32_t *cnt)
+MM_FN static void fix_bad_ends(const mm_reg1_t *r, const mm128_t *a, int bw, int min_match, int32_t *as, int32_t *cnt)
 { /* align.c:459-493: trim end anchors that sit off the main diagonal */
 	int32_t i, l, m;
 	*as = r->as, *cnt = r->cnt;
@@ -438,7 +438,7 @@ static void fix_bad_ends(const mm_reg1_t *r, const mm128_t *a, int bw, int min_m
 	}
 }
 
-static void max_stretch(const mm_reg1_t *r, const mm128_t *a, int32_t *as, int32_t *cnt)
+MM_FN static void max_stretch(const mm_reg1_t *r, const mm128_t *a, int32_t *as, int32_t *cnt)
 { /* align.c:495-521: short reads keep only the best run of anchors on one diagonal */
 	int32_t i, score, max_score = -1, len, max_i = -1, max_len = 0;
 	*as = r->as, *cnt = r->cnt;
@@ -459,7 +459,7 @@ static void max_stretch(const mm_reg1_t *r, const mm128_t *a, int32_t *as, int32
 
 /* ---- one region (align.c:565-788) */
 
-static void align1(walk_t *w, mm_reg1_t *r, mm_reg1_t *r2)
+MM_FN static void align1(walk_t *w, mm_reg1_t *r, mm_reg1_t *r2)
 {
 	const mm_mapopt_t *opt = w->opt;
 	const mm_idx_t *mi = w->mi;
@@ -668,7 +668,7 @@ static void align1(walk_t *w, mm_reg1_t *r, mm_reg1_t *r2)
 
 /* ---- inversion rescue between two pieces of a z-drop split (align.c:790-845) */
 
-static int align1_inv(walk_t *w, const mm_reg1_t *r1, const mm_reg1_t *r2, mm_reg1_t *r_inv)
+MM_FN static int align1_inv(walk_t *w, const mm_reg1_t *r1, const mm_reg1_t *r2, mm_reg1_t *r_inv)
 {
 	const mm_mapopt_t *opt = w->opt;
 	const mm_idx_t *mi = w->mi;
@@ -720,13 +720,13 @@ done:
 
 /* ---- the resumable skeleton (align.c:857-913) */
 
-void mm_aln_begin(mm_alnseg_t *s, int seq_id, int qlen, const char *qstr, int n_regs, mm_reg1_t *regs, mm128_t *a)
+MM_FN void mm_aln_begin(mm_alnseg_t *s, int seq_id, int qlen, const char *qstr, int n_regs, mm_reg1_t *regs, mm128_t *a)
 {
 	memset(s, 0, sizeof(*s));
 	s->seq_id = seq_id, s->qlen = qlen, s->qstr = qstr, s->n_regs = n_regs, s->regs = regs, s->a = a;
 }
 
-static mm_reg1_t *insert_reg(const mm_reg1_t *r, int i, int *n_regs, mm_reg1_t *regs)
+MM_FN static mm_reg1_t *insert_reg(const mm_reg1_t *r, int i, int *n_regs, mm_reg1_t *regs)
 { /* align.c:847-855 */
 	regs = (mm_reg1_t*)realloc(regs, (size_t)(*n_regs + 1) * sizeof(mm_reg1_t));
 	if (i + 1 != *n_regs) memmove(&regs[i + 2], &regs[i + 1], sizeof(mm_reg1_t) * (size_t)(*n_regs - i - 1));
@@ -735,7 +735,7 @@ static mm_reg1_t *insert_reg(const mm_reg1_t *r, int i, int *n_regs, mm_reg1_t *
 	return regs;
 }
 
-int mm_aln_step(mm_alnseg_t *s, const mm_mapopt_t *opt, const mm_idx_t *mi)
+MM_FN int mm_aln_step(mm_alnseg_t *s, const mm_mapopt_t *opt, const mm_idx_t *mi)
 {
 	walk_t w;
 	int i;
@@ -747,7 +747,11 @@ int mm_aln_step(mm_alnseg_t *s, const mm_mapopt_t *opt, const mm_idx_t *mi)
 		s->qseq0[0] = (uint8_t*)mm_amalloc((size_t)(s->qlen > 0 ? s->qlen : 1) * 2);
 		s->qseq0[1] = s->qseq0[0] + s->qlen;
 		for (i = 0; i < s->qlen; ++i) {
+#ifdef MM_DEVICE_BUILD
+			s->qseq0[0][i] = (uint8_t)mm_seq4_get(s->q4, s->q4_off + i); /* encoded by k_encode_reads with the same table */
+#else
 			s->qseq0[0][i] = seq_nt4_table[(uint8_t)s->qstr[i]];
+#endif
 			s->qseq0[1][s->qlen - 1 - i] = s->qseq0[0][i] < 4 ? 3 - s->qseq0[0][i] : 4;
 		}
 		s->n_a = mm_squeeze_a(s->n_regs, s->regs, s->a);
@@ -797,7 +801,7 @@ int mm_aln_step(mm_alnseg_t *s, const mm_mapopt_t *opt, const mm_idx_t *mi)
 	return 1;
 }
 
-void mm_aln_end(mm_alnseg_t *s)
+MM_FN void mm_aln_end(mm_alnseg_t *s)
 {
 	int i;
 	for (i = 0; i < s->cache.n; ++i) mm_afree(s->cache.a[i].cigar);

@@ -10,14 +10,15 @@
 #define RPOS(an) ((int32_t)(an).x)
 #define QPOS(an) ((int32_t)(an).y)
 
-static inline uint32_t wang_hash(uint32_t key) /* khash.h:400-409 */
+MM_FN static inline uint32_t wang_hash(uint32_t key) /* khash.h:400-409 */
 {
 	key += ~(key << 15); key ^= (key >> 10); key += (key << 3);
 	key ^= (key >> 6);   key += ~(key << 11); key ^= (key >> 16);
 	return key;
 }
 
-uint32_t mm_frag_hash(const char *qname, int qlen_sum, int seed)
+#ifndef MM_DEVICE_BUILD
+MM_FN uint32_t mm_frag_hash(const char *qname, int qlen_sum, int seed)
 { /* the per-fragment salt of map.c:291-293: X31 string hash of the name, mixed with length and seed */
 	uint32_t h = 0;
 	if (qname) {
@@ -28,8 +29,9 @@ uint32_t mm_frag_hash(const char *qname, int qlen_sum, int seed)
 	h ^= wang_hash((uint32_t)qlen_sum) + wang_hash((uint32_t)seed);
 	return wang_hash(h);
 }
+#endif
 
-static inline uint64_t mix64(uint64_t key) /* hit.c:40-50 (unmasked variant of the sketch hash) */
+MM_FN static inline uint64_t mix64(uint64_t key) /* hit.c:40-50 (unmasked variant of the sketch hash) */
 {
 	key = ~key + (key << 21);
 	key ^= key >> 24;
@@ -41,7 +43,7 @@ static inline uint64_t mix64(uint64_t key) /* hit.c:40-50 (unmasked variant of t
 	return key;
 }
 
-static void reg_set_coor(mm_reg1_t *r, int32_t qlen, const mm128_t *a)
+MM_FN static void reg_set_coor(mm_reg1_t *r, int32_t qlen, const mm128_t *a)
 { /* hit.c:8-38: coordinates and the fuzzy match/block lengths from the chain's anchors */
 	const mm128_t *first = &a[r->as], *last = &a[r->as + r->cnt - 1];
 	const int32_t q_span = SPAN(*first);
@@ -62,7 +64,7 @@ static void reg_set_coor(mm_reg1_t *r, int32_t qlen, const mm128_t *a)
 	}
 }
 
-mm_reg1_t *mm_gen_regs(uint32_t hash, int qlen, int n_u, uint64_t *u, mm128_t *a)
+MM_FN mm_reg1_t *mm_gen_regs(uint32_t hash, int qlen, int n_u, uint64_t *u, mm128_t *a)
 { /* hit.c:52-88 */
 	mm128_t *z;
 	mm_reg1_t *r;
@@ -91,7 +93,7 @@ mm_reg1_t *mm_gen_regs(uint32_t hash, int qlen, int n_u, uint64_t *u, mm128_t *a
 	return r;
 }
 
-void mm_split_reg(mm_reg1_t *r, mm_reg1_t *r2, int n, int qlen, mm128_t *a)
+MM_FN void mm_split_reg(mm_reg1_t *r, mm_reg1_t *r2, int n, int qlen, mm128_t *a)
 { /* hit.c:90-107 */
 	if (n <= 0 || n >= r->cnt) return;
 	*r2 = *r;
@@ -106,7 +108,7 @@ void mm_split_reg(mm_reg1_t *r, mm_reg1_t *r2, int n, int qlen, mm128_t *a)
 	r->split |= 1, r2->split |= 2;
 }
 
-void mm_set_parent(float mask_level, int n, mm_reg1_t *r, int sub_diff, int hard_mask_level)
+MM_FN void mm_set_parent(float mask_level, int n, mm_reg1_t *r, int sub_diff, int hard_mask_level)
 { /* hit.c:109-167 */
 	int i, j, k, *w;
 	uint64_t *cov;
@@ -166,7 +168,7 @@ new_primary:
 	mm_afree(cov); mm_afree(w);
 }
 
-void mm_hit_sort(int *n_regs, mm_reg1_t *r)
+MM_FN void mm_hit_sort(int *n_regs, mm_reg1_t *r)
 { /* hit.c:169-201: by dp_max (or chain score) then hash, descending; drops soft-deleted hits */
 	int32_t i, n_aux, n = *n_regs, has_cigar = 0, no_cigar = 0;
 	mm128_t *aux;
@@ -189,7 +191,7 @@ void mm_hit_sort(int *n_regs, mm_reg1_t *r)
 	mm_afree(aux); mm_afree(t);
 }
 
-int mm_set_sam_pri(int n, mm_reg1_t *r)
+MM_FN int mm_set_sam_pri(int n, mm_reg1_t *r)
 { /* hit.c:203-212 */
 	int i, n_pri = 0;
 	for (i = 0; i < n; ++i) {
@@ -199,7 +201,7 @@ int mm_set_sam_pri(int n, mm_reg1_t *r)
 	return n_pri;
 }
 
-void mm_sync_regs(int n_regs, mm_reg1_t *regs)
+MM_FN void mm_sync_regs(int n_regs, mm_reg1_t *regs)
 { /* hit.c:214-236: renumber ids after removals and remap parents */
 	int *map, i, max_id = -1, n_map;
 	if (n_regs <= 0) return;
@@ -219,7 +221,7 @@ void mm_sync_regs(int n_regs, mm_reg1_t *regs)
 	mm_set_sam_pri(n_regs, regs);
 }
 
-void mm_select_sub(float pri_ratio, int min_diff, int best_n, int *n_, mm_reg1_t *r)
+MM_FN void mm_select_sub(float pri_ratio, int min_diff, int best_n, int *n_, mm_reg1_t *r)
 { /* hit.c:238-255 */
 	int i, k, n = *n_, n_2nd = 0;
 	if (!(pri_ratio > 0.0f && n > 0)) return;
@@ -238,7 +240,7 @@ void mm_select_sub(float pri_ratio, int min_diff, int best_n, int *n_, mm_reg1_t
 	*n_ = k;
 }
 
-void mm_select_sub_multi(float pri_ratio, float pri1, float pri2, int max_gap_ref, int min_diff, int best_n, int n_segs, const int *qlens, int *n_, mm_reg1_t *r)
+MM_FN void mm_select_sub_multi(float pri_ratio, float pri1, float pri2, int max_gap_ref, int min_diff, int best_n, int n_segs, const int *qlens, int *n_, mm_reg1_t *r)
 { /* pe.c:6-43 */
 	int i, k, n = *n_, n_2nd = 0;
 	const int max_dist = n_segs == 2 ? qlens[0] + qlens[1] + max_gap_ref : 0;
@@ -266,7 +268,7 @@ void mm_select_sub_multi(float pri_ratio, float pri1, float pri2, int max_gap_re
 	*n_ = k;
 }
 
-void mm_filter_regs(const mm_mapopt_t *opt, int qlen, int *n_regs, mm_reg1_t *regs)
+MM_FN void mm_filter_regs(const mm_mapopt_t *opt, int qlen, int *n_regs, mm_reg1_t *regs)
 { /* hit.c:257-276 */
 	int i, k;
 	for (i = k = 0; i < *n_regs; ++i) {
@@ -286,7 +288,7 @@ void mm_filter_regs(const mm_mapopt_t *opt, int qlen, int *n_regs, mm_reg1_t *re
 	*n_regs = k;
 }
 
-int mm_squeeze_a(int n_regs, mm_reg1_t *regs, mm128_t *a)
+MM_FN int mm_squeeze_a(int n_regs, mm_reg1_t *regs, mm128_t *a)
 { /* hit.c:278-296: compact a[] to the anchors still referenced, in order of `as` */
 	int i, as = 0;
 	uint64_t *aux = (uint64_t*)mm_amalloc((size_t)(n_regs > 0 ? n_regs : 1) * 8);
@@ -304,7 +306,7 @@ int mm_squeeze_a(int n_regs, mm_reg1_t *regs, mm128_t *a)
 	return as;
 }
 
-void mm_join_long(const mm_mapopt_t *opt, int qlen, int *n_regs_, mm_reg1_t *regs, mm128_t *a)
+MM_FN void mm_join_long(const mm_mapopt_t *opt, int qlen, int *n_regs_, mm_reg1_t *regs, mm128_t *a)
 { /* hit.c:298-354 */
 	int i, n_aux, n_regs = *n_regs_, n_drop = 0;
 	uint64_t *aux;
@@ -351,7 +353,7 @@ void mm_join_long(const mm_mapopt_t *opt, int qlen, int *n_regs_, mm_reg1_t *reg
 	}
 }
 
-mm_seg_t *mm_seg_gen(uint32_t hash, int n_segs, const int *qlens, int n_regs0, const mm_reg1_t *regs0, int *n_regs, mm_reg1_t **regs, const mm128_t *a)
+MM_FN mm_seg_t *mm_seg_gen(uint32_t hash, int n_segs, const int *qlens, int n_regs0, const mm_reg1_t *regs0, int *n_regs, mm_reg1_t **regs, const mm128_t *a)
 { /* hit.c:356-410: split fragment chains into one chain list per segment, re-basing query coordinates */
 	int s, i, j, acc_qlen[MM_MAX_SEG+1], qlen_sum;
 	mm_seg_t *seg;
@@ -390,14 +392,15 @@ mm_seg_t *mm_seg_gen(uint32_t hash, int n_segs, const int *qlens, int n_regs0, c
 	return seg;
 }
 
-void mm_seg_free(int n_segs, mm_seg_t *segs)
+MM_FN void mm_seg_free(int n_segs, mm_seg_t *segs)
 {
 	int i;
 	for (i = 0; i < n_segs; ++i) { mm_afree(segs[i].u); mm_afree(segs[i].a); }
 	mm_afree(segs);
 }
 
-static void set_inv_mapq(int n_regs, mm_reg1_t *regs)
+#ifndef MM_DEVICE_BUILD /* MAPQ, pairing and the divergence estimate call logf(): host only */
+MM_FN static void set_inv_mapq(int n_regs, mm_reg1_t *regs)
 { /* hit.c:420-444: an inversion hit takes the smaller MAPQ of its flanking primaries */
 	int i, n_aux;
 	mm128_t *aux;
@@ -419,7 +422,7 @@ static void set_inv_mapq(int n_regs, mm_reg1_t *regs)
 	mm_afree(aux);
 }
 
-void mm_set_mapq(int n_regs, mm_reg1_t *regs, int min_chain_sc, int match_sc, int rep_len, int is_sr)
+MM_FN void mm_set_mapq(int n_regs, mm_reg1_t *regs, int min_chain_sc, int match_sc, int rep_len, int is_sr)
 { /* hit.c:446-491.  Expression shapes are kept: every product below is evaluated in float, left to right. */
 	static const float q_coef = 40.0f;
 	int64_t sum_sc = 0;
@@ -464,7 +467,7 @@ void mm_set_mapq(int n_regs, mm_reg1_t *regs, int min_chain_sc, int match_sc, in
 
 /* ---- pairing (pe.c:45-177) */
 
-static void set_pe_thru(const int *qlens, int *n_regs, mm_reg1_t **regs)
+MM_FN static void set_pe_thru(const int *qlens, int *n_regs, mm_reg1_t **regs)
 { /* both mates cover the same short fragment end to end */
 	int s, i, n_pri[2] = {0, 0}, pri[2] = {-1, -1};
 	for (s = 0; s < 2; ++s)
@@ -482,7 +485,7 @@ typedef struct { int s, rev; uint64_t key; mm_reg1_t *r; } pair_elem_t;
 #define KEY_PAIR(v) ((v).key)
 
 /* the reference sorts pair_arr_t with its radix sort (pe.c:67-68); same permutation here */
-static void pair_ins(pair_elem_t *b, pair_elem_t *e)
+MM_FN static void pair_ins(pair_elem_t *b, pair_elem_t *e)
 {
 	pair_elem_t *i, *j;
 	for (i = b + 1; i < e; ++i) {
@@ -492,7 +495,7 @@ static void pair_ins(pair_elem_t *b, pair_elem_t *e)
 		*j = t;
 	}
 }
-static void pair_lvl(pair_elem_t *b, pair_elem_t *e, int sh)
+MM_FN static void pair_lvl(pair_elem_t *b, pair_elem_t *e, int sh)
 {
 	size_t cnt[256]; pair_elem_t *hd[256], *tl[256], *i; int d;
 	memset(cnt, 0, sizeof(cnt));
@@ -516,7 +519,7 @@ static void pair_lvl(pair_elem_t *b, pair_elem_t *e, int sh)
 }
 static void sort_pairs(pair_elem_t *b, pair_elem_t *e) { if (e - b <= 64) pair_ins(b, e); else pair_lvl(b, e, 56); }
 
-void mm_pair(int max_gap_ref, int pe_bonus, int sub_diff, int match_sc, const int *qlens, int *n_regs, mm_reg1_t **regs)
+MM_FN void mm_pair(int max_gap_ref, int pe_bonus, int sub_diff, int match_sc, const int *qlens, int *n_regs, mm_reg1_t **regs)
 { /* pe.c:76-177 */
 	int i, j, s, n, last[2], dp_thres, segs = 0, max_idx[2];
 	int64_t max;
@@ -599,14 +602,14 @@ void mm_pair(int max_gap_ref, int pe_bonus, int sub_diff, int match_sc, const in
 
 /* ---- divergence estimate from the minimizers a chain did and did not use (esterr.c:6-64) */
 
-static inline int32_t fwd_qpos(int32_t qlen, const mm128_t *a)
+MM_FN static inline int32_t fwd_qpos(int32_t qlen, const mm128_t *a)
 {
 	int32_t x = QPOS(*a);
 	if (a->x >> 63) x = qlen - 1 - (x + 1 - SPAN(*a));
 	return x;
 }
 
-void mm_est_err(const mm_idx_t *mi, int qlen, int n_regs, mm_reg1_t *regs, const mm128_t *a, int32_t n, const uint64_t *mini_pos)
+MM_FN void mm_est_err(const mm_idx_t *mi, int qlen, int n_regs, mm_reg1_t *regs, const mm128_t *a, int32_t n, const uint64_t *mini_pos)
 {
 	int i;
 	uint64_t sum_k = 0;
@@ -643,3 +646,4 @@ void mm_est_err(const mm_idx_t *mi, int qlen, int n_regs, mm_reg1_t *regs, const
 		r->div = logf((float)n_tot / n_match) / avg_k;
 	}
 }
+#endif /* !MM_DEVICE_BUILD */

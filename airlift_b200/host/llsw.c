@@ -10,19 +10,19 @@
 
 #define LANES 8
 
-static inline int16_t sat_add16(int16_t a, int16_t b)
+MM_FN static inline int16_t sat_add16(int16_t a, int16_t b)
 {
 	int32_t s = (int32_t)a + b;
 	return (int16_t)(s > 32767 ? 32767 : s < -32768 ? -32768 : s);
 }
-static inline int16_t sat_subu16(int16_t a, int16_t b) /* unsigned saturating a-b on the bit patterns */
+MM_FN static inline int16_t sat_subu16(int16_t a, int16_t b) /* unsigned saturating a-b on the bit patterns */
 {
 	uint16_t ua = (uint16_t)a, ub = (uint16_t)b;
 	return (int16_t)(ua > ub ? ua - ub : 0);
 }
-static inline int16_t max16(int16_t a, int16_t b) { return a > b ? a : b; }
+MM_FN static inline int16_t max16(int16_t a, int16_t b) { return a > b ? a : b; }
 
-int mm_ll_i16(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat, int gapo, int gape, int *qe, int *te)
+MM_FN int mm_ll_i16(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat, int gapo, int gape, int *qe, int *te)
 {
 	const int slen = (qlen + LANES - 1) / LANES;
 	const int16_t gapoe = (int16_t)(gapo + gape), ge = (int16_t)gape;

@@ -84,6 +84,8 @@ typedef struct {          /* one GPU's share of a mini-batch */
 	frag_t *fr;
 	mmg_chains_t ch;
 	mm_b200_stats_t st;
+	mmg_post_out_t post;  /* device path: packed hits of every read of the shard */
+	uint32_t *frag_hash;
 	mm_arena_t arena;     /* per-fragment state of this shard: anchors, chains, per-mate copies, DP cache, temporaries */
 	pthread_mutex_t *gpu_token; /* held during device stages when the GPU is shared by several shards */
 	size_t *job_off;      /* [nf+1] first job of each fragment in the current DP round */
@@ -312,6 +314,99 @@ static void *shard_upload(void *data)
 	return 0;
 }
 
+
+/* ---- device path (short-read presets): hits, per-mate split, alignment walk and CIGAR post-processing run on the GPU
+ * (csrc/mmg_post.cu compiles hits.c / aln.c for the device); the host computes the name hash before and MAPQ / pairing after */
+
+static void stage_dev_hash(void *data, long i, int tid)
+{
+	shard_t *sh = (shard_t*)data;
+	const int f = sh->f0 + (int)i, off = sh->seg_off[f], ns = sh->n_seg[f];
+	int j, qlen_sum = 0;
+	for (j = 0; j < ns; ++j) qlen_sum += sh->seq[off + j].l_seq;
+	sh->frag_hash[i] = mm_frag_hash(sh->seq[off].name, qlen_sum, sh->opt->seed);
+}
+
+/* blob -> malloc'd mm_reg1_t / mm_extra_t (minimap.h:317-331 ownership), then MAPQ, pairing, mate un-flip (map.c:392-406, 486-497) */
+static void stage_dev_finish(void *data, long i, int tid)
+{
+	shard_t *sh = (shard_t*)data;
+	const mm_mapopt_t *opt = sh->opt;
+	const int f = sh->f0 + (int)i, off = sh->seg_off[f], ns = sh->n_seg[f], is_sr = !!(opt->flag & MM_F_SR);
+	int j, k, qlen_sum = 0, frag_gap, mapped, qlens[MM_MAX_SEG];
+	const int rep_len = sh->post.rep_len[i];
+	for (j = 0; j < ns && j < MM_MAX_SEG; ++j) qlens[j] = sh->seq[off + j].l_seq, qlen_sum += qlens[j];
+	frag_gap = chain_gap_ref(opt, qlen_sum);
+	for (j = 0; j < ns; ++j) {
+		const int rr = off + j - sh->s0, n = sh->post.n_reg[rr];
+		const unsigned char *b = sh->post.blob + sh->post.blob_off[rr], *e = b + (size_t)n * sizeof(mm_reg1_t);
+		mm_reg1_t *regs = 0;
+		if (n > 0) {
+			regs = (mm_reg1_t*)malloc((size_t)n * sizeof(mm_reg1_t));
+			memcpy(regs, b, (size_t)n * sizeof(mm_reg1_t));
+			for (k = 0; k < n; ++k)
+				if (regs[k].p) {
+					const mm_extra_t *src = (const mm_extra_t*)e;
+					const size_t bytes = sizeof(mm_extra_t) + (size_t)src->n_cigar * 4, cap = (size_t)src->capacity * 4;
+					regs[k].p = (mm_extra_t*)malloc(cap > bytes ? cap : bytes);
+					memcpy(regs[k].p, src, bytes);
+					e += (bytes + 7) & ~(size_t)7;
+				}
+		}
+		sh->n_reg[off + j] = n, sh->reg[off + j] = regs;
+	}
+	mapped = !(qlen_sum == 0 || ns <= 0 || ns > MM_MAX_SEG || (opt->max_qlen > 0 && qlen_sum > opt->max_qlen));
+	if (mapped) {
+		for (j = 0; j < ns; ++j) mm_set_mapq(sh->n_reg[off + j], sh->reg[off + j], opt->min_chain_score, opt->a, rep_len, is_sr);
+		if (ns == 2 && opt->pe_ori >= 0 && (opt->flag & MM_F_CIGAR))
+			mm_pair(frag_gap, opt->pe_bonus, opt->a * 2 + opt->b, opt->a, qlens, &sh->n_reg[off], &sh->reg[off]);
+		for (j = 0; j < ns; ++j)
+			if (mate_is_flipped(opt, ns, j)) /* the host copy of the read was never flipped on this path: only the coordinates are */
+				for (k = 0; k < sh->n_reg[off + j]; ++k) {
+					mm_reg1_t *r = &sh->reg[off + j][k];
+					const int t = r->qs;
+					r->qs = qlens[j] - r->qe, r->qe = qlens[j] - t, r->rev = !r->rev;
+				}
+	}
+	for (j = 0; j < ns; ++j) sh->rep_len[off + j] = rep_len, sh->frag_gap[off + j] = frag_gap;
+}
+
+static int use_device_path(const mm_mapopt_t *opt)
+{
+	static int host_only = -1;
+	if (host_only < 0) host_only = getenv("MM2_B200_HOSTPATH") != 0;
+	return !host_only && (opt->flag & MM_F_SR) && !(opt->flag & MM_F_SPLICE);
+}
+
+static void *map_shard_dev(shard_t *sh)
+{
+	const int nf = sh->f1 - sh->f0;
+	double t0 = realtime(), t1;
+	int rc;
+	if (sh->gpu_token) pthread_mutex_lock(sh->gpu_token);
+	rc = mmg_seed_chain_resident(sh->ctx, sh->didx, &sh->dopt, &sh->ch, 0);
+	if (sh->gpu_token) pthread_mutex_unlock(sh->gpu_token);
+	if (rc != MMG_OK) { shard_fail(sh, "seed/chain stage failed"); return 0; }
+	t1 = realtime();
+	sh->st.t_seedchain += t1 - t0, sh->st.t_seedchain_kernels += sh->ch.t_kernels_ms * 1e-3;
+	sh->st.n_minimizers += sh->ch.n_minimizers, sh->st.n_anchors += sh->ch.n_anchors, sh->st.n_chain_iter += sh->ch.n_chain_iter;
+	sh->frag_hash = (uint32_t*)malloc((size_t)nf * 4);
+	parallel_for(sh->n_threads, stage_dev_hash, sh, nf);
+	t0 = realtime(); sh->st.t_hits += t0 - t1;
+	if (sh->gpu_token) pthread_mutex_lock(sh->gpu_token);
+	rc = mmg_post_chain(sh->ctx, sh->didx, &sh->dopt, sh->opt, sizeof(mm_mapopt_t), sh->mi->flag, sh->frag_hash, &sh->post);
+	if (sh->gpu_token) pthread_mutex_unlock(sh->gpu_token);
+	free(sh->frag_hash); sh->frag_hash = 0;
+	if (rc != MMG_OK) { shard_fail(sh, "post-chaining device stages failed"); return 0; }
+	t1 = realtime();
+	sh->st.t_ksw_total += t1 - t0, sh->st.t_ksw_kernel += sh->post.t_ksw_ms * 1e-3;
+	sh->st.n_dp_jobs += sh->post.n_dp_jobs, sh->st.n_dp_cells += sh->post.n_dp_cells, sh->st.n_dp_rounds += sh->post.n_dp_rounds;
+	sh->st.n_dp_jobs_fast += sh->post.n_dp_jobs_fast, sh->st.n_dp_cells_fast += sh->post.n_dp_cells_fast;
+	parallel_for(sh->n_threads, stage_dev_finish, sh, nf);
+	sh->st.t_finish += realtime() - t1;
+	return 0;
+}
+
 /* map the fragments [f0,f1) whose reads are resident on the shard's GPU */
 static void *map_shard(void *data)
 {
@@ -320,6 +415,7 @@ static void *map_shard(void *data)
 	int i, j;
 	double t0, t1;
 	if (nf <= 0 || sh->rc) return 0;
+	if (use_device_path(sh->opt)) return map_shard_dev(sh);
 	t0 = realtime();
 	if (sh->gpu_token) pthread_mutex_lock(sh->gpu_token);
 	i = mmg_seed_chain_resident(sh->ctx, sh->didx, &sh->dopt, &sh->ch, 1);

@@ -57,54 +57,8 @@ __attribute__((constructor)) static void init_tables(void)
 	}
 }
 
-/* The reference sorts with klib's in-place MSD byte radix sort (insertion sort at <= 64 elements).  Where equal
- * keys can meet, the order they end up in is observable downstream, so the same permutation
- * is performed here: count, then cycle elements into their buckets starting from the lowest non-empty one. */
-#define RS_SMALL 64
-
-#define RADIX_IMPL(NAME, T, KEY) \
-static void NAME##_ins(T *b, T *e) \
-{ \
-	T *i, *j; \
-	for (i = b + 1; i < e; ++i) { \
-		if (!(KEY(*i) < KEY(*(i - 1)))) continue; \
-		T t = *i; \
-		for (j = i; j > b && KEY(t) < KEY(*(j - 1)); --j) *j = *(j - 1); \
-		*j = t; \
-	} \
-} \
-static void NAME##_lvl(T *b, T *e, int sh) \
-{ \
-	size_t cnt[256]; T *hd[256], *tl[256], *i; int d; \
-	memset(cnt, 0, sizeof(cnt)); \
-	for (i = b; i != e; ++i) ++cnt[(KEY(*i) >> sh) & 0xff]; \
-	for (d = 0, i = b; d < 256; ++d) hd[d] = i, i += cnt[d], tl[d] = i; \
-	for (d = 0; d < 256;) { \
-		int to; \
-		if (hd[d] == tl[d]) { ++d; continue; } \
-		to = (int)((KEY(*hd[d]) >> sh) & 0xff); \
-		if (to == d) { ++hd[d]; continue; } \
-		{ T carry = *hd[d], sw; \
-		  do { sw = carry; carry = *hd[to]; *hd[to]++ = sw; to = (int)((KEY(carry) >> sh) & 0xff); } while (to != d); \
-		  *hd[d]++ = carry; } \
-	} \
-	if (sh == 0) return; \
-	sh = sh > 8 ? sh - 8 : 0; \
-	for (d = 0, i = b; d < 256; i = tl[d], ++d) { \
-		if (tl[d] - i > RS_SMALL) NAME##_lvl(i, tl[d], sh); \
-		else if (tl[d] - i > 1) NAME##_ins(i, tl[d]); \
-	} \
-} \
-void NAME(T *beg, T *end) \
-{ \
-	if (end - beg <= RS_SMALL) NAME##_ins(beg, end); \
-	else NAME##_lvl(beg, end, 56); \
-}
-
-#define KEY_X(v) ((v).x)
-#define KEY_ID(v) (v)
-RADIX_IMPL(radix_sort_128x, mm128_t, KEY_X)
-RADIX_IMPL(radix_sort_64, uint64_t, KEY_ID)
+RADIX_IMPL(radix_sort_128x, mm128_t, RS_KEY_X, RS_TABLES_STACK)
+RADIX_IMPL(radix_sort_64, uint64_t, RS_KEY_ID, RS_TABLES_STACK)
 
 /* ---- shard-lifetime bump arena (see mm2b_priv.h) */
 

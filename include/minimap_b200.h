@@ -166,7 +166,10 @@ int64_t mm_idx_is_idx(const char *fn);
 mm_idx_t *mm_idx_str(int w, int k, int is_hpc, int bucket_bits, int n, const char **seq, const char **name);
 void mm_idx_stat(const mm_idx_t *idx);
 void mm_idx_destroy(mm_idx_t *mi);
-int mm_idx_getseq(const mm_idx_t *mi, uint32_t rid, uint32_t st, uint32_t en, uint8_t *seq);
+#ifndef MM_FN
+#define MM_FN
+#endif
+MM_FN int mm_idx_getseq(const mm_idx_t *mi, uint32_t rid, uint32_t st, uint32_t en, uint8_t *seq);
 int32_t mm_idx_cal_max_occ(const mm_idx_t *mi, float f);
 
 /* mapping (map.c) */

@@ -174,6 +174,23 @@ int  mmg_ksw_batch(mmg_ctx_t *ctx, const mmg_idx_t *idx, const mmg_mapopt_t *opt
 void mmg_ksw_last_split(const mmg_ctx_t *ctx, uint64_t *jobs_fast, uint64_t *cells_fast, uint64_t *jobs_literal, uint64_t *cells_literal);
 int  mmg_job_buffers(mmg_ctx_t *ctx, size_t n_jobs, mmg_ksw_job_t **jobs, mmg_ksw_res_t **res);
 
+/* ------------------------------------------- post-chaining stages on the device (short-read presets)
+ * What mm_map_frag does between mm_chain_dp and mm_set_mapq (map.c:376-400: mm_gen_regs, chain_post, mm_seg_gen,
+ * mm_align_skeleton with its ksw_extd2 calls, mm_update_extra, filters) for every fragment of the resident batch, right
+ * after mmg_seed_chain_resident(download = 0).  The host receives one blob and finishes with MAPQ / pairing (logf). */
+typedef struct {
+	const int32_t *n_reg;        /* [n_seq] hits per read */
+	const int64_t *blob_off;     /* [n_seq+1] byte offset of each read's records in blob */
+	const unsigned char *blob;   /* per read: n_reg mm_reg1_t, then for every hit with p != 0 its mm_extra_t + cigar, padded to 8 bytes */
+	const int32_t *rep_len;      /* [n_frag] */
+	double t_device_ms, t_ksw_ms;
+	uint64_t n_dp_jobs, n_dp_cells, n_dp_rounds, n_dp_jobs_fast, n_dp_cells_fast;
+} mmg_post_out_t;
+/* mapopt_full: the caller's mm_mapopt_t (minimap.h:107-150) as bytes; idx_flag: mm_idx_t::flag; frag_hash[n_frag]: the
+ * per-fragment salt of map.c:291-293 (it depends on the read name, which never leaves the host) */
+int  mmg_post_chain(mmg_ctx_t *ctx, const mmg_idx_t *idx, const mmg_mapopt_t *opt, const void *mapopt_full, size_t mapopt_bytes, int idx_flag,
+                    const uint32_t *frag_hash, mmg_post_out_t *out);
+
 #ifdef __cplusplus
 }
 #endif
