@@ -54,7 +54,7 @@ struct DFrag {
 struct Shard {
 	const mm_idx_t *mi;
 	mm_mapopt_t opt;
-	int nf, n_seq;
+	int nf, n_seq, nt;                          // nt: threads of the per-fragment kernels (nf rounded up to whole warps)
 	const int32_t *n_seg, *seg_off, *seq_len;   // per fragment / per read of the resident batch
 	const uint64_t *q_off;
 	const uint32_t *Q;
@@ -63,6 +63,7 @@ struct Shard {
 	uint64_t *u;
 	mm128_t *a;
 	const uint32_t *hash;
+	const int32_t *perm;                        // thread -> fragment: fragments with similar amounts of work share a warp
 	int32_t *n_reg;                             // per read
 	mm_reg1_t **reg;
 	DFrag *fr;
@@ -108,25 +109,49 @@ __device__ void *dev_malloc(size_t n)
 	*reinterpret_cast<size_t*>(p) = n;
 	return p + 16;
 }
-__device__ void *dev_calloc(size_t n, size_t sz) { void *p = dev_malloc(n * sz); memset(p, 0, n * sz); return p; }
-__device__ void *dev_realloc(void *p, size_t n)
+// memcpy / memset / memmove of the C sources: pool blocks are 16-byte aligned, CIGARs and records are word arrays, so
+// almost every call can move 16 or 4 bytes per step instead of the byte loop the compiler emits for unknown alignment
+__device__ void *dev_memcpy(void *dst, const void *src, size_t n)
 {
-	void *q = dev_malloc(n);
-	if (p) { const size_t old = *reinterpret_cast<size_t*>(static_cast<char*>(p) - 16); memcpy(q, p, old < n ? old : n); }
-	return q;
+	const size_t a = reinterpret_cast<size_t>(dst) | reinterpret_cast<size_t>(src);
+	size_t i = 0;
+	if ((a & 15) == 0) { uint4 *d = static_cast<uint4*>(dst); const uint4 *s = static_cast<const uint4*>(src); for (; i + 16 <= n; i += 16) d[i >> 4] = s[i >> 4]; }
+	if ((a & 3) == 0) { uint32_t *d = static_cast<uint32_t*>(dst); const uint32_t *s = static_cast<const uint32_t*>(src); for (; i + 4 <= n; i += 4) d[i >> 2] = s[i >> 2]; }
+	for (; i < n; ++i) static_cast<unsigned char*>(dst)[i] = static_cast<const unsigned char*>(src)[i];
+	return dst;
+}
+__device__ void *dev_memset(void *dst, int v, size_t n)
+{
+	const size_t a = reinterpret_cast<size_t>(dst);
+	const uint32_t w = 0x01010101u * (uint32_t)(unsigned char)v;
+	size_t i = 0;
+	if ((a & 15) == 0) { uint4 *d = static_cast<uint4*>(dst); const uint4 q = make_uint4(w, w, w, w); for (; i + 16 <= n; i += 16) d[i >> 4] = q; }
+	if ((a & 3) == 0) { uint32_t *d = static_cast<uint32_t*>(dst); for (; i + 4 <= n; i += 4) d[i >> 2] = w; }
+	for (; i < n; ++i) static_cast<unsigned char*>(dst)[i] = (unsigned char)v;
+	return dst;
 }
 __device__ void *dev_memmove(void *dst, const void *src, size_t n)
 {
 	unsigned char *d = static_cast<unsigned char*>(dst); const unsigned char *s = static_cast<const unsigned char*>(src);
-	if (d < s) for (size_t i = 0; i < n; ++i) d[i] = s[i];
-	else if (d > s) for (size_t i = n; i > 0; --i) d[i - 1] = s[i - 1];
+	if (d <= s || d >= s + n) return dev_memcpy(dst, src, n); // a forward copy never overwrites unread source bytes
+	if (((reinterpret_cast<size_t>(d) | reinterpret_cast<size_t>(s) | n) & 7) == 0) {
+		uint64_t *dd = static_cast<uint64_t*>(dst); const uint64_t *ss = static_cast<const uint64_t*>(src);
+		for (size_t i = n >> 3; i > 0; --i) dd[i - 1] = ss[i - 1];
+	} else for (size_t i = n; i > 0; --i) d[i - 1] = s[i - 1];
 	return dst;
+}
+__device__ void *dev_calloc(size_t n, size_t sz) { void *p = dev_malloc(n * sz); dev_memset(p, 0, n * sz); return p; }
+__device__ void *dev_realloc(void *p, size_t n)
+{
+	void *q = dev_malloc(n);
+	if (p) { const size_t old = *reinterpret_cast<size_t*>(static_cast<char*>(p) - 16); dev_memcpy(q, p, old < n ? old : n); }
+	return q;
 }
 
 // the arena interface of mm2b_priv.h, on the pool
 __device__ void *mm_amalloc(size_t n) { return dev_malloc(n); }
 __device__ void *mm_acalloc(size_t n, size_t sz) { return dev_calloc(n, sz); }
-__device__ void *mm_arealloc(void *p, size_t old_bytes, size_t new_bytes) { void *q = dev_malloc(new_bytes); if (p && old_bytes) memcpy(q, p, old_bytes < new_bytes ? old_bytes : new_bytes); return q; }
+__device__ void *mm_arealloc(void *p, size_t old_bytes, size_t new_bytes) { void *q = dev_malloc(new_bytes); if (p && old_bytes) dev_memcpy(q, p, old_bytes < new_bytes ? old_bytes : new_bytes); return q; }
 __device__ void mm_afree(void *) {}
 
 __device__ int mm_idx_getseq_dev(const mm_idx_t *mi, uint32_t rid, uint32_t st, uint32_t en, uint8_t *seq)
@@ -134,7 +159,15 @@ __device__ int mm_idx_getseq_dev(const mm_idx_t *mi, uint32_t rid, uint32_t st, 
 	if (rid >= mi->n_seq || st >= mi->seq[rid].len) return -1;
 	if (en > mi->seq[rid].len) en = mi->seq[rid].len;
 	const uint64_t st1 = mi->seq[rid].offset + st, en1 = mi->seq[rid].offset + en;
-	for (uint64_t i = st1; i < en1; ++i) seq[i - st1] = mm_seq4_get(mi->S, i);
+	uint64_t i = st1;
+	for (; i < en1 && (i & 7); ++i) seq[i - st1] = mm_seq4_get(mi->S, i);
+	for (; i + 8 <= en1; i += 8) { // one packed word = 8 bases
+		uint32_t w = mi->S[i >> 3];
+		uint8_t *o = seq + (i - st1);
+#pragma unroll
+		for (int k = 0; k < 8; ++k) o[k] = (uint8_t)(w >> (4 * k) & 0xf);
+	}
+	for (; i < en1; ++i) seq[i - st1] = mm_seq4_get(mi->S, i);
 	return (int)(en - st);
 }
 
@@ -144,6 +177,8 @@ __device__ int mm_idx_getseq_dev(const mm_idx_t *mi, uint32_t rid, uint32_t st, 
 #define realloc(p, n) mmdev::dev_realloc(p, n)
 #define free(p) ((void)(p))
 #define memmove(d, s, n) mmdev::dev_memmove(d, s, n)
+#define memcpy(d, s, n) mmdev::dev_memcpy(d, s, n)
+#define memset(d, v, n) mmdev::dev_memset(d, v, n)
 #define fprintf(...) ((void)0)
 #define exit(c) asm volatile("trap;")
 #define mm_verbose 0
@@ -163,6 +198,8 @@ RADIX_IMPL(radix_sort_64, uint64_t, RS_KEY_ID, RS_TABLES_ARENA)
 #undef realloc
 #undef free
 #undef memmove
+#undef memcpy
+#undef memset
 #undef fprintf
 #undef exit
 #undef mm_verbose
@@ -202,18 +239,19 @@ __device__ int frag_walk(Shard *sh, int i)
 	return n_new;
 }
 
-__global__ void __launch_bounds__(128) k_post_hits(Shard *shp)
+__global__ void __launch_bounds__(128, 5) k_post_hits(Shard *shp)
 { // chains -> hits for one fragment per thread (map.c:376-388, 390-400 up to the DP), then the first walk
 	if (threadIdx.x == 0) *reinterpret_cast<Shard**>(dyn_smem) = shp;
 	__syncthreads();
 	Shard *sh = shp;
-	const int i = cur_tid();
-	if (i >= sh->nf) return;
+	if (cur_tid() >= sh->nt) return;
+	const int i = sh->perm[cur_tid()];
+	if (i < 0) return;
 	const mm_mapopt_t *opt = &sh->opt;
 	const mm_idx_t *mi = sh->mi;
 	const int off = sh->seg_off[i], ns = sh->n_seg[i];
 	DFrag *fr = &sh->fr[i];
-	sh->tls[i].cur = sh->tls[i].end = nullptr;
+	sh->tls[cur_tid()].cur = sh->tls[cur_tid()].end = nullptr;
 	memset(fr, 0, sizeof(*fr));
 	sh->n_new[i] = 0;
 	fr->n_segs = ns;
@@ -260,8 +298,9 @@ __global__ void __launch_bounds__(128) k_post_hits(Shard *shp)
 __global__ void __launch_bounds__(128) k_post_gather(Shard *shp)
 { // copy the DP jobs a fragment queued in this round into the dense job array
 	Shard *sh = shp;
-	const int i = cur_tid();
-	if (i >= sh->nf) return;
+	if (cur_tid() >= sh->nt) return;
+	const int i = sh->perm[cur_tid()];
+	if (i < 0) return;
 	const DFrag *fr = &sh->fr[i];
 	if (!fr->active) return;
 	int64_t k = sh->job_off[i];
@@ -271,13 +310,14 @@ __global__ void __launch_bounds__(128) k_post_gather(Shard *shp)
 	}
 }
 
-__global__ void __launch_bounds__(128) k_post_align(Shard *shp)
+__global__ void __launch_bounds__(128, 5) k_post_align(Shard *shp)
 { // hand the results of this round back to the job caches (in the order they were gathered), then re-walk
 	if (threadIdx.x == 0) *reinterpret_cast<Shard**>(dyn_smem) = shp;
 	__syncthreads();
 	Shard *sh = shp;
-	const int i = cur_tid();
-	if (i >= sh->nf) return;
+	if (cur_tid() >= sh->nt) return;
+	const int i = sh->perm[cur_tid()];
+	if (i < 0) return;
 	DFrag *fr = &sh->fr[i];
 	if (!fr->active) { sh->n_new[i] = 0; return; }
 	int64_t k = sh->job_off[i];
@@ -336,6 +376,23 @@ __global__ void k_post_pack(Shard *shp, const int64_t *offs, unsigned char *blob
 		}
 }
 
+__global__ void k_post_keys(int nf, const int32_t *nu, const int32_t *nv, uint32_t *key, int32_t *idx)
+{ // work estimate of a fragment: its chains, then its chained anchors (descending, so the heavy warps start first)
+	const int i = cur_tid();
+	if (i >= nf) return;
+	const uint32_t u = nu[i] < 1023 ? (uint32_t)nu[i] : 1023u, v = nv[i] < 0xfffff ? (uint32_t)nv[i] : 0xfffffu;
+	key[i] = ~(u << 20 | v), idx[i] = i;
+}
+
+__global__ void k_post_spread(int nf, int n_warps, const int32_t *sorted, int32_t *perm)
+{ // rank r (heaviest first) -> warp r % n_warps, lane r / n_warps: every warp gets one fragment of each weight class, the
+  // heaviest fragments sit alone at the front of the launch instead of serialising inside one warp
+	const int t = cur_tid();
+	if (t >= n_warps * 32) return;
+	const int64_t r = (int64_t)(t & 31) * n_warps + (t >> 5);
+	perm[t] = r < nf ? sorted[r] : -1;
+}
+
 __global__ void k_post_mi(mm_idx_t *mi, mm_idx_seq_t *seq, int n_seq, const uint64_t *seq_off, const uint32_t *seq_len, uint32_t *S, int k, int w, int flag)
 { // device copy of the index header: what hits.c / aln.c read through mm_idx_t
 	const int i = cur_tid();
@@ -387,7 +444,7 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 	MMG_TRY(c->p_nreg.ensure((size_t)(n_seq + 1) * 4));
 	MMG_TRY(c->p_reg.ensure((size_t)(n_seq + 1) * 8));
 	MMG_TRY(c->p_fr.ensure((size_t)(nf + 1) * sizeof(DFrag)));
-	MMG_TRY(c->p_tls.ensure((size_t)(nf + 1) * sizeof(Tls)));
+	MMG_TRY(c->p_tls.ensure((size_t)(nf + 64) * sizeof(Tls)));
 	MMG_TRY(c->p_pool.ensure(pool_bytes));
 	MMG_TRY(c->p_ctr.ensure(64));
 	MMG_TRY(c->p_nnew.ensure((size_t)(nf + 2) * 4));
@@ -422,10 +479,25 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 		MMG_H2D(c, d_segoff, rb.seg_off.data(), (size_t)nf * 4);
 		hs.seg_off = d_segoff;
 	}
+	{ // thread -> fragment order
+		const int n_warps = (nf + 31) / 32;
+		hs.nt = n_warps * 32;
+		MMG_TRY(c->p_perm.ensure((size_t)(nf + 33) * 20));
+		uint32_t *key = c->p_perm.as<uint32_t>(), *key2 = key + nf + 1;
+		int32_t *idx = reinterpret_cast<int32_t*>(key2 + nf + 1), *sorted = idx + nf + 1, *perm = sorted + nf + 1;
+		MMG_LAUNCH(c, k_post_keys, mmg_blocks(nf, 256), 256, 0, nf, hs.nu, hs.nv, key, idx);
+		size_t tmp = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, sorted, nf, 0, 32, c->stream);
+		MMG_TRY(c->d_cub.ensure(tmp));
+		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, sorted, nf, 0, 32, c->stream));
+		++c->launches;
+		MMG_LAUNCH(c, k_post_spread, mmg_blocks(hs.nt, 256), 256, 0, nf, n_warps, sorted, perm);
+		hs.perm = perm;
+	}
 	MMG_H2D(c, c->p_shard.p, &hs, sizeof(hs));
 	MMG_CUDA(cudaStreamSynchronize(c->stream)); // hs lives on this stack frame
 	MMG_CUDA(cudaEventRecord(c->ev[0], c->stream));
-	MMG_LAUNCH(c, k_post_hits, mmg_blocks(nf, 128), 128, 16, c->p_shard.as<Shard>());
+	MMG_LAUNCH(c, k_post_hits, mmg_blocks(hs.nt, 128), 128, 16, c->p_shard.as<Shard>());
 	double ksw_ms = 0;
 	for (int round = 0;; ++round) {
 		unsigned long long ctr[3] = {0, 0, 0};
@@ -441,7 +513,7 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 		MMG_TRY(c->p_jobs.ensure((size_t)(n_jobs + 1) * sizeof(mmg_ksw_job_t)));
 		hs.jobs = c->p_jobs.as<mmg_ksw_job_t>();
 		MMG_H2D(c, reinterpret_cast<char*>(c->p_shard.p) + offsetof(Shard, jobs), &hs.jobs, sizeof(hs.jobs));
-		MMG_LAUNCH(c, k_post_gather, mmg_blocks(nf, 128), 128, 0, c->p_shard.as<Shard>());
+		MMG_LAUNCH(c, k_post_gather, mmg_blocks(hs.nt, 128), 128, 0, c->p_shard.as<Shard>());
 		const void *d_res = nullptr; const uint32_t *d_cig = nullptr; double kms = 0; uint64_t cells = 0;
 		MMG_TRY(mmg_ksw_device(c, mi, dopt, (int)n_jobs, hs.jobs, &d_res, &d_cig, &kms, &cells));
 		ksw_ms += kms;
@@ -451,7 +523,7 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 		MMG_H2D(c, reinterpret_cast<char*>(c->p_shard.p) + offsetof(Shard, res), &hs.res, sizeof(hs.res));
 		MMG_H2D(c, reinterpret_cast<char*>(c->p_shard.p) + offsetof(Shard, cig), &hs.cig, sizeof(hs.cig));
 		MMG_CUDA(cudaMemsetAsync(c->p_ctr.as<unsigned long long>() + 1, 0, 8, c->stream));
-		MMG_LAUNCH(c, k_post_align, mmg_blocks(nf, 128), 128, 16, c->p_shard.as<Shard>());
+		MMG_LAUNCH(c, k_post_align, mmg_blocks(hs.nt, 128), 128, 16, c->p_shard.as<Shard>());
 	}
 	// pack and download
 	int64_t *sizes = c->p_sizes.as<int64_t>();

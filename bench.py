@@ -226,7 +226,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip the whole-CLI (parse + map + SAM) timing at N=1")
-    ap.add_argument("--lanes", type=int, default=2, help="shards (streams) per GPU a batch is cut into")
+    ap.add_argument("--lanes", type=int, default=1, help="shards (streams) per GPU a batch is cut into")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -405,6 +405,8 @@ def main():
             "k_chain_fill": nanch * (16 + 16), "k_chain_tail_warp": nanch * (16 + 16 + 16 + 16),
             "k_ksw": (cells - cells_fast) * 1.0 + (jobs - jobs_fast) * 64, "k_ksw_tpj": cells_fast * 1.0 + jobs_fast * 64,
             "k_encode_reads": st_res.n_bases * 1.5,
+            # post-chaining bookkeeping (one fragment per thread): chained anchors in, query + target windows as 4-bit codes, hits out
+            "k_post_hits": nanch * 16 + st_res.n_bases * 1.0 + st_res.n_reads * 96, "k_post_align": cells * 0.0 + jobs * 64 + st_res.n_bases * 1.0 + st_res.n_reads * 160,
         }
         a_bytes = algo.get(dname, 0.0)
         achieved = a_bytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
