@@ -110,6 +110,7 @@ static int chain_gap_ref(const mm_mapopt_t *opt, int qlen_sum)
 	return opt->max_gap;
 }
 
+static int use_device_path(const mm_mapopt_t *opt);
 static void stage_align(void *data, long i, int tid);
 static void stage_finish(void *data, long i, int tid);
 
@@ -541,7 +542,9 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		mm_arena_init(&h->arena);
 		/* lanes of one GPU alternate between device and host stages, so each may use that GPU's whole share of host threads */
 		h->n_threads = n_threads / B->n_dev > 0 ? n_threads / B->n_dev : 1;
-		h->gpu_token = B->lanes > 1 ? &B->gpu_token[d / B->lanes] : 0;
+		/* host path: the lanes of a GPU take turns on the device while the others run host stages; device path: their kernels
+		 * may overlap freely (the latency-bound tails of one shard fill the gaps of the other) */
+		h->gpu_token = B->lanes > 1 && !use_device_path(opt) ? &B->gpu_token[d / B->lanes] : 0;
 		h->seq = s->seq, h->n_seg = s->n_seg, h->seg_off = s->seg_off, h->n_reg = s->n_reg, h->rep_len = s->rep_len, h->frag_gap = s->frag_gap, h->reg = s->reg;
 		h->f0 = f;
 		while (f < s->n_frag && (acc < goal || d == n_dev - 1)) {

@@ -441,6 +441,9 @@ def main():
             "host_s_per_step": {"seed_chain_call": st_res.t_seedchain / args.steps, "hits": st_res.t_hits / args.steps,
                                 "align_host": st_res.t_align_host / args.steps, "dp_call": st_res.t_ksw_total / args.steps,
                                 "finish": st_res.t_finish / args.steps, "dp_rounds": st_res.n_dp_rounds / args.steps},
+            "host_s_per_step_e2e": {"upload": st_e2e.t_upload / args.steps, "seed_chain_call": st_e2e.t_seedchain / args.steps, "hits": st_e2e.t_hits / args.steps,
+                                    "align_host": st_e2e.t_align_host / args.steps, "dp_call": st_e2e.t_ksw_total / args.steps, "finish": st_e2e.t_finish / args.steps,
+                                    "total": st_e2e.t_total / args.steps},
             "host_threads": n_threads, "index_build_s": t_index, "index_broadcast_bytes": bcast_bytes, "clocks": clocks_res,
         }
     # ---- CPU baseline next to it (rank 0, N=1 only): the reference fork on a bounded sample
