@@ -255,6 +255,20 @@ k_chain_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const int
 			while (st < i && ri > A[st].x + (uint64_t)P.max_dist_x) ++st;
 			if (i - st > P.max_iter) st = i - P.max_iter;
 			bool done = false;
+			if (i - st <= P.max_skip && i - st <= 32) {
+				// Short window: the skip counter (chain.c:76-80) needs more than max_skip marked predecessors to stop the scan, so it
+				// cannot fire, and the t[] marks it reads are private to this i.  What is left is "best score, first one met wins ties",
+				// i.e. the largest j: one warp-wide max over score * 32 + (31 - lane).
+				const int j = i - 1 - lane;
+				int32_t sc = 0;
+				bool valid = j >= st;
+				if (valid) { valid = mmg_chain_score(P, ri, qi, q_span, sidi, A[j], avg_qspan, &sc); if (valid) sc += F[j]; }
+				const int key = valid && sc > max_f ? sc * 32 + (31 - lane) : INT32_MIN;
+				const int best = __reduce_max_sync(0xffffffffu, key);
+				if (best != INT32_MIN) { const int bl = 31 - (best & 31); max_f = (best - (best & 31)) / 32, max_j = i - 1 - bl; }
+				iters += (unsigned)(i - st);
+				done = true;
+			}
 			for (int jhi = i - 1; jhi >= st && !done; jhi -= 32) {
 				const int j = jhi - lane;
 				bool valid = j >= st;
