@@ -102,7 +102,7 @@ struct mmg_ctx_s {
 	const void *k_last_res = nullptr; // device {ez, cigar offset} array of the last ksw_launch
 	uint64_t k_last_jobs_fast = 0, k_last_cells_fast = 0, k_last_jobs_literal = 0, k_last_cells_literal = 0;
 	// post-chaining stages on the device (mmg_post.cu)
-	DevBuf p_shard, p_mi, p_seq, p_hash, p_nreg, p_reg, p_fr, p_tls, p_pool, p_ctr, p_nnew, p_joboff, p_jobs, p_sizes, p_offs, p_blob, p_perm;
+	DevBuf p_shard, p_mi, p_seq, p_hash, p_nreg, p_reg, p_fr, p_tls, p_pool, p_ctr, p_nnew, p_joboff, p_jobs, p_sizes, p_offs, p_blob, p_perm, p_pre;
 	const void *p_mi_for = nullptr;
 	PinBuf h_p_hash, h_p_nreg, h_p_offs, h_p_blob, h_p_rep;
 	PinBuf h_in, h_meta, h_out_meta, h_out_u, h_out_a, h_out_mini, h_k_jobs, h_k_res, h_k_cig;

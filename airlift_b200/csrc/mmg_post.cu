@@ -63,6 +63,7 @@ struct Shard {
 	uint64_t *u;
 	mm128_t *a;
 	const uint32_t *hash;
+	mm_reg1_t **pre_regs;                       // per fragment: mm_gen_regs output made by k_post_regs_heavy (or null)
 	const int32_t *perm;                        // thread -> fragment: fragments with similar amounts of work share a warp
 	int32_t *n_reg;                             // per read
 	mm_reg1_t **reg;
@@ -70,7 +71,7 @@ struct Shard {
 	Tls *tls;
 	char *pool;
 	unsigned long long pool_size;
-	unsigned long long *pool_cur;               // [0] bump cursor, [1] active fragments, [2] error flag
+	unsigned long long *pool_cur;               // [0] bump cursor, [1] active fragments, [2] error flag, [3] debug: longest thread (cycles << 20 | chains)
 	int32_t *n_new;                             // per fragment: DP jobs queued by the last walk
 	const int64_t *job_off;
 	mmg_ksw_job_t *jobs;
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(128, 5) k_post_hits(Shard *shp)
 	if (cur_tid() >= sh->nt) return;
 	const int i = sh->perm[cur_tid()];
 	if (i < 0) return;
+	const long long t_begin = clock64();
 	const mm_mapopt_t *opt = &sh->opt;
 	const mm_idx_t *mi = sh->mi;
 	const int off = sh->seg_off[i], ns = sh->n_seg[i];
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(128, 5) k_post_hits(Shard *shp)
 	fr->frag_gap = chain_gap_ref(opt, fr->qlen_sum);
 	fr->n_u = sh->nu[i];
 	if (fr->n_u > 0) fr->u = sh->u + sh->uoff[i], fr->a = sh->a + sh->voff[i]; // used in place
-	fr->regs0 = mm_gen_regs(fr->hash, fr->qlen_sum, fr->n_u, fr->u, fr->a);
+	fr->regs0 = sh->pre_regs[i] ? sh->pre_regs[i] : mm_gen_regs(fr->hash, fr->qlen_sum, fr->n_u, fr->u, fr->a);
 	fr->n_regs0 = fr->n_u;
 	if (!(opt->flag & MM_F_ALL_CHAINS)) { // chain_post, map.c:249-258
 		mm_set_parent(opt->mask_level, fr->n_regs0, fr->regs0, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL);
@@ -292,6 +294,10 @@ __global__ void __launch_bounds__(128, 5) k_post_hits(Shard *shp)
 		const int n_new = frag_walk(sh, i);
 		sh->n_new[i] = n_new;
 		if (fr->active) atomicAdd(sh->pool_cur + 1, 1ULL);
+	}
+	{ // debug aid (MMG_POST_DEBUG): the longest-running thread of the launch and how many chains its fragment had
+		const unsigned long long dt = (unsigned long long)(clock64() - t_begin);
+		atomicMax(sh->pool_cur + 3, dt << 20 | (unsigned long long)(fr->n_u < 0xfffff ? fr->n_u : 0xfffff));
 	}
 }
 
@@ -337,6 +343,83 @@ __global__ void __launch_bounds__(128, 5) k_post_align(Shard *shp)
 	const int n_new = frag_walk(sh, i);
 	sh->n_new[i] = n_new;
 	if (fr->active) atomicAdd(sh->pool_cur + 1, 1ULL);
+}
+
+
+// ---- mm_gen_regs (hit.c:52-88) for fragments with many chains, one CTA per fragment ---------------------------------
+// A read pair from a high-copy repeat arrives with thousands of chains over ~10^5 anchors; walked by the single thread
+// of k_post_hits it set the duration of the whole launch (34 ms).  The sort key (score, salted hash of the first
+// anchor) is unique per chain unless two 32-bit hashes collide, so any sort gives klib's order; a collision is detected
+// and leaves the fragment to the literal serial code.
+#define POST_HEAVY_NU 128
+
+__global__ void k_post_heavy_list(int nf, const int32_t *nu, int32_t *list, unsigned long long *counter)
+{
+	const int i = cur_tid();
+	if (i < nf && nu[i] > POST_HEAVY_NU) list[atomicAdd(counter, 1ULL)] = i;
+}
+
+__global__ void __launch_bounds__(256) k_post_regs_heavy(Shard *shp, const int32_t *list)
+{
+	Shard *sh = shp;
+	const int i = list[blockIdx.x], n = sh->nu[i], tid = threadIdx.x, nt = blockDim.x;
+	const uint64_t *u = sh->u + sh->uoff[i];
+	const mm128_t *a = sh->a + sh->voff[i];
+	__shared__ char *s_base;
+	__shared__ int s_scan[256], s_carry, s_tie;
+	const size_t z_bytes = ((size_t)n * 16 + 15) & ~(size_t)15, r_bytes = (((size_t)n * sizeof(mm_reg1_t)) + 15) & ~(size_t)15;
+	if (tid == 0) {
+		const unsigned long long o = atomicAdd(sh->pool_cur, (unsigned long long)(z_bytes + r_bytes + 32));
+		if (o + z_bytes + r_bytes + 32 > sh->pool_size) { atomicExch(sh->pool_cur + 2, 1ULL); asm volatile("trap;"); }
+		s_base = sh->pool + o;
+		s_carry = 0, s_tie = 0;
+	}
+	__syncthreads();
+	mm128_t *z = reinterpret_cast<mm128_t*>(s_base + 16);
+	char *rblk = s_base + 16 + z_bytes;
+	mm_reg1_t *r = reinterpret_cast<mm_reg1_t*>(rblk + 16);
+	if (tid == 0) *reinterpret_cast<size_t*>(s_base) = (size_t)n * 16, *reinterpret_cast<size_t*>(rblk) = (size_t)n * sizeof(mm_reg1_t); // block headers (realloc reads them)
+	int qlen = 0;
+	for (int j = 0; j < sh->n_seg[i]; ++j) qlen += sh->seq_len[sh->seg_off[i] + j];
+	// first anchor of every chain: exclusive scan of the chain lengths, 256 at a time
+	for (int i0 = 0; i0 < n; i0 += nt) {
+		const int e = i0 + tid, cnt = e < n ? (int32_t)u[e] : 0;
+		s_scan[tid] = cnt;
+		__syncthreads();
+		for (int d = 1; d < nt; d <<= 1) { const int v = tid >= d ? s_scan[tid - d] : 0; __syncthreads(); s_scan[tid] += v; __syncthreads(); }
+		const int k = s_carry + s_scan[tid] - cnt;
+		if (e < n) {
+			const uint32_t h = (uint32_t)mix64((mix64(a[k].x) + mix64(a[k].y)) ^ sh->hash[i]);
+			z[e].x = u[e] ^ h, z[e].y = (uint64_t)k << 32 | (uint32_t)(int32_t)u[e];
+		}
+		__syncthreads();
+		if (tid == nt - 1) s_carry += s_scan[tid];
+		__syncthreads();
+	}
+	// descending by x: bitonic network oriented one way, so the virtual entries beyond n never move
+	int N = 2; while (N < n) N <<= 1;
+	for (int k = 2; k <= N; k <<= 1) {
+		for (int e = tid; e < n; e += nt) { const int l = e ^ (k - 1); if (l > e && l < n) { const mm128_t x = z[e], y = z[l]; if (y.x > x.x) z[e] = y, z[l] = x; } }
+		__syncthreads();
+		for (int j = k >> 2; j > 0; j >>= 1) {
+			for (int e = tid; e < n; e += nt) { const int l = e ^ j; if (l > e && l < n) { const mm128_t x = z[e], y = z[l]; if (y.x > x.x) z[e] = y, z[l] = x; } }
+			__syncthreads();
+		}
+	}
+	for (int e = tid + 1; e < n; e += nt) if (z[e].x == z[e - 1].x) s_tie = 1;
+	__syncthreads();
+	if (s_tie) return; // equal keys: klib's unstable order matters, k_post_hits runs the literal mm_gen_regs
+	for (int e = tid; e < n; e += nt) {
+		mm_reg1_t *ri = &r[e];
+		memset(ri, 0, sizeof(*ri));
+		ri->id = e, ri->parent = MM_PARENT_UNSET;
+		ri->score = ri->score0 = (int32_t)(z[e].x >> 32);
+		ri->hash = (uint32_t)z[e].x;
+		ri->cnt = (int32_t)z[e].y, ri->as = (int32_t)(z[e].y >> 32);
+		ri->div = -1.0f;
+		reg_set_coor(ri, qlen, a);
+	}
+	if (tid == 0) sh->pre_regs[i] = r;
 }
 
 // ---- results: every read's mm_reg1_t array followed by the mm_extra_t of each hit, 8-byte aligned pieces
@@ -494,9 +577,17 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 		MMG_LAUNCH(c, k_post_spread, mmg_blocks(hs.nt, 256), 256, 0, nf, n_warps, sorted, perm);
 		hs.perm = perm;
 	}
+	MMG_TRY(c->p_pre.ensure((size_t)(nf + 1) * 12 + 64));
+	hs.pre_regs = c->p_pre.as<mm_reg1_t*>();
+	int32_t *d_heavy = reinterpret_cast<int32_t*>(hs.pre_regs + nf + 1);
+	MMG_CUDA(cudaMemsetAsync(c->p_pre.p, 0, (size_t)(nf + 1) * 8, c->stream));
 	MMG_H2D(c, c->p_shard.p, &hs, sizeof(hs));
+	unsigned long long n_heavy = 0;
+	MMG_LAUNCH(c, k_post_heavy_list, mmg_blocks(nf, 256), 256, 0, nf, hs.nu, d_heavy, c->p_ctr.as<unsigned long long>() + 4);
+	MMG_D2H(c, &n_heavy, c->p_ctr.as<unsigned long long>() + 4, 8);
 	MMG_CUDA(cudaStreamSynchronize(c->stream)); // hs lives on this stack frame
 	MMG_CUDA(cudaEventRecord(c->ev[0], c->stream));
+	if (n_heavy) MMG_LAUNCH(c, k_post_regs_heavy, (unsigned)n_heavy, 256, 0, c->p_shard.as<Shard>(), d_heavy);
 	MMG_LAUNCH(c, k_post_hits, mmg_blocks(hs.nt, 128), 128, 16, c->p_shard.as<Shard>());
 	double ksw_ms = 0;
 	for (int round = 0;; ++round) {
@@ -551,10 +642,11 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 	float ms = 0;
 	cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
 	if (getenv("MMG_POST_DEBUG")) {
-		unsigned long long used = 0;
-		cudaMemcpy(&used, c->p_ctr.p, 8, cudaMemcpyDeviceToHost);
-		fprintf(stderr, "[mmg_post] %d fragments, pool used %.1f MB of %.1f MB (%.0f B per fragment), blob %.1f MB, %.1f ms on the device (K4 %.1f ms)\n", nf, used / 1e6,
-		        pool_bytes / 1e6, (double)used / nf, blob_bytes / 1e6, ms, ksw_ms);
+		unsigned long long ctr4[4] = {0, 0, 0, 0};
+		cudaMemcpy(ctr4, c->p_ctr.p, 32, cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[mmg_post] %d fragments, pool used %.1f MB of %.1f MB (%.0f B per fragment), blob %.1f MB, %.1f ms on the device (K4 %.1f ms); "
+		        "longest k_post_hits thread %.2f ms (fragment with %llu chains)\n", nf, ctr4[0] / 1e6, pool_bytes / 1e6, (double)ctr4[0] / nf, blob_bytes / 1e6, ms, ksw_ms,
+		        (double)(ctr4[3] >> 20) / 1.965e6, ctr4[3] & 0xfffff);
 	}
 	out->n_reg = c->h_p_nreg.as<int32_t>(), out->blob_off = c->h_p_offs.as<int64_t>(), out->blob = c->h_p_blob.as<unsigned char>();
 	out->rep_len = c->h_p_rep.as<int32_t>();
