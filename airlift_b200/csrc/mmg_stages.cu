@@ -496,6 +496,160 @@ k_chain_tail_warp(FragTab ft, const int32_t *__restrict__ list, int n_list, cons
 	}
 }
 
+
+// ---- K3 tail, one CTA per fragment: the same steps for the re-chain pass, whose few fragments carry ~10^5 anchors and
+// thousands of chains each.  One warp per fragment spent 10 ms per launch at 4 % issue utilisation on dependent walks; 256
+// threads walk eight times as many chains at once.  Orders that the warp form derives from ballots come from block scans.
+template <class T, class Before>
+__device__ __forceinline__ void block_bitonic(T *a, int n, Before before)
+{
+	const int tid = threadIdx.x, nt = blockDim.x;
+	int N = 2; while (N < n) N <<= 1;
+	for (int k = 2; k <= N; k <<= 1) {
+		for (int i = tid; i < n; i += nt) {
+			const int l = i ^ (k - 1);
+			if (l > i && l < n) { const T x = a[i], y = a[l]; if (before(y, x)) a[i] = y, a[l] = x; }
+		}
+		__syncthreads();
+		for (int j = k >> 2; j > 0; j >>= 1) {
+			for (int i = tid; i < n; i += nt) {
+				const int l = i ^ j;
+				if (l > i && l < n) { const T x = a[i], y = a[l]; if (before(y, x)) a[i] = y, a[l] = x; }
+			}
+			__syncthreads();
+		}
+	}
+}
+
+__device__ __forceinline__ int block_incl_scan(int v, int *s, int *total)
+{ // every thread of the CTA calls; blockDim.x <= 256
+	const int tid = threadIdx.x, nt = blockDim.x;
+	s[tid] = v;
+	__syncthreads();
+	for (int d = 1; d < nt; d <<= 1) { const int o = tid >= d ? s[tid - d] : 0; __syncthreads(); s[tid] += o; __syncthreads(); }
+	const int r = s[tid];
+	*total = s[nt - 1];
+	__syncthreads();
+	return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
+                   const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
+                   uint64_t *__restrict__ u, mm128 *__restrict__ bb, RsFrame *__restrict__ stack, int32_t *__restrict__ nu_out,
+                   int32_t *__restrict__ nv_out)
+{
+	__shared__ int s_scan[256], s_nu, s_tie;
+	const int li = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+	if (li >= n_list) return;
+	const int f = list ? list[li] : li;
+	const int64_t ao = aoff[li];
+	const int n = na[li], segs = n_seg[f];
+	int n_u = 0, n_v = 0;
+	mm128 *A = a + ao, *B = bb + ao;
+	uint64_t *U0 = u + ao * 2, *U1 = U0 + n;
+	if (n > 0) {
+		const ChainParams P = mmg_chain_params(co, ft.qlen[f], segs);
+		int32_t *F = work + ao * 8, *Pp = F + n, *T = Pp + n, *V = T + n;
+		mm128 *W = reinterpret_cast<mm128*>(F + 4 * (int64_t)n);
+		if (tid == 0) s_nu = 0, s_tie = 0;
+		// 1. chain ends (chain.c:88-90)
+		for (int i = tid; i < n; i += NT) T[i] = 0;
+		__syncthreads();
+		for (int i = tid; i < n; i += NT) { const int pj = Pp[i]; if (pj >= 0) T[pj] = 1; }
+		__syncthreads();
+		// 2. peaks of the ends that score enough (chain.c:99-106); their order does not matter, they are sorted next
+		for (int i = tid; i < n; i += NT)
+			if (T[i] == 0 && V[i] >= P.min_sc) {
+				int j = i;
+				while (j >= 0 && F[j] < V[j]) j = Pp[j];
+				if (j < 0) j = i;
+				U1[atomicAdd(&s_nu, 1)] = (uint64_t)F[j] << 32 | (uint32_t)j;
+			}
+		__syncthreads();
+		n_u = s_nu;
+		if (n_u > 0) {
+			// 3. rank by (peak score, anchor) descending (chain.c:107-111)
+			block_bitonic(U1, n_u, U64Desc());
+			for (int e = tid; e < n_u; e += NT) U0[e] = U1[e];
+			// 4. ownership: lowest rank whose walk passes through the anchor
+			for (int i = tid; i < n; i += NT) T[i] = 0x7fffffff;
+			__syncthreads();
+			for (int k = tid; k < n_u; k += NT) {
+				int j = (int32_t)U0[k];
+				while (j >= 0) { const int old = atomicMin(&T[j], k); if (old < k) break; j = Pp[j]; }
+			}
+			__syncthreads();
+			// 5. what each chain keeps (chain.c:115-129)
+			for (int k = tid; k < n_u; k += NT) {
+				const int j0 = (int32_t)U0[k];
+				const int32_t sc = (int32_t)(U0[k] >> 32);
+				int cnt = 1, j = Pp[j0];
+				while (j >= 0 && T[j] == k) ++cnt, j = Pp[j];
+				bool keep; int32_t score;
+				if (j < 0) keep = cnt >= P.min_cnt, score = sc;
+				else keep = (sc - F[j] >= P.min_sc) && cnt >= P.min_cnt, score = sc - F[j];
+				U1[k] = keep ? ((uint64_t)(uint32_t)score << 32 | (uint32_t)cnt) : 0;
+			}
+			__syncthreads();
+			// 6. kept chains in rank order -> b[], compacted u, chain-order keys w
+			int n_keep = 0;
+			for (int k0 = 0; k0 < n_u; k0 += NT) {
+				const int k = k0 + tid;
+				const uint64_t uk = k < n_u ? U1[k] : 0;
+				const int cnt = (int32_t)(uint32_t)uk;
+				int tot_cnt, tot_keep;
+				const int incl = block_incl_scan(cnt, s_scan, &tot_cnt), inclk = block_incl_scan(cnt > 0 ? 1 : 0, s_scan, &tot_keep);
+				const int kk = n_keep + inclk - 1;
+				if (cnt > 0) {
+					const int off = n_v + incl - cnt;
+					int j = (int32_t)U0[k];
+					for (int q = cnt - 1; q >= 0; --q) { B[off + q] = A[j]; j = Pp[j]; }
+					V[kk] = off;
+					W[kk].y = (uint64_t)off << 32 | (uint32_t)kk;
+				}
+				__syncthreads();
+				if (cnt > 0) U1[kk] = uk; // kk <= k, and every entry of this block of ranks was read above
+				n_v += tot_cnt, n_keep += tot_keep;
+				__syncthreads();
+			}
+			n_u = n_keep;
+			for (int kk = tid; kk < n_u; kk += NT) W[kk].x = B[V[kk]].x;
+			__syncthreads();
+			// 7. order chains by the position of their first anchor (chain.c:150): unique for distinct keys, literal replay otherwise
+			if (n_u <= 64) {
+				if (tid == 0) mmg_rs_sort_exact(W, (int64_t)n_u, stack + ao / 65 + 2 * (int64_t)li, KeyX());
+			} else {
+				block_bitonic(W, n_u, M128ByX());
+				for (int kk = tid + 1; kk < n_u; kk += NT) if (W[kk].x == W[kk - 1].x) s_tie = 1;
+				__syncthreads();
+				if (s_tie) {
+					for (int kk = tid; kk < n_u; kk += NT) { const int off = V[kk]; W[kk].x = B[off].x; W[kk].y = (uint64_t)off << 32 | (uint32_t)kk; }
+					__syncthreads();
+					if (tid == 0) mmg_rs_sort_exact(W, (int64_t)n_u, stack + ao / 65 + 2 * (int64_t)li, KeyX());
+				}
+			}
+			__syncthreads();
+			// 8. write chains back to a[] in that order (chain.c:152-159)
+			int dst = 0;
+			for (int i0 = 0; i0 < n_u; i0 += NT) {
+				const int i = i0 + tid;
+				uint64_t uk = 0; int src = 0;
+				if (i < n_u) { const uint64_t wy = W[i].y; uk = U1[(int32_t)(uint32_t)wy]; src = (int)(wy >> 32); }
+				const int nn = (int32_t)(uint32_t)uk;
+				int tot;
+				const int incl = block_incl_scan(nn, s_scan, &tot);
+				const int off = dst + incl - nn;
+				for (int q = 0; q < nn; ++q) A[off + q] = B[src + q];
+				if (i < n_u) U0[i] = uk;
+				dst += tot;
+			}
+			__syncthreads();
+		}
+	}
+	if (tid == 0) nu_out[li] = n_u, nv_out[li] = n_v;
+}
+
 // gather per-fragment results (first or second pass) into dense output arrays
 __global__ void k_gather(int n_frag, const int32_t *__restrict__ src_li /* second-pass slot or -1 */,
                          const int64_t *__restrict__ aoff1, const uint64_t *__restrict__ u1, const mm128 *__restrict__ a1,
@@ -722,9 +876,14 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		MMG_LAUNCH(c, k_chain_fill, 148 * 8, 128, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(),
 		           pb.a->as<mm128>(), pb.work->as<int32_t>(), c->d_seg_avg.as<float>(), seg_start, d_nseg, d_next, c->d_frag_iter.as<unsigned long long>());
 	}
-	MMG_LAUNCH(c, k_chain_tail_warp, mmg_blocks((size_t)n_list * 32, 128), 128, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
-	           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
-	           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), pb.rep->as<int32_t>(), opt->max_occ > opt->mid_occ ? 1 : 0, d_flag);
+	if (d_flag == nullptr) // the re-chain pass: few, very large fragments -> one CTA each
+		MMG_LAUNCH(c, k_chain_tail_block, n_list, 256, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+		           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
+		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>());
+	else
+		MMG_LAUNCH(c, k_chain_tail_warp, mmg_blocks((size_t)n_list * 32, 128), 128, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+		           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
+		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), pb.rep->as<int32_t>(), opt->max_occ > opt->mid_occ ? 1 : 0, d_flag);
 	return MMG_OK;
 }
 
