@@ -274,9 +274,9 @@ int main(int argc, char *argv[])
 		return 1;
 	}
 	if (opt.flag & MM_F_SPLICE) { fprintf(stderr, "[ERROR] spliced alignment (-x splice) is outside the scope of this build\n"); return 1; }
-	/* short-read presets run device-bound (post-chaining stages on the GPU): one shard per GPU gives the largest launches;
-	 * the other presets overlap their host stages with a second shard */
-	mm_b200_set_lanes((opt.flag & MM_F_SR) ? 1 : 2);
+	/* two shards per GPU: the host stages (or, for the short-read presets whose bookkeeping runs on the GPU, the upload and
+	 * the latency-bound kernel tails) of one overlap the kernels of the other */
+	mm_b200_set_lanes(2);
 	if (getenv("MM2_B200_LANES")) mm_b200_set_lanes(atoi(getenv("MM2_B200_LANES")));
 	if (mm_b200_set_devices(n_gpus, 0) < 0) { fprintf(stderr, "[ERROR] --gpus must be within 1 and 16\n"); return 1; }
 	idx_rdr = mm_idx_reader_open(argv[optind], &ipt, fnw);

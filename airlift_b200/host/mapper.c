@@ -88,6 +88,7 @@ typedef struct {          /* one GPU's share of a mini-batch */
 	uint32_t *frag_hash;
 	mm_arena_t arena;     /* per-fragment state of this shard: anchors, chains, per-mate copies, DP cache, temporaries */
 	pthread_mutex_t *gpu_token; /* held during device stages when the GPU is shared by several shards */
+	pthread_mutex_t *up_token;  /* device path: the shards of a GPU upload one after the other, so that the second upload runs under the first shard's kernels */
 	size_t *job_off;      /* [nf+1] first job of each fragment in the current DP round */
 	mmg_ksw_job_t *jobs;
 	mmg_ksw_res_t *res;
@@ -290,14 +291,16 @@ static void *shard_upload(void *data)
 	int32_t *n_seg, *seg_off, *seq_len;
 	uint64_t *seq_off;
 	mmg_batch_t b;
-	double t0 = realtime();
+	double t0;
 	sh->rc = 0;
 	if (nf <= 0) return 0;
+	if (sh->up_token) pthread_mutex_lock(sh->up_token);
+	t0 = realtime();
 	sh->s0 = sh->seg_off[sh->f0];
 	for (i = sh->f0; i < sh->f1; ++i) n_seq += sh->n_seg[i];
 	for (i = 0; i < n_seq; ++i) n_bases += sh->seq[sh->s0 + i].l_seq;
 	bases = (char*)mmg_staging(sh->ctx, n_bases + 1);
-	if (bases == 0) { shard_fail(sh, "cannot allocate the staging buffer"); return 0; }
+	if (bases == 0) { shard_fail(sh, "cannot allocate the staging buffer"); if (sh->up_token) pthread_mutex_unlock(sh->up_token); return 0; }
 	n_seg = (int32_t*)malloc((size_t)nf * 4), seg_off = (int32_t*)malloc((size_t)nf * 4);
 	seq_len = (int32_t*)malloc((size_t)(n_seq + 1) * 4), seq_off = (uint64_t*)malloc((size_t)(n_seq + 1) * 8);
 	for (i = 0, o = 0; i < n_seq; ++i) {
@@ -315,6 +318,7 @@ static void *shard_upload(void *data)
 	if (getenv("MM2_B200_TRACE")) fprintf(stderr, "[T::upload] +device upload %.4f s\n", realtime() - t0);
 	sh->st.n_frag += nf, sh->st.n_reads += n_seq, sh->st.n_bases += n_bases;
 	sh->st.t_upload += realtime() - t0;
+	if (sh->up_token) pthread_mutex_unlock(sh->up_token);
 	return 0;
 }
 
@@ -548,7 +552,9 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 	for (d = 0; d < s->n_seq; ++d) tot += s->seq[d].l_seq;
 	for (d = 0; d < n_dev; ++d) { /* contiguous fragment ranges balanced by bases; a fragment is never cut */
 		shard_t *h = &sh[d];
-		const int64_t goal = tot * (d + 1) / n_dev;
+		/* device path with two shards per GPU: the first shard is the smaller one, so that its upload (the only one no kernel
+		 * can hide) is short and the second, larger upload runs under its kernels */
+		const int64_t goal = (B->lanes == 2 && use_device_path(opt)) ? (tot * (d / 2) + (d % 2 == 0 ? tot * 3 / 10 : tot)) / B->n_dev : tot * (d + 1) / n_dev;
 		h->mi = mi, h->opt = opt, h->ctx = B->ctx[d], h->didx = B->didx[d / B->lanes];
 		mm_mapopt_to_dev(opt, &h->dopt);
 		mm_arena_init(&h->arena);
@@ -557,6 +563,7 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		/* host path: the lanes of a GPU take turns on the device while the others run host stages; device path: their kernels
 		 * may overlap freely (the latency-bound tails of one shard fill the gaps of the other) */
 		h->gpu_token = B->lanes > 1 && !use_device_path(opt) ? &B->gpu_token[d / B->lanes] : 0;
+		h->up_token = B->lanes > 1 && use_device_path(opt) ? &B->gpu_token[d / B->lanes] : 0;
 		h->seq = s->seq, h->n_seg = s->n_seg, h->seg_off = s->seg_off, h->n_reg = s->n_reg, h->rep_len = s->rep_len, h->frag_gap = s->frag_gap, h->reg = s->reg;
 		h->f0 = f;
 		while (f < s->n_frag && (acc < goal || d == n_dev - 1)) {
