@@ -64,7 +64,7 @@ __device__ __forceinline__ int frag_of_anchor(const int64_t *aoff, int n_list, i
 // K2b: collect_matches bookkeeping per fragment (map.c:90-123)
 __global__ void k_plan(FragTab ft, const int32_t *__restrict__ list, int n_list, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
                        int max_occ, int32_t *__restrict__ na, int32_t *__restrict__ rep, int32_t *__restrict__ nmini,
-                       uint64_t *__restrict__ mini /* may be null */, uint8_t *__restrict__ replay /* may be null */)
+                       uint64_t *__restrict__ mini /* may be null */, uint8_t *__restrict__ replay /* may be null */, int32_t *__restrict__ m_aoff)
 {
 	const int li = blockIdx.x * blockDim.x + threadIdx.x;
 	if (li >= n_list) return;
@@ -73,6 +73,14 @@ __global__ void k_plan(FragTab ft, const int32_t *__restrict__ list, int n_list,
 	int r, nm;
 	const int64_t n_a = mmg_frag_plan(mv + b, m_n + b, (int)(e - b), max_occ, &r, &nm, mini ? mini + b : nullptr);
 	na[li] = (int32_t)n_a, rep[li] = r, nmini[li] = nm;
+	{ // first anchor slot of every minimizer inside the fragment (k_expand finds an anchor's minimizer by bisection)
+		int32_t run = 0;
+		for (int i = 0; i < (int)(e - b); ++i) {
+			m_aoff[b + i] = run;
+			const int n = m_n[b + i];
+			if (n > 0 && n < max_occ) run += n;
+		}
+	}
 	if (replay) {
 		// Positions of different minimizers are disjoint, so two heap entries can only tie when two kept query minimizers
 		// carry the same hash (tandem k-mers, overlapping mates).  Only those fragments need the heap replayed.
@@ -93,7 +101,7 @@ __global__ void k_plan(FragTab ft, const int32_t *__restrict__ list, int n_list,
 __global__ void k_expand(FragTab ft, const int32_t *__restrict__ list, int n_list, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
                          const uint64_t *__restrict__ m_val, const uint64_t *__restrict__ pos, int max_occ, int64_t flag,
                          const int64_t *__restrict__ aoff, const uint8_t *__restrict__ replay, int64_t n_total,
-                         uint64_t *__restrict__ key, uint64_t *__restrict__ val, int32_t *__restrict__ n_skipped)
+                         uint64_t *__restrict__ key, uint64_t *__restrict__ val, int32_t *__restrict__ n_skipped, const int32_t *__restrict__ m_aoff)
 {
 	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= n_total) return;
@@ -102,12 +110,12 @@ __global__ void k_expand(FragTab ft, const int32_t *__restrict__ list, int n_lis
 	const int f = list ? list[li] : li;
 	const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]];
 	int64_t i = g - aoff[li];
-	int m = 0;
-	for (; b + m < e; ++m) {
-		const int n = m_n[b + m];
-		if (n <= 0 || n >= max_occ) continue;
-		if (i < n) break;
-		i -= n;
+	int m;
+	{ // last minimizer whose first slot is <= i: it is a kept one, because dropped minimizers have empty slot ranges
+		int lo = 0, hi = (int)(e - b) - 1;
+		while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (m_aoff[b + mid] <= i) lo = mid; else hi = mid - 1; }
+		m = lo;
+		i -= m_aoff[b + m];
 	}
 	const mm128 mz = mv[b + m];
 	const uint64_t r = mmg_hit_pos(pos, m_n[b + m], m_val[b + m], (uint32_t)i);
@@ -127,7 +135,7 @@ __global__ void k_sort_segments(int n_list, const int64_t *__restrict__ aoff, co
 
 __global__ void k_emit_sorted(int n_list, const int64_t *__restrict__ aoff, const uint8_t *__restrict__ replay, int64_t n_total,
                               const uint64_t *__restrict__ key, const uint64_t *__restrict__ val, const int32_t *__restrict__ n_skipped,
-                              int32_t *__restrict__ na, mm128 *__restrict__ a)
+                              int32_t *__restrict__ na, mm128 *__restrict__ a, uint8_t *__restrict__ tie /* may be null */)
 {
 	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= n_total) return;
@@ -141,6 +149,10 @@ __global__ void k_emit_sorted(int n_list, const int64_t *__restrict__ aoff, cons
 	an.x = (k & (1ULL << 63)) | (r & 0xffffffff00000000ULL) | ((uint32_t)r >> 1);
 	an.y = val[g];
 	a[g] = an;
+	if (tie && g > aoff[li]) { // radix-sort form (collect_seed_hits, map.c:215-247): two anchors with the same x leave klib's sort in an order only a replay gives
+		const uint64_t kp = key[g - 1], rp = kp & ~(1ULL << 63);
+		if (((kp & (1ULL << 63)) | (rp & 0xffffffff00000000ULL) | ((uint32_t)rp >> 1)) == an.x) tie[li] = 1;
+	}
 }
 
 // K2c: anchors per fragment, in the reference's order (map.c:149-247)
@@ -811,7 +823,7 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	MMG_CUDA(cudaMemsetAsync(pb.nmini->p, 0, (size_t)(n_list + 1) * 4, c->stream));
 	MMG_LAUNCH(c, k_plan, mmg_blocks(n_list, 128), 128, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), max_occ,
 	           pb.na->as<int32_t>(), pb.rep->as<int32_t>(), pb.nmini->as<int32_t>(), want_mini ? pb.mini->as<uint64_t>() : nullptr,
-	           heap_path ? c->d_replay.as<uint8_t>() : nullptr);
+	           heap_path ? c->d_replay.as<uint8_t>() : nullptr, c->d_m_aoff.as<int32_t>());
 	MMG_TRY(scan_i32_to_i64(c, pb.na->as<int32_t>(), pb.aoff->as<int64_t>(), n_list + 1));
 	int64_t tot = 0;
 	MMG_D2H(c, &tot, pb.aoff->as<int64_t>() + n_list, 8);
@@ -823,8 +835,15 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	MMG_TRY(pb.b->ensure((size_t)(tot + 1) * 16));
 	MMG_TRY(pb.stack->ensure((size_t)(tot / 65 + 2 * (size_t)n_list + 4) * sizeof(RsFrame)));
 	MMG_TRY(c->d_heap.ensure((size_t)(n_mv + 1) * 16));
-	if (heap_path && tot > 0) {
-		// fragments whose heap keys are all distinct: the merged order is simply the sorted order -> segmented sort
+	uint8_t *d_tie = nullptr;
+	if (!heap_path) { // radix-sort form: sort everything, replay only the fragments where two anchors share x
+		MMG_TRY(c->d_tie.ensure((size_t)n_list + 16));
+		d_tie = c->d_tie.as<uint8_t>();
+		MMG_CUDA(cudaMemsetAsync(d_tie, 0, (size_t)n_list + 16, c->stream));
+		MMG_CUDA(cudaMemsetAsync(c->d_replay.p, 0, (size_t)n_list + 16, c->stream));
+	}
+	if (tot > 0) {
+		// fragments whose keys are all distinct: the reference's order is simply the sorted order -> segmented sort
 		MMG_TRY(c->d_skey.ensure(((size_t)tot + 1) * 16)); MMG_TRY(c->d_sval.ensure(((size_t)tot + 1) * 16));
 		MMG_TRY(c->d_sseg.ensure(((size_t)n_list + 1) * 20 + 64));
 		uint64_t *k0 = c->d_skey.as<uint64_t>(), *k1 = k0 + tot + 1, *v0 = c->d_sval.as<uint64_t>(), *v1 = v0 + tot + 1;
@@ -832,7 +851,7 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		int32_t *n_skipped = reinterpret_cast<int32_t*>(seg_e + n_list + 1);
 		MMG_CUDA(cudaMemsetAsync(n_skipped, 0, (size_t)n_list * 4, c->stream));
 		MMG_LAUNCH(c, k_expand, mmg_blocks(tot, 256), 256, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
-		           mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), tot, k0, v0, n_skipped);
+		           mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), tot, k0, v0, n_skipped, c->d_m_aoff.as<int32_t>());
 		MMG_LAUNCH(c, k_sort_segments, mmg_blocks(n_list, 256), 256, 0, n_list, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), seg_b, seg_e);
 		{
 			size_t tmp = 0;
@@ -842,12 +861,12 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 			++c->launches;
 		}
 		MMG_LAUNCH(c, k_emit_sorted, mmg_blocks(tot, 256), 256, 0, n_list, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), tot, k1, v1, n_skipped,
-		           pb.na->as<int32_t>(), pb.a->as<mm128>());
+		           pb.na->as<int32_t>(), pb.a->as<mm128>(), d_tie);
 	}
 	// literal replay: the heap merge for fragments with repeated hashes; fill + klib radix sort for the non-heap presets
 	MMG_LAUNCH(c, k_fill, mmg_blocks(n_list, 64), 64, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
 	           mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>(), c->d_heap.as<mm128>(),
-	           pb.stack->as<RsFrame>(), heap_path ? c->d_replay.as<uint8_t>() : nullptr);
+	           pb.stack->as<RsFrame>(), heap_path ? c->d_replay.as<uint8_t>() : d_tie);
 	ChainOptDev co;
 	co.bw = opt->bw, co.max_gap = opt->max_gap, co.max_gap_ref = opt->max_gap_ref, co.max_frag_len = opt->max_frag_len;
 	co.max_skip = opt->max_chain_skip, co.max_iter = opt->max_chain_iter, co.min_cnt = opt->min_cnt, co.min_sc = opt->min_chain_score;
@@ -904,6 +923,7 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 	// K2a
 	MMG_TRY(c->d_m_n.ensure((size_t)(n_mv + 1) * 4));
 	MMG_TRY(c->d_m_val.ensure((size_t)(n_mv + 1) * 8));
+	MMG_TRY(c->d_m_aoff.ensure((size_t)(n_mv + 1) * 4));
 	if (n_mv) MMG_LAUNCH(c, k_lookup, mmg_blocks(n_mv, 256), 256, 0, mi->view(), c->d_mv.as<mm128>(), n_mv, c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>());
 	FragTab ft;
 	ft.unit0 = c->d_frag_unit0.as<int32_t>(), ft.unit_off = c->d_unit_off.as<int64_t>(), ft.qlen = c->d_frag_qlen.as<int32_t>();

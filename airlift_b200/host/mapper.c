@@ -379,6 +379,11 @@ static void stage_dev_finish(void *data, long i, int tid)
 	for (j = 0; j < ns; ++j) sh->rep_len[off + j] = rep_len, sh->frag_gap[off + j] = frag_gap;
 }
 
+static int g_serial_shards = 0;
+/* bench.py's kernel-profile pass: the shards of a GPU take turns on the device, so that per-kernel CUDA-event times are not
+ * stretched by kernels of the other shard running next to them */
+void mm_b200_set_serial(int on) { g_serial_shards = on; }
+
 static int use_device_path(const mm_mapopt_t *opt)
 {
 	static int host_only = -1;
@@ -562,7 +567,7 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		h->n_threads = n_threads / B->n_dev > 0 ? n_threads / B->n_dev : 1;
 		/* host path: the lanes of a GPU take turns on the device while the others run host stages; device path: their kernels
 		 * may overlap freely (the latency-bound tails of one shard fill the gaps of the other) */
-		h->gpu_token = B->lanes > 1 && !use_device_path(opt) ? &B->gpu_token[d / B->lanes] : 0;
+		h->gpu_token = B->lanes > 1 && (!use_device_path(opt) || g_serial_shards) ? &B->gpu_token[d / B->lanes] : 0;
 		h->up_token = B->lanes > 1 && use_device_path(opt) ? &B->gpu_token[d / B->lanes] : 0;
 		h->seq = s->seq, h->n_seg = s->n_seg, h->seg_off = s->seg_off, h->n_reg = s->n_reg, h->rep_len = s->rep_len, h->frag_gap = s->frag_gap, h->reg = s->reg;
 		h->f0 = f;

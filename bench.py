@@ -92,6 +92,7 @@ def load_lib():
     L.mm_b200_batch_digest.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.mm_b200_stats.argtypes = [C.POINTER(Stats), C.c_int]
     L.mm_b200_profile.argtypes = [C.c_void_p, C.c_int]
+    L.mm_b200_set_serial.argtypes = [C.c_int]
     L.mm_b200_profile_fetch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_long)]
     L.mm_b200_idx_image.argtypes = [C.c_void_p, C.c_void_p]
     L.mm_b200_idx_alloc.restype = C.c_void_p
@@ -254,7 +255,7 @@ def main():
     if world > 1:
         dist.barrier()
     fa = make_ref(d)
-    n_steps_total = args.warmup + 2 * args.steps
+    n_steps_total = args.warmup + 3 * args.steps
     f1, f2 = make_reads(d, fa, args.pairs * n_steps_total, 44 + rank, f"sr_r{rank}_{args.pairs}x{n_steps_total}")
 
     L = load_lib()
@@ -385,8 +386,13 @@ def main():
         return secs, total_reads, st, prof, launches, clocks, wall
 
     secs_e2e, reads_e2e, st_e2e, prof_e2e, launches_e2e, clocks_e2e, wall_e2e = timed(False)
-    secs_res, reads_res, st_res, prof_res, launches_res, clocks_res, wall_res = timed(True)
+    secs_res, reads_res, st_res, prof_val, launches_res, clocks_res, wall_res = timed(True)
     per_rank_ms = timed.per_rank_ms
+    # Kernel profile: a third pass in which the shards of a GPU take turns on the device.  In the timed passes the two shards'
+    # kernels overlap on purpose, which stretches every per-kernel CUDA-event interval; the roofline figures need clean ones.
+    L.mm_b200_set_serial(1)
+    _, _, st_res, prof_res, _, _, _ = timed(True)
+    L.mm_b200_set_serial(0)
 
     out = None
     if rank == 0:
@@ -443,6 +449,8 @@ def main():
             "ksw_gcups": k4["gcups"], "k4": k4,
             "seed_lookup_gbs": algo["k_lookup"] / (lookup_ms * 1e-3) / 1e9 if lookup_ms else None,
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof_res.items(), key=lambda kv: -kv[1][0])},
+            "kernel_profile": "CUDA events around every launch in a separate pass of the same K steps with the two shards of a GPU serialised "
+                              "(in the timed passes their kernels overlap, which stretches per-kernel intervals)",
             "host_s_per_step": {"seed_chain_call": st_res.t_seedchain / args.steps, "hits": st_res.t_hits / args.steps,
                                 "align_host": st_res.t_align_host / args.steps, "dp_call": st_res.t_ksw_total / args.steps,
                                 "finish": st_res.t_finish / args.steps, "dp_rounds": st_res.n_dp_rounds / args.steps},

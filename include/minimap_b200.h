@@ -211,6 +211,7 @@ typedef struct { /* accumulated over mm_b200_map_batch / mm_map_file_frag calls;
 	uint64_t n_frag, n_reads, n_bases, n_minimizers, n_anchors, n_chain_iter, n_dp_jobs, n_dp_cells, n_dp_rounds, h2d_bytes, d2h_bytes, n_dp_jobs_fast, n_dp_cells_fast;
 } mm_b200_stats_t;
 void mm_b200_stats(mm_b200_stats_t *out, int reset);
+void mm_b200_set_serial(int on);                        /* shards of a GPU take turns on the device (clean per-kernel timing) */
 void mm_b200_profile(const mm_idx_t *mi, int enable);   /* CUDA-event timing of every kernel launch */
 int  mm_b200_profile_fetch(const mm_idx_t *mi, int max, const char **names, double *ms, long *launches);
 void mm_b200_report(const mm_idx_t *mi, FILE *fp);
