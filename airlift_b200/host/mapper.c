@@ -663,7 +663,6 @@ static void write_chunk(void *data, long c, int tid)
 		for (i = seg_st; i < seg_en; ++i) {
 			for (j = 0; j < s->n_reg[i]; ++j) free(s->reg[i][j].p);
 			free(s->reg[i]);
-			mm_bseq_free1(&s->seq[i], 1);
 		}
 	}
 	free(str.s);
@@ -678,7 +677,11 @@ static void step_write(pipeline_t *p, step_t *s)
 	w.p = p, w.s = s, w.frags_per_chunk = fpc;
 	w.buf = (char**)calloc(n_chunks > 0 ? n_chunks : 1, sizeof(char*));
 	w.len = (size_t*)calloc(n_chunks > 0 ? n_chunks : 1, sizeof(size_t));
-	parallel_for(p->n_threads, write_chunk, &w, n_chunks);
+	{
+		const double t0 = realtime();
+		parallel_for(p->n_threads, write_chunk, &w, n_chunks);
+		if (getenv("MM2_B200_TRACE")) fprintf(stderr, "[T::write] formatted %d chunks in %.3f s\n", n_chunks, realtime() - t0);
+	}
 	for (c = 0; c < n_chunks; ++c) {
 		if (w.len[c] && fwrite(w.buf[c], 1, w.len[c], stdout) != w.len[c]) { /* a short write is fatal (misc.c:123-131) */
 			perror("[ERROR] failed to write the results");
@@ -687,6 +690,9 @@ static void step_write(pipeline_t *p, step_t *s)
 		free(w.buf[c]);
 	}
 	free(w.buf); free(w.len);
+	/* the reads were allocated by the read-ahead threads: sixteen workers returning them to those two malloc arenas contend on
+	 * their locks (it was half of the writer's time), one thread does not */
+	for (c = 0; c < s->n_seq; ++c) mm_bseq_free1(&s->seq[c], 1);
 	if (mm_verbose >= 3)
 		fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", "worker_pipeline", realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), s->n_seq);
 	free(s->reg); free(s->n_reg); free(s->seq);
