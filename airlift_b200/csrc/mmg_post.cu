@@ -270,12 +270,18 @@ __global__ void __launch_bounds__(128, 5) k_post_hits(Shard *shp)
 	if (fr->n_u > 0) fr->u = sh->u + sh->uoff[i], fr->a = sh->a + sh->voff[i]; // used in place
 	fr->regs0 = sh->pre_regs[i] ? sh->pre_regs[i] : mm_gen_regs(fr->hash, fr->qlen_sum, fr->n_u, fr->u, fr->a);
 	fr->n_regs0 = fr->n_u;
+	const bool dbg_big = fr->n_u > 1000;
+	long long t_ph = clock64();
+#define PHASE(k) do { if (dbg_big) { const long long t_ = clock64(); atomicMax(sh->pool_cur + 5 + (k), (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
+	PHASE(0);
 	if (!(opt->flag & MM_F_ALL_CHAINS)) { // chain_post, map.c:249-258
 		mm_set_parent(opt->mask_level, fr->n_regs0, fr->regs0, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL);
+		PHASE(1);
 		if (ns <= 1) mm_select_sub(opt->pri_ratio, mi->k * 2, opt->best_n, &fr->n_regs0, fr->regs0);
 		else mm_select_sub_multi(opt->pri_ratio, 0.2f, 0.7f, fr->frag_gap, mi->k * 2, opt->best_n, ns, fr->qlens, &fr->n_regs0, fr->regs0);
 		if (!(opt->flag & (MM_F_SPLICE|MM_F_SR|MM_F_NO_LJOIN))) mm_join_long(opt, fr->qlen_sum, &fr->n_regs0, fr->regs0, fr->a);
 	}
+	PHASE(2);
 	fr->aln = (mm_alnseg_t*)mm_acalloc(ns, sizeof(mm_alnseg_t));
 	if (ns == 1) {
 		sh->n_reg[off] = fr->n_regs0, sh->reg[off] = fr->regs0;
@@ -289,12 +295,15 @@ __global__ void __launch_bounds__(128, 5) k_post_hits(Shard *shp)
 			fr->aln[j].q4 = sh->Q, fr->aln[j].q4_off = sh->q_off[off + j];
 		}
 	}
+	PHASE(3);
 	fr->active = (opt->flag & MM_F_CIGAR) ? 1 : 0;
 	if (fr->active) {
 		const int n_new = frag_walk(sh, i);
 		sh->n_new[i] = n_new;
 		if (fr->active) atomicAdd(sh->pool_cur + 1, 1ULL);
 	}
+	PHASE(4);
+#undef PHASE
 	{ // debug aid (MMG_POST_DEBUG): the longest-running thread of the launch and how many chains its fragment had
 		const unsigned long long dt = (unsigned long long)(clock64() - t_begin);
 		atomicMax(sh->pool_cur + 3, dt << 20 | (unsigned long long)(fr->n_u < 0xfffff ? fr->n_u : 0xfffff));
@@ -529,13 +538,13 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 	MMG_TRY(c->p_fr.ensure((size_t)(nf + 1) * sizeof(DFrag)));
 	MMG_TRY(c->p_tls.ensure((size_t)(nf + 64) * sizeof(Tls)));
 	MMG_TRY(c->p_pool.ensure(pool_bytes));
-	MMG_TRY(c->p_ctr.ensure(64));
+	MMG_TRY(c->p_ctr.ensure(128));
 	MMG_TRY(c->p_nnew.ensure((size_t)(nf + 2) * 4));
 	MMG_TRY(c->p_joboff.ensure((size_t)(nf + 2) * 8));
 	MMG_TRY(c->h_p_hash.ensure((size_t)(nf + 1) * 4));
 	memcpy(c->h_p_hash.p, frag_hash, (size_t)nf * 4);
 	MMG_H2D(c, c->p_hash.p, c->h_p_hash.p, (size_t)nf * 4);
-	MMG_CUDA(cudaMemsetAsync(c->p_ctr.p, 0, 64, c->stream));
+	MMG_CUDA(cudaMemsetAsync(c->p_ctr.p, 0, 128, c->stream));
 	MMG_CUDA(cudaMemsetAsync(c->p_nnew.p, 0, (size_t)(nf + 2) * 4, c->stream));
 	Shard hs;
 	memset(&hs, 0, sizeof(hs));
@@ -642,8 +651,10 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 	float ms = 0;
 	cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
 	if (getenv("MMG_POST_DEBUG")) {
-		unsigned long long ctr4[4] = {0, 0, 0, 0};
-		cudaMemcpy(ctr4, c->p_ctr.p, 32, cudaMemcpyDeviceToHost);
+		unsigned long long ctr4[10] = {0};
+		cudaMemcpy(ctr4, c->p_ctr.p, 80, cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[mmg_post] phases of fragments with > 1000 chains, ms (max): gen_regs %.2f set_parent %.2f select_sub %.2f seg_gen+begin %.2f first walk %.2f\n",
+		        ctr4[5] / 1.965e6, ctr4[6] / 1.965e6, ctr4[7] / 1.965e6, ctr4[8] / 1.965e6, ctr4[9] / 1.965e6);
 		fprintf(stderr, "[mmg_post] %d fragments, pool used %.1f MB of %.1f MB (%.0f B per fragment), blob %.1f MB, %.1f ms on the device (K4 %.1f ms); "
 		        "longest k_post_hits thread %.2f ms (fragment with %llu chains)\n", nf, ctr4[0] / 1e6, pool_bytes / 1e6, (double)ctr4[0] / nf, blob_bytes / 1e6, ms, ksw_ms,
 		        (double)(ctr4[3] >> 20) / 1.965e6, ctr4[3] & 0xfffff);
