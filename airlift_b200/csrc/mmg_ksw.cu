@@ -49,7 +49,9 @@ __device__ __forceinline__ int ksw_ncol(int qlen, int tlen, int w)
 // Fast-form size classes: a job whose band never clips runs one-thread-per-job (k_ksw_tpj) in the first class it fits:
 // min(qlen,tlen) <= mc (depth of the circular state window), tlen <= tc, qlen <= qc; nt = threads (jobs) per CTA.
 #define KSW_N_FAST 3
-#define KSW_CLS_LITERAL KSW_N_FAST
+#define KSW_CLS_LITERAL KSW_N_FAST            /* literal form, 16 lanes per job */
+#define KSW_CLS_LITERAL_WIDE (KSW_N_FAST + 1)  /* literal form, 32 lanes per job: bands wider than two SSE blocks */
+#define KSW_N_CLS (KSW_N_FAST + 2)
 struct KswFastClass { int32_t mc, tc, qc, nt; };
 struct KswFastTab { KswFastClass c[KSW_N_FAST]; };
 static inline size_t ksw_fast_smem(const KswFastClass &k) { return (size_t)k.nt * ((size_t)(k.mc + 1) * 8 + (size_t)k.tc + (size_t)k.qc); }
@@ -86,11 +88,12 @@ __global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, KswSco
 				}
 				c = (uint64_t)qlen + tlen + 2;
 				if (cls == KSW_CLS_LITERAL) {
+					{ int bw = qlen < tlen ? qlen : tlen; if (g.w + 1 < bw) bw = g.w + 1; if (bw > 32 && !g.bail) cls = KSW_CLS_LITERAL_WIDE; }
 					const size_t mem_bytes = mmg_ksw_mem_bytes(qlen, tlen), H_bytes = (size_t)((tlen + 15) / 16) * 64;
 					if (mem_bytes + H_bytes > KSW_SMEM_PER_JOB) m = (mem_bytes + H_bytes + 63) & ~(size_t)63;
 					if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = ((uint64_t)(qlen + tlen - 1) * ksw_ncol(qlen, tlen, j.w) + 1) * 16;
 					const uint64_t est = (uint64_t)(qlen + tlen) * (uint64_t)(qlen < tlen ? qlen : tlen);
-					k = (uint32_t)KSW_CLS_LITERAL << 28 | (63u - (uint32_t)(63 - __clzll((long long)(est | 1)))); // big jobs first
+					k = (uint32_t)cls << 28 | (63u - (uint32_t)(63 - __clzll((long long)(est | 1)))); // big jobs first
 				} else {
 					if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = mmg_ksw_fast_p_bytes(qlen, tlen);
 					const uint32_t mode = (j.flag & MMG_EZ_SCORE_ONLY) ? 0u : (j.flag & MMG_EZ_RIGHT) ? 2u : 1u;
@@ -101,7 +104,7 @@ __global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, KswSco
 		}
 		mem_sz[i] = m, p_sz[i] = p, cig_sz[i] = c, key[i] = k;
 	}
-	for (int q = 0; q <= KSW_N_FAST; ++q) {
+	for (int q = 0; q < KSW_N_CLS; ++q) {
 		const unsigned b = __ballot_sync(0xffffffffu, cls == q);
 		unsigned long long cq = cls == q ? cells : 0;
 		for (int d = 16; d >= 1; d >>= 1) cq += __shfl_xor_sync(0xffffffffu, cq, d);
@@ -111,10 +114,13 @@ __global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, KswSco
 	if ((threadIdx.x & 31) == 0 && cells) atomicAdd(cells_total, cells);
 }
 
-template <int kMode>
+// G lanes walk one job: 16 (one SSE register per step, two jobs per warp) or 32 (two neighbouring 16-lane blocks per step,
+// one job per warp: fewer steps per anti-diagonal and no divergence between two jobs for the wide bands of the large jobs)
+template <int kMode, int G>
 __device__ __forceinline__ void ksw_run(const KswGeom &g, const KswJobDev &jb, int8_t *mem, int32_t *H, uint8_t *p, KswEz &ez,
                                         const int lane, const unsigned gmask)
 {
+	const int l16 = lane & 15, half = lane >> 4; // lane inside its 16-lane block; which block of the pair (always 0 when G == 16)
 	const int tl16 = g.tlen_ * 16;
 	int8_t *u = mem, *v = u + tl16, *x = v + tl16, *y = x + tl16, *x2 = y + tl16, *y2 = x2 + tl16, *s = y2 + tl16;
 	const uint8_t *sf = reinterpret_cast<const uint8_t*>(s + tl16), *qr = sf + tl16;
@@ -140,21 +146,41 @@ __device__ __forceinline__ void ksw_run(const KswGeom &g, const KswJobDev &jb, i
 		}
 		{ // scores, 16-byte chunks starting at st0 (ksw2_extd2_sse.c:158-172)
 			const uint8_t *qrr = qr + (qlen - 1 - r);
-			for (int t = st0; t <= en0; t += 16) s[t + lane] = mmg_ksw_score(g, sf[t + lane], qrr[t + lane]);
+			for (int t = st0 + half * 16; t <= en0; t += G) s[t + l16] = mmg_ksw_score(g, sf[t + l16], qrr[t + l16]);
 		}
 		__syncwarp(gmask);
 		const int st_ = st / 16, en_ = en / 16;
-		for (int blk = st_; blk <= en_; ++blk) {
-			const int i = blk * 16 + lane;
-			const int xo = x[i], vo = v[i], x2o = x2[i];
-			int xt1 = __shfl_up_sync(gmask, xo, 1, KSW_GROUP), vt1 = __shfl_up_sync(gmask, vo, 1, KSW_GROUP), x2t1 = __shfl_up_sync(gmask, x2o, 1, KSW_GROUP);
-			if (lane == 0) xt1 = x1, vt1 = v1, x2t1 = x21;
-			x1 = __shfl_sync(gmask, xo, KSW_GROUP - 1, KSW_GROUP);
-			v1 = __shfl_sync(gmask, vo, KSW_GROUP - 1, KSW_GROUP);
-			x21 = __shfl_sync(gmask, x2o, KSW_GROUP - 1, KSW_GROUP);
-			const KswCell c = mmg_ksw_cell<kMode>(g, s[i], (int8_t)xt1, (int8_t)vt1, u[i], y[i], (int8_t)x2t1, y2[i]);
-			u[i] = c.u, v[i] = c.v, x[i] = c.x, y[i] = c.y, x2[i] = c.x2, y2[i] = c.y2;
-			if (kMode) p[((size_t)r * g.n_col_ + (blk - st_)) * 16 + lane] = c.d;
+		if (G == 16) {
+			for (int blk = st_; blk <= en_; ++blk) {
+				const int i = blk * 16 + lane;
+				const int xo = x[i], vo = v[i], x2o = x2[i];
+				int xt1 = __shfl_up_sync(gmask, xo, 1, 16), vt1 = __shfl_up_sync(gmask, vo, 1, 16), x2t1 = __shfl_up_sync(gmask, x2o, 1, 16);
+				if (lane == 0) xt1 = x1, vt1 = v1, x2t1 = x21;
+				x1 = __shfl_sync(gmask, xo, 15, 16);
+				v1 = __shfl_sync(gmask, vo, 15, 16);
+				x21 = __shfl_sync(gmask, x2o, 15, 16);
+				const KswCell c = mmg_ksw_cell<kMode>(g, s[i], (int8_t)xt1, (int8_t)vt1, u[i], y[i], (int8_t)x2t1, y2[i]);
+				u[i] = c.u, v[i] = c.v, x[i] = c.x, y[i] = c.y, x2[i] = c.x2, y2[i] = c.y2;
+				if (kMode) p[((size_t)r * g.n_col_ + (blk - st_)) * 16 + lane] = c.d;
+			}
+		} else {
+			for (int bp = st_ >> 1; bp <= en_ >> 1; ++bp) { // blocks 2bp and 2bp+1 side by side; a block outside [st_, en_] sits out
+				const int blk = bp * 2 + half, i = bp * 32 + lane;
+				const bool act = blk >= st_ && blk <= en_;
+				int xo = 0, vo = 0, x2o = 0;
+				if (act) xo = x[i], vo = v[i], x2o = x2[i];
+				int xt1 = __shfl_up_sync(gmask, xo, 1, 32), vt1 = __shfl_up_sync(gmask, vo, 1, 32), x2t1 = __shfl_up_sync(gmask, x2o, 1, 32);
+				// lane 0 of the band's first block takes the carry-in; so does the first lane of every pair (old values of the pair before)
+				if (lane == 0 || (lane == 16 && blk == st_)) xt1 = x1, vt1 = v1, x2t1 = x21;
+				x1 = __shfl_sync(gmask, xo, 31, 32);
+				v1 = __shfl_sync(gmask, vo, 31, 32);
+				x21 = __shfl_sync(gmask, x2o, 31, 32);
+				if (act) {
+					const KswCell c = mmg_ksw_cell<kMode>(g, s[i], (int8_t)xt1, (int8_t)vt1, u[i], y[i], (int8_t)x2t1, y2[i]);
+					u[i] = c.u, v[i] = c.v, x[i] = c.x, y[i] = c.y, x2[i] = c.x2, y2[i] = c.y2;
+					if (kMode) p[((size_t)r * g.n_col_ + (blk - st_)) * 16 + l16] = c.d;
+				}
+			}
 		}
 		__syncwarp(gmask);
 		if (!approx) { // exact max over the band with the reference's tie order (ksw2_extd2_sse.c:315-358)
@@ -163,7 +189,7 @@ __device__ __forceinline__ void ksw_run(const KswGeom &g, const KswJobDev &jb, i
 				H_en0 = en0 > 0 ? H[en0 - 1] + u[en0] : H[en0] + v[en0];
 				__syncwarp(gmask);
 				int32_t bh = H_en0, bt = en0; uint32_t br = 0;
-				for (int t = st0 + lane; t < en0; t += 16) {
+				for (int t = st0 + lane; t < en0; t += G) {
 					const int32_t h = H[t] + v[t];
 					H[t] = h;
 					const uint32_t rk = mmg_ksw_max_rank(t, st0, en0);
@@ -171,9 +197,9 @@ __device__ __forceinline__ void ksw_run(const KswGeom &g, const KswJobDev &jb, i
 				}
 				if (lane == 0) H[en0] = H_en0;
 #pragma unroll
-				for (int d = 8; d >= 1; d >>= 1) {
-					const int32_t oh = __shfl_xor_sync(gmask, bh, d, KSW_GROUP), ot = __shfl_xor_sync(gmask, bt, d, KSW_GROUP);
-					const uint32_t orank = __shfl_xor_sync(gmask, br, d, KSW_GROUP);
+				for (int d = G / 2; d >= 1; d >>= 1) {
+					const int32_t oh = __shfl_xor_sync(gmask, bh, d, G), ot = __shfl_xor_sync(gmask, bt, d, G);
+					const uint32_t orank = __shfl_xor_sync(gmask, br, d, G);
 					if (oh > bh || (oh == bh && orank < br)) bh = oh, bt = ot, br = orank;
 				}
 				max_H = bh, max_t = bt;
@@ -206,17 +232,18 @@ __device__ __forceinline__ void ksw_run(const KswGeom &g, const KswJobDev &jb, i
 	}
 }
 
-__global__ void __launch_bounds__(KSW_GROUP * KSW_JOBS_PER_BLOCK)
+template <int G>
+__global__ void __launch_bounds__(G * KSW_JOBS_PER_BLOCK)
 k_ksw(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order, int n_jobs, KswScore sc, const uint32_t *__restrict__ Q,
       const uint32_t *__restrict__ S, const uint64_t *__restrict__ q_off, const int32_t *__restrict__ read_len, const uint64_t *__restrict__ ref_off,
       const uint64_t *__restrict__ mem_off, const uint64_t *__restrict__ p_off, const uint64_t *__restrict__ cig_off,
       int8_t *__restrict__ gmem, uint8_t *__restrict__ gp, uint32_t *__restrict__ gcig, KswEz *__restrict__ res)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
-	const int grp = threadIdx.x / KSW_GROUP, lane = threadIdx.x % KSW_GROUP;
+	const int grp = threadIdx.x / G, lane = threadIdx.x % G;
 	const int slot = blockIdx.x * KSW_JOBS_PER_BLOCK + grp;
 	if (slot >= n_jobs) return;
-	const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+	const unsigned gmask = G == 32 ? 0xffffffffu : 0xffffu << (threadIdx.x & 16);
 	const int ji = order[slot];
 	const mmg_ksw_job_t hj = jobs[ji];
 	KswJobDev jb;
@@ -242,7 +269,7 @@ k_ksw(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order,
 	{
 		int8_t *u = mem;
 		const int8_t n1 = (int8_t)(-g.q - g.e), n2 = (int8_t)(-g.q2 - g.e2);
-		for (int i = lane; i < tl16; i += KSW_GROUP) {
+		for (int i = lane; i < tl16; i += G) {
 			u[i] = n1, u[tl16 + i] = n1, u[2 * tl16 + i] = n1, u[3 * tl16 + i] = n1; // u v x y
 			u[4 * tl16 + i] = n2, u[5 * tl16 + i] = n2;                              // x2 y2
 			u[6 * tl16 + i] = 0;                                                      // s (kcalloc)
@@ -251,14 +278,14 @@ k_ksw(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order,
 		}
 		int8_t *qr = u + 8 * tl16;
 		const int qn = g.qlen_ * 16 + 16;
-		for (int i = lane; i < qn; i += KSW_GROUP) qr[i] = i < jb.q_len ? (int8_t)ksw_qbase(Q, jb, jb.q_len - 1 - i) : 0;
+		for (int i = lane; i < qn; i += G) qr[i] = i < jb.q_len ? (int8_t)ksw_qbase(Q, jb, jb.q_len - 1 - i) : 0;
 	}
 	__syncwarp(gmask);
 	uint8_t *p = gp + jb.p_off;
 	const bool with_cigar = !(jb.flag & MMG_EZ_SCORE_ONLY);
-	if (!with_cigar) ksw_run<0>(g, jb, mem, H, p, ez, lane, gmask);
-	else if (!(jb.flag & MMG_EZ_RIGHT)) ksw_run<1>(g, jb, mem, H, p, ez, lane, gmask);
-	else ksw_run<2>(g, jb, mem, H, p, ez, lane, gmask);
+	if (!with_cigar) ksw_run<0, G>(g, jb, mem, H, p, ez, lane, gmask);
+	else if (!(jb.flag & MMG_EZ_RIGHT)) ksw_run<1, G>(g, jb, mem, H, p, ez, lane, gmask);
+	else ksw_run<2, G>(g, jb, mem, H, p, ez, lane, gmask);
 	__syncwarp(gmask);
 	if (lane == 0) {
 		int i0, j0;
@@ -363,32 +390,33 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 	uint64_t *mem_sz = c->k_cig_off.as<uint64_t>(), *p_sz = mem_sz + n1, *cig_sz = p_sz + n1;
 	int64_t *mem_off = reinterpret_cast<int64_t*>(cig_sz + n1), *p_off = mem_off + n1, *cg_off = p_off + n1, *nc_off = cg_off + n1;
 	unsigned long long *d_cells = reinterpret_cast<unsigned long long*>(nc_off + n1);
-	uint32_t *d_cls = reinterpret_cast<uint32_t*>(d_cells + 6); // d_cells: total, then per class; d_cls: KSW_N_FAST + 1 job counters
+	uint32_t *d_cls = reinterpret_cast<uint32_t*>(d_cells + 2 + KSW_N_CLS); // d_cells: total, then per class; d_cls: KSW_N_CLS job counters
 	uint32_t *key = d_cls + 8, *key2 = key + n1;
 	int32_t *idx = reinterpret_cast<int32_t*>(key2 + n1), *order = idx + n1, *ncig = order + n1;
 	static const KswFastTab ftab = {{{24, 56, 56, 128}, {48, 104, 104, 128}, {80, 160, 160, 64}}};
-	MMG_CUDA(cudaMemsetAsync(d_cells, 0, 48 + 32, c->stream));
+	MMG_CUDA(cudaMemsetAsync(d_cells, 0, (2 + KSW_N_CLS) * 8 + 32, c->stream));
 	MMG_LAUNCH(c, k_ksw_prep, mmg_blocks(n1, 128), 128, 0, d_jobs, n, sc, ftab, mem_sz, p_sz, cig_sz, key, idx, d_cells, d_cls);
 	MMG_TRY(scan_excl(c, mem_sz, mem_off, (int)n1));
 	MMG_TRY(scan_excl(c, p_sz, p_off, (int)n1));
 	MMG_TRY(scan_excl(c, cig_sz, cg_off, (int)n1));
 	{ // stable sort of job indices by scheduling key
 		size_t tmp = 0;
-		cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, order, n, 0, 30, c->stream);
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, order, n, 0, 31, c->stream);
 		MMG_TRY(c->d_cub.ensure(tmp));
-		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, order, n, 0, 30, c->stream));
+		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, order, n, 0, 31, c->stream));
 		++c->launches;
 	}
-	int64_t tot[3]; unsigned long long h_cells[2 + KSW_N_FAST]; uint32_t h_cls[KSW_N_FAST + 1];
+	int64_t tot[3]; unsigned long long h_cells[1 + KSW_N_CLS]; uint32_t h_cls[KSW_N_CLS];
 	MMG_D2H(c, &tot[0], mem_off + n, 8); MMG_D2H(c, &tot[1], p_off + n, 8); MMG_D2H(c, &tot[2], cg_off + n, 8);
 	MMG_D2H(c, h_cells, d_cells, sizeof(h_cells)); MMG_D2H(c, h_cls, d_cls, sizeof(h_cls));
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	if (cells) *cells = h_cells[0];
-	c->k_last_jobs_literal = h_cls[KSW_CLS_LITERAL], c->k_last_cells_literal = h_cells[1 + KSW_CLS_LITERAL];
-	c->k_last_jobs_fast = (uint64_t)n - h_cls[KSW_CLS_LITERAL], c->k_last_cells_fast = h_cells[0] - h_cells[1 + KSW_CLS_LITERAL];
+	c->k_last_jobs_literal = h_cls[KSW_CLS_LITERAL] + h_cls[KSW_CLS_LITERAL_WIDE];
+	c->k_last_cells_literal = h_cells[1 + KSW_CLS_LITERAL] + h_cells[1 + KSW_CLS_LITERAL_WIDE];
+	c->k_last_jobs_fast = (uint64_t)n - c->k_last_jobs_literal, c->k_last_cells_fast = h_cells[0] - c->k_last_cells_literal;
 	if (getenv("MMG_KSW_DEBUG")) {
 		fprintf(stderr, "[mmg_ksw] %d jobs, %llu cells:", n, h_cells[0]);
-		for (int q = 0; q <= KSW_N_FAST; ++q) fprintf(stderr, " class %d: %u jobs %llu cells;", q, h_cls[q], h_cells[1 + q]);
+		for (int q = 0; q < KSW_N_CLS; ++q) fprintf(stderr, " class %d: %u jobs %llu cells;", q, h_cls[q], h_cells[1 + q]);
 		fprintf(stderr, " p %ld B, mem %ld B\n", (long)tot[1], (long)tot[0]);
 	}
 	MMG_TRY(c->k_mem.ensure((size_t)tot[0] + 64));
@@ -417,8 +445,14 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 		first += nq;
 	}
 	if (h_cls[KSW_CLS_LITERAL])
-		MMG_LAUNCH(c, k_ksw, mmg_blocks(h_cls[KSW_CLS_LITERAL], KSW_JOBS_PER_BLOCK), KSW_GROUP * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
+		MMG_LAUNCH(c, k_ksw<16>, mmg_blocks(h_cls[KSW_CLS_LITERAL], KSW_JOBS_PER_BLOCK), 16 * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
 		           d_jobs, order + first, (int)h_cls[KSW_CLS_LITERAL], sc, d_Q, d_S, d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off),
+		           reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(),
+		           c->k_cig.as<uint32_t>(), d_ez);
+	first += h_cls[KSW_CLS_LITERAL];
+	if (h_cls[KSW_CLS_LITERAL_WIDE])
+		MMG_LAUNCH(c, k_ksw<32>, mmg_blocks(h_cls[KSW_CLS_LITERAL_WIDE], KSW_JOBS_PER_BLOCK), 32 * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
+		           d_jobs, order + first, (int)h_cls[KSW_CLS_LITERAL_WIDE], sc, d_Q, d_S, d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off),
 		           reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(),
 		           c->k_cig.as<uint32_t>(), d_ez);
 	MMG_CUDA(cudaEventRecord(c->ev[1], c->stream));
