@@ -51,10 +51,19 @@ __device__ __forceinline__ int ksw_ncol(int qlen, int tlen, int w)
 #define KSW_N_FAST 3
 #define KSW_CLS_LITERAL KSW_N_FAST            /* literal form, 16 lanes per job */
 #define KSW_CLS_LITERAL_WIDE (KSW_N_FAST + 1)  /* literal form, 32 lanes per job: bands wider than two SSE blocks */
-#define KSW_N_CLS (KSW_N_FAST + 2)
+#define KSW_CLS_WAVE (KSW_N_FAST + 2)          /* wavefront form: one warp per large job whose band never clips */
+#define KSW_N_CLS (KSW_N_FAST + 3)
 struct KswFastClass { int32_t mc, tc, qc, nt; };
 struct KswFastTab { KswFastClass c[KSW_N_FAST]; };
 static inline size_t ksw_fast_smem(const KswFastClass &k) { return (size_t)k.nt * ((size_t)(k.mc + 1) * 8 + (size_t)k.tc + (size_t)k.qc); }
+
+// wavefront form (k_ksw_wave below): geometry of its traceback rows and of its per-job arena
+#define KW_S 8
+#define KW_WARPS 4
+MMG_HD size_t ksw_wave_tpad(int tlen) { return ((size_t)tlen + 7) & ~(size_t)7; }
+MMG_HD size_t ksw_wave_p_bytes(int qlen, int tlen) { return ((size_t)qlen * ksw_wave_tpad(tlen) + 63) & ~(size_t)63; }
+// arena per job: diag keys 8 B x (qlen + tlen) | last row H 4 B x tlen | last column H 4 B x qlen | edge of the last lane 16 B x qlen
+MMG_HD size_t ksw_wave_mem_bytes(int qlen, int tlen) { return (((size_t)(qlen + tlen) * 8 + (size_t)tlen * 4 + (size_t)qlen * 4 + (size_t)qlen * 16) + 127) & ~(size_t)63; }
 
 // per job: arena sizes, the scheduling key (form and size class, then shape so that the threads of a warp walk the same
 // loops), and the true-band cell count
@@ -87,7 +96,13 @@ __global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, KswSco
 						if (mn <= ft.c[q].mc && tlen <= ft.c[q].tc && qlen <= ft.c[q].qc) cls = q;
 				}
 				c = (uint64_t)qlen + tlen + 2;
-				if (cls == KSW_CLS_LITERAL) {
+				if (cls == KSW_CLS_LITERAL && !g.bail && !clips && mmg_ksw_fast_ok(g) && (qlen < tlen ? qlen : tlen) >= 32 && qlen + tlen < 65000 && !(j.flag & MMG_EZ_APPROX_DROP)) {
+					cls = KSW_CLS_WAVE; // too large for the thread-per-job classes: one warp, eight target columns per lane
+					m = ksw_wave_mem_bytes(qlen, tlen);
+					if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = ksw_wave_p_bytes(qlen, tlen);
+					const uint64_t est = (uint64_t)qlen * (uint64_t)tlen;
+					k = (uint32_t)cls << 28 | (63u - (uint32_t)(63 - __clzll((long long)(est | 1))));
+				} else if (cls == KSW_CLS_LITERAL) {
 					// 32 lanes pay off for wide bands whose lane arrays sit in shared memory (measured: +9 % on the short-read jobs, -5 % on
 					// long-read jobs whose arrays live in the HBM arena)
 					{ int bw = qlen < tlen ? qlen : tlen; if (g.w + 1 < bw) bw = g.w + 1;
@@ -350,6 +365,156 @@ k_ksw_tpj(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ or
 	res[ji] = ez;
 }
 
+
+// ---- K4, wavefront form: one warp per large job whose band never clips ------------------------------------------
+// Cell (t, j) of the difference recurrence needs x, v, x2 of (t-1, j) and y, u, y2 of (t, j-1) -- nothing else (the
+// anti-diagonal order of the SSE program is one valid schedule among many once no stale lane can be read, see
+// mmg_ksw_fast_run).  Each lane owns KW_S consecutive target columns and keeps their (u, y, y2) in registers; lane l works
+// on query row j = step - l, receives the (x, v, x2, H) of its left neighbour's last column by one shuffle per step and
+// sweeps its columns with the carry in registers.  Targets wider than 32 * KW_S columns take several passes; the last
+// lane's edge values go through a per-row array.  What the reference derives per anti-diagonal (first-max with its tie
+// order, z-drop, mqe, mte) is rebuilt after the sweep from a per-diagonal atomicMax key, the last row and the last column.
+
+template <int kMode>
+__device__ __forceinline__ void ksw_wave_sweep(const KswGeom &g, const KswJobDev &jb, const uint32_t *__restrict__ Q, const uint32_t *__restrict__ S,
+                                               uint8_t *__restrict__ p2, unsigned long long *__restrict__ diag, int32_t *__restrict__ hrow,
+                                               int32_t *__restrict__ hcol, int4 *__restrict__ edge, const bool exact, const int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int qlen = g.qlen, tlen = g.tlen;
+	const int32_t n1 = -g.q - g.e, n2 = -g.q2 - g.e2;
+	const size_t tpad = ksw_wave_tpad(tlen);
+	const int n_pass = (tlen + 32 * KW_S - 1) / (32 * KW_S);
+	for (int pass = 0; pass < n_pass; ++pass) {
+		const int a = pass * 32 * KW_S + lane * KW_S; // first column of this lane
+		const int nc = tlen - a < 0 ? 0 : tlen - a > KW_S ? KW_S : tlen - a;
+		int32_t tb[KW_S], cu[KW_S], cy[KW_S], cy2[KW_S];
+#pragma unroll
+		for (int k = 0; k < KW_S; ++k) {
+			tb[k] = k < nc ? (int32_t)ksw_tbase(S, jb, a + k) : 4;
+			cu[k] = mmg_ksw_first_col(g, a + k), cy[k] = n1, cy2[k] = n2; // the row above row 0: first-row boundary (ksw2_extd2_sse.c:152-156)
+		}
+		int32_t ex = n1, ev = n1, ex2 = n2, eH = 0; // what this lane hands to the next one: its last column of the row it just did
+		int32_t hm1 = 0;                              // H of the column left of column 0 (lane 0 of the first pass)
+		for (int st = 0; st < qlen + 31; ++st) {
+			const int j = st - lane;
+			int32_t lx = __shfl_up_sync(FULL, ex, 1), lv = __shfl_up_sync(FULL, ev, 1), lx2 = __shfl_up_sync(FULL, ex2, 1), lH = __shfl_up_sync(FULL, eH, 1);
+			if (j < 0 || j >= qlen || nc == 0) continue;
+			if (lane == 0) {
+				if (pass == 0) {
+					const int32_t fc = mmg_ksw_first_col(g, j);
+					hm1 = j == 0 ? -g.qe_pre : hm1 + fc; // H(-1, j): the first-column boundary, see the derivation in DESIGN.md section 4
+					lx = n1, lx2 = n2, lv = fc, lH = hm1;
+				} else { const int4 e4 = edge[j]; lx = e4.x, lv = e4.y, lx2 = e4.z, lH = e4.w; }
+			}
+			const uint32_t qb = ksw_qbase(Q, jb, j);
+			int32_t cx = lx, cv = lv, cx2 = lx2, H = lH;
+			unsigned long long dw = 0;
+#pragma unroll
+			for (int k = 0; k < KW_S; ++k)
+				if (k < nc) {
+					const uint32_t tbase = (uint32_t)tb[k];
+					int32_t sc = tbase == qb ? g.sc_mch : g.sc_mis;
+					if ((tbase | qb) & 4) sc = g.sc_N;
+					const KswCell32 c = mmg_ksw_cell32<kMode>(g, sc, cx, cv, cu[k], cy[k], cx2, cy2[k]);
+					cu[k] = c.u, cy[k] = c.y, cy2[k] = c.y2;
+					cx = c.x, cv = c.v, cx2 = c.x2;
+					H += c.u;
+					if (kMode) dw |= (unsigned long long)c.d << (8 * k);
+					if (exact) {
+						const int t = a + k, r = t + j;
+						const int st0 = r - qlen + 1 > 0 ? r - qlen + 1 : 0, en0 = r < tlen - 1 ? r : tlen - 1;
+						uint32_t pref = 0xffffu;
+						if (t != en0) {
+							const int d = t - st0, en1k = (en0 - st0) / 4 * 4;
+							const uint32_t rk = d < en1k ? ((uint32_t)(d & 3) << 13 | (uint32_t)(d >> 2)) : (4u << 13 | (uint32_t)(d - en1k));
+							pref = 0xfffeu - rk;
+						}
+						atomicMax(&diag[r], (unsigned long long)(uint32_t)(H + 0x40000000) << 32 | (unsigned long long)pref << 16 | (unsigned long long)(uint32_t)t);
+						if (j == qlen - 1) hrow[t] = H;
+					}
+					if (a + k == tlen - 1) hcol[j] = H; // last column: mte in exact mode, and its last entry is the global score in every mode
+				}
+			if (kMode) *reinterpret_cast<unsigned long long*>(p2 + (size_t)j * tpad + a) = dw;
+			ex = cx, ev = cv, ex2 = cx2, eH = H;
+			if (lane == 31 && pass + 1 < n_pass) edge[j] = make_int4(ex, ev, ex2, eH);
+		}
+		__syncwarp();
+	}
+}
+
+MMG_HDN inline int ksw_wave_backtrack(const KswGeom &g, int is_rev, const uint8_t *p2, size_t tpad, int i0, int j0, uint32_t *cigar)
+{ // ksw_backtrack (ksw2.h:119-151) over rows of query positions; the walk cannot leave the matrix
+	int n = 0, i = i0, j = j0, state = 0;
+#define MMG_PUSH(op, len) do { if (n == 0 || (uint32_t)(op) != (cigar[n - 1] & 0xf)) cigar[n++] = (uint32_t)(len) << 4 | (uint32_t)(op); else cigar[n - 1] += (uint32_t)(len) << 4; } while (0)
+	while (i >= 0 && j >= 0) {
+		const uint32_t tmp = p2[(size_t)j * tpad + i];
+		if (state == 0) state = tmp & 7;
+		else if (!(tmp >> (state + 2) & 1)) state = 0;
+		if (state == 0) state = tmp & 7;
+		if (state == 0) { MMG_PUSH(0, 1); --i, --j; }
+		else if (state == 1 || state == 3) { MMG_PUSH(2, 1); --i; }
+		else { MMG_PUSH(1, 1); --j; }
+	}
+	if (i >= 0) MMG_PUSH(2, i + 1);
+	if (j >= 0) MMG_PUSH(1, j + 1);
+#undef MMG_PUSH
+	if (!is_rev)
+		for (int k = 0; k < n >> 1; ++k) { uint32_t t = cigar[k]; cigar[k] = cigar[n - 1 - k]; cigar[n - 1 - k] = t; }
+	return n;
+}
+
+__global__ void __launch_bounds__(32 * KW_WARPS)
+k_ksw_wave(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order, int n_jobs, KswScore sc, const uint32_t *__restrict__ Q,
+           const uint32_t *__restrict__ S, const uint64_t *__restrict__ q_off, const int32_t *__restrict__ read_len, const uint64_t *__restrict__ ref_off,
+           const uint64_t *__restrict__ mem_off, const uint64_t *__restrict__ p_off, const uint64_t *__restrict__ cig_off,
+           int8_t *__restrict__ gmem, uint8_t *__restrict__ gp, uint32_t *__restrict__ gcig, KswEz *__restrict__ res)
+{
+	const int lane = threadIdx.x & 31, slot = blockIdx.x * KW_WARPS + (threadIdx.x >> 5);
+	if (slot >= n_jobs) return;
+	const int ji = order[slot];
+	const mmg_ksw_job_t hj = jobs[ji];
+	KswJobDev jb;
+	jb.q_base = q_off[hj.seq_id], jb.q_readlen = read_len[hj.seq_id], jb.q_rev = hj.q_rev, jb.q_start = hj.q_start, jb.q_len = hj.q_len;
+	jb.t_base = ref_off[hj.rid] + (uint64_t)hj.t_start, jb.t_len = hj.t_len, jb.reversed = hj.reversed;
+	jb.w = hj.w, jb.zdrop = hj.zdrop, jb.end_bonus = hj.end_bonus, jb.flag = hj.flag;
+	const KswGeom g = mmg_ksw_geom(jb.q_len, jb.t_len, sc.m, sc.mat, sc.q, sc.e, sc.q2, sc.e2, jb.w);
+	const int qlen = g.qlen, tlen = g.tlen, R = qlen + tlen - 1;
+	unsigned long long *diag = reinterpret_cast<unsigned long long*>(gmem + mem_off[ji]);
+	int32_t *hrow = reinterpret_cast<int32_t*>(diag + (qlen + tlen)), *hcol = hrow + tlen;
+	int4 *edge = reinterpret_cast<int4*>((reinterpret_cast<size_t>(hcol + qlen) + 15) & ~(size_t)15);
+	uint8_t *p2 = gp + p_off[ji];
+	const bool with_cigar = !(jb.flag & MMG_EZ_SCORE_ONLY), exact = !(jb.flag & MMG_EZ_APPROX_MAX);
+	if (exact) for (int r = lane; r < R; r += 32) diag[r] = 0;
+	__syncwarp();
+	if (!with_cigar) ksw_wave_sweep<0>(g, jb, Q, S, p2, diag, hrow, hcol, edge, exact, lane);
+	else if (!(jb.flag & MMG_EZ_RIGHT)) ksw_wave_sweep<1>(g, jb, Q, S, p2, diag, hrow, hcol, edge, exact, lane);
+	else ksw_wave_sweep<2>(g, jb, Q, S, p2, diag, hrow, hcol, edge, exact, lane);
+	__threadfence_block();
+	__syncwarp();
+	if (lane != 0) return;
+	KswEz ez;
+	mmg_ksw_reset(&ez);
+	if (exact) { // the per-diagonal bookkeeping of ksw2_extd2_sse.c:350-358, in diagonal order
+		for (int r = 0; r < R; ++r) {
+			const int st0 = r - qlen + 1 > 0 ? r - qlen + 1 : 0, en0 = r < tlen - 1 ? r : tlen - 1;
+			const unsigned long long key = diag[r];
+			const int32_t max_H = (int32_t)(uint32_t)(key >> 32) - 0x40000000, max_t = (int32_t)(key & 0xffff);
+			if (en0 == tlen - 1) { const int32_t H_en0 = hcol[r - (tlen - 1)]; if (H_en0 > ez.mte) ez.mte = H_en0, ez.mte_q = r - ((en0 + 16) / 16 * 16 - 1); }
+			if (r - st0 == qlen - 1) { const int32_t hs = hrow[st0]; if (hs > ez.mqe) ez.mqe = hs, ez.mqe_t = st0; }
+			if (mmg_ksw_zdrop(&ez, max_H, r, max_t, jb.zdrop, g.e2)) break;
+			if (r == R - 1 && en0 == tlen - 1) ez.score = hcol[qlen - 1];
+		}
+	} else { // approximate mode without APPROX_DROP (ksw2_extd2_sse.c:359-375): H0 telescopes along a path of neighbouring cells that
+		// ends in the corner, so only H of the corner cell is observable
+		ez.score = hcol[qlen - 1];
+	}
+	int i0, j0;
+	if (with_cigar && mmg_ksw_trace_start(g, jb.flag, jb.end_bonus, &ez, &i0, &j0))
+		ez.n_cigar = ksw_wave_backtrack(g, !!(jb.flag & MMG_EZ_REV_CIGAR), p2, ksw_wave_tpad(tlen), i0, j0, gcig + cig_off[ji]);
+	res[ji] = ez;
+}
+
 __global__ void k_res_ncig(int n_jobs, const KswEz *__restrict__ res, int32_t *__restrict__ ncig)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -414,7 +579,7 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 	MMG_D2H(c, h_cells, d_cells, sizeof(h_cells)); MMG_D2H(c, h_cls, d_cls, sizeof(h_cls));
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	if (cells) *cells = h_cells[0];
-	c->k_last_jobs_literal = h_cls[KSW_CLS_LITERAL] + h_cls[KSW_CLS_LITERAL_WIDE];
+	c->k_last_jobs_literal = h_cls[KSW_CLS_LITERAL] + h_cls[KSW_CLS_LITERAL_WIDE]; // the wavefront form counts as a fast form
 	c->k_last_cells_literal = h_cells[1 + KSW_CLS_LITERAL] + h_cells[1 + KSW_CLS_LITERAL_WIDE];
 	c->k_last_jobs_fast = (uint64_t)n - c->k_last_jobs_literal, c->k_last_cells_fast = h_cells[0] - c->k_last_cells_literal;
 	if (getenv("MMG_KSW_DEBUG")) {
@@ -458,6 +623,11 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 		           d_jobs, order + first, (int)h_cls[KSW_CLS_LITERAL_WIDE], sc, d_Q, d_S, d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off),
 		           reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(),
 		           c->k_cig.as<uint32_t>(), d_ez);
+	first += h_cls[KSW_CLS_LITERAL_WIDE];
+	if (h_cls[KSW_CLS_WAVE])
+		MMG_LAUNCH(c, k_ksw_wave, mmg_blocks(h_cls[KSW_CLS_WAVE], KW_WARPS), 32 * KW_WARPS, 0, d_jobs, order + first, (int)h_cls[KSW_CLS_WAVE], sc, d_Q, d_S, d_q_off,
+		           d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off), reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off),
+		           c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(), c->k_cig.as<uint32_t>(), d_ez);
 	MMG_CUDA(cudaEventRecord(c->ev[1], c->stream));
 	MMG_LAUNCH(c, k_res_ncig, mmg_blocks(n1, 256), 256, 0, n, d_ez, ncig);
 	MMG_TRY(scan_excl(c, ncig, nc_off, (int)n1));

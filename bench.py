@@ -434,7 +434,7 @@ def main():
                 "note": "the chaining and DP kernels are integer/latency-bound, not HBM-bound: their HBM fraction is small by construction; "
                         "see k4 (GCUPS against the integer-pipe roofline) and DESIGN.md section 4"}
         ksw_lit_ms = prof_res.get("k_ksw", (0.0, 0))[0]
-        ksw_fast_ms = prof_res.get("k_ksw_tpj", (0.0, 0))[0]
+        ksw_fast_ms = prof_res.get("k_ksw_tpj", (0.0, 0))[0] + prof_res.get("k_ksw_wave", (0.0, 0))[0]
         ksw_ms = ksw_lit_ms + ksw_fast_ms
         lookup_ms = prof_res.get("k_lookup", (0.0, 0))[0]
         gc = lambda c, ms: c / (ms * 1e-3) / 1e9 if ms else None
