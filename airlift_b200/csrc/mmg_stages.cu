@@ -159,10 +159,12 @@ __global__ void k_emit_sorted(int n_list, const int64_t *__restrict__ aoff, cons
 __global__ void k_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
                        const uint64_t *__restrict__ m_val, const uint64_t *__restrict__ pos, int max_occ, int64_t flag,
                        const int64_t *__restrict__ aoff, int32_t *__restrict__ na, mm128 *__restrict__ a, mm128 *__restrict__ heap, RsFrame *__restrict__ stack,
-                       const uint8_t *__restrict__ replay /* null: every fragment */)
+                       const uint8_t *__restrict__ replay /* null: every fragment */, int per_warp)
 {
-	const int li = blockIdx.x * blockDim.x + threadIdx.x;
-	if (li >= n_list) return;
+	// per_warp: one fragment per warp (lane 0 works).  The re-chain pass lists a few hundred fragments of ~10^5 anchors each; as
+	// neighbouring threads of one warp their serial replays diverged and ran one after the other (36 ms for 192 fragments)
+	const int gt = blockIdx.x * blockDim.x + threadIdx.x, li = per_warp ? gt >> 5 : gt;
+	if (li >= n_list || (per_warp && (gt & 31))) return;
 	if (replay && !replay[li]) return;
 	const int f = list ? list[li] : li;
 	const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]];
@@ -864,9 +866,12 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		           pb.na->as<int32_t>(), pb.a->as<mm128>(), d_tie);
 	}
 	// literal replay: the heap merge for fragments with repeated hashes; fill + klib radix sort for the non-heap presets
-	MMG_LAUNCH(c, k_fill, mmg_blocks(n_list, 64), 64, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
-	           mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>(), c->d_heap.as<mm128>(),
-	           pb.stack->as<RsFrame>(), heap_path ? c->d_replay.as<uint8_t>() : d_tie);
+	{
+		const int per_warp = d_flag == nullptr || n_list <= 4096 ? 1 : 0; // the re-chain pass (and any small list): spread over warps
+		MMG_LAUNCH(c, k_fill, mmg_blocks(per_warp ? (size_t)n_list * 32 : (size_t)n_list, 64), 64, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(),
+		           c->d_m_val.as<uint64_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>(), c->d_heap.as<mm128>(),
+		           pb.stack->as<RsFrame>(), heap_path ? c->d_replay.as<uint8_t>() : d_tie, per_warp);
+	}
 	ChainOptDev co;
 	co.bw = opt->bw, co.max_gap = opt->max_gap, co.max_gap_ref = opt->max_gap_ref, co.max_frag_len = opt->max_frag_len;
 	co.max_skip = opt->max_chain_skip, co.max_iter = opt->max_chain_iter, co.min_cnt = opt->min_cnt, co.min_sc = opt->min_chain_score;
