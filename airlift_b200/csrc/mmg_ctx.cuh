@@ -21,7 +21,7 @@ struct DevBuf {
 		if (bytes <= cap) return MMG_OK;
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
-		size_t want = bytes + bytes / 4 + 256;
+		size_t want = bytes + bytes / 2 + 256; // generous: a re-allocation in the middle of a run costs a device synchronisation
 		cudaError_t e = cudaMalloc(&p, want);
 		if (e != cudaSuccess) { mmg_set_error("cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); p = nullptr; return MMG_ENOMEM; }
 		cap = want;
@@ -37,7 +37,7 @@ struct PinBuf {
 		if (bytes <= cap) return MMG_OK;
 		if (p) cudaFreeHost(p);
 		p = nullptr; cap = 0;
-		size_t want = bytes + bytes / 4 + 256;
+		size_t want = bytes + bytes / 2 + 256; // page-locking hundreds of MB again takes ~0.1 s
 		cudaError_t e = cudaMallocHost(&p, want);
 		if (e != cudaSuccess) { mmg_set_error("cudaMallocHost(%zu): %s", want, cudaGetErrorString(e)); p = nullptr; return MMG_ENOMEM; }
 		cap = want;
