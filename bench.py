@@ -227,6 +227,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip the whole-CLI (parse + map + SAM) timing at N=1")
+    ap.add_argument("--data-seed", type=int, default=0, help="seed of the synthetic reads (default 44 + rank)")
     ap.add_argument("--lanes", type=int, default=2, help="shards (streams) per GPU a batch is cut into")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -256,7 +257,8 @@ def main():
         dist.barrier()
     fa = make_ref(d)
     n_steps_total = args.warmup + 3 * args.steps
-    f1, f2 = make_reads(d, fa, args.pairs * n_steps_total, 44 + rank, f"sr_r{rank}_{args.pairs}x{n_steps_total}")
+    seed = args.data_seed or 44 + rank
+    f1, f2 = make_reads(d, fa, args.pairs * n_steps_total, seed, f"sr_s{seed}_{args.pairs}x{n_steps_total}")
 
     L = load_lib()
     dev = (C.c_int * 1)(local_rank)
