@@ -155,6 +155,53 @@ __global__ void k_emit_sorted(int n_list, const int64_t *__restrict__ aoff, cons
 	}
 }
 
+// mmg_fill_heap (mmg_core.h) for one fragment per warp: same pops in the same order; the heap and the next position of every
+// list live in shared memory, and the position after that is fetched while the heap is sifted, so that the L2 latency of the
+// position arrays is off the critical path of the serial replay (a repeat-family fragment makes ~2 x 10^5 pops).
+__device__ int64_t fill_heap_prefetch(const mm128 *mv, const int32_t *m_n, const uint64_t *m_val, int n_mv, int max_occ, const uint64_t *pos,
+                                      int64_t flag, int qlen, int64_t n_a_planned, mm128 *heap, uint64_t *nxt, mm128 *a)
+{
+	size_t hs = 0;
+	int64_t n_for = 0, n_rev = 0, n_a = n_a_planned;
+	for (int i = 0; i < n_mv; ++i)
+		if (m_n[i] > 0 && m_n[i] < max_occ) {
+			heap[hs].x = mmg_hit_pos(pos, m_n[i], m_val[i], 0);
+			heap[hs].y = (uint64_t)i << 32;
+			nxt[i] = m_n[i] > 1 ? mmg_hit_pos(pos, m_n[i], m_val[i], 1) : 0;
+			++hs;
+		}
+	if (hs > 1) for (int64_t j = (int64_t)(hs >> 1) - 1; j >= 0; --j) mmg_heap_down((size_t)j, hs, heap);
+	while (hs > 0) {
+		const int i = (int)(heap[0].y >> 32);
+		const uint32_t off = (uint32_t)heap[0].y;
+		const uint64_t r = heap[0].x;
+		const int32_t n = m_n[i];
+		const uint64_t val = m_val[i];
+		const mm128 mz = mv[i];
+		const bool more = off < (uint32_t)n - 1;
+		const uint64_t pending = more && off + 2 < (uint32_t)n ? pos[val + off + 2] : 0; // needed two pops of this list from now
+		if (more) { ++heap[0].y; heap[0].x = nxt[i]; }
+		else { heap[0] = heap[hs - 1]; --hs; }
+		if (hs > 0) mmg_heap_down(0, hs, heap);
+		if (!mmg_skip_seed(flag, r, (uint32_t)mz.y)) {
+			const mm128 an = mmg_make_anchor(r, mz, mmg_is_tandem(mv, n_mv, i), qlen);
+			if ((r & 1) == ((uint32_t)mz.y & 1)) a[n_for++] = an;
+			else a[n_a - (++n_rev)] = an;
+		}
+		if (more) nxt[i] = pending;
+	}
+	for (int64_t j = 0; j < n_rev >> 1; ++j) { // map.c:203-207
+		mm128 t = a[n_a - 1 - j];
+		a[n_a - 1 - j] = a[n_a - (n_rev - j)];
+		a[n_a - (n_rev - j)] = t;
+	}
+	if (n_a > n_for + n_rev) { // map.c:208-211 (only with strand filters)
+		for (int64_t j = 0; j < n_rev; ++j) a[n_for + j] = a[n_a - n_rev + j];
+		n_a = n_for + n_rev;
+	}
+	return n_a;
+}
+
 // K2c: anchors per fragment, in the reference's order (map.c:149-247)
 __global__ void k_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
                        const uint64_t *__restrict__ m_val, const uint64_t *__restrict__ pos, int max_occ, int64_t flag,
@@ -170,8 +217,13 @@ __global__ void k_fill(FragTab ft, const int32_t *__restrict__ list, int n_list,
 	const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]];
 	const int64_t ao = aoff[li];
 	int64_t n;
-	if (flag & MMG_F_HEAP_SORT)
-		n = mmg_fill_heap(mv + b, m_n + b, m_val + b, (int)(e - b), max_occ, pos, flag, ft.qlen[f], na[li], heap + b, a + ao);
+	if (flag & MMG_F_HEAP_SORT) {
+		__shared__ mm128 s_heap[2][128];
+		__shared__ uint64_t s_nxt[2][128];
+		if (per_warp && e - b <= 128)
+			n = fill_heap_prefetch(mv + b, m_n + b, m_val + b, (int)(e - b), max_occ, pos, flag, ft.qlen[f], na[li], s_heap[threadIdx.x >> 5], s_nxt[threadIdx.x >> 5], a + ao);
+		else n = mmg_fill_heap(mv + b, m_n + b, m_val + b, (int)(e - b), max_occ, pos, flag, ft.qlen[f], na[li], heap + b, a + ao);
+	}
 	else
 		n = mmg_fill_flat(mv + b, m_n + b, m_val + b, (int)(e - b), max_occ, pos, flag, ft.qlen[f], a + ao, stack + ao / 65 + 2 * (int64_t)li);
 	na[li] = (int32_t)n;
