@@ -530,7 +530,8 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 		           mi->d_seq_len, mi->d_S, mi->k, mi->w, idx_flag);
 		c->p_mi_for = mi;
 	}
-	const size_t pool_bytes = (size_t)nf * 24576 + ((size_t)512 << 20); // measured use: see MMG_POST_DEBUG
+	// measured use on 2x150 bp pairs: ~10 KB per fragment (MMG_POST_DEBUG prints it); the per-base term covers long queries
+	const size_t pool_bytes = (size_t)nf * 24576 + (size_t)rb.n_bases * 32 + ((size_t)512 << 20);
 	MMG_TRY(c->p_shard.ensure(sizeof(Shard)));
 	MMG_TRY(c->p_hash.ensure((size_t)(nf + 1) * 4));
 	MMG_TRY(c->p_nreg.ensure((size_t)(n_seq + 1) * 4));
