@@ -588,7 +588,7 @@ __device__ __forceinline__ void block_bitonic(T *a, int n, Before before)
 }
 
 __device__ __forceinline__ int block_incl_scan(int v, int *s, int *total)
-{ // every thread of the CTA calls; blockDim.x <= 256
+{ // every thread of the CTA calls; blockDim.x <= 1024
 	const int tid = threadIdx.x, nt = blockDim.x;
 	s[tid] = v;
 	__syncthreads();
@@ -599,13 +599,13 @@ __device__ __forceinline__ int block_incl_scan(int v, int *s, int *total)
 	return r;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
                    const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
                    uint64_t *__restrict__ u, mm128 *__restrict__ bb, RsFrame *__restrict__ stack, int32_t *__restrict__ nu_out,
                    int32_t *__restrict__ nv_out)
 {
-	__shared__ int s_scan[256], s_nu, s_tie;
+	__shared__ int s_scan[1024], s_nu, s_tie;
 	const int li = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
 	if (li >= n_list) return;
 	const int f = list ? list[li] : li;
@@ -953,7 +953,7 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		           pb.a->as<mm128>(), pb.work->as<int32_t>(), c->d_seg_avg.as<float>(), seg_start, d_nseg, d_next, c->d_frag_iter.as<unsigned long long>());
 	}
 	if (d_flag == nullptr) // the re-chain pass: few, very large fragments -> one CTA each
-		MMG_LAUNCH(c, k_chain_tail_block, n_list, 256, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+		MMG_LAUNCH(c, k_chain_tail_block, n_list, 1024, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
 		           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
 		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>());
 	else
