@@ -512,3 +512,70 @@ extern "C" int mmg_memcpy_d2d(void *dst, const void *src, size_t bytes)
 	MMG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
 	return MMG_OK;
 }
+
+// ---- table export in the reference's bucket order (input of mm_idx_dump, index.c:438-477)
+
+struct SlotLive { __device__ bool operator()(const IdxSlot &s) const { return s.key != MMG_SLOT_EMPTY; } };
+
+// sort key = (minimizer & bucket mask, minimizer >> b): the order worker_post (index.c:191-243) visits keys in
+__global__ void k_bucket_keys(const IdxSlot *__restrict__ live, int64_t n, int b, int kbits, uint64_t *__restrict__ skey, uint64_t *__restrict__ sidx)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t m = live[i].key & ~MMG_SLOT_SINGLE;
+	skey[i] = (m & ((1ULL << b) - 1)) << (kbits - b) | m >> b;
+	sidx[i] = (uint64_t)i;
+}
+
+__global__ void k_bucket_gather(const IdxSlot *__restrict__ live, const uint64_t *__restrict__ sidx, int64_t n, uint64_t *__restrict__ keys, uint64_t *__restrict__ vals)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const IdxSlot s = live[sidx[i]];
+	keys[i] = s.key, vals[i] = s.val;
+}
+
+extern "C" int mmg_idx_export_sorted(mmg_ctx_t *c, const mmg_idx_t *mi, int b, uint64_t *keys, uint64_t *vals, uint64_t *pos)
+{
+	const int kbits = 2 * mi->k;
+	if (b < 0 || b > kbits || kbits > 62) { mmg_set_error("mmg_idx_export_sorted: bucket bits %d do not fit a %d-bit minimizer", b, kbits); return MMG_EINVAL; }
+	MMG_CUDA(cudaSetDevice(mi->dev));
+	const int64_t n = mi->n_keys;
+	if (pos && mi->n_pos) MMG_CUDA(cudaMemcpy(pos, mi->d_pos, mi->n_pos * 8, cudaMemcpyDeviceToHost));
+	if (n == 0) return MMG_OK;
+	IdxSlot *d_live = nullptr; int64_t *d_n = nullptr; void *d_tmp = nullptr;
+	uint64_t *d_k[2] = {nullptr, nullptr}, *d_v[2] = {nullptr, nullptr}, *d_ok = nullptr, *d_ov = nullptr;
+	auto cleanup = [&]() { cudaFree(d_live); cudaFree(d_n); cudaFree(d_tmp); cudaFree(d_k[0]); cudaFree(d_k[1]); cudaFree(d_v[0]); cudaFree(d_v[1]); cudaFree(d_ok); cudaFree(d_ov); };
+#define EXP_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { mmg_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); cleanup(); return MMG_ECUDA; } } while (0)
+	EXP_CUDA(cudaMalloc(&d_live, (size_t)n * sizeof(IdxSlot)));
+	EXP_CUDA(cudaMalloc(&d_n, 8));
+	size_t tmp = 0, tmp2 = 0;
+	cub::DeviceSelect::If(nullptr, tmp, mi->d_slots, d_live, d_n, (int64_t)mi->n_slots, SlotLive(), c->stream);
+	for (int i = 0; i < 2; ++i) { EXP_CUDA(cudaMalloc(&d_k[i], (size_t)n * 8)); EXP_CUDA(cudaMalloc(&d_v[i], (size_t)n * 8)); }
+	cub::DoubleBuffer<uint64_t> kb(d_k[0], d_k[1]), vb(d_v[0], d_v[1]);
+	cub::DeviceRadixSort::SortPairs(nullptr, tmp2, kb, vb, n, 0, kbits, c->stream);
+	if (tmp2 > tmp) tmp = tmp2;
+	EXP_CUDA(cudaMalloc(&d_tmp, tmp + 16));
+	size_t t1 = tmp;
+	EXP_CUDA(cub::DeviceSelect::If(d_tmp, t1, mi->d_slots, d_live, d_n, (int64_t)mi->n_slots, SlotLive(), c->stream));
+	++c->launches;
+	int64_t n_live = 0;
+	EXP_CUDA(cudaMemcpyAsync(&n_live, d_n, 8, cudaMemcpyDeviceToHost, c->stream));
+	EXP_CUDA(cudaStreamSynchronize(c->stream));
+	if (n_live != n) { mmg_set_error("index table holds %lld keys, %lld expected", (long long)n_live, (long long)n); cleanup(); return MMG_EINVAL; }
+	k_bucket_keys<<<mmg_blocks(n, 256), 256, 0, c->stream>>>(d_live, n, b, kbits, d_k[0], d_v[0]); ++c->launches;
+	EXP_CUDA(cudaGetLastError());
+	t1 = tmp;
+	EXP_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, t1, kb, vb, n, 0, kbits, c->stream));
+	++c->launches;
+	EXP_CUDA(cudaMalloc(&d_ok, (size_t)n * 8));
+	EXP_CUDA(cudaMalloc(&d_ov, (size_t)n * 8));
+	k_bucket_gather<<<mmg_blocks(n, 256), 256, 0, c->stream>>>(d_live, vb.Current(), n, d_ok, d_ov); ++c->launches;
+	EXP_CUDA(cudaGetLastError());
+	EXP_CUDA(cudaMemcpyAsync(keys, d_ok, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+	EXP_CUDA(cudaMemcpyAsync(vals, d_ov, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+	EXP_CUDA(cudaStreamSynchronize(c->stream));
+	cleanup();
+	return MMG_OK;
+#undef EXP_CUDA
+}

@@ -284,7 +284,7 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "[ERROR] failed to open file '%s': %s\n", argv[optind], strerror(errno));
 		return 1;
 	}
-	if (fnw == 0 && argc - optind < 2) {
+	if (!idx_rdr->is_idx && fnw == 0 && argc - optind < 2) {
 		fprintf(stderr, "[ERROR] missing input: please specify a query file to map or option -d to keep the index\n");
 		mm_idx_reader_close(idx_rdr);
 		return 1;

@@ -124,7 +124,187 @@ void mm_idx_stat(const mm_idx_t *mi)
 			__func__, realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), (int)n, 100.0 * n1 / n, (double)sum / n, (double)len / sum);
 }
 
-/* ---- reader (index.c:533-602).  Only FASTA/FASTQ input builds an index here; a prebuilt .mmi is rejected. */
+/* ---- index files (index.c:438-531).  A .mmi keeps, per bucket, the position array p[] and the (key, value) pairs of a
+ * klib hash table in slot order.  The device table has another shape, so mm_idx_dump() asks the device for the keys in
+ * bucket order and replays khash's placement (khash.h:232-330) on slot numbers alone: the file comes out byte for byte
+ * as the reference writes it.  mm_idx_load() takes the parameters, names and the 4-bit sequence from the file and
+ * re-derives the tables on the GPU -- they are a function of exactly those -- then checks the counts the file states. */
+
+typedef struct { int32_t *slot; uint8_t *live, *taken; uint32_t cap; } kh_replay_t;
+
+static void kh_replay_reserve(kh_replay_t *o, uint32_t nb)
+{
+	if (nb <= o->cap) return;
+	o->slot = (int32_t*)realloc(o->slot, (size_t)nb * 4);
+	o->live = (uint8_t*)realloc(o->live, nb);
+	o->taken = (uint8_t*)realloc(o->taken, nb);
+	o->cap = nb;
+}
+
+/* Slot of each of n distinct keys inserted in array order into an empty table pre-sized for n (index.c:211-212,219).
+ * h[e] is the 32-bit hash of entry e.  Returns the table size; o->slot[i] = entry in slot i, or -1. */
+static uint32_t kh_replay(kh_replay_t *o, const uint32_t *h, uint32_t n)
+{
+	uint32_t nb = 4, bound, e, i, step;
+	while (nb < n) nb <<= 1;
+	kh_replay_reserve(o, nb);
+	memset(o->slot, 0xff, (size_t)nb * 4);
+	bound = (uint32_t)(nb * 0.77 + 0.5);
+	for (e = 0; e < n; ++e) {
+		if (e >= bound) { /* load limit reached: the table doubles and every entry is re-placed where it stands */
+			const uint32_t old = nb, mask = nb * 2 - 1;
+			uint32_t j;
+			nb <<= 1;
+			kh_replay_reserve(o, nb);
+			for (j = 0; j < old; ++j) o->live[j] = o->slot[j] >= 0;
+			memset(o->taken, 0, nb);
+			for (j = 0; j < old; ++j) {
+				int32_t cur;
+				if (!o->live[j]) continue;
+				cur = o->slot[j], o->live[j] = 0;
+				for (;;) { /* an entry landing on one that has not moved yet takes its place and evicts it */
+					for (i = h[cur] & mask, step = 0; o->taken[i]; i = (i + (++step)) & mask) {}
+					o->taken[i] = 1;
+					if (i < old && o->live[i]) { const int32_t t = o->slot[i]; o->slot[i] = cur, cur = t, o->live[i] = 0; }
+					else { o->slot[i] = cur; break; }
+				}
+			}
+			for (j = 0; j < nb; ++j) if (!o->taken[j]) o->slot[j] = -1;
+			bound = (uint32_t)(nb * 0.77 + 0.5);
+		}
+		for (i = h[e] & (nb - 1), step = 0; o->slot[i] >= 0; i = (i + (++step)) & (nb - 1)) {}
+		o->slot[i] = (int32_t)e;
+	}
+	return nb;
+}
+
+/* test hook: slot order for n hashes; slot_out must hold 2 * max(4, n rounded up to a power of two) entries */
+uint32_t mm_b200_kh_replay(const uint32_t *h, uint32_t n, int32_t *slot_out)
+{
+	kh_replay_t o = {0, 0, 0, 0};
+	const uint32_t nb = kh_replay(&o, h, n);
+	memcpy(slot_out, o.slot, (size_t)nb * 4);
+	free(o.slot); free(o.live); free(o.taken);
+	return nb;
+}
+
+#define KEY_ONCE (1ULL << 63)
+
+void mm_idx_dump(FILE *fp, const mm_idx_t *mi)
+{
+	const int64_t n_keys = mmg_idx_n_keys(mi->B->didx[0]), n_pos = mmg_idx_n_minimizers(mi->B->didx[0]);
+	uint64_t *keys = (uint64_t*)malloc((size_t)(n_keys + 1) * 8), *vals = (uint64_t*)malloc((size_t)(n_keys + 1) * 8);
+	uint64_t *pos = (uint64_t*)malloc((size_t)(n_pos + 1) * 8), *p = 0, sum_len = 0;
+	uint32_t x[5], i, *h = 0, m_h = 0, m_p = 0;
+	const uint64_t bmask = (1ULL << mi->b) - 1;
+	kh_replay_t o = {0, 0, 0, 0};
+	int64_t at = 0;
+	if (mmg_idx_export_sorted(mi->B->ctx[0], mi->B->didx[0], mi->b, keys, vals, pos) != MMG_OK) die_gpu("mm_idx_dump");
+	x[0] = mi->w, x[1] = mi->k, x[2] = mi->b, x[3] = mi->n_seq, x[4] = mi->flag;
+	fwrite(MM_IDX_MAGIC, 1, 4, fp);
+	fwrite(x, 4, 5, fp);
+	for (i = 0; i < mi->n_seq; ++i) {
+		const uint8_t l = mi->seq[i].name ? (uint8_t)strlen(mi->seq[i].name) : 0;
+		fwrite(&l, 1, 1, fp);
+		if (l) fwrite(mi->seq[i].name, 1, l, fp);
+		fwrite(&mi->seq[i].len, 4, 1, fp);
+		sum_len += mi->seq[i].len;
+	}
+	for (i = 0; i < 1U << mi->b; ++i) {
+		int64_t end = at;
+		uint32_t size, e, nb, n_p = 0, start_p = 0;
+		while (end < n_keys && ((keys[end] & ~KEY_ONCE) & bmask) == i) ++end;
+		size = (uint32_t)(end - at);
+		for (e = 0; e < size; ++e) if (!(keys[at + e] & KEY_ONCE)) n_p += (uint32_t)vals[at + e];
+		if (n_p > m_p) { m_p = n_p + (n_p >> 1); p = (uint64_t*)realloc(p, (size_t)m_p * 8); }
+		if (size > m_h) { m_h = size + (size >> 1); h = (uint32_t*)realloc(h, (size_t)m_h * 4); }
+		for (e = 0; e < size; ++e) { /* p[]: the position lists of the repeated minimizers, in key order (index.c:226-233) */
+			const uint64_t k = keys[at + e], v = vals[at + e];
+			h[e] = (uint32_t)((k & ~KEY_ONCE) >> mi->b);
+			if (!(k & KEY_ONCE)) {
+				const uint32_t n = (uint32_t)v;
+				memcpy(p + start_p, pos + (v >> 32), (size_t)n * 8);
+				vals[at + e] = (uint64_t)start_p << 32 | n;
+				start_p += n;
+			}
+		}
+		fwrite(&n_p, 4, 1, fp);
+		fwrite(p, 8, n_p, fp);
+		fwrite(&size, 4, 1, fp);
+		if (size) {
+			nb = kh_replay(&o, h, size);
+			for (e = 0; e < nb; ++e) {
+				uint64_t y[2];
+				const int32_t t = o.slot[e];
+				if (t < 0) continue;
+				y[0] = (keys[at + t] & ~KEY_ONCE) >> mi->b << 1 | keys[at + t] >> 63, y[1] = vals[at + t];
+				fwrite(y, 8, 2, fp);
+			}
+		}
+		at = end;
+	}
+	if (!(mi->flag & MM_I_NO_SEQ)) fwrite(mi->S, 4, (sum_len + 7) / 8, fp);
+	fflush(fp);
+	free(keys); free(vals); free(pos); free(p); free(h); free(o.slot); free(o.live); free(o.taken);
+}
+
+mm_idx_t *mm_idx_load(FILE *fp)
+{
+	char magic[4], **seq, **name;
+	uint32_t x[5], i, *len, *S;
+	uint64_t sum_len = 0, off = 0, n_keys = 0, n_listed = 0, j;
+	mm_idx_t *mi;
+	if (fread(magic, 1, 4, fp) != 4) return 0;
+	if (strncmp(magic, MM_IDX_MAGIC, 4) != 0) return 0;
+	if (fread(x, 4, 5, fp) != 5) return 0;
+	if (x[4] & MM_I_NO_SEQ) {
+		fprintf(stderr, "[ERROR] the prebuilt index doesn't contain sequences; this build needs them on the GPU\n");
+		exit(1);
+	}
+	seq = (char**)calloc(x[3], sizeof(char*)), name = (char**)calloc(x[3], sizeof(char*)), len = (uint32_t*)calloc(x[3], 4);
+	for (i = 0; i < x[3]; ++i) {
+		uint8_t l;
+		if (fread(&l, 1, 1, fp) != 1) goto truncated;
+		if (l) {
+			name[i] = (char*)calloc((size_t)l + 1, 1);
+			if (fread(name[i], 1, l, fp) != l) goto truncated;
+		}
+		if (fread(&len[i], 4, 1, fp) != 1) goto truncated;
+		sum_len += len[i];
+	}
+	for (i = 0; i < 1U << x[2]; ++i) { /* the tables are rebuilt from the sequence; only their sizes are taken from the file */
+		int32_t n;
+		uint32_t size;
+		if (fread(&n, 4, 1, fp) != 1 || fseeko(fp, (off_t)n * 8, SEEK_CUR) != 0) goto truncated;
+		if (fread(&size, 4, 1, fp) != 1 || fseeko(fp, (off_t)size * 16, SEEK_CUR) != 0) goto truncated;
+		n_listed += (uint64_t)n, n_keys += size;
+	}
+	S = (uint32_t*)malloc(((sum_len + 7) / 8 + 1) * 4);
+	if (fread(S, 4, (sum_len + 7) / 8, fp) != (sum_len + 7) / 8) goto truncated;
+	for (i = 0; i < x[3]; ++i) {
+		seq[i] = (char*)malloc((size_t)len[i] + 1);
+		for (j = 0; j < len[i]; ++j) seq[i][j] = "ACGTN"[mm_seq4_get(S, off + j) > 4 ? 4 : mm_seq4_get(S, off + j)];
+		seq[i][len[i]] = 0;
+		off += len[i];
+	}
+	free(S);
+	mi = idx_from_seqs((int)x[0], (int)x[1], (int)x[2], (int)x[4], (int)x[3], seq, len, name);
+	for (i = 0; i < x[3]; ++i) { free(seq[i]); free(name[i]); }
+	free(seq); free(name); free(len);
+	if ((uint64_t)mmg_idx_n_keys(mi->B->didx[0]) != n_keys ||
+		(uint64_t)(mmg_idx_n_minimizers(mi->B->didx[0]) - mmg_idx_n_singletons(mi->B->didx[0])) != n_listed) {
+		fprintf(stderr, "[ERROR] the index file states %llu distinct minimizers and %llu listed positions, its sequences give %lld and %lld\n",
+				(unsigned long long)n_keys, (unsigned long long)n_listed, (long long)mmg_idx_n_keys(mi->B->didx[0]),
+				(long long)(mmg_idx_n_minimizers(mi->B->didx[0]) - mmg_idx_n_singletons(mi->B->didx[0])));
+		exit(1);
+	}
+	return mi;
+truncated:
+	fprintf(stderr, "[ERROR] the index file is truncated\n");
+	exit(1);
+}
+
+/* ---- reader (index.c:533-602) */
 
 int64_t mm_idx_is_idx(const char *fn)
 {
@@ -147,28 +327,54 @@ mm_idx_reader_t *mm_idx_reader_open(const char *fn, const mm_idxopt_t *opt, cons
 	const int64_t is_idx = mm_idx_is_idx(fn);
 	mm_idx_reader_t *r;
 	if (is_idx < 0) return 0;
-	if (is_idx > 0) {
-		fprintf(stderr, "[ERROR] '%s' is a prebuilt .mmi index; this build constructs its index on the GPU from FASTA (seconds), please pass the FASTA\n", fn);
-		return 0;
-	}
-	if (fn_out) { fprintf(stderr, "[ERROR] -d (index dump) is not supported by this build\n"); return 0; }
 	r = (mm_idx_reader_t*)calloc(1, sizeof(mm_idx_reader_t));
+	r->is_idx = is_idx > 0;
 	if (opt) r->opt = *opt;
 	else mm_idxopt_init(&r->opt);
-	r->fp.seq = mm_bseq_open(fn);
-	if (r->fp.seq == 0) { free(r); return 0; }
+	if (r->is_idx) {
+		r->fp.idx = fopen(fn, "rb");
+		r->idx_size = is_idx;
+		if (r->fp.idx == 0) { free(r); return 0; }
+	} else {
+		r->fp.seq = mm_bseq_open(fn);
+		if (r->fp.seq == 0) { free(r); return 0; }
+	}
+	if (fn_out) r->fp_out = fopen(fn_out, "wb");
 	return r;
 }
 
 void mm_idx_reader_close(mm_idx_reader_t *r)
 {
-	mm_bseq_close(r->fp.seq);
+	if (r->is_idx) fclose(r->fp.idx);
+	else mm_bseq_close(r->fp.seq);
+	if (r->fp_out) fclose(r->fp_out);
 	free(r);
 }
 
-int mm_idx_reader_eof(const mm_idx_reader_t *r) { return mm_bseq_eof(r->fp.seq); }
+int mm_idx_reader_eof(const mm_idx_reader_t *r)
+{
+	return r->is_idx ? (feof(r->fp.idx) || ftello(r->fp.idx) == r->idx_size) : mm_bseq_eof(r->fp.seq);
+}
+
+static mm_idx_t *idx_gen(mm_idx_reader_t *r);
 
 mm_idx_t *mm_idx_reader_read(mm_idx_reader_t *r, int n_threads)
+{
+	mm_idx_t *mi;
+	(void)n_threads;
+	if (r->is_idx) {
+		mi = mm_idx_load(r->fp.idx);
+		if (mi && mm_verbose >= 2 && (mi->k != r->opt.k || mi->w != r->opt.w || (mi->flag & MM_I_HPC) != (r->opt.flag & MM_I_HPC)))
+			fprintf(stderr, "[WARNING]\033[1;31m Indexing parameters (-k, -w or -H) overridden by parameters used in the prebuilt index.\033[0m\n");
+	} else mi = idx_gen(r);
+	if (mi) {
+		if (r->fp_out) mm_idx_dump(r->fp_out, mi);
+		mi->index = r->n_parts++;
+	}
+	return mi;
+}
+
+static mm_idx_t *idx_gen(mm_idx_reader_t *r)
 { /* one index part: sequences are taken in mini-batches until batch_size bases are exceeded (index.c:284-331,353-372) */
 	mm_bseq_file_t *fp = r->fp.seq;
 	const uint64_t batch_size = r->opt.batch_size;
@@ -200,7 +406,6 @@ mm_idx_t *mm_idx_reader_read(mm_idx_reader_t *r, int n_threads)
 	mi = idx_from_seqs(r->opt.w, r->opt.k, r->opt.bucket_bits, r->opt.flag, n, seq, len, name);
 	for (i = 0; i < n; ++i) { free(seq[i]); free(name[i]); }
 	free(seq); free(name); free(len);
-	mi->index = r->n_parts++;
 	return mi;
 }
 

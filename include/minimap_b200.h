@@ -162,6 +162,8 @@ mm_idx_reader_t *mm_idx_reader_open(const char *fn, const mm_idxopt_t *opt, cons
 mm_idx_t *mm_idx_reader_read(mm_idx_reader_t *r, int n_threads);
 void mm_idx_reader_close(mm_idx_reader_t *r);
 int mm_idx_reader_eof(const mm_idx_reader_t *r);
+void mm_idx_dump(FILE *fp, const mm_idx_t *mi);   /* index.c:438: byte-identical .mmi */
+mm_idx_t *mm_idx_load(FILE *fp);                   /* index.c:479: one index part from a .mmi */
 int64_t mm_idx_is_idx(const char *fn);
 mm_idx_t *mm_idx_str(int w, int k, int is_hpc, int bucket_bits, int n, const char **seq, const char **name);
 void mm_idx_stat(const mm_idx_t *idx);

@@ -80,6 +80,12 @@ int  mmg_idx_clone_to(mmg_ctx_t *ctx, const mmg_idx_t *src, mmg_idx_t **dst);
 /* after the buffers of an mmg_idx_alloc_like() index were filled (e.g. by an NCCL broadcast) */
 int  mmg_idx_finalize(mmg_idx_t *idx);
 int64_t mmg_idx_n_singletons(const mmg_idx_t *idx);
+/* every distinct minimizer in the order the reference's index file keeps them (mm_idx_dump, index.c:438-477, after
+ * worker_post, index.c:191-243): by bucket = minimizer & ((1<<b)-1), then by minimizer>>b.  keys[i] = minimizer, bit 63
+ * set when it occurs once; vals[i] = that one position, or first<<32|n with `first` indexing pos[].  pos (may be NULL)
+ * receives all mmg_idx_n_minimizers() positions grouped by minimizer, ascending within a group (index.c:230).
+ * keys/vals hold mmg_idx_n_keys() entries (host memory). */
+int  mmg_idx_export_sorted(mmg_ctx_t *ctx, const mmg_idx_t *idx, int b, uint64_t *keys, uint64_t *vals, uint64_t *pos);
 int  mmg_memcpy_d2d(void *dst, const void *src, size_t bytes);
 
 /* ----------------------------------------------------- per-kernel entry points */
