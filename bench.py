@@ -129,11 +129,12 @@ def make_ref(d):
     return fa
 
 
-def make_reads(d, fa, n_pairs, seed, tag):
+def make_reads(d, fa, n_pairs, seed, tag, read_seed=0):
+    """seed fixes the updated regions (a property of the reference pair); read_seed, when given, the reads drawn from them"""
     f1, f2 = os.path.join(d, f"{tag}_1.fq"), os.path.join(d, f"{tag}_2.fq")
     if not (os.path.exists(f1) and os.path.exists(f2)):
         t1, t2 = f1 + f".tmp{os.getpid()}", f2 + f".tmp{os.getpid()}"
-        subprocess.check_call([SYNTH, "sr", fa, t1, t2, str(n_pairs), str(seed)])
+        subprocess.check_call([SYNTH, "sr", fa, t1, t2, str(n_pairs), str(seed)] + (["0.02", str(read_seed)] if read_seed else []))
         os.replace(t1, f1)
         os.replace(t2, f2)
     return f1, f2
@@ -214,7 +215,9 @@ def run_reference(args, d, fa):
 def workload_config(pairs_per_step):
     return {"workload": f"C. elegans-size synthetic pair ({GENOME_BP // 10**6} Mbp, {N_CONTIGS} contigs), 2x150bp reads from updated regions, "
                         f"minimap2 -ax sr; {pairs_per_step} pairs per step", "preset": "sr", "k": 21, "w": 11,
-            "pairs_per_step": pairs_per_step, "l2_policy": "inputs larger than L2 (150 MB of reads + index per step), a different batch every step"}
+            "pairs_per_step": pairs_per_step,
+            "shards": "one job sharded by reads: every rank maps reads drawn (read seed 44 + rank) from the same updated regions (seed 44)",
+            "l2_policy": "inputs larger than L2 (150 MB of reads + index per step), a different batch every step"}
 
 
 def main():
@@ -257,8 +260,9 @@ def main():
         dist.barrier()
     fa = make_ref(d)
     n_steps_total = args.warmup + 3 * args.steps
-    seed = args.data_seed or 44 + rank
-    f1, f2 = make_reads(d, fa, args.pairs * n_steps_total, seed, f"sr_s{seed}_{args.pairs}x{n_steps_total}")
+    # one job, sharded: every rank maps reads of the same updated regions (seed 44); rank r draws its own reads
+    seed, read_seed = args.data_seed or 44, (0 if args.data_seed or rank == 0 else 44 + rank)
+    f1, f2 = make_reads(d, fa, args.pairs * n_steps_total, seed, f"sr_s{seed}r{read_seed}_{args.pairs}x{n_steps_total}", read_seed)
 
     L = load_lib()
     dev = (C.c_int * 1)(local_rank)

@@ -2,7 +2,7 @@
  * re-alignment workloads named in BASELINE.json.
  *
  *   mmsynth ref   <out.fa> <genome_bp> <n_contigs> <seed>
- *   mmsynth sr    <ref.fa> <out_1.fq> <out_2.fq> <n_pairs> <seed> [region_frac]
+ *   mmsynth sr    <ref.fa> <out_1.fq> <out_2.fq> <n_pairs> <seed> [region_frac [read_seed]]
  *   mmsynth long  <ref.fa> <out.fq> <n_reads> <seed> [mean_len]
  *
  * ref : uniform random ACGT, split into n_contigs contigs "chr1..", with
@@ -159,7 +159,7 @@ static void revcomp(char *s, int l)
 
 typedef struct { int ctg; int64_t st, en; } region_t;
 
-static int gen_sr(const char *ref_fn, const char *fn1, const char *fn2, int64_t n_pairs, uint64_t seed, double region_frac)
+static int gen_sr(const char *ref_fn, const char *fn1, const char *fn2, int64_t n_pairs, uint64_t seed, double region_frac, uint64_t read_seed)
 {
 	ref_t *R = load_ref(ref_fn);
 	if (!R) return 1;
@@ -174,6 +174,8 @@ static int gen_sr(const char *ref_fn, const char *fn1, const char *fn2, int64_t 
 		if (n_reg == m_reg) { m_reg = m_reg ? m_reg * 2 : 256; reg = (region_t*)realloc(reg, m_reg * sizeof(region_t)); }
 		reg[n_reg].ctg = c; reg[n_reg].st = st; reg[n_reg].en = st + len; ++n_reg; cov += len;
 	}
+	/* the updated regions belong to the reference pair (seed); shards of one job draw different reads (read_seed) from them */
+	if (read_seed && read_seed != seed) rng_seed(&r, read_seed);
 	/* cumulative lengths for sampling a region proportional to (len + 2*150) */
 	double *cum = (double*)malloc(n_reg * sizeof(double)); double tot = 0;
 	for (int i = 0; i < n_reg; ++i) { tot += (double)(reg[i].en - reg[i].st + 300); cum[i] = tot; }
@@ -240,9 +242,9 @@ int main(int argc, char **argv)
 	if (argc >= 6 && strcmp(argv[1], "ref") == 0)
 		return gen_ref(argv[2], atoll(argv[3]), atoi(argv[4]), strtoull(argv[5], 0, 10));
 	if (argc >= 7 && strcmp(argv[1], "sr") == 0)
-		return gen_sr(argv[2], argv[3], argv[4], atoll(argv[5]), strtoull(argv[6], 0, 10), argc > 7 ? atof(argv[7]) : 0.02);
+		return gen_sr(argv[2], argv[3], argv[4], atoll(argv[5]), strtoull(argv[6], 0, 10), argc > 7 ? atof(argv[7]) : 0.02, argc > 8 ? strtoull(argv[8], 0, 10) : 0);
 	if (argc >= 6 && strcmp(argv[1], "long") == 0)
 		return gen_long(argv[2], argv[3], atoll(argv[4]), strtoull(argv[5], 0, 10), argc > 6 ? atof(argv[6]) : 10000.0);
-	fprintf(stderr, "usage: mmsynth ref <out.fa> <bp> <n_ctg> <seed> | sr <ref.fa> <o1.fq> <o2.fq> <n_pairs> <seed> [frac] | long <ref.fa> <out.fq> <n> <seed> [mean]\n");
+	fprintf(stderr, "usage: mmsynth ref <out.fa> <bp> <n_ctg> <seed> | sr <ref.fa> <o1.fq> <o2.fq> <n_pairs> <seed> [frac [read_seed]] | long <ref.fa> <out.fq> <n> <seed> [mean]\n");
 	return 2;
 }
