@@ -113,11 +113,16 @@ def ensure_tools():
         subprocess.check_call(["make", "-C", ROOT, "tools"], stdout=subprocess.DEVNULL)
 
 
-def workdir():
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
-    d = os.path.join(base, "airlift_b200_bench")
-    os.makedirs(d, exist_ok=True)
-    return d
+def workdir(need_bytes=0):
+    """/dev/shm when it can hold the synthetic files of all ranks (what is already there from an earlier run counts), else the
+    temp dir.  Every rank evaluates this before anything is written, so all ranks pick the same place."""
+    import shutil
+    for base in (["/dev/shm"] if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else []) + [tempfile.gettempdir()]:
+        d = os.path.join(base, "airlift_b200_bench")
+        have = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d)) if os.path.isdir(d) else 0
+        if base != "/dev/shm" or shutil.disk_usage(base).free + have >= need_bytes * 1.1 + (1 << 30):
+            os.makedirs(d, exist_ok=True)
+            return d
 
 
 def make_ref(d):
@@ -239,7 +244,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     ensure_tools()
-    d = workdir()
+    # 2 x ~330 bytes of FASTQ per pair, warm-up + three timed passes, every rank its own files
+    d = workdir(world * args.pairs * (args.warmup + 3 * args.steps) * 700 if args.impl == "b200" else 0)
     if args.impl == "reference":
         if rank == 0:
             fa = make_ref(d)
