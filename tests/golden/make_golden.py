@@ -49,6 +49,23 @@ def kernels():
     for i, s in enumerate(seqs):
         G[f"ref{i}"] = u8(s)
     G["n_ref"] = np.array(len(seqs))
+    import ctypes as C
+    for ii, (w, k) in enumerate([(11, 21), (10, 15)]):   # mm_idx_get (index.c:81) and mm_idx_cal_max_occ (index.c:164)
+        mi = L.ref().mm_idx_str(w, k, 0, 14, len(seqs), L.c_str_array(seqs), None)
+        keys = set()
+        for s in seqs:
+            keys.update((L.ref_sketch(s[:4000], w, k)["x"] >> np.uint64(8)).tolist())
+        keys.update(np.random.default_rng(5 + ii).integers(0, 1 << (2 * k), 300).tolist())   # own stream: the vectors below keep theirs
+        keys = np.array(sorted(keys), dtype=np.uint64)
+        cnt, pos, n1 = [], [], C.c_int(0)
+        for key in keys.tolist():
+            p = L.ref().mm_idx_get(mi, key, C.byref(n1))
+            cnt.append(n1.value)
+            pos.extend(p[j] for j in range(n1.value))
+        G[f"ix{ii}_par"], G[f"ix{ii}_keys"], G[f"ix{ii}_n"], G[f"ix{ii}_pos"] = np.array([w, k]), keys, np.array(cnt, dtype=np.int32), np.array(pos, dtype=np.uint64)
+        G[f"ix{ii}_occ"] = np.array([L.ref().mm_idx_cal_max_occ(mi, C.c_float(f)) for f in (2e-4, 1e-2, 0.2)], dtype=np.int32)
+        L.ref().mm_idx_destroy(mi)
+    G["n_ix"] = np.array(2)
     n = 0
     for mode in ["sr", "ont"]:
         w, k = (11, 21) if mode == "sr" else (10, 15)

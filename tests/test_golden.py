@@ -4,6 +4,7 @@
   * GPU (-m gpu): the CUDA stages through the C-ABI reproduce the same vectors, and the CLI reproduces the
     reference's SAM/PAF for the committed inputs (sr paired/single, low occurrence cut-offs, many secondaries,
     edge-case reads, map-ont with cs, an inversion that needs the tp:A:I path)."""
+import ctypes as C
 import gzip
 import json
 import os
@@ -80,6 +81,22 @@ def test_oracle_seeds_and_chain_golden(G):
             L.oracle().orc_idx_destroy(h)
 
 
+def test_oracle_index_golden(G):
+    seqs = _refseqs(G)
+    for ii in range(int(G["n_ix"])):
+        w, k = (int(x) for x in G[f"ix{ii}_par"])
+        oi = L.oracle().orc_idx_build(w, k, 0, len(seqs), L.c_str_array(seqs))
+        try:
+            assert [L.oracle().orc_idx_cal_max_occ(oi, f) for f in (2e-4, 1e-2, 0.2)] == G[f"ix{ii}_occ"].tolist()
+            n1, at, pos = C.c_int(0), 0, G[f"ix{ii}_pos"]
+            for key, n in zip(G[f"ix{ii}_keys"].tolist(), G[f"ix{ii}_n"].tolist()):
+                p = L.oracle().orc_idx_get(oi, key, C.byref(n1))
+                assert n1.value == n and [p[j] for j in range(n)] == pos[at:at + n].tolist()
+                at += n
+        finally:
+            L.oracle().orc_idx_destroy(oi)
+
+
 def test_oracle_ksw_golden(G):
     _check_ksw(G, L.orc_ksw)
 
@@ -117,6 +134,26 @@ def test_cuda_seeds_and_chain_golden(G, ctx):
     finally:
         for h in idx.values():
             h.close()
+
+
+@pytest.mark.gpu
+def test_cuda_index_golden(G, ctx):
+    import airlift_b200.api as A
+    seqs = _refseqs(G)
+    for ii in range(int(G["n_ix"])):
+        w, k = (int(x) for x in G[f"ix{ii}_par"])
+        idx = A.Index(ctx, seqs, w, k)
+        try:
+            assert [idx.cal_max_occ(f) for f in (2e-4, 1e-2, 0.2)] == G[f"ix{ii}_occ"].tolist()
+            want_n, want_pos = G[f"ix{ii}_n"], G[f"ix{ii}_pos"]
+            n, pos = idx.get(G[f"ix{ii}_keys"], int(want_n.max()) + 1)
+            assert (np.asarray(n) == want_n).all()
+            at = 0
+            for i, m in enumerate(want_n.tolist()):
+                assert pos[i, :m].tolist() == want_pos[at:at + m].tolist()
+                at += m
+        finally:
+            idx.close()
 
 
 @pytest.mark.gpu
