@@ -553,7 +553,7 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 	int64_t tot = 0, acc = 0;
 	const double t_start = realtime();
 	mm_b200_tune_malloc();
-	if (opt->flag & MM_F_INDEPEND_SEG) { fprintf(stderr, "[ERROR] --no-pairing is not supported by this build\n"); return -1; }
+	if (mm_b200_check_opt(opt) < 0) { free(sh); free(tid); return -1; }
 	for (d = 0; d < s->n_seq; ++d) tot += s->seq[d].l_seq;
 	for (d = 0; d < n_dev; ++d) { /* contiguous fragment ranges balanced by bases; a fragment is never cut */
 		shard_t *h = &sh[d];
@@ -770,7 +770,7 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 	int i;
 	if (n_segs < 1) return -1;
 	if (idx == 0 || idx->B == 0 || idx->B->n_dev < 1) { fprintf(stderr, "[ERROR] the index is not resident on a GPU\n"); return -1; }
-	if (opt->split_prefix) { fprintf(stderr, "[ERROR] --split-prefix is not supported by this build (the index is a single part in HBM)\n"); return -1; }
+	if (mm_b200_check_opt(opt) < 0) return -1;
 	memset(&pl, 0, sizeof(pl));
 	pl.n_fp = n_segs;
 	pl.fp = (mm_bseq_file_t**)calloc(n_segs, sizeof(mm_bseq_file_t*));
@@ -817,6 +817,19 @@ int mm_map_file(const mm_idx_t *idx, const char *fn, const mm_mapopt_t *opt, int
 /* ------------------------------------------------------------------ per-fragment API (a batch of one) */
 
 struct mm_tbuf_s { int rep_len, frag_gap; };
+int mm_b200_check_opt(const mm_mapopt_t *opt)
+{ /* what the device stages do not implement is refused with a message; nothing is silently dropped */
+	const char *what = 0;
+	if (opt->flag & MM_F_SPLICE) what = "spliced alignment (--splice, ksw_exts2)";
+	else if (opt->flag & MM_F_INDEPEND_SEG) what = "--no-pairing";
+	else if (opt->flag & (MM_F_NO_DIAG | MM_F_NO_DUAL)) what = "the self/dual-hit filters of the all-vs-all modes (-D, -X, --dual=no, ava-ont, ava-pb; map.c:128-137)";
+	else if (opt->sdust_thres > 0) what = "SDUST masking of query minimizers (-T, map.c:41-62)";
+	else if (opt->split_prefix) what = "--split-prefix (the index is a single part in HBM)";
+	if (what == 0) return 0;
+	fprintf(stderr, "[ERROR] %s is not supported by this build\n", what);
+	return -1;
+}
+
 mm_tbuf_t *mm_tbuf_init(void) { return (mm_tbuf_t*)calloc(1, sizeof(mm_tbuf_t)); }
 void mm_tbuf_destroy(mm_tbuf_t *b) { free(b); }
 
@@ -830,6 +843,9 @@ void mm_map_frag(const mm_idx_t *mi, int n_segs, const int *qlens, const char **
 	for (j = 0; j < n_segs; ++j) n_regs[j] = 0, regs[j] = 0;
 	if (n_segs <= 0 || n_segs > MM_MAX_SEG) return;
 	if (mi == 0 || mi->B == 0 || mi->B->n_dev < 1) { fprintf(stderr, "[ERROR] the index is not resident on a GPU\n"); exit(1); }
+	if (mm_b200_check_opt(opt) < 0) exit(1);
+	/* the resident batch, staging buffers and pools belong to ctx[0], not to the caller's mm_tbuf_t: one call at a time */
+	pthread_mutex_lock(&mi->B->api_mu);
 	seq = (mm_bseq1_t*)calloc(n_segs, sizeof(mm_bseq1_t));
 	for (j = 0; j < n_segs; ++j) {
 		seq[j].l_seq = qlens[j], seq[j].name = (char*)qname, seq[j].seq = (char*)malloc((size_t)qlens[j] + 1);
@@ -852,6 +868,7 @@ void mm_map_frag(const mm_idx_t *mi, int n_segs, const int *qlens, const char **
 	if (b) b->rep_len = rep[0], b->frag_gap = gap[0];
 	for (j = 0; j < n_segs; ++j) free(seq[j].seq);
 	free(seq);
+	pthread_mutex_unlock(&mi->B->api_mu);
 }
 
 mm_reg1_t *mm_map(const mm_idx_t *mi, int qlen, const char *seq, int *n_regs, mm_tbuf_t *b, const mm_mapopt_t *opt, const char *qname)

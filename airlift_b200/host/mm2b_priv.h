@@ -59,6 +59,7 @@ struct mm_idx_bucket_s {
 	mmg_idx_t *didx[16];
 	pthread_mutex_t gpu_token[16]; /* with lanes > 1: one shard per GPU runs device stages at a time, the others do their host stages */
 	int32_t max_occ_cache_set; float max_occ_cache_f; int32_t max_occ_cache;
+	pthread_mutex_t api_mu; /* mm_map_frag()/mm_map() share ctx[0]: concurrent callers take turns */
 };
 
 extern unsigned char seq_nt4_table[256];

@@ -48,6 +48,7 @@ static mm_idx_t *idx_from_seqs(int w, int k, int b, int flag, int n, char **seq,
 	}
 	B->n_dev = g_n_dev;
 	B->lanes = g_lanes;
+	pthread_mutex_init(&B->api_mu, 0);
 	for (d = 0; d < g_n_dev; ++d) {
 		int l;
 		pthread_mutex_init(&B->gpu_token[d], 0);
@@ -414,45 +415,68 @@ static mm_idx_t *idx_gen(mm_idx_reader_t *r)
 
 int mm_b200_idx_image(const mm_idx_t *mi, mmg_idx_image_t *img) { return mmg_idx_export(mi->B->didx[0], img); }
 
-/* names/lengths come from the FASTA (cheap); the minimizer table, positions and packed sequence are allocated
- * uninitialised on the GPU with the shape given by `shape`; their device pointers are returned in `ptrs` */
-mm_idx_t *mm_b200_idx_alloc(const char *fn, const mm_idxopt_t *opt, const mmg_idx_image_t *shape, mmg_idx_image_t *ptrs)
+/* the replica's host side: names/lengths as given, the minimizer table, positions and packed sequence allocated uninitialised on
+ * the GPU with the shape given by `shape`; their device pointers are returned in `ptrs` */
+mm_idx_t *mm_b200_idx_alloc_named(const mm_idxopt_t *opt, int n_seq, const char *const *names, const uint32_t *lens,
+                                  const mmg_idx_image_t *shape, mmg_idx_image_t *ptrs)
 {
-	mm_bseq_file_t *fp = mm_bseq_open(fn);
 	mm_idx_t *mi;
 	struct mm_idx_bucket_s *B;
-	int n_seq, i, d = 0, b = opt->bucket_bits;
+	int i, b = opt->bucket_bits;
 	uint64_t sum = 0;
-	if (fp == 0) return 0;
+	for (i = 0; i < n_seq; ++i) sum += lens[i];
+	if (n_seq != shape->n_seq || sum != shape->total_len) {
+		fprintf(stderr, "[ERROR] the sequence table does not match the index being received (%d sequences, %lu bases expected)\n", shape->n_seq, (unsigned long)shape->total_len);
+		exit(1);
+	}
 	mi = (mm_idx_t*)calloc(1, sizeof(mm_idx_t));
 	B = (struct mm_idx_bucket_s*)calloc(1, sizeof(*B));
 	if (opt->k * 2 < b) b = opt->k * 2;
-	mi->w = opt->w < 1 ? 1 : opt->w, mi->k = opt->k, mi->b = b, mi->flag = opt->flag, mi->B = B;
-	mi->seq = (mm_idx_seq_t*)calloc(shape->n_seq > 0 ? shape->n_seq : 1, sizeof(mm_idx_seq_t));
-	while (d < shape->n_seq) {
-		mm_bseq1_t *s = mm_bseq_read3(fp, 1 << 28, 0, 0, 0, &n_seq);
-		if (s == 0) break;
-		for (i = 0; i < n_seq && d < shape->n_seq; ++i, ++d) {
-			mi->seq[d].name = s[i].name, mi->seq[d].len = (uint32_t)s[i].l_seq, mi->seq[d].offset = sum;
-			sum += (uint64_t)s[i].l_seq;
-			free(s[i].seq);
-		}
-		for (; i < n_seq; ++i) { free(s[i].seq); free(s[i].name); }
-		free(s);
-	}
-	mm_bseq_close(fp);
-	mi->n_seq = d;
-	if (d != shape->n_seq || sum != shape->total_len) {
-		fprintf(stderr, "[ERROR] '%s' does not match the index being received (%d sequences, %lu bases expected)\n", fn, shape->n_seq, (unsigned long)shape->total_len);
-		exit(1);
+	mi->w = opt->w < 1 ? 1 : opt->w, mi->k = opt->k, mi->b = b, mi->flag = opt->flag, mi->B = B, mi->n_seq = n_seq;
+	mi->seq = (mm_idx_seq_t*)calloc(n_seq > 0 ? n_seq : 1, sizeof(mm_idx_seq_t));
+	for (i = 0, sum = 0; i < n_seq; ++i) {
+		mi->seq[i].name = names && names[i] ? strdup(names[i]) : 0, mi->seq[i].len = lens[i], mi->seq[i].offset = sum;
+		sum += lens[i];
 	}
 	B->n_dev = 1, B->lanes = g_lanes, B->dev_id[0] = g_dev[0];
+	pthread_mutex_init(&B->api_mu, 0);
 	pthread_mutex_init(&B->gpu_token[0], 0);
 	for (i = 0; i < B->lanes; ++i)
 		if (mmg_init(g_dev[0], &B->ctx[i]) != MMG_OK) die_gpu("cannot initialise the GPU");
 	*ptrs = *shape;
 	if (mmg_idx_alloc_like(B->ctx[0], ptrs, &B->didx[0]) != MMG_OK) die_gpu("cannot allocate the index replica");
 	return mi;
+}
+
+/* same, names/lengths read from the FASTA the source rank indexed */
+mm_idx_t *mm_b200_idx_alloc(const char *fn, const mm_idxopt_t *opt, const mmg_idx_image_t *shape, mmg_idx_image_t *ptrs)
+{
+	mm_bseq_file_t *fp = mm_bseq_open(fn);
+	mm_idx_t *mi;
+	char **names = (char**)calloc(shape->n_seq > 0 ? shape->n_seq : 1, sizeof(char*));
+	uint32_t *lens = (uint32_t*)calloc(shape->n_seq > 0 ? shape->n_seq : 1, 4);
+	int n_seq, i, d = 0;
+	if (fp == 0) return 0;
+	while (d < shape->n_seq) {
+		mm_bseq1_t *s = mm_bseq_read3(fp, 1 << 28, 0, 0, 0, &n_seq);
+		if (s == 0) break;
+		for (i = 0; i < n_seq && d < shape->n_seq; ++i, ++d) { names[d] = s[i].name, lens[d] = (uint32_t)s[i].l_seq; free(s[i].seq); }
+		for (; i < n_seq; ++i) { free(s[i].seq); free(s[i].name); }
+		free(s);
+	}
+	mm_bseq_close(fp);
+	mi = mm_b200_idx_alloc_named(opt, d, (const char *const*)names, lens, shape, ptrs);
+	for (i = 0; i < d; ++i) free(names[i]);
+	free(names); free(lens);
+	return mi;
+}
+
+/* name and length of sequence i (for callers that replicate the index to other processes) */
+int mm_b200_idx_seq(const mm_idx_t *mi, int i, const char **name, uint32_t *len)
+{
+	if (i < 0 || (uint32_t)i >= mi->n_seq) return -1;
+	*name = mi->seq[i].name, *len = mi->seq[i].len;
+	return 0;
 }
 
 int mm_b200_idx_finalize(mm_idx_t *mi)

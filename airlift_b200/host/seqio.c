@@ -250,11 +250,13 @@ static void *ra_main(void *arg)
 		blk.a = (mm_bseq1_t*)malloc(RA_BLOCK * sizeof(mm_bseq1_t)), blk.n = 0, blk.ret = 0;
 		while (blk.n < RA_BLOCK && (blk.ret = next_direct(fp, &blk.a[blk.n], fp->ra_with_qual, fp->ra_with_comment)) >= 0) ++blk.n;
 		pthread_mutex_lock(&fp->ra_mu);
-		while (fp->ra_tail - fp->ra_head == RA_RING && !fp->ra_stop) pthread_cond_wait(&fp->ra_cv, &fp->ra_mu);
+		/* a full ring always drains: the consumer takes blocks, and mm_bseq_close() keeps taking them after it asked us to stop */
+		while (fp->ra_tail - fp->ra_head == RA_RING) pthread_cond_wait(&fp->ra_cv, &fp->ra_mu);
+		if (fp->ra_stop && blk.ret >= 0) blk.ret = -1; /* asked to stop: this block is the last one, the consumer must see an end */
 		fp->ring[fp->ra_tail % RA_RING] = blk; ++fp->ra_tail;
 		pthread_cond_broadcast(&fp->ra_cv);
 		pthread_mutex_unlock(&fp->ra_mu);
-		if (blk.ret < 0 || fp->ra_stop) break;
+		if (blk.ret < 0) break;
 	}
 	return 0;
 }

@@ -189,7 +189,14 @@ int mm_b200_set_devices(int n_gpus, const int *dev_ids); /* before building the 
  * the same shape (mm_b200_idx_alloc), a collective fills the five buffers, mm_b200_idx_finalize completes the replica */
 int mm_b200_idx_image(const mm_idx_t *mi, mmg_idx_image_t *img);
 mm_idx_t *mm_b200_idx_alloc(const char *fasta, const mm_idxopt_t *opt, const mmg_idx_image_t *shape, mmg_idx_image_t *ptrs);
+mm_idx_t *mm_b200_idx_alloc_named(const mm_idxopt_t *opt, int n_seq, const char *const *names, const uint32_t *lens,
+                                  const mmg_idx_image_t *shape, mmg_idx_image_t *ptrs); /* same, without re-reading the FASTA */
+int mm_b200_idx_seq(const mm_idx_t *mi, int i, const char **name, uint32_t *len);
 int mm_b200_idx_finalize(mm_idx_t *mi);
+/* options this build does not implement (splice, --no-pairing, -D/-X/--dual=no, -T, --split-prefix) are refused, never
+ * ignored: 0 if opt can be mapped with, else -1 after an [ERROR] line.  mm_map_frag()/mm_map() take turns on a lock (one
+ * resident batch per GPU context), so concurrent callers are safe but serialised. */
+int mm_b200_check_opt(const mm_mapopt_t *opt);
 int mm_b200_set_lanes(int lanes); /* shards (streams) per GPU a batch is cut into, 1..4; before building the index */
 
 /* Batch interface = the drop-in cut point of SURVEY.md §8b (worker_pipeline step 1, map.c:590-593): a mini-batch of

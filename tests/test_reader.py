@@ -153,3 +153,28 @@ def test_two_files_zip_and_stop_at_the_shorter(libs, tmp_path):
         assert [len(b) for b in want] == [len(b) for b in got]
         assert want == got
     assert sum(len(b) for b in got) == 2 * 8990
+
+
+@pytest.mark.timeout(120)
+def test_close_before_eof_does_not_hang(libs, tmp_path):
+    """Mate files of very different lengths: the reader stops at the shorter one (bseq.c:136-145) and the longer file is closed
+    while its read-ahead thread still has most of the file in front of it; closing must return (it used to wait for ever)."""
+    new, ref = libs
+    rng = np.random.default_rng(13)
+    f1, f2 = str(tmp_path / "a.fq"), str(tmp_path / "b.fq")
+    open(f1, "w").write(_fastq(rng, 100, "/1"))
+    open(f2, "w").write(_fastq(rng, 60000, "/2"))
+    want = _ref_batches(ref, [f1, f2], 500000, 1, 0, 0)
+    got = _new_batches(new, [f1, f2], 500000, 0x008)
+    assert want == got and sum(len(b) for b in got) == 200
+    # and a reader closed without having been read at all / after one small batch
+    fns = (C.c_char_p * 2)(f2.encode(), f2.encode())
+    rd = new.mm_b200_open_reads(2, fns)
+    new.mm_b200_close_reads(rd)
+    import bench
+    opt = bench.MapOptFull(); opt.flag = 0x008
+    rd = new.mm_b200_open_reads(2, fns)
+    b = new.mm_b200_read_batch(rd, C.byref(opt), 1000)
+    assert b
+    new.mm_b200_free_batch(b)
+    new.mm_b200_close_reads(rd)
