@@ -42,7 +42,7 @@ $(BUILD)/mmsynth: tools/mmsynth.c | $(BUILD)
 	$(CC) -O2 -Wno-misleading-indentation -o $@ $< -lm
 
 # CPU emulation of the per-thread device code (test harness only; never linked into the product)
-$(BUILD)/libmmg_emu.so: tests/emu/emu.cpp $(CSRC)/mmg_core.h | $(BUILD)
+$(BUILD)/libmmg_emu.so: tests/emu/emu.cpp $(CSRC)/mmg_core.h $(CSRC)/mmg_hits.h $(CSRC)/mmg_aln.h $(CSRC)/mmg_post.h | $(BUILD)
 	g++ -O2 -g -std=c++17 -fPIC -shared -ffp-contract=off -I$(CSRC) $< -o $@
 
 oracle:

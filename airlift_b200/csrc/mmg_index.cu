@@ -79,9 +79,11 @@ extern "C" int mmg_profile_fetch(mmg_ctx_t *c, int max, const char **names, doub
 	cudaSetDevice(c->dev);
 	cudaStreamSynchronize(c->stream);
 	int n = 0;
+	const bool trace = getenv("MMG_TRACE_LAUNCHES") != nullptr; // every launch longer than 0.5 ms, in issue order
 	for (const ProfRec &r : c->prof) {
 		float t = 0;
 		cudaEventElapsedTime(&t, r.a, r.b);
+		if (trace && t > 0.5f) fprintf(stderr, "[mmg::launch] ctx %p %-22s %9.3f ms\n", (void*)c, r.name, t);
 		int i;
 		for (i = 0; i < n; ++i) if (names[i] == r.name || strcmp(names[i], r.name) == 0) break;
 		if (i == n) { if (n == max) { c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b); continue; } names[n] = r.name, ms[n] = 0, launches[n] = 0, ++n; }

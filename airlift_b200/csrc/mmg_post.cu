@@ -587,6 +587,18 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 		MMG_LAUNCH(c, k_post_spread, mmg_blocks(hs.nt, 256), 256, 0, nf, n_warps, sorted, perm);
 		hs.perm = perm;
 	}
+	if (getenv("MMG_TRACE")) { // chains per fragment of this shard (debug aid; synchronises)
+		std::vector<int32_t> hu((size_t)nf), hv((size_t)nf);
+		cudaStreamSynchronize(c->stream);
+		cudaMemcpy(hu.data(), hs.nu, (size_t)nf * 4, cudaMemcpyDeviceToHost);
+		cudaMemcpy(hv.data(), hs.nv, (size_t)nf * 4, cudaMemcpyDeviceToHost);
+		const int lim[8] = {0, 1, 2, 4, 16, 128, 1024, 1 << 30};
+		long long cnt[8] = {0}, ch[8] = {0}, an[8] = {0};
+		for (int i = 0; i < nf; ++i) { int b = 0; while (hu[i] > lim[b]) ++b; ++cnt[b], ch[b] += hu[i], an[b] += hv[i]; }
+		fprintf(stderr, "[mmg::post] %d fragments; chains per fragment (fragments/chains/chained anchors):", nf);
+		for (int b = 0; b < 8; ++b) fprintf(stderr, " <=%d: %lld/%lld/%lld", lim[b], cnt[b], ch[b], an[b]);
+		fprintf(stderr, "\n");
+	}
 	MMG_TRY(c->p_pre.ensure((size_t)(nf + 1) * 12 + 64));
 	hs.pre_regs = c->p_pre.as<mm_reg1_t*>();
 	int32_t *d_heavy = reinterpret_cast<int32_t*>(hs.pre_regs + nf + 1);

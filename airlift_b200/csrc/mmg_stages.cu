@@ -924,6 +924,20 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		           c->d_m_val.as<uint64_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>(), c->d_heap.as<mm128>(),
 		           pb.stack->as<RsFrame>(), heap_path ? c->d_replay.as<uint8_t>() : d_tie, per_warp);
 	}
+	if (getenv("MMG_TRACE")) { // distribution of the literal-replay work of this pass (debug aid; synchronises)
+		std::vector<uint8_t> hr((size_t)n_list); std::vector<int32_t> hn((size_t)n_list);
+		cudaStreamSynchronize(c->stream);
+		cudaMemcpy(hr.data(), heap_path ? c->d_replay.p : (void*)d_tie, (size_t)n_list, cudaMemcpyDeviceToHost);
+		cudaMemcpy(hn.data(), pb.na->p, (size_t)n_list * 4, cudaMemcpyDeviceToHost);
+		int64_t nr = 0, ar = 0, amax = 0, big = 0, abig = 0, big_all = 0, abig_all = 0;
+		for (int i = 0; i < n_list; ++i) {
+			if (hn[i] > 4096) ++big_all, abig_all += hn[i];
+			if (!hr[i]) continue;
+			++nr, ar += hn[i]; if (hn[i] > amax) amax = hn[i]; if (hn[i] > 4096) ++big, abig += hn[i];
+		}
+		fprintf(stderr, "[mmg::pass] max_occ %d: %d fragments, %lld anchors; > 4096 anchors: %lld fragments with %lld anchors; literal replay: %lld fragments, %lld anchors, largest %lld, "
+		        "of which > 4096 anchors: %lld fragments with %lld anchors\n", max_occ, n_list, (long long)tot, (long long)big_all, (long long)abig_all, (long long)nr, (long long)ar, (long long)amax, (long long)big, (long long)abig);
+	}
 	ChainOptDev co;
 	co.bw = opt->bw, co.max_gap = opt->max_gap, co.max_gap_ref = opt->max_gap_ref, co.max_frag_len = opt->max_frag_len;
 	co.max_skip = opt->max_chain_skip, co.max_iter = opt->max_chain_iter, co.min_cnt = opt->min_cnt, co.min_sc = opt->min_chain_score;

@@ -2,8 +2,10 @@
 // airlift_b200/csrc/mmg_core.h with g++ so the `-m "not gpu"` tests can check the very code the
 // kernels execute against the oracle without a GPU.  Never linked into libmm2b200.so.
 #include <vector>
+#include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 static long g_ksw_range_viol; // values of valid cells that left the int8 range (must stay 0: the fast form computes in 32 bits)
 #define MMG_KSW_RANGE(v) do { if ((v) < -128 || (v) > 127) ++g_ksw_range_viol; } while (0)
 #include "mmg_core.h"
@@ -128,4 +130,141 @@ int emu_ksw_fast(int qlen, const uint8_t *query, int tlen, const uint8_t *target
 	return g_ksw_range_viol != viol0 ? -2 : 0;
 }
 
+}
+
+// ---- the post-chaining stages (mmg_post.h) for ONE fragment, every step run the way the kernels of mmg_post.cu run it,
+// with the DP jobs answered by the scalar ksw walk above.  reads: 0..4 codes in mapping orientation.
+#include <math.h>
+#include "mmg_post.h"
+
+extern "C" int emu_post_frag(const HitOpt *opt, int idx_k, uint32_t hash, int n_segs, const int32_t *qlens, const uint8_t *const *reads, const uint8_t *flip,
+                             int n_ref, const uint8_t *const *refs, const uint32_t *ref_len, int n_u, const uint64_t *u_in, const mm128 *a_in, int rep_len,
+                             int32_t *n_regs_out, HitRec *regs_out, int regs_cap, uint32_t *xw_out, int64_t xw_cap, int64_t *xw_used)
+{
+	PostShard sh;
+	memset(&sh, 0, sizeof(sh));
+	sh.opt = *opt, sh.nf = 1, sh.n_seq = n_segs, sh.idx_k = idx_k;
+	// log tables: the host's own logf, exactly what the product builds at start-up
+	std::vector<float> ld(1 << 16), li(1 << 16);
+	for (int i = 0; i < (1 << 16); ++i) ld[i] = logf((float)i / opt->a), li[i] = logf((float)i);
+	sh.lt.ld = ld.data(), sh.lt.li = li.data(), sh.lt.n = 1 << 16;
+	// batch
+	std::vector<int32_t> n_seg(1, n_segs), seg_off(1, 0), seq_len(qlens, qlens + n_segs);
+	std::vector<uint64_t> q_off(n_segs + 1, 0);
+	for (int j = 0; j < n_segs; ++j) q_off[j + 1] = q_off[j] + ((uint64_t)qlens[j] + 7) / 8 * 8;
+	std::vector<uint32_t> Q(q_off[n_segs] / 8 + 4, 0);
+	for (int j = 0; j < n_segs; ++j) for (int i = 0; i < qlens[j]; ++i) Q[(q_off[j] + i) >> 3] |= (uint32_t)reads[j][i] << (((q_off[j] + i) & 7) << 2);
+	std::vector<uint64_t> ref_off(n_ref + 1, 0);
+	for (int j = 0; j < n_ref; ++j) ref_off[j + 1] = ref_off[j] + ref_len[j];
+	std::vector<uint32_t> S(ref_off[n_ref] / 8 + 4, 0);
+	for (int j = 0; j < n_ref; ++j) for (uint32_t i = 0; i < ref_len[j]; ++i) S[(ref_off[j] + i) >> 3] |= (uint32_t)refs[j][i] << (((ref_off[j] + i) & 7) << 2);
+	sh.n_seg = n_seg.data(), sh.seg_off = seg_off.data(), sh.seq_len = seq_len.data(), sh.q_off = q_off.data(), sh.flip = flip;
+	sh.Q = Q.data(), sh.S = S.data(), sh.ref_off = ref_off.data(), sh.ref_len = ref_len;
+	// chains
+	int64_t n_v = 0;
+	for (int i = 0; i < n_u; ++i) n_v += (int32_t)u_in[i];
+	std::vector<int32_t> nu(1, n_u), rep(1, rep_len);
+	std::vector<int64_t> uoff = {0, n_u}, voff = {0, n_v};
+	std::vector<uint64_t> u(u_in, u_in + n_u);
+	std::vector<mm128> a(a_in, a_in + n_v), a1(n_v + 1);
+	std::vector<uint32_t> hv(1, hash);
+	sh.nu = nu.data(), sh.rep = rep.data(), sh.uoff = uoff.data(), sh.voff = voff.data(), sh.u = u.data(), sh.a = a.data(), sh.hash = hv.data(), sh.a1 = a1.data();
+	const int m = n_u + 1;
+	std::vector<uint64_t> key_in(m), key(m), ascnt(m), cov(m);
+	std::vector<HitRec> r0(m);
+	std::vector<int32_t> w(m), n0(1);
+	std::vector<mm128> big(m);
+	std::vector<RsFrame> stack(m / 65 + 4);
+	sh.key_in = key_in.data(), sh.key = key.data(), sh.ascnt = ascnt.data(), sh.r0 = r0.data(), sh.w = w.data(), sh.cov = cov.data(), sh.big = big.data(), sh.stack = stack.data(), sh.n0 = n0.data();
+	std::vector<int32_t> cap(n_segs + 1, 0), n_reg(n_segs + 1, 0);
+	std::vector<int64_t> roff(n_segs + 2, 0), a1_off(n_segs + 1, 0);
+	std::vector<unsigned int> ctr(4, 0), n_jobs(1, 0);
+	sh.cap = cap.data(), sh.n_reg = n_reg.data(), sh.a1_off = a1_off.data(), sh.ctr = ctr.data(), sh.n_jobs = n_jobs.data();
+	// H1: keys as the key kernel writes them, the order the stable descending sort gives (emulated by its specification), records
+	{
+		std::vector<int64_t> pre(n_u + 1, 0);
+		for (int i = 0; i < n_u; ++i) pre[i + 1] = pre[i] + (int32_t)u[i];
+		std::vector<uint64_t> val_in(m);
+		for (int g = 0; g < n_u; ++g) post_chain_key(sh, g, pre.data(), key_in.data(), val_in.data());
+		std::vector<int> ord(n_u);
+		for (int i = 0; i < n_u; ++i) ord[i] = i;
+		std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return key_in[x] > key_in[y]; });
+		for (int i = 0; i < n_u; ++i) key[i] = key_in[ord[i]], ascnt[i] = val_in[ord[i]];
+		for (int g = 0; g < n_u; ++g) post_hit_record(sh, g);
+	}
+	post_hits_select(sh, 0);
+	for (int j = 0; j < n_segs; ++j) roff[j + 1] = roff[j] + cap[j];
+	const int64_t slots = roff[n_segs] + 1;
+	std::vector<HitRec> r1(slots), tmp1(slots);
+	std::vector<RegionPlan> pl(slots);
+	std::vector<uint32_t> xsize(slots, 0);
+	std::vector<int64_t> xoff(slots + 1, 0);
+	std::vector<uint64_t> skey(slots);
+	std::vector<int32_t> sidx(slots);
+	std::vector<mm128> sbig(slots);
+	std::vector<RsFrame> sstack(slots / 65 + 2 * n_segs + 4);
+	sh.roff = roff.data(), sh.r1 = r1.data(), sh.tmp1 = tmp1.data(), sh.pl = pl.data(), sh.xsize = xsize.data(), sh.xoff = xoff.data();
+	sh.skey = skey.data(), sh.sidx = sidx.data(), sh.sbig = sbig.data(), sh.sstack = sstack.data();
+	post_mates(sh, 0);
+	std::vector<uint32_t> xw;
+	if (opt->flag & HIT_F_CIGAR) {
+		int8_t mat[25];
+		for (int i = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) mat[i * 5 + j] = (int8_t)aln_mat(*opt, i, j);
+		for (int round = 0; round < 64; ++round) {
+			std::vector<DpJob> jobs(3 * slots + 4);
+			sh.jobs = jobs.data(), sh.job_cap = (unsigned int)jobs.size(), n_jobs[0] = 0, ctr[0] = 0;
+			for (int j = 0; j < n_segs; ++j) post_plan(sh, 0, j);
+			// K4, scalar
+			std::vector<DpRes> res(n_jobs[0] + 1);
+			std::vector<uint32_t> cig;
+			for (unsigned int k = 0; k < n_jobs[0]; ++k) {
+				const DpJob &jb = jobs[k];
+				const SeqView v = post_seq_view(sh, jb.seq_id);
+				std::vector<uint8_t> q(jb.q_len), t(jb.t_len);
+				for (int i = 0; i < jb.q_len; ++i) q[i] = (uint8_t)aln_q(v, jb.q_rev, jb.q_start + i);
+				for (int i = 0; i < jb.t_len; ++i) t[i] = (uint8_t)aln_t(v, jb.rid, jb.t_start + i);
+				if (jb.reversed) { std::reverse(q.begin(), q.end()); std::reverse(t.begin(), t.end()); }
+				std::vector<uint32_t> cg(jb.q_len + jb.t_len + 4);
+				KswEz ez;
+				emu_ksw(jb.q_len, q.data(), jb.t_len, t.data(), mat, opt->q, opt->e, opt->q2, opt->e2, jb.w, jb.zdrop, jb.end_bonus, jb.flag, &ez, cg.data());
+				res[k].ez = ez, res[k].cigar_off = cig.size();
+				cig.insert(cig.end(), cg.begin(), cg.begin() + ez.n_cigar);
+			}
+			cig.push_back(0);
+			sh.dp.res = res.data(), sh.dp.cig = cig.data();
+			for (int j = 0; j < n_segs; ++j) post_size(sh, j);
+			int64_t tot = 0;
+			for (int64_t s = 0; s < slots; ++s) { xoff[s] = tot; tot += xsize[s]; }
+			sh.x_base = (int64_t)xw.size();
+			xw.resize(xw.size() + tot + 1);
+			sh.xw = xw.data();
+			for (int j = 0; j < n_segs; ++j) post_build(sh, 0, j);
+			if (getenv("EMU_DEBUG")) { fprintf(stderr, "round %d: jobs %u new %u err %u;", round, n_jobs[0], ctr[0], ctr[1]); for (int j = 0; j < n_segs; ++j) { fprintf(stderr, " read %d cap %d:", j, cap[j]); for (int i = 0; i < n_reg[j]; ++i) fprintf(stderr, " [st %d cnt %d as %d split %u]", pl[roff[j] + i].state, r1[roff[j] + i].cnt, r1[roff[j] + i].as, HB_SPLIT(r1[roff[j] + i].bits)); } fprintf(stderr, "\n"); }
+			xw.pop_back();
+			if (ctr[0] == 0) break;
+		}
+		sh.xw = xw.data();
+		for (int j = 0; j < n_segs; ++j) post_final(sh, j);
+	}
+	sh.xw = xw.data();
+	post_finish(sh, 0);
+	if (ctr[1]) return -(int)ctr[1];
+	int64_t used = 0;
+	for (int j = 0; j < n_segs; ++j) {
+		n_regs_out[j] = n_reg[j];
+		if (n_reg[j] > regs_cap) return -100;
+		for (int i = 0; i < n_reg[j]; ++i) {
+			HitRec h = r1[roff[j] + i];
+			if (h.p) {
+				const HitExtra *x = hit_ext(xw.data(), h.p);
+				const int64_t wds = (int64_t)(sizeof(HitExtra) / 4) + x->n_cigar;
+				if (used + wds > xw_cap) return -101;
+				memcpy(xw_out + used, x, (size_t)wds * 4);
+				h.p = (uint64_t)used + 1, used += wds;
+			}
+			regs_out[(size_t)j * regs_cap + i] = h;
+		}
+	}
+	*xw_used = used;
+	return 0;
 }
