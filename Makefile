@@ -24,7 +24,7 @@ emu: $(BUILD)/libmmg_emu.so
 $(BUILD):
 	mkdir -p $(BUILD)
 
-$(BUILD)/mmg_post.o: $(HOST)/hits.c $(HOST)/aln.c $(HOST)/llsw.c $(HOST)/mm2b_priv.h include/minimap_b200.h
+$(BUILD)/mmg_post.o: $(CSRC)/mmg_hits.h $(CSRC)/mmg_aln.h $(CSRC)/mmg_post.h
 
 $(BUILD)/%.o: $(CSRC)/%.cu $(CSRC)/mmg_core.h $(CSRC)/mmg_ctx.cuh include/mmg.h | $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; false)

@@ -27,6 +27,18 @@ struct DevBuf {
 		cap = want;
 		return MMG_OK;
 	}
+	int ensure_keep(size_t bytes, size_t keep, cudaStream_t st) { // grow, carrying the first `keep` bytes over
+		if (bytes <= cap) return MMG_OK;
+		void *q = nullptr;
+		const size_t want = bytes + bytes / 2 + 256;
+		cudaError_t e = cudaMalloc(&q, want);
+		if (e != cudaSuccess) { mmg_set_error("cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); return MMG_ENOMEM; }
+		if (p && keep) { e = cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, st); if (e == cudaSuccess) e = cudaStreamSynchronize(st); }
+		if (e != cudaSuccess) { mmg_set_error("growing a device buffer: %s", cudaGetErrorString(e)); cudaFree(q); return MMG_ECUDA; }
+		if (p) cudaFree(p);
+		p = q, cap = want;
+		return MMG_OK;
+	}
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 	template <class T> T *as() const { return reinterpret_cast<T*>(p); }
 };
@@ -101,9 +113,13 @@ struct mmg_ctx_s {
 	DevBuf k_jobs, k_mem, k_H, k_p, k_cig, k_res, k_cig_out, k_cig_off;
 	const void *k_last_res = nullptr; // device {ez, cigar offset} array of the last ksw_launch
 	uint64_t k_last_jobs_fast = 0, k_last_cells_fast = 0, k_last_jobs_literal = 0, k_last_cells_literal = 0;
-	// post-chaining stages on the device (mmg_post.cu)
-	DevBuf p_shard, p_mi, p_seq, p_hash, p_nreg, p_reg, p_fr, p_tls, p_pool, p_ctr, p_nnew, p_joboff, p_jobs, p_sizes, p_offs, p_blob, p_perm, p_pre;
-	const void *p_mi_for = nullptr;
+	// post-chaining stages on the device (mmg_post.cu): flat arrays sized by prefix sums, kept across batches
+	enum { PB_SHARD, PB_HASH, PB_SEGOFF, PB_READ_FRAG, PB_PERM, PB_CNT, PB_PRE, PB_KEY_IN, PB_VAL_IN, PB_KEY, PB_ASCNT, PB_R0, PB_W, PB_COV, PB_BIG, PB_STACK, PB_N0,
+	       PB_CAP, PB_ROFF, PB_NREG, PB_R1, PB_TMP1, PB_PLAN, PB_XSIZE, PB_XOFF, PB_SKEY, PB_SIDX, PB_SBIG, PB_SSTACK, PB_A1, PB_A1OFF, PB_JOBS, PB_CTR, PB_XW,
+	       PB_SIZES, PB_OFFS, PB_BLOB, PB_LOGTAB, PB_COUNT };
+	DevBuf pb[PB_COUNT];
+	int post_logtab_a = 0;             // match score the resident logf tables were made for
+	int64_t last_tot_u = 0, last_tot_v = 0; // chains / chained anchors left on the device by the last mmg_seed_chain_resident
 	PinBuf h_p_hash, h_p_nreg, h_p_offs, h_p_blob, h_p_rep;
 	PinBuf h_in, h_meta, h_out_meta, h_out_u, h_out_a, h_out_mini, h_k_jobs, h_k_res, h_k_cig;
 };

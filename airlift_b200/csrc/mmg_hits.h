@@ -65,6 +65,23 @@ struct HitOpt {   // the fields of mm_mapopt_t / mm_idx_t these stages read
 #define HIT_F_HARD_MLEVEL  0x20000000LL
 #define HIT_F_SR           0x1000LL
 
+MMG_HD int mmg_popc(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+	return __popc(x);
+#else
+	return __builtin_popcount(x);
+#endif
+}
+MMG_HD int mmg_ffs(uint32_t x) // 1-based index of the lowest set bit, 0 if none
+{
+#ifdef __CUDA_ARCH__
+	return __ffs((int)x);
+#else
+	return __builtin_ffs((int)x);
+#endif
+}
+
 MMG_HD HitExtra *hit_ext(uint32_t *xw, uint64_t p) { return reinterpret_cast<HitExtra*>(xw + (p - 1)); }
 
 MMG_HD int32_t hit_span(const mm128 &an) { return (int32_t)(an.y >> 32 & 0xff); }
@@ -600,4 +617,85 @@ MMG_HDN inline bool hit_pair(int max_gap_ref, int pe_bonus, int sub_diff, int ma
 		}
 	}
 	return ok;
+}
+
+// ---- warp-cooperative mm_set_parent for fragments with many chains -------------------------------------------------------
+// A read pair drawn from a high-copy repeat arrives with thousands of chains.  The hits are still judged one after the other
+// (each against the primaries before it), but the two scans over the primaries that the judgement needs become O(1):
+//   * the part of hit i no primary covers (hit.c:128-141) is a population count: the query positions covered by ANY primary
+//     are kept as a bitmap, 32 positions per lane (a primary that does not overlap hit i covers none of its positions);
+//   * the first primary that masks hit i (hit.c:143-161) is found by one ballot over 32 primaries at a time.
+// The code is written against a tiny warp interface so that tests/emu/ can run it on the CPU: ballot(f) / sum(f) evaluate f(lane)
+// on every lane and combine; each(f) runs f(lane) on every lane; everything else is computed redundantly by all lanes.
+struct WarpEmu { // 32 lanes, one after the other
+	template <class F> unsigned ballot(F &&f) const { unsigned m = 0; for (int l = 0; l < 32; ++l) if (f(l)) m |= 1u << l; return m; }
+	template <class F> int sum(F &&f) const { int s = 0; for (int l = 0; l < 32; ++l) s += f(l); return s; }
+	template <class F> void each(F &&f) const { for (int l = 0; l < 32; ++l) f(l); }
+	template <class F> void one(F &&f) const { f(); }
+};
+#ifdef __CUDACC__
+struct WarpDev {
+	int lane;
+	template <class F> __device__ unsigned ballot(F &&f) const { return __ballot_sync(0xffffffffu, f(lane)); }
+	template <class F> __device__ int sum(F &&f) const { return __reduce_add_sync(0xffffffffu, f(lane)); }
+	template <class F> __device__ void each(F &&f) const { f(lane); __syncwarp(); }
+	template <class F> __device__ void one(F &&f) const { if (lane == 0) f(); __syncwarp(); }
+};
+#endif
+
+#define HIT_COVER_BITS 2048  // query positions the coverage bitmap holds (two words per lane)
+
+MMG_HD uint32_t hit_range_word(int s, int e, int word)
+{ // bits of [s, e) that fall into positions [32 word, 32 word + 32)
+	const int lo = s - 32 * word, hi = e - 32 * word;
+	if (hi <= 0 || lo >= 32) return 0;
+	const uint32_t a = lo <= 0 ? 0xffffffffu : 0xffffffffu << lo, b = hi >= 32 ? 0xffffffffu : ~(0xffffffffu << hi);
+	return a & b;
+}
+
+// n hits with 0 <= qs < qe <= HIT_COVER_BITS, no alignment records yet; w[]: n ints; cb[]: 64 words.  Result == hit_set_parent's.
+template <class W>
+MMG_HDN inline void hit_set_parent_warp(const W &wp, float mask_level, int n, HitRec *r, bool hard_mask_level, int32_t *w, uint32_t *cb)
+{
+	if (n <= 0) return;
+	wp.each([&](int l) { for (int i = l; i < n; i += 32) r[i].id = i; cb[l] = 0, cb[l + 32] = 0; });
+	wp.one([&]() { w[0] = 0, r[0].parent = 0; });
+	wp.each([&](int l) { cb[l] |= hit_range_word(r[0].qs, r[0].qe, l), cb[l + 32] |= hit_range_word(r[0].qs, r[0].qe, l + 32); });
+	int k = 1;
+	for (int i = 1; i < n; ++i) {
+		const int si = r[i].qs, ei = r[i].qe;
+		int uncov_len = 0, j = -1;
+		bool judge = true;
+		if (!hard_mask_level) {
+			const int cov = wp.sum([&](int l) { return (int)(mmg_popc(cb[l] & hit_range_word(si, ei, l)) + mmg_popc(cb[l + 32] & hit_range_word(si, ei, l + 32))); });
+			if (cov == 0) judge = false;
+			else uncov_len = (ei - si) - cov;
+		}
+		if (judge)
+			for (int base = 0; base < k && j < 0; base += 32) {
+				const unsigned m = wp.ballot([&](int l) {
+					const int t = base + l;
+					if (t >= k) return false;
+					const HitRec *rp = &r[w[t]];
+					const int sj = rp->qs, ej = rp->qe;
+					if (ej <= si || sj >= ei) return false;
+					const int mn = ej - sj < ei - si ? ej - sj : ei - si, mx = ej - sj > ei - si ? ej - sj : ei - si;
+					const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
+					return (float)ol / mn - (float)uncov_len / mx > mask_level;
+				});
+				if (m) j = base + mmg_ffs(m) - 1;
+			}
+		if (j >= 0) {
+			wp.one([&]() {
+				HitRec *ri = &r[i], *rp = &r[w[j]];
+				ri->parent = rp->parent;
+				rp->subsc = rp->subsc > ri->score ? rp->subsc : ri->score;
+				if (ri->cnt >= rp->cnt) ++rp->n_sub;
+			});
+		} else {
+			wp.one([&]() { w[k] = i, r[i].parent = i, r[i].n_sub = 0; });
+			wp.each([&](int l) { cb[l] |= hit_range_word(si, ei, l), cb[l + 32] |= hit_range_word(si, ei, l + 32); });
+			++k;
+		}
+	}
 }

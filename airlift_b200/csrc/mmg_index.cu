@@ -51,7 +51,9 @@ extern "C" void mmg_destroy(mmg_ctx_t *c)
 		&c->d2_a, &c->d2_work, &c->d2_u, &c->d2_b, &c->d2_stack, &c->d2_frag_nu, &c->d2_frag_nv, &c->k_jobs, &c->k_mem, &c->k_H,
 		&c->k_p, &c->k_cig, &c->k_res, &c->k_cig_out, &c->k_cig_off};
 	for (DevBuf *b : bufs) b->release();
-	PinBuf *pins[] = {&c->h_in, &c->h_meta, &c->h_out_meta, &c->h_out_u, &c->h_out_a, &c->h_out_mini, &c->h_k_jobs, &c->h_k_res, &c->h_k_cig};
+	for (DevBuf &b : c->pb) b.release();
+	PinBuf *pins[] = {&c->h_in, &c->h_meta, &c->h_out_meta, &c->h_out_u, &c->h_out_a, &c->h_out_mini, &c->h_k_jobs, &c->h_k_res, &c->h_k_cig,
+	                  &c->h_p_hash, &c->h_p_nreg, &c->h_p_offs, &c->h_p_blob, &c->h_p_rep};
 	for (PinBuf *b : pins) b->release();
 	for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (const ProfRec &r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -1,505 +1,156 @@
-// mmg_post.cu -- everything between chaining and MAPQ on the device, for the short-read presets.
+// mmg_post.cu -- everything between chaining and the hit records handed back to the caller, on the device, for the
+// short-read presets: hits, primary/secondary tree, per-mate split, base-level alignment around batched DP, filters,
+// MAPQ, pairing (map.c:376-406 per fragment in the reference).
 //
-// The reference does this bookkeeping per fragment inside mm_map_frag (map.c:376-400): chains -> mm_reg1_t
-// (hit.c), primary/secondary selection, per-mate split (mm_seg_gen), the alignment skeleton with its DP calls
-// (align.c), CIGAR post-processing, filters.  The host build of this repository runs the same steps from
-// airlift_b200/host/{hits,aln}.c on the worker threads, which made the step host-bound.
-// Here the SAME C SOURCES are compiled for the device (MM_DEVICE_BUILD, MM_FN = __device__) and run one fragment per
-// thread, with the resumable DP-request mechanism of aln.c feeding K4 directly in device memory:
+// The work is laid out as data-parallel steps over flat arrays (mmg_post.h): one thread per chain builds hit records from
+// device-sorted keys, one thread per fragment / read runs the small serial pieces on its own slots, the DP jobs of all
+// reads go through K4 in one batch per round, and a prefix sum reserves the room of every alignment record before it is
+// written.  There is no device-side heap and no per-fragment object; nothing here includes host sources.
 //
-//     k_post_hits      chains -> hits -> per-mate regions -> first walk (queues the DP jobs)
-//   { k_post_gather    jobs of all fragments -> one dense array
-//     K4               mmg_ksw_device (results stay on the device)
-//     k_post_align   } results -> job caches, re-walk (CIGAR stitching, mm_update_extra, filters, sorting)
-//     k_post_sizes/pack  mm_reg1_t + mm_extra_t of every read -> one blob -> one D2H
-//
-// MAPQ and pairing (logf), the mate un-flip and the malloc'd API objects are made by the host from the blob.
-// Memory for the per-fragment state comes from a bump pool in HBM (one atomicAdd per 2 KB chunk per thread).
+//     k_post_cnt/keys   chain -> sort key (device-wide scan gives the first anchor of every chain)
+//     segmented sort    keys of every fragment in the reference's hit order (stable, descending; see hit_order_desc)
+//     k_post_records    hit records with coordinates                      [thread per chain]
+//     k_post_select     tree + secondary selection                         [thread per fragment; warp per fragment above 32 chains]
+//     k_post_mates      per-mate hit lists                                 [thread per fragment]
+//   { k_post_plan       stretch, windows, DP jobs                          [thread per read]
+//     K4                mmg_ksw_device
+//     k_post_size/build CIGAR stitching, coordinates, clean-up, cuts }     [thread per read]   (one round unless a hit is cut)
+//     k_post_final      filters, order, tree, selection                    [thread per read]
+//     k_post_finish     MAPQ, pairing, mate un-flip                        [thread per fragment]
+//     k_post_sizes/pack records of every read -> one blob -> one D2H
 #include <cub/cub.cuh>
 #include <math.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <stdint.h>
-#include <assert.h>
-#include <ctype.h>
-#include <pthread.h>
 #include "mmg_ctx.cuh"
+#include "mmg_post.h"
 
 int mmg_ksw_device(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, int n_jobs, const mmg_ksw_job_t *d_jobs, const void **d_res,
                    const uint32_t **d_cigars, double *kernel_ms, uint64_t *cells);
 
-// The mapper's types and C sources live in a namespace of their own in this translation unit: the same declarations exist
-// as host functions in the library, and the device twins must not be confused with them.
-namespace mmdev {
-#define MM_FN __device__
-#define MM_DEVICE_BUILD 1
-#include "../host/mm2b_priv.h"
+static_assert(sizeof(DpJob) == sizeof(mmg_ksw_job_t), "DpJob must match mmg_ksw_job_t");
+static_assert(sizeof(HitRec) == 80 && sizeof(HitExtra) == 24, "record layouts");
 
-struct KswResD { mmg_extz_t ez; uint64_t cigar_off; }; // == KswResDev of mmg_ksw.cu
+// ---- kernels: one work item per thread, all logic in mmg_post.h ------------------------------------------------------
+#define POST_TID ((int64_t)blockIdx.x * blockDim.x + threadIdx.x)
 
-struct Tls { char *cur, *end; };
-
-struct DFrag {
-	int n_segs, qlen_sum, frag_gap, active, n_regs0, n_u;
-	uint32_t hash;
-	int *qlens;
-	mm128_t *a;
-	uint64_t *u;
-	mm_reg1_t *regs0;
-	mm_seg_t *seg;
-	mm_alnseg_t *aln;
-};
-
-struct Shard {
-	const mm_idx_t *mi;
-	mm_mapopt_t opt;
-	int nf, n_seq, nt;                          // nt: threads of the per-fragment kernels (nf rounded up to whole warps)
-	const int32_t *n_seg, *seg_off, *seq_len;   // per fragment / per read of the resident batch
-	const uint64_t *q_off;
-	const uint32_t *Q;
-	const int32_t *nu, *nv;                     // chains per fragment (dense outputs of mmg_seed_chain_resident)
-	const int64_t *uoff, *voff;
-	uint64_t *u;
-	mm128_t *a;
-	const uint32_t *hash;
-	mm_reg1_t **pre_regs;                       // per fragment: mm_gen_regs output made by k_post_regs_heavy (or null)
-	const int32_t *perm;                        // thread -> fragment: fragments with similar amounts of work share a warp
-	int32_t *n_reg;                             // per read
-	mm_reg1_t **reg;
-	DFrag *fr;
-	Tls *tls;
-	char *pool;
-	unsigned long long pool_size;
-	unsigned long long *pool_cur;               // [0] bump cursor, [1] active fragments, [2] error flag, [3] debug: longest thread (cycles << 20 | chains)
-	int32_t *n_new;                             // per fragment: DP jobs queued by the last walk
-	const int64_t *job_off;
-	mmg_ksw_job_t *jobs;
-	const KswResD *res;
-	const uint32_t *cig;
-};
-
-// ---- device runtime the C sources run on --------------------------------------------------------------------
-extern __shared__ __align__(16) unsigned char dyn_smem[];
-__device__ __forceinline__ Shard *cur_shard() { return *reinterpret_cast<Shard**>(dyn_smem); }
-__device__ __forceinline__ int cur_tid() { return blockIdx.x * blockDim.x + threadIdx.x; }
-
-#define POOL_CHUNK 4096
-
-__device__ void *dev_malloc(size_t n)
-{ // 16-byte header (the size, for realloc) + payload, bumped inside the thread's current chunk
-	Shard *sh = cur_shard();
-	Tls *t = &sh->tls[cur_tid()];
-	const size_t need = ((n + 15) & ~(size_t)15) + 16;
-	if (t->cur == nullptr || t->cur + need > t->end) {
-		const size_t chunk = need > POOL_CHUNK ? need : POOL_CHUNK;
-		const unsigned long long o = atomicAdd(sh->pool_cur, (unsigned long long)chunk);
-		if (o + chunk > sh->pool_size) { // out of pool: flag it; the host reports and stops (no CPU fallback hides it)
-			atomicExch(sh->pool_cur + 2, 1ULL);
-			asm volatile("trap;");
-		}
-		if (need > POOL_CHUNK) { // a large block gets its own chunk; the current one keeps filling
-			char *p = sh->pool + o;
-			*reinterpret_cast<size_t*>(p) = n;
-			return p + 16;
-		}
-		t->cur = sh->pool + o, t->end = t->cur + chunk;
-	}
-	char *p = t->cur;
-	t->cur += need;
-	*reinterpret_cast<size_t*>(p) = n;
-	return p + 16;
-}
-// memcpy / memset / memmove of the C sources: pool blocks are 16-byte aligned, CIGARs and records are word arrays, so
-// almost every call can move 16 or 4 bytes per step instead of the byte loop the compiler emits for unknown alignment
-__device__ void *dev_memcpy(void *dst, const void *src, size_t n)
+__global__ void k_post_cnt(const uint64_t *__restrict__ u, int64_t n, int32_t *__restrict__ cnt)
 {
-	const size_t a = reinterpret_cast<size_t>(dst) | reinterpret_cast<size_t>(src);
-	size_t i = 0;
-	if ((a & 15) == 0) { uint4 *d = static_cast<uint4*>(dst); const uint4 *s = static_cast<const uint4*>(src); for (; i + 16 <= n; i += 16) d[i >> 4] = s[i >> 4]; }
-	if ((a & 3) == 0) { uint32_t *d = static_cast<uint32_t*>(dst); const uint32_t *s = static_cast<const uint32_t*>(src); for (; i + 4 <= n; i += 4) d[i >> 2] = s[i >> 2]; }
-	for (; i < n; ++i) static_cast<unsigned char*>(dst)[i] = static_cast<const unsigned char*>(src)[i];
-	return dst;
+	const int64_t g = POST_TID;
+	if (g < n) cnt[g] = (int32_t)u[g];
 }
-__device__ void *dev_memset(void *dst, int v, size_t n)
+
+__global__ void k_post_keys(const PostShard *__restrict__ shp, int64_t n, const int64_t *__restrict__ pre, uint64_t *__restrict__ key_in, uint64_t *__restrict__ val_in)
 {
-	const size_t a = reinterpret_cast<size_t>(dst);
-	const uint32_t w = 0x01010101u * (uint32_t)(unsigned char)v;
-	size_t i = 0;
-	if ((a & 15) == 0) { uint4 *d = static_cast<uint4*>(dst); const uint4 q = make_uint4(w, w, w, w); for (; i + 16 <= n; i += 16) d[i >> 4] = q; }
-	if ((a & 3) == 0) { uint32_t *d = static_cast<uint32_t*>(dst); for (; i + 4 <= n; i += 4) d[i >> 2] = w; }
-	for (; i < n; ++i) static_cast<unsigned char*>(dst)[i] = (unsigned char)v;
-	return dst;
+	const int64_t g = POST_TID;
+	if (g < n) post_chain_key(*shp, g, pre, key_in, val_in);
 }
-__device__ void *dev_memmove(void *dst, const void *src, size_t n)
+
+__global__ void k_post_records(const PostShard *__restrict__ shp, int64_t n)
 {
-	unsigned char *d = static_cast<unsigned char*>(dst); const unsigned char *s = static_cast<const unsigned char*>(src);
-	if (d <= s || d >= s + n) return dev_memcpy(dst, src, n); // a forward copy never overwrites unread source bytes
-	if (((reinterpret_cast<size_t>(d) | reinterpret_cast<size_t>(s) | n) & 7) == 0) {
-		uint64_t *dd = static_cast<uint64_t*>(dst); const uint64_t *ss = static_cast<const uint64_t*>(src);
-		for (size_t i = n >> 3; i > 0; --i) dd[i - 1] = ss[i - 1];
-	} else for (size_t i = n; i > 0; --i) d[i - 1] = s[i - 1];
-	return dst;
+	const int64_t g = POST_TID;
+	if (g < n) post_hit_record(*shp, g);
 }
-__device__ void *dev_calloc(size_t n, size_t sz) { void *p = dev_malloc(n * sz); dev_memset(p, 0, n * sz); return p; }
-__device__ void *dev_realloc(void *p, size_t n)
+
+__global__ void k_post_perm_keys(int nf, const int32_t *__restrict__ nu, uint32_t *__restrict__ key, int32_t *__restrict__ idx)
+{ // fragments with the most chains first, so that a warp holds fragments of similar weight
+	const int i = (int)POST_TID;
+	if (i < nf) key[i] = ~(uint32_t)nu[i], idx[i] = i;
+}
+
+__global__ void __launch_bounds__(128) k_post_select(const PostShard *__restrict__ shp, const int32_t *__restrict__ perm)
+{ // fragments with few chains: one thread each
+	const int t = (int)POST_TID;
+	if (t >= shp->nf) return;
+	const int f = perm[t];
+	if (shp->nu[f] <= POST_WARP_MIN_CHAINS) post_hits_select(*shp, f);
+}
+
+__global__ void __launch_bounds__(128) k_post_select_warp(const PostShard *__restrict__ shp, const int32_t *__restrict__ perm)
+{ // fragments with many chains (read pairs from high-copy repeats): one warp each; perm lists them first
+	const int t = (int)(POST_TID >> 5);
+	if (t >= shp->nf) return;
+	const int f = perm[t];
+	if (shp->nu[f] <= POST_WARP_MIN_CHAINS) return;
+	WarpDev wp = {(int)(threadIdx.x & 31)};
+	post_hits_select_warp(wp, *shp, f);
+}
+
+__global__ void __launch_bounds__(128) k_post_mates(const PostShard *__restrict__ shp, const int32_t *__restrict__ perm)
 {
-	void *q = dev_malloc(n);
-	if (p) { const size_t old = *reinterpret_cast<size_t*>(static_cast<char*>(p) - 16); dev_memcpy(q, p, old < n ? old : n); }
-	return q;
+	const int t = (int)POST_TID;
+	if (t < shp->nf) post_mates(*shp, perm[t]);
 }
 
-// the arena interface of mm2b_priv.h, on the pool
-__device__ void *mm_amalloc(size_t n) { return dev_malloc(n); }
-__device__ void *mm_acalloc(size_t n, size_t sz) { return dev_calloc(n, sz); }
-__device__ void *mm_arealloc(void *p, size_t old_bytes, size_t new_bytes) { void *q = dev_malloc(new_bytes); if (p && old_bytes) dev_memcpy(q, p, old_bytes < new_bytes ? old_bytes : new_bytes); return q; }
-__device__ void mm_afree(void *) {}
-
-__device__ int mm_idx_getseq_dev(const mm_idx_t *mi, uint32_t rid, uint32_t st, uint32_t en, uint8_t *seq)
-{ // index.c:152-162 on the device copy of the index header (S, seq[] are device pointers)
-	if (rid >= mi->n_seq || st >= mi->seq[rid].len) return -1;
-	if (en > mi->seq[rid].len) en = mi->seq[rid].len;
-	const uint64_t st1 = mi->seq[rid].offset + st, en1 = mi->seq[rid].offset + en;
-	uint64_t i = st1;
-	for (; i < en1 && (i & 7); ++i) seq[i - st1] = mm_seq4_get(mi->S, i);
-	for (; i + 8 <= en1; i += 8) { // one packed word = 8 bases
-		uint32_t w = mi->S[i >> 3];
-		uint8_t *o = seq + (i - st1);
-#pragma unroll
-		for (int k = 0; k < 8; ++k) o[k] = (uint8_t)(w >> (4 * k) & 0xf);
-	}
-	for (; i < en1; ++i) seq[i - st1] = mm_seq4_get(mi->S, i);
-	return (int)(en - st);
-}
-
-// ---- the C sources, compiled for the device -------------------------------------------------------------------
-#define malloc(n) mmdev::dev_malloc(n)
-#define calloc(n, s) mmdev::dev_calloc(n, s)
-#define realloc(p, n) mmdev::dev_realloc(p, n)
-#define free(p) ((void)(p))
-#define memmove(d, s, n) mmdev::dev_memmove(d, s, n)
-#define memcpy(d, s, n) mmdev::dev_memcpy(d, s, n)
-#define memset(d, v, n) mmdev::dev_memset(d, v, n)
-#define fprintf(...) ((void)0)
-#define exit(c) asm volatile("trap;")
-#define mm_verbose 0
-#define mm_idx_getseq mm_idx_getseq_dev /* the header's name has C linkage and belongs to the host library */
-#undef assert
-#define assert(x) ((void)0)
-
-RADIX_IMPL(radix_sort_128x, mm128_t, RS_KEY_X, RS_TABLES_ARENA)
-RADIX_IMPL(radix_sort_64, uint64_t, RS_KEY_ID, RS_TABLES_ARENA)
-
-#include "../host/llsw.c"
-#include "../host/hits.c"
-#include "../host/aln.c"
-
-#undef malloc
-#undef calloc
-#undef realloc
-#undef free
-#undef memmove
-#undef memcpy
-#undef memset
-#undef fprintf
-#undef exit
-#undef mm_verbose
-#undef mm_idx_getseq
-
-// ---- per-fragment stages (the device twins of mapper.c's stage_hits / stage_align / stage_scatter_results) -----
-
-__device__ __forceinline__ int chain_gap_ref(const mm_mapopt_t *opt, int qlen_sum)
-{ // map.c:344-349
-	if (opt->max_gap_ref > 0) return opt->max_gap_ref;
-	if (opt->max_frag_len > 0) { const int g = opt->max_frag_len - qlen_sum; return g < opt->max_gap ? opt->max_gap : g; }
-	return opt->max_gap;
-}
-
-// one resumable pass over the regions of an active fragment (align_regs, map.c:260-270); returns the jobs it queued
-__device__ int frag_walk(Shard *sh, int i)
+__global__ void __launch_bounds__(128) k_post_plan(const PostShard *__restrict__ shp, const int32_t *__restrict__ read_frag)
 {
-	DFrag *fr = &sh->fr[i];
-	const mm_mapopt_t *opt = &sh->opt;
-	int all_done = 1, n_new = 0;
-	if (!fr->active) return 0;
-	for (int j = 0; j < fr->n_segs; ++j) {
-		mm_alnseg_t *s = &fr->aln[j];
-		const int off = sh->seg_off[i] + j;
-		if (s->finished) continue;
-		if (mm_aln_step(s, opt, sh->mi)) {
-			if (!(opt->flag & MM_F_ALL_CHAINS)) {
-				mm_set_parent(opt->mask_level, s->n_regs, s->regs, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL);
-				mm_select_sub(opt->pri_ratio, sh->mi->k * 2, opt->best_n, &s->n_regs, s->regs);
-				mm_set_sam_pri(s->n_regs, s->regs);
-			}
-			sh->n_reg[off] = s->n_regs, sh->reg[off] = s->regs;
-		} else all_done = 0;
-		n_new += s->cache.n - s->cache.n_sent;
-	}
-	if (all_done) fr->active = 0;
-	return n_new;
+	const int r = (int)POST_TID;
+	if (r < shp->n_seq) post_plan(*shp, read_frag[r], r);
 }
 
-__global__ void __launch_bounds__(128, 5) k_post_hits(Shard *shp)
-{ // chains -> hits for one fragment per thread (map.c:376-388, 390-400 up to the DP), then the first walk
-	if (threadIdx.x == 0) *reinterpret_cast<Shard**>(dyn_smem) = shp;
-	__syncthreads();
-	Shard *sh = shp;
-	if (cur_tid() >= sh->nt) return;
-	const int i = sh->perm[cur_tid()];
-	if (i < 0) return;
-	const long long t_begin = clock64();
-	const mm_mapopt_t *opt = &sh->opt;
-	const mm_idx_t *mi = sh->mi;
-	const int off = sh->seg_off[i], ns = sh->n_seg[i];
-	DFrag *fr = &sh->fr[i];
-	sh->tls[cur_tid()].cur = sh->tls[cur_tid()].end = nullptr;
-	memset(fr, 0, sizeof(*fr));
-	sh->n_new[i] = 0;
-	fr->n_segs = ns;
-	fr->qlens = (int*)mm_amalloc((size_t)(ns > 0 ? ns : 1) * sizeof(int));
-	for (int j = 0; j < ns; ++j) {
-		sh->n_reg[off + j] = 0, sh->reg[off + j] = nullptr;
-		fr->qlens[j] = sh->seq_len[off + j], fr->qlen_sum += fr->qlens[j];
-	}
-	if (fr->qlen_sum == 0 || ns <= 0 || ns > MM_MAX_SEG) return;
-	if (opt->max_qlen > 0 && fr->qlen_sum > opt->max_qlen) return;
-	fr->hash = sh->hash[i];
-	fr->frag_gap = chain_gap_ref(opt, fr->qlen_sum);
-	fr->n_u = sh->nu[i];
-	if (fr->n_u > 0) fr->u = sh->u + sh->uoff[i], fr->a = sh->a + sh->voff[i]; // used in place
-	fr->regs0 = sh->pre_regs[i] ? sh->pre_regs[i] : mm_gen_regs(fr->hash, fr->qlen_sum, fr->n_u, fr->u, fr->a);
-	fr->n_regs0 = fr->n_u;
-	const bool dbg_big = fr->n_u > 1000;
-	long long t_ph = clock64();
-#define PHASE(k) do { if (dbg_big) { const long long t_ = clock64(); atomicMax(sh->pool_cur + 5 + (k), (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
-	PHASE(0);
-	if (!(opt->flag & MM_F_ALL_CHAINS)) { // chain_post, map.c:249-258
-		mm_set_parent(opt->mask_level, fr->n_regs0, fr->regs0, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL);
-		PHASE(1);
-		if (ns <= 1) mm_select_sub(opt->pri_ratio, mi->k * 2, opt->best_n, &fr->n_regs0, fr->regs0);
-		else mm_select_sub_multi(opt->pri_ratio, 0.2f, 0.7f, fr->frag_gap, mi->k * 2, opt->best_n, ns, fr->qlens, &fr->n_regs0, fr->regs0);
-		if (!(opt->flag & (MM_F_SPLICE|MM_F_SR|MM_F_NO_LJOIN))) mm_join_long(opt, fr->qlen_sum, &fr->n_regs0, fr->regs0, fr->a);
-	}
-	PHASE(2);
-	fr->aln = (mm_alnseg_t*)mm_acalloc(ns, sizeof(mm_alnseg_t));
-	if (ns == 1) {
-		sh->n_reg[off] = fr->n_regs0, sh->reg[off] = fr->regs0;
-		mm_aln_begin(&fr->aln[0], off, fr->qlens[0], nullptr, fr->n_regs0, fr->regs0, fr->a);
-		fr->aln[0].q4 = sh->Q, fr->aln[0].q4_off = sh->q_off[off];
-	} else {
-		fr->seg = mm_seg_gen(fr->hash, ns, fr->qlens, fr->n_regs0, fr->regs0, &sh->n_reg[off], &sh->reg[off], fr->a);
-		for (int j = 0; j < ns; ++j) {
-			mm_set_parent(opt->mask_level, sh->n_reg[off + j], sh->reg[off + j], opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL);
-			mm_aln_begin(&fr->aln[j], off + j, fr->qlens[j], nullptr, sh->n_reg[off + j], sh->reg[off + j], fr->seg[j].a);
-			fr->aln[j].q4 = sh->Q, fr->aln[j].q4_off = sh->q_off[off + j];
-		}
-	}
-	PHASE(3);
-	fr->active = (opt->flag & MM_F_CIGAR) ? 1 : 0;
-	if (fr->active) {
-		const int n_new = frag_walk(sh, i);
-		sh->n_new[i] = n_new;
-		if (fr->active) atomicAdd(sh->pool_cur + 1, 1ULL);
-	}
-	PHASE(4);
-#undef PHASE
-	{ // debug aid (MMG_POST_DEBUG): the longest-running thread of the launch and how many chains its fragment had
-		const unsigned long long dt = (unsigned long long)(clock64() - t_begin);
-		atomicMax(sh->pool_cur + 3, dt << 20 | (unsigned long long)(fr->n_u < 0xfffff ? fr->n_u : 0xfffff));
-	}
-}
-
-__global__ void __launch_bounds__(128) k_post_gather(Shard *shp)
-{ // copy the DP jobs a fragment queued in this round into the dense job array
-	Shard *sh = shp;
-	if (cur_tid() >= sh->nt) return;
-	const int i = sh->perm[cur_tid()];
-	if (i < 0) return;
-	const DFrag *fr = &sh->fr[i];
-	if (!fr->active) return;
-	int64_t k = sh->job_off[i];
-	for (int j = 0; j < fr->n_segs; ++j) {
-		const mm_dpcache_t *c = &fr->aln[j].cache;
-		for (int q = c->n_sent; q < c->n; ++q) sh->jobs[k++] = c->a[q].job;
-	}
-}
-
-__global__ void __launch_bounds__(128, 5) k_post_align(Shard *shp)
-{ // hand the results of this round back to the job caches (in the order they were gathered), then re-walk
-	if (threadIdx.x == 0) *reinterpret_cast<Shard**>(dyn_smem) = shp;
-	__syncthreads();
-	Shard *sh = shp;
-	if (cur_tid() >= sh->nt) return;
-	const int i = sh->perm[cur_tid()];
-	if (i < 0) return;
-	DFrag *fr = &sh->fr[i];
-	if (!fr->active) { sh->n_new[i] = 0; return; }
-	int64_t k = sh->job_off[i];
-	for (int j = 0; j < fr->n_segs; ++j) {
-		mm_dpcache_t *c = &fr->aln[j].cache;
-		for (; c->n_sent < c->n; ++c->n_sent, ++k) {
-			mm_dpjob_t *dj = &c->a[c->n_sent];
-			dj->ez = sh->res[k].ez;
-			if (dj->ez.n_cigar > 0) {
-				dj->cigar = (uint32_t*)mm_amalloc((size_t)dj->ez.n_cigar * 4);
-				const uint32_t *src = sh->cig + sh->res[k].cigar_off;
-				for (int q = 0; q < dj->ez.n_cigar; ++q) dj->cigar[q] = src[q];
-			}
-			dj->done = 1;
-		}
-	}
-	const int n_new = frag_walk(sh, i);
-	sh->n_new[i] = n_new;
-	if (fr->active) atomicAdd(sh->pool_cur + 1, 1ULL);
-}
-
-
-// ---- mm_gen_regs (hit.c:52-88) for fragments with many chains, one CTA per fragment ---------------------------------
-// A read pair from a high-copy repeat arrives with thousands of chains over ~10^5 anchors; walked by the single thread
-// of k_post_hits it set the duration of the whole launch (34 ms).  The sort key (score, salted hash of the first
-// anchor) is unique per chain unless two 32-bit hashes collide, so any sort gives klib's order; a collision is detected
-// and leaves the fragment to the literal serial code.
-#define POST_HEAVY_NU 128
-
-__global__ void k_post_heavy_list(int nf, const int32_t *nu, int32_t *list, unsigned long long *counter)
+__global__ void __launch_bounds__(128) k_post_size(const PostShard *__restrict__ shp)
 {
-	const int i = cur_tid();
-	if (i < nf && nu[i] > POST_HEAVY_NU) list[atomicAdd(counter, 1ULL)] = i;
+	const int r = (int)POST_TID;
+	if (r < shp->n_seq) post_size(*shp, r);
 }
 
-__global__ void __launch_bounds__(256) k_post_regs_heavy(Shard *shp, const int32_t *list)
+__global__ void __launch_bounds__(128) k_post_build(const PostShard *__restrict__ shp, const int32_t *__restrict__ read_frag)
 {
-	Shard *sh = shp;
-	const int i = list[blockIdx.x], n = sh->nu[i], tid = threadIdx.x, nt = blockDim.x;
-	const uint64_t *u = sh->u + sh->uoff[i];
-	const mm128_t *a = sh->a + sh->voff[i];
-	__shared__ char *s_base;
-	__shared__ int s_scan[256], s_carry, s_tie;
-	const size_t z_bytes = ((size_t)n * 16 + 15) & ~(size_t)15, r_bytes = (((size_t)n * sizeof(mm_reg1_t)) + 15) & ~(size_t)15;
-	if (tid == 0) {
-		const unsigned long long o = atomicAdd(sh->pool_cur, (unsigned long long)(z_bytes + r_bytes + 32));
-		if (o + z_bytes + r_bytes + 32 > sh->pool_size) { atomicExch(sh->pool_cur + 2, 1ULL); asm volatile("trap;"); }
-		s_base = sh->pool + o;
-		s_carry = 0, s_tie = 0;
-	}
-	__syncthreads();
-	mm128_t *z = reinterpret_cast<mm128_t*>(s_base + 16);
-	char *rblk = s_base + 16 + z_bytes;
-	mm_reg1_t *r = reinterpret_cast<mm_reg1_t*>(rblk + 16);
-	if (tid == 0) *reinterpret_cast<size_t*>(s_base) = (size_t)n * 16, *reinterpret_cast<size_t*>(rblk) = (size_t)n * sizeof(mm_reg1_t); // block headers (realloc reads them)
-	int qlen = 0;
-	for (int j = 0; j < sh->n_seg[i]; ++j) qlen += sh->seq_len[sh->seg_off[i] + j];
-	// first anchor of every chain: exclusive scan of the chain lengths, 256 at a time
-	for (int i0 = 0; i0 < n; i0 += nt) {
-		const int e = i0 + tid, cnt = e < n ? (int32_t)u[e] : 0;
-		s_scan[tid] = cnt;
-		__syncthreads();
-		for (int d = 1; d < nt; d <<= 1) { const int v = tid >= d ? s_scan[tid - d] : 0; __syncthreads(); s_scan[tid] += v; __syncthreads(); }
-		const int k = s_carry + s_scan[tid] - cnt;
-		if (e < n) {
-			const uint32_t h = (uint32_t)mix64((mix64(a[k].x) + mix64(a[k].y)) ^ sh->hash[i]);
-			z[e].x = u[e] ^ h, z[e].y = (uint64_t)k << 32 | (uint32_t)(int32_t)u[e];
-		}
-		__syncthreads();
-		if (tid == nt - 1) s_carry += s_scan[tid];
-		__syncthreads();
-	}
-	// descending by x: bitonic network oriented one way, so the virtual entries beyond n never move
-	int N = 2; while (N < n) N <<= 1;
-	for (int k = 2; k <= N; k <<= 1) {
-		for (int e = tid; e < n; e += nt) { const int l = e ^ (k - 1); if (l > e && l < n) { const mm128_t x = z[e], y = z[l]; if (y.x > x.x) z[e] = y, z[l] = x; } }
-		__syncthreads();
-		for (int j = k >> 2; j > 0; j >>= 1) {
-			for (int e = tid; e < n; e += nt) { const int l = e ^ j; if (l > e && l < n) { const mm128_t x = z[e], y = z[l]; if (y.x > x.x) z[e] = y, z[l] = x; } }
-			__syncthreads();
-		}
-	}
-	for (int e = tid + 1; e < n; e += nt) if (z[e].x == z[e - 1].x) s_tie = 1;
-	__syncthreads();
-	if (s_tie) return; // equal keys: klib's unstable order matters, k_post_hits runs the literal mm_gen_regs
-	for (int e = tid; e < n; e += nt) {
-		mm_reg1_t *ri = &r[e];
-		memset(ri, 0, sizeof(*ri));
-		ri->id = e, ri->parent = MM_PARENT_UNSET;
-		ri->score = ri->score0 = (int32_t)(z[e].x >> 32);
-		ri->hash = (uint32_t)z[e].x;
-		ri->cnt = (int32_t)z[e].y, ri->as = (int32_t)(z[e].y >> 32);
-		ri->div = -1.0f;
-		reg_set_coor(ri, qlen, a);
-	}
-	if (tid == 0) sh->pre_regs[i] = r;
+	const int r = (int)POST_TID;
+	if (r < shp->n_seq) post_build(*shp, read_frag[r], r);
 }
 
-// ---- results: every read's mm_reg1_t array followed by the mm_extra_t of each hit, 8-byte aligned pieces
-__device__ __forceinline__ size_t extra_bytes(const mm_extra_t *p) { return (sizeof(mm_extra_t) + (size_t)p->n_cigar * 4 + 7) & ~(size_t)7; }
-
-__global__ void k_post_sizes(Shard *shp, int64_t *sizes)
+__global__ void __launch_bounds__(128) k_post_final(const PostShard *__restrict__ shp)
 {
-	Shard *sh = shp;
-	const int r = cur_tid();
-	if (r > sh->n_seq) return;
+	const int r = (int)POST_TID;
+	if (r < shp->n_seq) post_final(*shp, r);
+}
+
+__global__ void __launch_bounds__(128) k_post_finish(const PostShard *__restrict__ shp)
+{
+	const int f = (int)POST_TID;
+	if (f < shp->nf) post_finish(*shp, f);
+}
+
+// ---- results: every read's hit records followed by the alignment record of each hit, 8-byte aligned pieces
+__device__ __forceinline__ int64_t post_extra_bytes(const HitExtra *x) { return (int64_t)((sizeof(HitExtra) + (size_t)x->n_cigar * 4 + 7) & ~(size_t)7); }
+
+__global__ void k_post_sizes(const PostShard *__restrict__ shp, int64_t *__restrict__ sizes)
+{
+	const PostShard &sh = *shp;
+	const int r = (int)POST_TID;
+	if (r > sh.n_seq) return;
 	int64_t b = 0;
-	if (r < sh->n_seq) {
-		const int n = sh->n_reg[r];
-		b = (int64_t)n * (int64_t)sizeof(mm_reg1_t);
-		for (int i = 0; i < n; ++i) if (sh->reg[r][i].p) b += (int64_t)extra_bytes(sh->reg[r][i].p);
+	if (r < sh.n_seq) {
+		const int n = sh.n_reg[r];
+		const HitRec *h = sh.r1 + sh.roff[r];
+		b = (int64_t)n * (int64_t)sizeof(HitRec);
+		for (int i = 0; i < n; ++i) if (h[i].p) b += post_extra_bytes(hit_ext(sh.xw, h[i].p));
 	}
 	sizes[r] = b;
 }
 
-__global__ void k_post_pack(Shard *shp, const int64_t *offs, unsigned char *blob)
+__global__ void k_post_pack(const PostShard *__restrict__ shp, const int64_t *__restrict__ offs, unsigned char *__restrict__ blob)
 {
-	Shard *sh = shp;
-	const int r = cur_tid();
-	if (r >= sh->n_seq) return;
-	const int n = sh->n_reg[r];
+	const PostShard &sh = *shp;
+	const int r = (int)POST_TID;
+	if (r >= sh.n_seq) return;
+	const int n = sh.n_reg[r];
+	const HitRec *h = sh.r1 + sh.roff[r];
 	unsigned char *o = blob + offs[r];
-	const mm_reg1_t *regs = sh->reg[r];
-	for (int i = 0; i < n; ++i) reinterpret_cast<mm_reg1_t*>(o)[i] = regs[i];
-	o += (size_t)n * sizeof(mm_reg1_t);
+	for (int i = 0; i < n; ++i) reinterpret_cast<HitRec*>(o)[i] = h[i];
+	o += (size_t)n * sizeof(HitRec);
 	for (int i = 0; i < n; ++i)
-		if (regs[i].p) {
-			const size_t b = sizeof(mm_extra_t) + (size_t)regs[i].p->n_cigar * 4;
-			const uint32_t *src = reinterpret_cast<const uint32_t*>(regs[i].p);
+		if (h[i].p) {
+			const HitExtra *x = hit_ext(sh.xw, h[i].p);
+			const uint32_t *src = reinterpret_cast<const uint32_t*>(x);
 			uint32_t *dst = reinterpret_cast<uint32_t*>(o);
-			for (size_t w = 0; w < b / 4; ++w) dst[w] = src[w];
-			o += extra_bytes(regs[i].p);
+			const uint32_t words = (uint32_t)(sizeof(HitExtra) / 4) + x->n_cigar;
+			for (uint32_t w = 0; w < words; ++w) dst[w] = src[w];
+			o += post_extra_bytes(x);
 		}
 }
 
-__global__ void k_post_keys(int nf, const int32_t *nu, const int32_t *nv, uint32_t *key, int32_t *idx)
-{ // work estimate of a fragment: its chains, then its chained anchors (descending, so the heavy warps start first)
-	const int i = cur_tid();
-	if (i >= nf) return;
-	const uint32_t u = nu[i] < 1023 ? (uint32_t)nu[i] : 1023u, v = nv[i] < 0xfffff ? (uint32_t)nv[i] : 0xfffffu;
-	key[i] = ~(u << 20 | v), idx[i] = i;
-}
-
-__global__ void k_post_spread(int nf, int n_warps, const int32_t *sorted, int32_t *perm)
-{ // rank r (heaviest first) -> warp r % n_warps, lane r / n_warps: every warp gets one fragment of each weight class, the
-  // heaviest fragments sit alone at the front of the launch instead of serialising inside one warp
-	const int t = cur_tid();
-	if (t >= n_warps * 32) return;
-	const int64_t r = (int64_t)(t & 31) * n_warps + (t >> 5);
-	perm[t] = r < nf ? sorted[r] : -1;
-}
-
-__global__ void k_post_mi(mm_idx_t *mi, mm_idx_seq_t *seq, int n_seq, const uint64_t *seq_off, const uint32_t *seq_len, uint32_t *S, int k, int w, int flag)
-{ // device copy of the index header: what hits.c / aln.c read through mm_idx_t
-	const int i = cur_tid();
-	if (i < n_seq) seq[i].name = nullptr, seq[i].offset = seq_off[i], seq[i].len = seq_len[i];
-	if (i == 0) {
-		memset(mi, 0, sizeof(*mi));
-		mi->k = k, mi->w = w, mi->flag = flag, mi->n_seq = (uint32_t)n_seq, mi->seq = seq, mi->S = S;
-	}
-}
-
-} // namespace mmdev
-
-using namespace mmdev;
-
-template <class T> static int post_scan(mmg_ctx_t *c, const T *d_in, int64_t *d_out, int n)
+// ---- driver --------------------------------------------------------------------------------------------------------
+template <class T> static int post_scan(mmg_ctx_t *c, const T *d_in, int64_t *d_out, int64_t n)
 {
 	size_t tmp = 0;
 	cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_in, d_out, n, c->stream);
@@ -509,153 +160,212 @@ template <class T> static int post_scan(mmg_ctx_t *c, const T *d_in, int64_t *d_
 	return MMG_OK;
 }
 
+#define POST_LOGTAB_N (1 << 17)
+
+static int post_logtab(mmg_ctx_t *c, int match_sc, LogTab *lt)
+{ // logf is evaluated by the host's libm for every integer argument the MAPQ formulas can produce (hit.c:446-491, pe.c:159)
+	DevBuf &b = c->pb[mmg_ctx_s::PB_LOGTAB];
+	if (c->post_logtab_a != match_sc || b.p == nullptr) {
+		std::vector<float> t((size_t)POST_LOGTAB_N * 2);
+		for (int i = 0; i < POST_LOGTAB_N; ++i) t[i] = logf((float)i / match_sc), t[POST_LOGTAB_N + i] = logf((float)i);
+		MMG_TRY(b.ensure(t.size() * 4));
+		MMG_CUDA(cudaMemcpyAsync(b.p, t.data(), t.size() * 4, cudaMemcpyHostToDevice, c->stream));
+		MMG_CUDA(cudaStreamSynchronize(c->stream));
+		c->post_logtab_a = match_sc;
+	}
+	lt->ld = b.as<float>(), lt->li = b.as<float>() + POST_LOGTAB_N, lt->n = POST_LOGTAB_N;
+	return MMG_OK;
+}
+
 // Runs the stages above for the batch resident on `c`, right after mmg_seed_chain_resident(download = 0).
 extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *dopt, const void *opt_full, size_t opt_bytes, int idx_flag,
                               const uint32_t *frag_hash, mmg_post_out_t *out)
 {
+	typedef mmg_ctx_s X;
+	struct FullOpt { // mm_mapopt_t (minimap.h:107-150), read field by field below
+		int64_t flag; int seed, sdust_thres, max_qlen, bw, max_gap, max_gap_ref, max_frag_len, max_chain_skip, max_chain_iter, min_cnt, min_chain_score;
+		float mask_level, pri_ratio; int best_n, max_join_long, max_join_short, min_join_flank_sc; float min_join_flank_ratio;
+		int a, b, q, e, q2, e2, sc_ambi, noncan, junc_bonus, zdrop, zdrop_inv, end_bonus, min_dp_max, min_ksw_len, anchor_ext_len, anchor_ext_shift;
+		float max_clip_ratio; int pe_ori, pe_bonus; float mid_occ_frac; int32_t min_mid_occ, mid_occ, max_occ; int mini_batch_size; int64_t max_sw_mat; const char *split_prefix;
+	};
 	memset(out, 0, sizeof(*out));
-	if (opt_bytes != sizeof(mm_mapopt_t)) { mmg_set_error("mmg_post_chain: mm_mapopt_t size mismatch"); return MMG_EINVAL; }
+	if (opt_bytes != sizeof(FullOpt)) { mmg_set_error("mmg_post_chain: mm_mapopt_t size mismatch"); return MMG_EINVAL; }
+	(void)idx_flag;
 	MMG_CUDA(cudaSetDevice(c->dev));
 	const ResidentBatch &rb = c->rb;
 	const int nf = rb.n_frag, n_seq = rb.n_seq;
 	if (nf == 0) return MMG_OK;
-	{ // once per process: room for the per-thread call stacks of the compiled C code
-		static bool stack_set[16] = {false};
-		if (c->dev < 16 && !stack_set[c->dev]) { MMG_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, 8192)); stack_set[c->dev] = true; }
-	}
-	if (c->p_mi_for != mi) { // device copy of the index header
-		MMG_TRY(c->p_mi.ensure(sizeof(mm_idx_t) + 64));
-		MMG_TRY(c->p_seq.ensure((size_t)(mi->n_seq + 1) * sizeof(mm_idx_seq_t)));
-		MMG_LAUNCH(c, k_post_mi, mmg_blocks(mi->n_seq > 0 ? mi->n_seq : 1, 128), 128, 0, c->p_mi.as<mm_idx_t>(), c->p_seq.as<mm_idx_seq_t>(), mi->n_seq, mi->d_seq_off,
-		           mi->d_seq_len, mi->d_S, mi->k, mi->w, idx_flag);
-		c->p_mi_for = mi;
-	}
-	// measured use on 2x150 bp pairs: ~10 KB per fragment (MMG_POST_DEBUG prints it); the per-base term covers long queries
-	const size_t pool_bytes = (size_t)nf * 24576 + (size_t)rb.n_bases * 32 + ((size_t)512 << 20);
-	MMG_TRY(c->p_shard.ensure(sizeof(Shard)));
-	MMG_TRY(c->p_hash.ensure((size_t)(nf + 1) * 4));
-	MMG_TRY(c->p_nreg.ensure((size_t)(n_seq + 1) * 4));
-	MMG_TRY(c->p_reg.ensure((size_t)(n_seq + 1) * 8));
-	MMG_TRY(c->p_fr.ensure((size_t)(nf + 1) * sizeof(DFrag)));
-	MMG_TRY(c->p_tls.ensure((size_t)(nf + 64) * sizeof(Tls)));
-	MMG_TRY(c->p_pool.ensure(pool_bytes));
-	MMG_TRY(c->p_ctr.ensure(128));
-	MMG_TRY(c->p_nnew.ensure((size_t)(nf + 2) * 4));
-	MMG_TRY(c->p_joboff.ensure((size_t)(nf + 2) * 8));
-	MMG_TRY(c->h_p_hash.ensure((size_t)(nf + 1) * 4));
-	memcpy(c->h_p_hash.p, frag_hash, (size_t)nf * 4);
-	MMG_H2D(c, c->p_hash.p, c->h_p_hash.p, (size_t)nf * 4);
-	MMG_CUDA(cudaMemsetAsync(c->p_ctr.p, 0, 128, c->stream));
-	MMG_CUDA(cudaMemsetAsync(c->p_nnew.p, 0, (size_t)(nf + 2) * 4, c->stream));
-	Shard hs;
+	const FullOpt &fo = *static_cast<const FullOpt*>(opt_full);
+	const int64_t tot_u = c->last_tot_u, tot_v = c->last_tot_v;
+	PostShard hs;
 	memset(&hs, 0, sizeof(hs));
-	hs.mi = c->p_mi.as<mm_idx_t>();
-	memcpy(&hs.opt, opt_full, sizeof(mm_mapopt_t));
-	hs.opt.split_prefix = nullptr;
-	hs.nf = nf, hs.n_seq = n_seq;
-	hs.n_seg = c->d_misc.as<int32_t>(), hs.seg_off = nullptr, hs.seq_len = c->d_seq_len.as<int32_t>();
-	hs.q_off = c->d_q_off.as<uint64_t>(), hs.Q = c->d_Q.as<uint32_t>();
-	hs.nu = c->d_frag_nu.as<int32_t>(), hs.nv = c->d_frag_nv.as<int32_t>();
-	hs.uoff = c->d_uoff.as<int64_t>(), hs.voff = c->d_voff.as<int64_t>();
-	hs.u = c->d_out_u.as<uint64_t>(), hs.a = c->d_out_a.as<mm128_t>();
-	hs.hash = c->p_hash.as<uint32_t>();
-	hs.n_reg = c->p_nreg.as<int32_t>(), hs.reg = c->p_reg.as<mm_reg1_t*>();
-	hs.fr = c->p_fr.as<DFrag>(), hs.tls = c->p_tls.as<Tls>();
-	hs.pool = c->p_pool.as<char>(), hs.pool_size = pool_bytes, hs.pool_cur = c->p_ctr.as<unsigned long long>();
-	hs.n_new = c->p_nnew.as<int32_t>(), hs.job_off = c->p_joboff.as<int64_t>();
-	// first read of each fragment: the resident batch keeps it on the host; upload once per batch
-	MMG_TRY(c->d_frag_list.ensure((size_t)(nf + 1) * 8));
-	{
-		// d_frag_list's upper half ([nf, 2nf)) holds the second-pass source slots until the gather; seg_off goes to its own buffer
-		MMG_TRY(c->p_sizes.ensure((size_t)(n_seq + nf + 4) * 8));
-		int32_t *d_segoff = reinterpret_cast<int32_t*>(c->p_sizes.as<int64_t>() + n_seq + 2);
-		MMG_H2D(c, d_segoff, rb.seg_off.data(), (size_t)nf * 4);
-		hs.seg_off = d_segoff;
+	hs.opt.flag = fo.flag, hs.opt.mask_level = fo.mask_level, hs.opt.pri_ratio = fo.pri_ratio, hs.opt.max_clip_ratio = fo.max_clip_ratio;
+	hs.opt.best_n = fo.best_n, hs.opt.a = fo.a, hs.opt.b = fo.b, hs.opt.q = fo.q, hs.opt.e = fo.e, hs.opt.q2 = fo.q2, hs.opt.e2 = fo.e2, hs.opt.sc_ambi = fo.sc_ambi;
+	hs.opt.zdrop = fo.zdrop, hs.opt.zdrop_inv = fo.zdrop_inv, hs.opt.end_bonus = fo.end_bonus, hs.opt.min_dp_max = fo.min_dp_max, hs.opt.min_cnt = fo.min_cnt;
+	hs.opt.min_chain_score = fo.min_chain_score, hs.opt.bw = fo.bw, hs.opt.pe_ori = fo.pe_ori, hs.opt.pe_bonus = fo.pe_bonus, hs.opt.max_gap = fo.max_gap;
+	hs.opt.max_gap_ref = fo.max_gap_ref, hs.opt.max_frag_len = fo.max_frag_len, hs.opt.k = mi->k, hs.opt.max_qlen = fo.max_qlen, hs.opt.max_sw_mat = fo.max_sw_mat;
+	MMG_TRY(post_logtab(c, fo.a, &hs.lt));
+	hs.nf = nf, hs.n_seq = n_seq, hs.idx_k = mi->k;
+	DevBuf *B = c->pb;
+	// ---- per-batch tables
+	MMG_TRY(B[X::PB_SHARD].ensure(sizeof(PostShard)));
+	MMG_TRY(B[X::PB_HASH].ensure((size_t)(nf + 1) * 4));
+	MMG_TRY(B[X::PB_SEGOFF].ensure((size_t)(nf + 1) * 4));
+	MMG_TRY(B[X::PB_READ_FRAG].ensure((size_t)(n_seq + 1) * 4));
+	MMG_TRY(B[X::PB_PERM].ensure((size_t)(nf + 1) * 16));
+	MMG_TRY(B[X::PB_N0].ensure((size_t)(nf + 1) * 4));
+	MMG_TRY(B[X::PB_CAP].ensure((size_t)(n_seq + 2) * 4));
+	MMG_TRY(B[X::PB_ROFF].ensure((size_t)(n_seq + 2) * 8));
+	MMG_TRY(B[X::PB_NREG].ensure((size_t)(n_seq + 1) * 4));
+	MMG_TRY(B[X::PB_A1OFF].ensure((size_t)(n_seq + 1) * 8));
+	MMG_TRY(B[X::PB_CTR].ensure(64));
+	MMG_TRY(c->h_p_hash.ensure((size_t)(nf + n_seq + 2) * 4));
+	{ // the name hash of every fragment (computed by the host: read names never leave it) and the fragment of every read
+		int32_t *h = c->h_p_hash.as<int32_t>();
+		memcpy(h, frag_hash, (size_t)nf * 4);
+		int32_t *rf = h + nf;
+		for (int f = 0; f < nf; ++f) for (int j = 0; j < rb.n_seg[f]; ++j) rf[rb.seg_off[f] + j] = f;
+		MMG_H2D(c, B[X::PB_HASH].p, h, (size_t)nf * 4);
+		MMG_H2D(c, B[X::PB_READ_FRAG].p, rf, (size_t)n_seq * 4);
+		MMG_H2D(c, B[X::PB_SEGOFF].p, rb.seg_off.data(), (size_t)nf * 4);
 	}
-	{ // thread -> fragment order
-		const int n_warps = (nf + 31) / 32;
-		hs.nt = n_warps * 32;
-		MMG_TRY(c->p_perm.ensure((size_t)(nf + 33) * 20));
-		uint32_t *key = c->p_perm.as<uint32_t>(), *key2 = key + nf + 1;
-		int32_t *idx = reinterpret_cast<int32_t*>(key2 + nf + 1), *sorted = idx + nf + 1, *perm = sorted + nf + 1;
-		MMG_LAUNCH(c, k_post_keys, mmg_blocks(nf, 256), 256, 0, nf, hs.nu, hs.nv, key, idx);
-		size_t tmp = 0;
-		cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, sorted, nf, 0, 32, c->stream);
-		MMG_TRY(c->d_cub.ensure(tmp));
-		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, sorted, nf, 0, 32, c->stream));
-		++c->launches;
-		MMG_LAUNCH(c, k_post_spread, mmg_blocks(hs.nt, 256), 256, 0, nf, n_warps, sorted, perm);
-		hs.perm = perm;
-	}
-	if (getenv("MMG_TRACE")) { // chains per fragment of this shard (debug aid; synchronises)
-		std::vector<int32_t> hu((size_t)nf), hv((size_t)nf);
-		cudaStreamSynchronize(c->stream);
-		cudaMemcpy(hu.data(), hs.nu, (size_t)nf * 4, cudaMemcpyDeviceToHost);
-		cudaMemcpy(hv.data(), hs.nv, (size_t)nf * 4, cudaMemcpyDeviceToHost);
-		const int lim[8] = {0, 1, 2, 4, 16, 128, 1024, 1 << 30};
-		long long cnt[8] = {0}, ch[8] = {0}, an[8] = {0};
-		for (int i = 0; i < nf; ++i) { int b = 0; while (hu[i] > lim[b]) ++b; ++cnt[b], ch[b] += hu[i], an[b] += hv[i]; }
-		fprintf(stderr, "[mmg::post] %d fragments; chains per fragment (fragments/chains/chained anchors):", nf);
-		for (int b = 0; b < 8; ++b) fprintf(stderr, " <=%d: %lld/%lld/%lld", lim[b], cnt[b], ch[b], an[b]);
-		fprintf(stderr, "\n");
-	}
-	MMG_TRY(c->p_pre.ensure((size_t)(nf + 1) * 12 + 64));
-	hs.pre_regs = c->p_pre.as<mm_reg1_t*>();
-	int32_t *d_heavy = reinterpret_cast<int32_t*>(hs.pre_regs + nf + 1);
-	MMG_CUDA(cudaMemsetAsync(c->p_pre.p, 0, (size_t)(nf + 1) * 8, c->stream));
-	MMG_H2D(c, c->p_shard.p, &hs, sizeof(hs));
-	unsigned long long n_heavy = 0;
-	MMG_LAUNCH(c, k_post_heavy_list, mmg_blocks(nf, 256), 256, 0, nf, hs.nu, d_heavy, c->p_ctr.as<unsigned long long>() + 4);
-	MMG_D2H(c, &n_heavy, c->p_ctr.as<unsigned long long>() + 4, 8);
-	MMG_CUDA(cudaStreamSynchronize(c->stream)); // hs lives on this stack frame
+	MMG_CUDA(cudaMemsetAsync(B[X::PB_CTR].p, 0, 64, c->stream));
+	MMG_CUDA(cudaMemsetAsync(B[X::PB_CAP].p, 0, (size_t)(n_seq + 2) * 4, c->stream));
+	hs.n_seg = c->d_misc.as<int32_t>(), hs.seg_off = B[X::PB_SEGOFF].as<int32_t>(), hs.seq_len = c->d_seq_len.as<int32_t>();
+	hs.q_off = c->d_q_off.as<uint64_t>(), hs.flip = c->d_flip.as<uint8_t>(), hs.Q = c->d_Q.as<uint32_t>(), hs.S = mi->d_S;
+	hs.ref_off = mi->d_seq_off, hs.ref_len = mi->d_seq_len;
+	hs.nu = c->d_frag_nu.as<int32_t>(), hs.rep = c->d_frag_rep.as<int32_t>(), hs.uoff = c->d_uoff.as<int64_t>(), hs.voff = c->d_voff.as<int64_t>();
+	hs.u = c->d_out_u.as<uint64_t>(), hs.a = c->d_out_a.as<mm128>(), hs.hash = B[X::PB_HASH].as<uint32_t>();
+	// ---- fragment-level hit arrays (one slot per chain)
+	const size_t nu1 = (size_t)tot_u + 1;
+	MMG_TRY(B[X::PB_CNT].ensure(nu1 * 4)); MMG_TRY(B[X::PB_PRE].ensure((nu1 + 1) * 8));
+	MMG_TRY(B[X::PB_KEY_IN].ensure(nu1 * 8)); MMG_TRY(B[X::PB_VAL_IN].ensure(nu1 * 8));
+	MMG_TRY(B[X::PB_KEY].ensure(nu1 * 8)); MMG_TRY(B[X::PB_ASCNT].ensure(nu1 * 8));
+	MMG_TRY(B[X::PB_R0].ensure(nu1 * sizeof(HitRec)));
+	MMG_TRY(B[X::PB_W].ensure(nu1 * 4)); MMG_TRY(B[X::PB_COV].ensure(nu1 * 8)); MMG_TRY(B[X::PB_BIG].ensure(nu1 * 16));
+	MMG_TRY(B[X::PB_STACK].ensure((nu1 / 65 + 2 * (size_t)nf + 4) * sizeof(RsFrame)));
+	MMG_TRY(B[X::PB_A1].ensure(((size_t)tot_v + 1) * 16));
+	hs.key_in = B[X::PB_KEY_IN].as<uint64_t>(), hs.key = B[X::PB_KEY].as<uint64_t>(), hs.ascnt = B[X::PB_ASCNT].as<uint64_t>(), hs.r0 = B[X::PB_R0].as<HitRec>();
+	hs.w = B[X::PB_W].as<int32_t>(), hs.cov = B[X::PB_COV].as<uint64_t>(), hs.big = B[X::PB_BIG].as<mm128>(), hs.stack = B[X::PB_STACK].as<RsFrame>();
+	hs.n0 = B[X::PB_N0].as<int32_t>(), hs.cap = B[X::PB_CAP].as<int32_t>(), hs.roff = B[X::PB_ROFF].as<int64_t>(), hs.n_reg = B[X::PB_NREG].as<int32_t>();
+	hs.a1 = B[X::PB_A1].as<mm128>(), hs.a1_off = B[X::PB_A1OFF].as<int64_t>(), hs.ctr = B[X::PB_CTR].as<unsigned int>(), hs.n_jobs = hs.ctr + 2;
+	PostShard *d_sh = B[X::PB_SHARD].as<PostShard>();
 	MMG_CUDA(cudaEventRecord(c->ev[0], c->stream));
-	if (n_heavy) MMG_LAUNCH(c, k_post_regs_heavy, (unsigned)n_heavy, 256, 0, c->p_shard.as<Shard>(), d_heavy);
-	MMG_LAUNCH(c, k_post_hits, mmg_blocks(hs.nt, 128), 128, 16, c->p_shard.as<Shard>());
-	double ksw_ms = 0;
-	for (int round = 0;; ++round) {
-		unsigned long long ctr[3] = {0, 0, 0};
-		int64_t n_jobs = 0;
-		MMG_TRY(post_scan(c, hs.n_new, c->p_joboff.as<int64_t>(), nf + 1));
-		MMG_D2H(c, ctr, c->p_ctr.p, 24);
-		MMG_D2H(c, &n_jobs, c->p_joboff.as<int64_t>() + nf, 8);
-		cudaError_t e = cudaStreamSynchronize(c->stream);
-		if (e != cudaSuccess) { mmg_set_error("post-chaining stages: %s%s", cudaGetErrorString(e), " (device pool exhausted or a kernel fault)"); return MMG_ECUDA; }
-		if (ctr[1] == 0) break; // no active fragment left
-		if (n_jobs == 0) { mmg_set_error("post-chaining stages: alignment made no progress"); return MMG_ECUDA; }
-		if (n_jobs > 0x7fffffff) { mmg_set_error("post-chaining stages: too many DP jobs in one round"); return MMG_ELIMIT; }
-		MMG_TRY(c->p_jobs.ensure((size_t)(n_jobs + 1) * sizeof(mmg_ksw_job_t)));
-		hs.jobs = c->p_jobs.as<mmg_ksw_job_t>();
-		MMG_H2D(c, reinterpret_cast<char*>(c->p_shard.p) + offsetof(Shard, jobs), &hs.jobs, sizeof(hs.jobs));
-		MMG_LAUNCH(c, k_post_gather, mmg_blocks(hs.nt, 128), 128, 0, c->p_shard.as<Shard>());
-		const void *d_res = nullptr; const uint32_t *d_cig = nullptr; double kms = 0; uint64_t cells = 0;
-		MMG_TRY(mmg_ksw_device(c, mi, dopt, (int)n_jobs, hs.jobs, &d_res, &d_cig, &kms, &cells));
-		ksw_ms += kms;
-		out->n_dp_jobs += (uint64_t)n_jobs, out->n_dp_cells += cells, out->n_dp_rounds += 1;
-		out->n_dp_jobs_fast += c->k_last_jobs_fast, out->n_dp_cells_fast += c->k_last_cells_fast;
-		hs.res = static_cast<const KswResD*>(d_res), hs.cig = d_cig;
-		MMG_H2D(c, reinterpret_cast<char*>(c->p_shard.p) + offsetof(Shard, res), &hs.res, sizeof(hs.res));
-		MMG_H2D(c, reinterpret_cast<char*>(c->p_shard.p) + offsetof(Shard, cig), &hs.cig, sizeof(hs.cig));
-		MMG_CUDA(cudaMemsetAsync(c->p_ctr.as<unsigned long long>() + 1, 0, 8, c->stream));
-		MMG_LAUNCH(c, k_post_align, mmg_blocks(hs.nt, 128), 128, 16, c->p_shard.as<Shard>());
+	MMG_H2D(c, d_sh, &hs, sizeof(hs));
+	// thread -> fragment order for the per-fragment steps
+	int32_t *perm;
+	{
+		uint32_t *key = B[X::PB_PERM].as<uint32_t>(), *key2 = key + nf;
+		int32_t *idx = reinterpret_cast<int32_t*>(key2 + nf);
+		perm = idx + nf;
+		MMG_LAUNCH(c, k_post_perm_keys, mmg_blocks(nf, 256), 256, 0, nf, hs.nu, key, idx);
+		size_t tmp = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, perm, nf, 0, 32, c->stream);
+		MMG_TRY(c->d_cub.ensure(tmp));
+		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, perm, nf, 0, 32, c->stream));
+		++c->launches;
 	}
-	// pack and download
-	int64_t *sizes = c->p_sizes.as<int64_t>();
-	MMG_TRY(c->p_offs.ensure((size_t)(n_seq + 2) * 8));
-	MMG_LAUNCH(c, k_post_sizes, mmg_blocks(n_seq + 1, 128), 128, 0, c->p_shard.as<Shard>(), sizes);
-	MMG_TRY(post_scan(c, sizes, c->p_offs.as<int64_t>(), n_seq + 1));
-	int64_t blob_bytes = 0;
-	MMG_D2H(c, &blob_bytes, c->p_offs.as<int64_t>() + n_seq, 8);
+	if (tot_u > 0) { // keys -> hit order -> records
+		MMG_LAUNCH(c, k_post_cnt, mmg_blocks(tot_u, 256), 256, 0, hs.u, tot_u, B[X::PB_CNT].as<int32_t>());
+		MMG_TRY(post_scan(c, B[X::PB_CNT].as<int32_t>(), B[X::PB_PRE].as<int64_t>(), tot_u));
+		MMG_LAUNCH(c, k_post_keys, mmg_blocks(tot_u, 256), 256, 0, d_sh, tot_u, B[X::PB_PRE].as<int64_t>(), B[X::PB_KEY_IN].as<uint64_t>(), B[X::PB_VAL_IN].as<uint64_t>());
+		size_t tmp = 0;
+		cub::DeviceSegmentedSort::StableSortPairsDescending(nullptr, tmp, hs.key_in, hs.key, B[X::PB_VAL_IN].as<uint64_t>(), hs.ascnt, tot_u, nf, hs.uoff, hs.uoff + 1, c->stream);
+		MMG_TRY(c->d_cub.ensure(tmp));
+		MMG_CUDA(cub::DeviceSegmentedSort::StableSortPairsDescending(c->d_cub.p, tmp, hs.key_in, hs.key, B[X::PB_VAL_IN].as<uint64_t>(), hs.ascnt, tot_u, nf, hs.uoff, hs.uoff + 1, c->stream));
+		++c->launches;
+		MMG_LAUNCH(c, k_post_records, mmg_blocks(tot_u, 128), 128, 0, d_sh, tot_u);
+	}
+	MMG_LAUNCH(c, k_post_select_warp, mmg_blocks((size_t)nf * 32, 128), 128, 0, d_sh, perm);
+	MMG_LAUNCH(c, k_post_select, mmg_blocks(nf, 128), 128, 0, d_sh, perm);
+	// ---- per-read hit slots
+	MMG_TRY(post_scan(c, hs.cap, B[X::PB_ROFF].as<int64_t>(), (int64_t)n_seq + 1));
+	int64_t slots = 0;
+	MMG_D2H(c, &slots, B[X::PB_ROFF].as<int64_t>() + n_seq, 8);
+	MMG_CUDA(cudaStreamSynchronize(c->stream)); // also: `hs` was read by the copy above
+	const size_t ns1 = (size_t)slots + 1;
+	MMG_TRY(B[X::PB_R1].ensure(ns1 * sizeof(HitRec))); MMG_TRY(B[X::PB_TMP1].ensure(ns1 * sizeof(HitRec)));
+	MMG_TRY(B[X::PB_PLAN].ensure(ns1 * sizeof(RegionPlan)));
+	MMG_TRY(B[X::PB_XSIZE].ensure((ns1 + 1) * 4)); MMG_TRY(B[X::PB_XOFF].ensure((ns1 + 1) * 8));
+	MMG_TRY(B[X::PB_SKEY].ensure(ns1 * 8)); MMG_TRY(B[X::PB_SIDX].ensure(ns1 * 4)); MMG_TRY(B[X::PB_SBIG].ensure(ns1 * 16));
+	MMG_TRY(B[X::PB_SSTACK].ensure((ns1 / 65 + 2 * (size_t)n_seq + 4) * sizeof(RsFrame)));
+	const unsigned int job_cap = (unsigned int)(slots * 3 < 0x7fffffff ? slots * 3 + 16 : 0x7fffffff);
+	MMG_TRY(B[X::PB_JOBS].ensure((size_t)job_cap * sizeof(DpJob)));
+	hs.r1 = B[X::PB_R1].as<HitRec>(), hs.tmp1 = B[X::PB_TMP1].as<HitRec>(), hs.pl = B[X::PB_PLAN].as<RegionPlan>();
+	hs.xsize = B[X::PB_XSIZE].as<uint32_t>(), hs.xoff = B[X::PB_XOFF].as<int64_t>();
+	hs.skey = B[X::PB_SKEY].as<uint64_t>(), hs.sidx = B[X::PB_SIDX].as<int32_t>(), hs.sbig = B[X::PB_SBIG].as<mm128>(), hs.sstack = B[X::PB_SSTACK].as<RsFrame>();
+	hs.jobs = B[X::PB_JOBS].as<DpJob>(), hs.job_cap = job_cap;
+	hs.xw = B[X::PB_XW].as<uint32_t>();
+	MMG_H2D(c, d_sh, &hs, sizeof(hs));
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
-	MMG_TRY(c->p_blob.ensure((size_t)blob_bytes + 64));
-	MMG_LAUNCH(c, k_post_pack, mmg_blocks(n_seq, 128), 128, 0, c->p_shard.as<Shard>(), c->p_offs.as<int64_t>(), c->p_blob.as<unsigned char>());
+	const int32_t *read_frag = B[X::PB_READ_FRAG].as<int32_t>();
+	MMG_LAUNCH(c, k_post_mates, mmg_blocks(nf, 128), 128, 0, d_sh, perm);
+	double ksw_ms = 0;
+	int64_t x_used = 0;
+	if (fo.flag & HIT_F_CIGAR) {
+		for (int round = 0;; ++round) {
+			unsigned int ctr[4] = {0, 0, 0, 0};
+			MMG_CUDA(cudaMemsetAsync(hs.ctr, 0, 4, c->stream));       // hits cut off in this round
+			MMG_CUDA(cudaMemsetAsync(hs.n_jobs, 0, 4, c->stream));
+			MMG_LAUNCH(c, k_post_plan, mmg_blocks(n_seq, 128), 128, 0, d_sh, read_frag);
+			MMG_D2H(c, ctr, hs.ctr, 16);
+			MMG_CUDA(cudaStreamSynchronize(c->stream));
+			if (ctr[1] & POST_ERR_JOBS) { mmg_set_error("post-chaining stages: DP job buffer too small"); return MMG_ELIMIT; }
+			const int n_jobs = (int)ctr[2];
+			const void *d_res = nullptr; const uint32_t *d_cig = nullptr; double kms = 0; uint64_t cells = 0;
+			if (n_jobs > 0) {
+				MMG_TRY(mmg_ksw_device(c, mi, dopt, n_jobs, reinterpret_cast<const mmg_ksw_job_t*>(hs.jobs), &d_res, &d_cig, &kms, &cells));
+				ksw_ms += kms;
+				out->n_dp_jobs += (uint64_t)n_jobs, out->n_dp_cells += cells, out->n_dp_rounds += 1;
+				out->n_dp_jobs_fast += c->k_last_jobs_fast, out->n_dp_cells_fast += c->k_last_cells_fast;
+			}
+			hs.dp.res = static_cast<const DpRes*>(d_res), hs.dp.cig = d_cig;
+			MMG_H2D(c, reinterpret_cast<char*>(d_sh) + offsetof(PostShard, dp), &hs.dp, sizeof(hs.dp));
+			MMG_LAUNCH(c, k_post_size, mmg_blocks(n_seq, 128), 128, 0, d_sh);
+			MMG_TRY(post_scan(c, hs.xsize, B[X::PB_XOFF].as<int64_t>(), slots + 1));
+			int64_t words = 0;
+			MMG_D2H(c, &words, B[X::PB_XOFF].as<int64_t>() + slots, 8);
+			MMG_CUDA(cudaStreamSynchronize(c->stream));
+			MMG_TRY(B[X::PB_XW].ensure_keep((size_t)(x_used + words + 16) * 4, (size_t)x_used * 4, c->stream));
+			hs.xw = B[X::PB_XW].as<uint32_t>(), hs.x_base = x_used;
+			MMG_H2D(c, reinterpret_cast<char*>(d_sh) + offsetof(PostShard, xw), &hs.xw, sizeof(hs.xw));
+			MMG_H2D(c, reinterpret_cast<char*>(d_sh) + offsetof(PostShard, x_base), &hs.x_base, sizeof(hs.x_base));
+			MMG_LAUNCH(c, k_post_build, mmg_blocks(n_seq, 128), 128, 0, d_sh, read_frag);
+			x_used += words;
+			MMG_D2H(c, ctr, hs.ctr, 16);
+			{
+				cudaError_t e = cudaStreamSynchronize(c->stream);
+				if (e != cudaSuccess) { mmg_set_error("post-chaining stages: %s", cudaGetErrorString(e)); return MMG_ECUDA; }
+			}
+			if (ctr[1] & POST_ERR_SLOTS) { mmg_set_error("post-chaining stages: a read was cut at z-drops more often than its hit slots allow"); return MMG_ELIMIT; }
+			if (ctr[0] == 0) break; // no hit was cut: every hit is aligned
+			if (round > 64) { mmg_set_error("post-chaining stages: alignment made no progress"); return MMG_ECUDA; }
+		}
+		MMG_LAUNCH(c, k_post_final, mmg_blocks(n_seq, 128), 128, 0, d_sh);
+	}
+	MMG_LAUNCH(c, k_post_finish, mmg_blocks(nf, 128), 128, 0, d_sh);
+	// ---- pack and download
+	MMG_TRY(B[X::PB_SIZES].ensure((size_t)(n_seq + 2) * 8));
+	MMG_TRY(B[X::PB_OFFS].ensure((size_t)(n_seq + 2) * 8));
+	int64_t *sizes = B[X::PB_SIZES].as<int64_t>();
+	MMG_LAUNCH(c, k_post_sizes, mmg_blocks((size_t)n_seq + 1, 128), 128, 0, d_sh, sizes);
+	MMG_TRY(post_scan(c, sizes, B[X::PB_OFFS].as<int64_t>(), (int64_t)n_seq + 1));
+	int64_t blob_bytes = 0;
+	unsigned int ctr[4] = {0, 0, 0, 0};
+	MMG_D2H(c, &blob_bytes, B[X::PB_OFFS].as<int64_t>() + n_seq, 8);
+	MMG_D2H(c, ctr, hs.ctr, 16);
+	MMG_CUDA(cudaStreamSynchronize(c->stream));
+	if (ctr[1] & POST_ERR_LOGTAB) { mmg_set_error("post-chaining stages: a MAPQ argument lies outside the logf table (alignment score above %d)", POST_LOGTAB_N); return MMG_ELIMIT; }
+	MMG_TRY(B[X::PB_BLOB].ensure((size_t)blob_bytes + 64));
+	MMG_LAUNCH(c, k_post_pack, mmg_blocks(n_seq, 128), 128, 0, d_sh, B[X::PB_OFFS].as<int64_t>(), B[X::PB_BLOB].as<unsigned char>());
 	MMG_CUDA(cudaEventRecord(c->ev[1], c->stream));
 	MMG_TRY(c->h_p_nreg.ensure((size_t)(n_seq + 1) * 4));
 	MMG_TRY(c->h_p_offs.ensure((size_t)(n_seq + 2) * 8));
 	MMG_TRY(c->h_p_blob.ensure((size_t)blob_bytes + 64));
 	MMG_TRY(c->h_p_rep.ensure((size_t)(nf + 1) * 4));
-	MMG_D2H(c, c->h_p_nreg.p, c->p_nreg.p, (size_t)n_seq * 4);
-	MMG_D2H(c, c->h_p_offs.p, c->p_offs.p, (size_t)(n_seq + 1) * 8);
-	if (blob_bytes) MMG_D2H(c, c->h_p_blob.p, c->p_blob.p, (size_t)blob_bytes);
+	MMG_D2H(c, c->h_p_nreg.p, hs.n_reg, (size_t)n_seq * 4);
+	MMG_D2H(c, c->h_p_offs.p, B[X::PB_OFFS].p, (size_t)(n_seq + 1) * 8);
+	if (blob_bytes) MMG_D2H(c, c->h_p_blob.p, B[X::PB_BLOB].p, (size_t)blob_bytes);
 	MMG_D2H(c, c->h_p_rep.p, c->d_frag_rep.p, (size_t)nf * 4);
 	{
 		cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -663,17 +373,12 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 	}
 	float ms = 0;
 	cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-	if (getenv("MMG_POST_DEBUG")) {
-		unsigned long long ctr4[10] = {0};
-		cudaMemcpy(ctr4, c->p_ctr.p, 80, cudaMemcpyDeviceToHost);
-		fprintf(stderr, "[mmg_post] phases of fragments with > 1000 chains, ms (max): gen_regs %.2f set_parent %.2f select_sub %.2f seg_gen+begin %.2f first walk %.2f\n",
-		        ctr4[5] / 1.965e6, ctr4[6] / 1.965e6, ctr4[7] / 1.965e6, ctr4[8] / 1.965e6, ctr4[9] / 1.965e6);
-		fprintf(stderr, "[mmg_post] %d fragments, pool used %.1f MB of %.1f MB (%.0f B per fragment), blob %.1f MB, %.1f ms on the device (K4 %.1f ms); "
-		        "longest k_post_hits thread %.2f ms (fragment with %llu chains)\n", nf, ctr4[0] / 1e6, pool_bytes / 1e6, (double)ctr4[0] / nf, blob_bytes / 1e6, ms, ksw_ms,
-		        (double)(ctr4[3] >> 20) / 1.965e6, ctr4[3] & 0xfffff);
-	}
+	if (getenv("MMG_TRACE"))
+		fprintf(stderr, "[mmg::post] %d fragments, %lld chains -> %lld hit slots, alignment records %.1f MB, blob %.1f MB, %.1f ms on the device (K4 %.1f ms, %llu DP rounds)\n",
+		        nf, (long long)tot_u, (long long)slots, x_used * 4 / 1e6, blob_bytes / 1e6, ms, ksw_ms, (unsigned long long)out->n_dp_rounds);
 	out->n_reg = c->h_p_nreg.as<int32_t>(), out->blob_off = c->h_p_offs.as<int64_t>(), out->blob = c->h_p_blob.as<unsigned char>();
 	out->rep_len = c->h_p_rep.as<int32_t>();
 	out->t_device_ms = ms, out->t_ksw_ms = ksw_ms;
+	out->finished = 1;
 	return MMG_OK;
 }

@@ -148,6 +148,36 @@ MMG_HDN inline void post_hits_select(const PostShard &sh, int f)
 	for (int j = 0; j < ns; ++j) sh.cap[sh.seg_off[f] + j] = n > 0 ? POST_SLOTS(n) : 0;
 }
 
+// the same step for a fragment with many chains, run by one warp: the tree is built cooperatively (hit_set_parent_warp), the
+// selection stays with one lane (it is a single pass whose reads depend on its own earlier writes, pe.c:13-40)
+#define POST_WARP_MIN_CHAINS 32
+template <class W>
+MMG_HDN inline void post_hits_select_warp(const W &wp, const PostShard &sh, int f)
+{
+	const int ns = sh.n_seg[f], qlen_sum = post_qlen_sum(sh, f);
+	const int64_t o = sh.uoff[f];
+	const int n_in = post_frag_mapped(sh, f, qlen_sum) ? sh.nu[f] : 0;
+	const bool tree = n_in > 0 && !(sh.opt.flag & HIT_F_ALL_CHAINS);
+	if (n_in > 0) wp.one([&]() { post_hits_fix_order(sh, f); });
+	if (tree) {
+		if (qlen_sum <= HIT_COVER_BITS) hit_set_parent_warp(wp, sh.opt.mask_level, n_in, sh.r0 + o, (sh.opt.flag & HIT_F_HARD_MLEVEL) != 0, sh.w + o, reinterpret_cast<uint32_t*>(sh.cov + o));
+		else wp.one([&]() { hit_set_parent(sh.opt.mask_level, n_in, sh.r0 + o, sh.opt.a * 2 + sh.opt.b, (sh.opt.flag & HIT_F_HARD_MLEVEL) != 0, sh.w + o, sh.cov + o, nullptr); });
+	}
+	wp.one([&]() {
+		int n = n_in;
+		if (tree) {
+			if (ns <= 1) n = hit_select_sub(sh.opt.pri_ratio, sh.idx_k * 2, sh.opt.best_n, n, sh.r0 + o, sh.w + o);
+			else {
+				int32_t ql[8];
+				for (int j = 0; j < ns; ++j) ql[j] = sh.seq_len[sh.seg_off[f] + j];
+				n = hit_select_sub_multi(sh.opt.pri_ratio, 0.2f, 0.7f, post_frag_gap(sh.opt, qlen_sum), sh.idx_k * 2, sh.opt.best_n, ns, ql, n, sh.r0 + o, sh.w + o);
+			}
+		}
+		sh.n0[f] = n;
+		for (int j = 0; j < ns; ++j) sh.cap[sh.seg_off[f] + j] = n > 0 ? POST_SLOTS(n) : 0;
+	});
+}
+
 // mm_seg_gen + per-mate mm_set_parent (map.c:395-399), or the single-segment hand-over (map.c:390-393)
 MMG_HDN inline void post_mates(const PostShard &sh, int f)
 {

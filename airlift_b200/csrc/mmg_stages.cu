@@ -1040,6 +1040,7 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 	MMG_D2H(c, &tot[1], c->d_voff.as<int64_t>() + nf, 8);
 	if (want_mini) MMG_D2H(c, &tot[2], c->d_moff.as<int64_t>() + nf, 8);
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
+	c->last_tot_u = tot[0], c->last_tot_v = tot[1];
 	MMG_TRY(c->d_out_u.ensure((size_t)(tot[0] + 1) * 8));
 	MMG_TRY(c->d_out_a.ensure((size_t)(tot[1] + 1) * 16));
 	MMG_TRY(c->d_out_mini.ensure((size_t)(tot[2] + 1) * 8));

@@ -111,7 +111,7 @@ static int chain_gap_ref(const mm_mapopt_t *opt, int qlen_sum)
 	return opt->max_gap;
 }
 
-static int use_device_path(const mm_mapopt_t *opt);
+static int use_device_path(const mm_idx_t *mi, const mm_mapopt_t *opt);
 static void stage_align(void *data, long i, int tid);
 static void stage_finish(void *data, long i, int tid);
 
@@ -364,7 +364,7 @@ static void stage_dev_finish(void *data, long i, int tid)
 		sh->n_reg[off + j] = n, sh->reg[off + j] = regs;
 	}
 	mapped = !(qlen_sum == 0 || ns <= 0 || ns > MM_MAX_SEG || (opt->max_qlen > 0 && qlen_sum > opt->max_qlen));
-	if (mapped) {
+	if (mapped && !sh->post.finished) { /* a device layer that stops before MAPQ leaves these three steps to the host */
 		for (j = 0; j < ns; ++j) mm_set_mapq(sh->n_reg[off + j], sh->reg[off + j], opt->min_chain_score, opt->a, rep_len, is_sr);
 		if (ns == 2 && opt->pe_ori >= 0 && (opt->flag & MM_F_CIGAR))
 			mm_pair(frag_gap, opt->pe_bonus, opt->a * 2 + opt->b, opt->a, qlens, &sh->n_reg[off], &sh->reg[off]);
@@ -384,11 +384,11 @@ static int g_serial_shards = 0;
  * stretched by kernels of the other shard running next to them */
 void mm_b200_set_serial(int on) { g_serial_shards = on; }
 
-static int use_device_path(const mm_mapopt_t *opt)
-{
+static int use_device_path(const mm_idx_t *mi, const mm_mapopt_t *opt)
+{ /* the device post-chaining stages cover the short-read presets; =/X CIGARs and HPC indexes take the host stages */
 	static int host_only = -1;
 	if (host_only < 0) host_only = getenv("MM2_B200_HOSTPATH") != 0;
-	return !host_only && (opt->flag & MM_F_SR) && !(opt->flag & MM_F_SPLICE);
+	return !host_only && (opt->flag & MM_F_SR) && !(opt->flag & (MM_F_SPLICE | MM_F_EQX)) && !(mi->flag & MM_I_HPC);
 }
 
 static void *dev_hash_main(void *data)
@@ -437,7 +437,7 @@ static void *map_shard(void *data)
 	int i, j;
 	double t0, t1;
 	if (nf <= 0 || sh->rc) return 0;
-	if (use_device_path(sh->opt)) return map_shard_dev(sh);
+	if (use_device_path(sh->mi, sh->opt)) return map_shard_dev(sh);
 	t0 = realtime();
 	if (sh->gpu_token) pthread_mutex_lock(sh->gpu_token);
 	i = mmg_seed_chain_resident(sh->ctx, sh->didx, &sh->dopt, &sh->ch, 1);
@@ -559,7 +559,7 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		shard_t *h = &sh[d];
 		/* device path with two shards per GPU: the first shard is the smaller one, so that its upload (the only one no kernel
 		 * can hide) is short and the second, larger upload runs under its kernels */
-		const int64_t goal = (B->lanes == 2 && use_device_path(opt)) ? (tot * (d / 2) + (d % 2 == 0 ? tot * 3 / 10 : tot)) / B->n_dev : tot * (d + 1) / n_dev;
+		const int64_t goal = (B->lanes == 2 && use_device_path(mi, opt)) ? (tot * (d / 2) + (d % 2 == 0 ? tot * 3 / 10 : tot)) / B->n_dev : tot * (d + 1) / n_dev;
 		h->mi = mi, h->opt = opt, h->ctx = B->ctx[d], h->didx = B->didx[d / B->lanes];
 		mm_mapopt_to_dev(opt, &h->dopt);
 		mm_arena_init(&h->arena);
@@ -567,8 +567,8 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		h->n_threads = n_threads / B->n_dev > 0 ? n_threads / B->n_dev : 1;
 		/* host path: the lanes of a GPU take turns on the device while the others run host stages; device path: their kernels
 		 * may overlap freely (the latency-bound tails of one shard fill the gaps of the other) */
-		h->gpu_token = B->lanes > 1 && (!use_device_path(opt) || g_serial_shards) ? &B->gpu_token[d / B->lanes] : 0;
-		h->up_token = B->lanes > 1 && use_device_path(opt) ? &B->gpu_token[d / B->lanes] : 0;
+		h->gpu_token = B->lanes > 1 && (!use_device_path(mi, opt) || g_serial_shards) ? &B->gpu_token[d / B->lanes] : 0;
+		h->up_token = B->lanes > 1 && use_device_path(mi, opt) ? &B->gpu_token[d / B->lanes] : 0;
 		h->seq = s->seq, h->n_seg = s->n_seg, h->seg_off = s->seg_off, h->n_reg = s->n_reg, h->rep_len = s->rep_len, h->frag_gap = s->frag_gap, h->reg = s->reg;
 		h->f0 = f;
 		while (f < s->n_frag && (acc < goal || d == n_dev - 1)) {

@@ -181,9 +181,9 @@ void mmg_ksw_last_split(const mmg_ctx_t *ctx, uint64_t *jobs_fast, uint64_t *cel
 int  mmg_job_buffers(mmg_ctx_t *ctx, size_t n_jobs, mmg_ksw_job_t **jobs, mmg_ksw_res_t **res);
 
 /* ------------------------------------------- post-chaining stages on the device (short-read presets)
- * What mm_map_frag does between mm_chain_dp and mm_set_mapq (map.c:376-400: mm_gen_regs, chain_post, mm_seg_gen,
- * mm_align_skeleton with its ksw_extd2 calls, mm_update_extra, filters) for every fragment of the resident batch, right
- * after mmg_seed_chain_resident(download = 0).  The host receives one blob and finishes with MAPQ / pairing (logf). */
+ * What mm_map_frag does between mm_chain_dp and its return (map.c:376-406: mm_gen_regs, chain_post, mm_seg_gen,
+ * mm_align_skeleton with its ksw_extd2 calls, mm_update_extra, filters, mm_set_mapq, mm_pair) for every fragment of the
+ * resident batch, right after mmg_seed_chain_resident(download = 0).  The host receives one blob of finished records. */
 typedef struct {
 	const int32_t *n_reg;        /* [n_seq] hits per read */
 	const int64_t *blob_off;     /* [n_seq+1] byte offset of each read's records in blob */
@@ -191,6 +191,7 @@ typedef struct {
 	const int32_t *rep_len;      /* [n_frag] */
 	double t_device_ms, t_ksw_ms;
 	uint64_t n_dp_jobs, n_dp_cells, n_dp_rounds, n_dp_jobs_fast, n_dp_cells_fast;
+	int32_t finished;            /* 1: MAPQ, pairing and the mate un-flip (map.c:392-406,486-497) were done on the device as well */
 } mmg_post_out_t;
 /* mapopt_full: the caller's mm_mapopt_t (minimap.h:107-150) as bytes; idx_flag: mm_idx_t::flag; frag_hash[n_frag]: the
  * per-fragment salt of map.c:291-293 (it depends on the read name, which never leaves the host) */

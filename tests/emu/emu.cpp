@@ -169,7 +169,7 @@ extern "C" int emu_post_frag(const HitOpt *opt, int idx_k, uint32_t hash, int n_
 	std::vector<mm128> a(a_in, a_in + n_v), a1(n_v + 1);
 	std::vector<uint32_t> hv(1, hash);
 	sh.nu = nu.data(), sh.rep = rep.data(), sh.uoff = uoff.data(), sh.voff = voff.data(), sh.u = u.data(), sh.a = a.data(), sh.hash = hv.data(), sh.a1 = a1.data();
-	const int m = n_u + 1;
+	const int m = n_u + 40; // the warp form keeps a 64-word bitmap in the cov scratch
 	std::vector<uint64_t> key_in(m), key(m), ascnt(m), cov(m);
 	std::vector<HitRec> r0(m);
 	std::vector<int32_t> w(m), n0(1);
@@ -192,7 +192,8 @@ extern "C" int emu_post_frag(const HitOpt *opt, int idx_k, uint32_t hash, int n_
 		for (int i = 0; i < n_u; ++i) key[i] = key_in[ord[i]], ascnt[i] = val_in[ord[i]];
 		for (int g = 0; g < n_u; ++g) post_hit_record(sh, g);
 	}
-	post_hits_select(sh, 0);
+	if (getenv("EMU_WARP") && n_u >= atoi(getenv("EMU_WARP"))) post_hits_select_warp(WarpEmu(), sh, 0); // the warp-cooperative form, lanes emulated one after the other
+	else post_hits_select(sh, 0);
 	for (int j = 0; j < n_segs; ++j) roff[j + 1] = roff[j] + cap[j];
 	const int64_t slots = roff[n_segs] + 1;
 	std::vector<HitRec> r1(slots), tmp1(slots);

@@ -155,9 +155,16 @@ def make_world(rng, variant):
     return refseqs
 
 
-@pytest.mark.parametrize("variant,cigar", [("plain", True), ("plain", False), ("dup", True), ("noisy", True), ("zdrop", True), ("single", True)])
-def test_post_stages_match_mm_map_frag(env, variant, cigar):
+@pytest.mark.parametrize("variant,cigar,warp", [("plain", True, 0), ("plain", False, 0), ("dup", True, 0), ("noisy", True, 0), ("zdrop", True, 0), ("single", True, 0),
+                                                ("plain", True, 2), ("dup", True, 2), ("single", True, 2)])
+def test_post_stages_match_mm_map_frag(env, variant, cigar, warp, monkeypatch):
+    """warp > 0: fragments with at least that many chains take the warp-cooperative tree construction (hit_set_parent_warp, the form
+    the device uses for fragments from high-copy repeats), its 32 lanes emulated one after the other"""
     E, R = env
+    if warp:
+        monkeypatch.setenv("EMU_WARP", str(warp))
+    else:
+        monkeypatch.delenv("EMU_WARP", raising=False)
     rng = np.random.default_rng({"plain": 5, "dup": 6, "noisy": 7, "single": 8, "zdrop": 9}[variant] + (0 if cigar else 100))
     refseqs = make_world(rng, variant)
     w, k = 11, 21
