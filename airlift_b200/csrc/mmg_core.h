@@ -314,6 +314,40 @@ MMG_HDN inline int64_t mmg_fill_heap(const mm128 *mv, const int32_t *m_n, const 
 	return n_a;
 }
 
+// The same merge replayed on RANKS.  Which of two equal positions leaves the heap first depends on the heap's shape, so the
+// order of equal-x anchors can only come from running klib's heap; but the heap only ever COMPARES positions.
+// A device-wide sort gives every planned hit the index of the first hit with its position (equal positions: equal index), and
+// the replay then runs on 32-bit words `rank << 8 | list` without touching the position arrays: same comparisons, same
+// sift-downs, same pops.  K[s]: rank of planned slot s (slots of list j: first[j] .. first[j] + cnt[j]); pop[t] receives the
+// slot popped t-th.  Lists: up to 256; ranks: below 2^24.  heap/cur: n_lists words of scratch each.
+MMG_HD void mmg_rank_heap_down(uint32_t i, uint32_t n, uint32_t *l)
+{
+	uint32_t k = i;
+	const uint32_t tmp = l[i];
+	while ((k = (k << 1) + 1) < n) {
+		if (k != n - 1 && (l[k] >> 8) > (l[k + 1] >> 8)) ++k;
+		if ((l[k] >> 8) > (tmp >> 8)) break;
+		l[i] = l[k]; i = k;
+	}
+	l[i] = tmp;
+}
+
+MMG_HDN inline int64_t mmg_heap_replay_ranks(int n_lists, const int32_t *first, const int32_t *cnt, const uint32_t *K, uint32_t *heap, uint32_t *cur, uint32_t *pop)
+{
+	uint32_t hs = 0;
+	int64_t t = 0;
+	for (int j = 0; j < n_lists; ++j) { heap[hs++] = K[first[j]] << 8 | (uint32_t)j; cur[j] = 0; }
+	if (hs > 1) for (int32_t j = (int32_t)(hs >> 1) - 1; j >= 0; --j) mmg_rank_heap_down((uint32_t)j, hs, heap);
+	while (hs > 0) {
+		const uint32_t j = heap[0] & 0xff;
+		pop[t++] = (uint32_t)first[j] + cur[j];
+		if (cur[j] + 1 < (uint32_t)cnt[j]) { ++cur[j]; heap[0] = K[(uint32_t)first[j] + cur[j]] << 8 | j; }
+		else { heap[0] = heap[hs - 1]; --hs; }
+		if (hs > 0) mmg_rank_heap_down(0, hs, heap);
+	}
+	return t;
+}
+
 // --- klib's in-place MSD radix sort (ksort.h:101-151) replayed exactly, recursion turned into an
 // explicit stack (stack[] needs n/65+2 frames).  Needed wherever equal keys may meet in an array of
 // more than 64 elements: the order they end in is defined by this permutation.

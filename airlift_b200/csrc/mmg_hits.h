@@ -627,15 +627,17 @@ MMG_HDN inline bool hit_pair(int max_gap_ref, int pe_bonus, int sub_diff, int ma
 //   * the first primary that masks hit i (hit.c:143-161) is found by one ballot over 32 primaries at a time.
 // The code is written against a tiny warp interface so that tests/emu/ can run it on the CPU: ballot(f) / sum(f) evaluate f(lane)
 // on every lane and combine; each(f) runs f(lane) on every lane; everything else is computed redundantly by all lanes.
-struct WarpEmu { // 32 lanes, one after the other
+struct WarpEmu { // 32 lanes, one after the other; per-lane variables are arrays
+	template <class T> struct Var { T v[32]; T &operator()(int l) { return v[l]; } const T &operator()(int l) const { return v[l]; } };
 	template <class F> unsigned ballot(F &&f) const { unsigned m = 0; for (int l = 0; l < 32; ++l) if (f(l)) m |= 1u << l; return m; }
 	template <class F> int sum(F &&f) const { int s = 0; for (int l = 0; l < 32; ++l) s += f(l); return s; }
 	template <class F> void each(F &&f) const { for (int l = 0; l < 32; ++l) f(l); }
 	template <class F> void one(F &&f) const { f(); }
 };
 #ifdef __CUDACC__
-struct WarpDev {
+struct WarpDev { // per-lane variables are registers
 	int lane;
+	template <class T> struct Var { T v; __device__ T &operator()(int) { return v; } __device__ const T &operator()(int) const { return v; } };
 	template <class F> __device__ unsigned ballot(F &&f) const { return __ballot_sync(0xffffffffu, f(lane)); }
 	template <class F> __device__ int sum(F &&f) const { return __reduce_add_sync(0xffffffffu, f(lane)); }
 	template <class F> __device__ void each(F &&f) const { f(lane); __syncwarp(); }
@@ -653,21 +655,26 @@ MMG_HD uint32_t hit_range_word(int s, int e, int word)
 	return a & b;
 }
 
-// n hits with 0 <= qs < qe <= HIT_COVER_BITS, no alignment records yet; w[]: n ints; cb[]: 64 words.  Result == hit_set_parent's.
+#ifndef HIT_PRIM_CACHE
+#define HIT_PRIM_CACHE 96   // primaries whose query interval and counters are kept in fast memory (shared memory on the device)
+#endif
+
+// n hits with 0 <= qs < qe <= HIT_COVER_BITS, no alignment records yet.  w[]: n ints (the primaries, as in hit_set_parent);
+// pc[]: 4 * HIT_PRIM_CACHE ints of fast scratch (qs, qe, subsc, n_sub of the first primaries).  Result == hit_set_parent's.
 template <class W>
-MMG_HDN inline void hit_set_parent_warp(const W &wp, float mask_level, int n, HitRec *r, bool hard_mask_level, int32_t *w, uint32_t *cb)
+MMG_HDN inline void hit_set_parent_warp(const W &wp, float mask_level, int n, HitRec *r, bool hard_mask_level, int32_t *w, int32_t *pc)
 {
 	if (n <= 0) return;
-	wp.each([&](int l) { for (int i = l; i < n; i += 32) r[i].id = i; cb[l] = 0, cb[l + 32] = 0; });
-	wp.one([&]() { w[0] = 0, r[0].parent = 0; });
-	wp.each([&](int l) { cb[l] |= hit_range_word(r[0].qs, r[0].qe, l), cb[l + 32] |= hit_range_word(r[0].qs, r[0].qe, l + 32); });
+	typename W::template Var<uint32_t> c0, c1; // query positions covered by a primary: lane l holds positions [32 l, 32 l + 32) and [1024 + 32 l, ...)
+	wp.each([&](int l) { for (int i = l; i < n; i += 32) r[i].id = i; c0(l) = hit_range_word(r[0].qs, r[0].qe, l), c1(l) = hit_range_word(r[0].qs, r[0].qe, l + 32); });
+	wp.one([&]() { w[0] = 0, r[0].parent = 0; pc[0] = r[0].qs, pc[1] = r[0].qe, pc[2] = r[0].subsc, pc[3] = r[0].n_sub; });
 	int k = 1;
 	for (int i = 1; i < n; ++i) {
 		const int si = r[i].qs, ei = r[i].qe;
 		int uncov_len = 0, j = -1;
 		bool judge = true;
 		if (!hard_mask_level) {
-			const int cov = wp.sum([&](int l) { return (int)(mmg_popc(cb[l] & hit_range_word(si, ei, l)) + mmg_popc(cb[l + 32] & hit_range_word(si, ei, l + 32))); });
+			const int cov = wp.sum([&](int l) { return (int)(mmg_popc(c0(l) & hit_range_word(si, ei, l)) + mmg_popc(c1(l) & hit_range_word(si, ei, l + 32))); });
 			if (cov == 0) judge = false;
 			else uncov_len = (ei - si) - cov;
 		}
@@ -676,8 +683,9 @@ MMG_HDN inline void hit_set_parent_warp(const W &wp, float mask_level, int n, Hi
 				const unsigned m = wp.ballot([&](int l) {
 					const int t = base + l;
 					if (t >= k) return false;
-					const HitRec *rp = &r[w[t]];
-					const int sj = rp->qs, ej = rp->qe;
+					int sj, ej;
+					if (t < HIT_PRIM_CACHE) sj = pc[4 * t], ej = pc[4 * t + 1];
+					else sj = r[w[t]].qs, ej = r[w[t]].qe;
 					if (ej <= si || sj >= ei) return false;
 					const int mn = ej - sj < ei - si ? ej - sj : ei - si, mx = ej - sj > ei - si ? ej - sj : ei - si;
 					const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
@@ -687,15 +695,26 @@ MMG_HDN inline void hit_set_parent_warp(const W &wp, float mask_level, int n, Hi
 			}
 		if (j >= 0) {
 			wp.one([&]() {
-				HitRec *ri = &r[i], *rp = &r[w[j]];
-				ri->parent = rp->parent;
-				rp->subsc = rp->subsc > ri->score ? rp->subsc : ri->score;
-				if (ri->cnt >= rp->cnt) ++rp->n_sub;
+				HitRec *ri = &r[i];
+				const int pi = w[j];
+				ri->parent = pi; // a primary is its own parent
+				if (j < HIT_PRIM_CACHE) {
+					if (pc[4 * j + 2] < ri->score) pc[4 * j + 2] = ri->score;
+					if (ri->cnt >= r[pi].cnt) ++pc[4 * j + 3];
+				} else {
+					HitRec *rp = &r[pi];
+					rp->subsc = rp->subsc > ri->score ? rp->subsc : ri->score;
+					if (ri->cnt >= rp->cnt) ++rp->n_sub;
+				}
 			});
 		} else {
-			wp.one([&]() { w[k] = i, r[i].parent = i, r[i].n_sub = 0; });
-			wp.each([&](int l) { cb[l] |= hit_range_word(si, ei, l), cb[l + 32] |= hit_range_word(si, ei, l + 32); });
+			wp.one([&]() {
+				w[k] = i, r[i].parent = i, r[i].n_sub = 0;
+				if (k < HIT_PRIM_CACHE) pc[4 * k] = si, pc[4 * k + 1] = ei, pc[4 * k + 2] = r[i].subsc, pc[4 * k + 3] = 0;
+			});
+			wp.each([&](int l) { c0(l) |= hit_range_word(si, ei, l), c1(l) |= hit_range_word(si, ei, l + 32); });
 			++k;
 		}
 	}
+	wp.each([&](int l) { for (int t = l; t < k && t < HIT_PRIM_CACHE; t += 32) r[w[t]].subsc = pc[4 * t + 2], r[w[t]].n_sub = pc[4 * t + 3]; });
 }

@@ -70,8 +70,9 @@ __global__ void __launch_bounds__(128) k_post_select_warp(const PostShard *__res
 	if (t >= shp->nf) return;
 	const int f = perm[t];
 	if (shp->nu[f] <= POST_WARP_MIN_CHAINS) return;
+	__shared__ int32_t s_fast[4][4 * HIT_PRIM_CACHE];
 	WarpDev wp = {(int)(threadIdx.x & 31)};
-	post_hits_select_warp(wp, *shp, f);
+	post_hits_select_warp(wp, *shp, f, s_fast[threadIdx.x >> 5]);
 }
 
 __global__ void __launch_bounds__(128) k_post_mates(const PostShard *__restrict__ shp, const int32_t *__restrict__ perm)

@@ -152,7 +152,7 @@ MMG_HDN inline void post_hits_select(const PostShard &sh, int f)
 // selection stays with one lane (it is a single pass whose reads depend on its own earlier writes, pe.c:13-40)
 #define POST_WARP_MIN_CHAINS 32
 template <class W>
-MMG_HDN inline void post_hits_select_warp(const W &wp, const PostShard &sh, int f)
+MMG_HDN inline void post_hits_select_warp(const W &wp, const PostShard &sh, int f, int32_t *fast /* 4 * HIT_PRIM_CACHE ints */)
 {
 	const int ns = sh.n_seg[f], qlen_sum = post_qlen_sum(sh, f);
 	const int64_t o = sh.uoff[f];
@@ -160,7 +160,7 @@ MMG_HDN inline void post_hits_select_warp(const W &wp, const PostShard &sh, int 
 	const bool tree = n_in > 0 && !(sh.opt.flag & HIT_F_ALL_CHAINS);
 	if (n_in > 0) wp.one([&]() { post_hits_fix_order(sh, f); });
 	if (tree) {
-		if (qlen_sum <= HIT_COVER_BITS) hit_set_parent_warp(wp, sh.opt.mask_level, n_in, sh.r0 + o, (sh.opt.flag & HIT_F_HARD_MLEVEL) != 0, sh.w + o, reinterpret_cast<uint32_t*>(sh.cov + o));
+		if (qlen_sum <= HIT_COVER_BITS) hit_set_parent_warp(wp, sh.opt.mask_level, n_in, sh.r0 + o, (sh.opt.flag & HIT_F_HARD_MLEVEL) != 0, sh.w + o, fast);
 		else wp.one([&]() { hit_set_parent(sh.opt.mask_level, n_in, sh.r0 + o, sh.opt.a * 2 + sh.opt.b, (sh.opt.flag & HIT_F_HARD_MLEVEL) != 0, sh.w + o, sh.cov + o, nullptr); });
 	}
 	wp.one([&]() {

@@ -92,6 +92,11 @@ __global__ void k_plan(FragTab ft, const int32_t *__restrict__ list, int n_list,
 			for (int j = i + 1; j < m; ++j)
 				if (mv[b + j].x >> 8 == h && m_n[b + j] > 0 && m_n[b + j] < max_occ) { dup = 1; break; }
 		}
+		if (dup) { // 1: the heap is replayed on ranks (k_heap_replay); 2: too many lists or anchors for its packed words -> literal replay (k_fill)
+			int kept = 0;
+			for (int i = 0; i < m; ++i) kept += m_n[b + i] > 0 && m_n[b + i] < max_occ;
+			dup = (kept <= 256 && n_a < (1 << 24)) ? 1 : 2;
+		}
 		replay[li] = dup;
 	}
 }
@@ -106,7 +111,7 @@ __global__ void k_expand(FragTab ft, const int32_t *__restrict__ list, int n_lis
 	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= n_total) return;
 	const int li = frag_of_anchor(aoff, n_list, g);
-	if (replay[li]) return; // segment of length zero in the sort
+	if (replay[li] == 2) return; // segment of length zero in the sort
 	const int f = list ? list[li] : li;
 	const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]];
 	int64_t i = g - aoff[li];
@@ -119,6 +124,7 @@ __global__ void k_expand(FragTab ft, const int32_t *__restrict__ list, int n_lis
 	}
 	const mm128 mz = mv[b + m];
 	const uint64_t r = mmg_hit_pos(pos, m_n[b + m], m_val[b + m], (uint32_t)i);
+	if (replay[li] == 1) { key[g] = r, val[g] = (uint64_t)(g - aoff[li]); return; } // heap replay: ordered by position alone, the planned slot as payload
 	if (mmg_skip_seed(flag, r, (uint32_t)mz.y)) { key[g] = MMG_NONE, val[g] = 0; atomicAdd(&n_skipped[li], 1); return; }
 	const mm128 an = mmg_make_anchor(r, mz, mmg_is_tandem(mv + b, (int)(e - b), m), ft.qlen[f]);
 	key[g] = (an.x & (1ULL << 63)) | r; // r < 2^63
@@ -130,7 +136,7 @@ __global__ void k_sort_segments(int n_list, const int64_t *__restrict__ aoff, co
 	const int li = blockIdx.x * blockDim.x + threadIdx.x;
 	if (li >= n_list) return;
 	seg_b[li] = aoff[li];
-	seg_e[li] = replay[li] ? aoff[li] : aoff[li + 1];
+	seg_e[li] = replay[li] == 2 ? aoff[li] : aoff[li + 1];
 }
 
 __global__ void k_emit_sorted(int n_list, const int64_t *__restrict__ aoff, const uint8_t *__restrict__ replay, int64_t n_total,
@@ -152,6 +158,103 @@ __global__ void k_emit_sorted(int n_list, const int64_t *__restrict__ aoff, cons
 	if (tie && g > aoff[li]) { // radix-sort form (collect_seed_hits, map.c:215-247): two anchors with the same x leave klib's sort in an order only a replay gives
 		const uint64_t kp = key[g - 1], rp = kp & ~(1ULL << 63);
 		if (((kp & (1ULL << 63)) | (rp & 0xffffffff00000000ULL) | ((uint32_t)rp >> 1)) == an.x) tie[li] = 1;
+	}
+}
+
+// ---- K2c, heap replay on ranks (fragments in which two kept query minimizers share a hash: equal positions meet in the heap,
+// and the order they leave it in is defined by klib's heap).  The sort above ordered the fragment's planned hits
+// by position; the heap replay itself then needs no position at all (mmg_heap_replay_ranks).
+
+// rank of every planned hit: index of the first hit with the same position
+__global__ void k_heap_rank(int n_list, const int64_t *__restrict__ aoff, const uint8_t *__restrict__ replay, int64_t n_total,
+                            const uint64_t *__restrict__ key, const uint64_t *__restrict__ val, uint32_t *__restrict__ K)
+{
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n_total) return;
+	const int li = frag_of_anchor(aoff, n_list, g);
+	if (replay[li] != 1) return;
+	const int64_t ao = aoff[li];
+	int64_t l = g;
+	const uint64_t k = key[g];
+	while (l > ao && key[l - 1] == k) --l;
+	K[ao + (int64_t)val[g]] = (uint32_t)(l - ao);
+}
+
+__global__ void k_heap_list(int n_list, const uint8_t *__restrict__ replay, int32_t *__restrict__ out, int32_t *__restrict__ counters)
+{
+	const int li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li < n_list && replay[li] == 1) out[atomicAdd(&counters[0], 1)] = li;
+}
+
+#define HEAP_MAX_LISTS 256
+// one warp per listed fragment, pulled from a counter: lane 0 replays the heap (state in shared memory), then the warp turns the
+// pop order into anchors -- forward-strand hits in pop order, then reverse-strand hits in pop order (map.c:176-211)
+__global__ void __launch_bounds__(64)
+k_heap_replay(FragTab ft, const int32_t *__restrict__ list, const int32_t *__restrict__ rlist, int32_t *__restrict__ counters, const mm128 *__restrict__ mv,
+              const int32_t *__restrict__ m_n, const uint64_t *__restrict__ m_val, const int32_t *__restrict__ m_aoff, const uint64_t *__restrict__ pos, int max_occ,
+              int64_t flag, const int64_t *__restrict__ aoff, const uint32_t *__restrict__ K, uint32_t *__restrict__ P, int32_t *__restrict__ na, mm128 *__restrict__ a)
+{
+	__shared__ uint32_t s_heap[2][HEAP_MAX_LISTS], s_cur[2][HEAP_MAX_LISTS];
+	__shared__ int32_t s_first[2][HEAP_MAX_LISTS], s_cnt[2][HEAP_MAX_LISTS], s_m[2][HEAP_MAX_LISTS];
+	const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const unsigned FULL = 0xffffffffu;
+	const int n_work = counters[0];
+	for (;;) {
+		int t = 0;
+		if (lane == 0) t = atomicAdd(&counters[1], 1);
+		t = __shfl_sync(FULL, t, 0);
+		if (t >= n_work) break;
+		const int li = rlist[t], f = list ? list[li] : li;
+		const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]], ao = aoff[li];
+		const int n_mv = (int)(e - b), qlen = ft.qlen[f];
+		int n_lists = 0;
+		if (lane == 0) {
+			for (int i = 0; i < n_mv; ++i)
+				if (m_n[b + i] > 0 && m_n[b + i] < max_occ) s_first[wi][n_lists] = m_aoff[b + i], s_cnt[wi][n_lists] = m_n[b + i], s_m[wi][n_lists] = i, ++n_lists;
+			mmg_heap_replay_ranks(n_lists, s_first[wi], s_cnt[wi], K + ao, s_heap[wi], s_cur[wi], P + ao);
+		}
+		n_lists = __shfl_sync(FULL, n_lists, 0);
+		__syncwarp();
+		const int n_a = n_lists ? s_first[wi][n_lists - 1] + s_cnt[wi][n_lists - 1] : 0;
+		// pass 1: strand class of every pop (kept in the two top bits of its word), totals
+		int n_for = 0, n_rev = 0;
+		for (int t0 = 0; t0 < n_a; t0 += 32) {
+			const int tt = t0 + lane;
+			int cls = 0;
+			if (tt < n_a) {
+				const uint32_t slot = P[ao + tt];
+				int lo = 0, hi = n_lists - 1; // list of the slot
+				while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((uint32_t)s_first[wi][mid] <= slot) lo = mid; else hi = mid - 1; }
+				const int m = s_m[wi][lo];
+				const uint64_t r = mmg_hit_pos(pos, m_n[b + m], m_val[b + m], slot - (uint32_t)s_first[wi][lo]);
+				const uint32_t qp = (uint32_t)mv[b + m].y;
+				cls = mmg_skip_seed(flag, r, qp) ? 0 : ((r & 1) == (qp & 1) ? 1 : 2);
+				P[ao + tt] = slot | (uint32_t)cls << 30;
+			}
+			n_for += __popc(__ballot_sync(FULL, cls == 1)), n_rev += __popc(__ballot_sync(FULL, cls == 2));
+		}
+		__syncwarp();
+		// pass 2: anchors
+		int run_for = 0, run_rev = 0;
+		for (int t0 = 0; t0 < n_a; t0 += 32) {
+			const int tt = t0 + lane;
+			int cls = 0; uint32_t slot = 0;
+			if (tt < n_a) { const uint32_t w = P[ao + tt]; cls = (int)(w >> 30), slot = w & 0x3fffffffu; }
+			const unsigned mf = __ballot_sync(FULL, cls == 1), mr = __ballot_sync(FULL, cls == 2);
+			if (cls) {
+				int lo = 0, hi = n_lists - 1;
+				while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((uint32_t)s_first[wi][mid] <= slot) lo = mid; else hi = mid - 1; }
+				const int m = s_m[wi][lo];
+				const uint64_t r = mmg_hit_pos(pos, m_n[b + m], m_val[b + m], slot - (uint32_t)s_first[wi][lo]);
+				const mm128 an = mmg_make_anchor(r, mv[b + m], mmg_is_tandem(mv + b, n_mv, m), qlen);
+				const unsigned below = (1u << lane) - 1u;
+				if (cls == 1) a[ao + run_for + __popc(mf & below)] = an;
+				else a[ao + n_for + run_rev + __popc(mr & below)] = an;
+			}
+			run_for += __popc(mf), run_rev += __popc(mr);
+		}
+		if (lane == 0) na[li] = n_for + n_rev;
+		__syncwarp();
 	}
 }
 
@@ -206,13 +309,13 @@ __device__ int64_t fill_heap_prefetch(const mm128 *mv, const int32_t *m_n, const
 __global__ void k_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
                        const uint64_t *__restrict__ m_val, const uint64_t *__restrict__ pos, int max_occ, int64_t flag,
                        const int64_t *__restrict__ aoff, int32_t *__restrict__ na, mm128 *__restrict__ a, mm128 *__restrict__ heap, RsFrame *__restrict__ stack,
-                       const uint8_t *__restrict__ replay /* null: every fragment */, int per_warp)
+                       const uint8_t *__restrict__ replay /* null: every fragment */, int want /* value of replay[] that selects a fragment */, int per_warp)
 {
 	// per_warp: one fragment per warp (lane 0 works).  The re-chain pass lists a few hundred fragments of ~10^5 anchors each; as
 	// neighbouring threads of one warp their serial replays diverged and ran one after the other (36 ms for 192 fragments)
 	const int gt = blockIdx.x * blockDim.x + threadIdx.x, li = per_warp ? gt >> 5 : gt;
 	if (li >= n_list || (per_warp && (gt & 31))) return;
-	if (replay && !replay[li]) return;
+	if (replay && replay[li] != want) return;
 	const int f = list ? list[li] : li;
 	const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]];
 	const int64_t ao = aoff[li];
@@ -917,12 +1020,25 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		MMG_LAUNCH(c, k_emit_sorted, mmg_blocks(tot, 256), 256, 0, n_list, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), tot, k1, v1, n_skipped,
 		           pb.na->as<int32_t>(), pb.a->as<mm128>(), d_tie);
 	}
-	// literal replay: the heap merge for fragments with repeated hashes; fill + klib radix sort for the non-heap presets
+	if (heap_path && tot > 0) { // fragments where equal positions meet in the heap: replay it on the ranks the sort just produced
+		MMG_TRY(c->d_hrank.ensure(((size_t)tot + 1) * 4));
+		MMG_TRY(c->d_hpop.ensure(((size_t)tot + 1) * 4));
+		MMG_TRY(c->d_hlist.ensure(((size_t)n_list + 8) * 4));
+		int32_t *counters = c->d_hlist.as<int32_t>(), *rlist = counters + 4;
+		const uint64_t *k1 = c->d_skey.as<uint64_t>() + tot + 1, *v1 = c->d_sval.as<uint64_t>() + tot + 1;
+		MMG_CUDA(cudaMemsetAsync(counters, 0, 16, c->stream));
+		MMG_LAUNCH(c, k_heap_rank, mmg_blocks(tot, 256), 256, 0, n_list, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), tot, k1, v1, c->d_hrank.as<uint32_t>());
+		MMG_LAUNCH(c, k_heap_list, mmg_blocks(n_list, 256), 256, 0, n_list, c->d_replay.as<uint8_t>(), rlist, counters);
+		MMG_LAUNCH(c, k_heap_replay, 148 * 4, 64, 0, ft, d_list, rlist, counters, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
+		           c->d_m_aoff.as<int32_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_hrank.as<uint32_t>(), c->d_hpop.as<uint32_t>(),
+		           pb.na->as<int32_t>(), pb.a->as<mm128>());
+	}
+	// literal replay: the heap merge for the few fragments the rank replay does not take; fill + klib radix sort for the non-heap presets
 	{
 		const int per_warp = d_flag == nullptr || n_list <= 4096 ? 1 : 0; // the re-chain pass (and any small list): spread over warps
 		MMG_LAUNCH(c, k_fill, mmg_blocks(per_warp ? (size_t)n_list * 32 : (size_t)n_list, 64), 64, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(),
 		           c->d_m_val.as<uint64_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>(), c->d_heap.as<mm128>(),
-		           pb.stack->as<RsFrame>(), heap_path ? c->d_replay.as<uint8_t>() : d_tie, per_warp);
+		           pb.stack->as<RsFrame>(), heap_path ? c->d_replay.as<uint8_t>() : d_tie, heap_path ? 2 : 1, per_warp);
 	}
 	if (getenv("MMG_TRACE")) { // distribution of the literal-replay work of this pass (debug aid; synchronises)
 		std::vector<uint8_t> hr((size_t)n_list); std::vector<int32_t> hn((size_t)n_list);

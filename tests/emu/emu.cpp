@@ -72,6 +72,40 @@ int64_t emu_collect(void *idx, int heap_sort, int64_t flag, int max_occ, int n_m
 	return mmg_fill_flat(mv, m_n.data(), m_val.data(), n_mv, max_occ, e->v.pos, flag, qlen, a, stack.data());
 }
 
+// collect_seed_hits_heap the way the device does it for fragments whose heap order matters: plan -> expand (key = position) ->
+// sort -> tie-group ranks -> mmg_heap_replay_ranks -> anchors in pop order, forward strand first (map.c:149-213)
+int64_t emu_collect_ranked(void *idx, int64_t flag, int max_occ, int n_mv, const mm128 *mv, int qlen, mm128 *a, int64_t a_cap, int *rep_len, int *n_mini)
+{
+	EmuIdx *e = (EmuIdx*)idx;
+	std::vector<int32_t> m_n(n_mv + 1), m_aoff(n_mv + 1); std::vector<uint64_t> m_val(n_mv + 1);
+	for (int i = 0; i < n_mv; ++i) m_n[i] = mmg_idx_probe(e->v, mv[i].x >> 8, &m_val[i]);
+	const int64_t n_a = mmg_frag_plan(mv, m_n.data(), n_mv, max_occ, rep_len, n_mini, nullptr);
+	if (n_a > a_cap) return n_a;
+	std::vector<int32_t> first, cnt, list_m;
+	int32_t run = 0;
+	for (int i = 0; i < n_mv; ++i) { m_aoff[i] = run; if (m_n[i] > 0 && m_n[i] < max_occ) { first.push_back(run), cnt.push_back(m_n[i]), list_m.push_back(i); run += m_n[i]; } }
+	if ((int)first.size() > 256 || n_a >= (1 << 24)) return -1;
+	std::vector<uint64_t> key(n_a); std::vector<int32_t> slot_m(n_a), slot_i(n_a), ord(n_a);
+	for (size_t j = 0; j < first.size(); ++j)
+		for (int i = 0; i < cnt[j]; ++i) { const int s = first[j] + i; key[s] = mmg_hit_pos(e->v.pos, m_n[list_m[j]], m_val[list_m[j]], (uint32_t)i); slot_m[s] = list_m[j], slot_i[s] = i; ord[s] = s; }
+	std::sort(ord.begin(), ord.end(), [&](int x, int y) { return key[x] < key[y] || (key[x] == key[y] && x > y); }); // ties in any order: here, reversed
+	std::vector<uint32_t> K(n_a + 1), heap(first.size() + 1), cur(first.size() + 1), pop(n_a + 1);
+	for (int64_t g = 0; g < n_a; ++g) { int64_t l = g; while (l > 0 && key[ord[l - 1]] == key[ord[g]]) --l; K[ord[g]] = (uint32_t)l; }
+	const int64_t np = mmg_heap_replay_ranks((int)first.size(), first.data(), cnt.data(), K.data(), heap.data(), cur.data(), pop.data());
+	if (np != n_a) return -2;
+	std::vector<mm128> fw, rv;
+	for (int64_t t = 0; t < n_a; ++t) {
+		const int m = slot_m[pop[t]];
+		const uint64_t r = key[pop[t]];
+		if (mmg_skip_seed(flag, r, (uint32_t)mv[m].y)) continue;
+		const mm128 an = mmg_make_anchor(r, mv[m], mmg_is_tandem(mv, n_mv, m), qlen);
+		((r & 1) == ((uint32_t)mv[m].y & 1) ? fw : rv).push_back(an);
+	}
+	std::copy(fw.begin(), fw.end(), a);
+	std::copy(rv.begin(), rv.end(), a + fw.size());
+	return (int64_t)(fw.size() + rv.size());
+}
+
 int emu_chain(int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc, int is_cdna, int n_segs,
               int64_t n, mm128 *a, uint64_t *u_out)
 {
@@ -135,6 +169,7 @@ int emu_ksw_fast(int qlen, const uint8_t *query, int tlen, const uint8_t *target
 // ---- the post-chaining stages (mmg_post.h) for ONE fragment, every step run the way the kernels of mmg_post.cu run it,
 // with the DP jobs answered by the scalar ksw walk above.  reads: 0..4 codes in mapping orientation.
 #include <math.h>
+#define HIT_PRIM_CACHE 2 // tiny on purpose: the third primary of a fragment already takes the path the device uses beyond its cache
 #include "mmg_post.h"
 
 extern "C" int emu_post_frag(const HitOpt *opt, int idx_k, uint32_t hash, int n_segs, const int32_t *qlens, const uint8_t *const *reads, const uint8_t *flip,
@@ -169,7 +204,7 @@ extern "C" int emu_post_frag(const HitOpt *opt, int idx_k, uint32_t hash, int n_
 	std::vector<mm128> a(a_in, a_in + n_v), a1(n_v + 1);
 	std::vector<uint32_t> hv(1, hash);
 	sh.nu = nu.data(), sh.rep = rep.data(), sh.uoff = uoff.data(), sh.voff = voff.data(), sh.u = u.data(), sh.a = a.data(), sh.hash = hv.data(), sh.a1 = a1.data();
-	const int m = n_u + 40; // the warp form keeps a 64-word bitmap in the cov scratch
+	const int m = n_u + 1;
 	std::vector<uint64_t> key_in(m), key(m), ascnt(m), cov(m);
 	std::vector<HitRec> r0(m);
 	std::vector<int32_t> w(m), n0(1);
@@ -192,7 +227,7 @@ extern "C" int emu_post_frag(const HitOpt *opt, int idx_k, uint32_t hash, int n_
 		for (int i = 0; i < n_u; ++i) key[i] = key_in[ord[i]], ascnt[i] = val_in[ord[i]];
 		for (int g = 0; g < n_u; ++g) post_hit_record(sh, g);
 	}
-	if (getenv("EMU_WARP") && n_u >= atoi(getenv("EMU_WARP"))) post_hits_select_warp(WarpEmu(), sh, 0); // the warp-cooperative form, lanes emulated one after the other
+	if (getenv("EMU_WARP") && n_u >= atoi(getenv("EMU_WARP"))) { std::vector<int32_t> fast(4 * HIT_PRIM_CACHE); post_hits_select_warp(WarpEmu(), sh, 0, fast.data()); } // the warp-cooperative form, lanes emulated one after the other
 	else post_hits_select(sh, 0);
 	for (int j = 0; j < n_segs; ++j) roff[j + 1] = roff[j] + cap[j];
 	const int64_t slots = roff[n_segs] + 1;

@@ -29,6 +29,8 @@ def emu():
     E.emu_collect.restype = C.c_int64
     E.emu_collect.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+    E.emu_collect_ranked.restype = C.c_int64
+    E.emu_collect_ranked.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     E.emu_chain.restype = C.c_int
     E.emu_chain.argtypes = [C.c_int] * 9 + [C.c_int64, C.c_void_p, C.c_void_p]
     E.emu_rs_sort_128x.argtypes = [C.c_void_p, C.c_int64]
@@ -107,6 +109,11 @@ def test_seed_and_chain(emu, mode):
                                          C.byref(rep2), C.byref(nm2), mp2.ctypes.data)
                     assert n2 == len(a1) and rep2.value == rep1 and (mp2[:nm2.value] == mp1).all()
                     assert a2[:n2].tobytes() == a1.tobytes()
+                    if mode == "sr":  # the rank-based heap replay (what the device runs when equal positions meet in the heap)
+                        a3 = np.zeros(len(a0) + 64, dtype=L.mm128)
+                        rep3, nm3 = C.c_int(0), C.c_int(0)
+                        n3 = emu.emu_collect_ranked(ei, flag, max_occ, len(mv), mv.ctypes.data, qlen, a3.ctypes.data, len(a3), C.byref(rep3), C.byref(nm3))
+                        assert n3 == len(a1) and rep3.value == rep1 and a3[:n3].tobytes() == a1.tobytes()
                 params = SR_CHAIN if mode == "sr" else ONT_CHAIN
                 a1, _, _ = L.orc_collect(oi, mode == "sr", 0, max_occ, mv, qlen)
                 u1, b1 = L.chain_call(L.oracle().orc_chain_dp, params, a1)
