@@ -120,6 +120,11 @@ struct mmg_ctx_s {
 	DevBuf pb[PB_COUNT];
 	int post_logtab_a = 0;             // match score the resident logf tables were made for
 	int64_t last_tot_u = 0, last_tot_v = 0; // chains / chained anchors left on the device by the last mmg_seed_chain_resident
+	// how many work items took each data-dependent path (mmg_path_counts): [0] fragments re-chained with max_occ, [1] fragments whose
+	// heap order was replayed on ranks, [2] ... replayed literally, [3] fragments whose hit tree was built by a warp, [4] extra DP rounds
+	// after z-drop cuts, [5] hits cut at a z-drop
+	uint64_t path[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	PinBuf h_path;                     // device counters of the pass in flight land here
 	PinBuf h_p_hash, h_p_nreg, h_p_offs, h_p_blob, h_p_rep;
 	PinBuf h_in, h_meta, h_out_meta, h_out_u, h_out_a, h_out_mini, h_k_jobs, h_k_res, h_k_cig;
 };

@@ -633,6 +633,8 @@ struct WarpEmu { // 32 lanes, one after the other; per-lane variables are arrays
 	template <class F> int sum(F &&f) const { int s = 0; for (int l = 0; l < 32; ++l) s += f(l); return s; }
 	template <class F> void each(F &&f) const { for (int l = 0; l < 32; ++l) f(l); }
 	template <class F> void one(F &&f) const { f(); }
+	static void amax(int32_t *p, int32_t v) { if (*p < v) *p = v; }
+	static void aadd(int32_t *p, int32_t v) { *p += v; }
 };
 #ifdef __CUDACC__
 struct WarpDev { // per-lane variables are registers
@@ -642,6 +644,8 @@ struct WarpDev { // per-lane variables are registers
 	template <class F> __device__ int sum(F &&f) const { return __reduce_add_sync(0xffffffffu, f(lane)); }
 	template <class F> __device__ void each(F &&f) const { f(lane); __syncwarp(); }
 	template <class F> __device__ void one(F &&f) const { if (lane == 0) f(); __syncwarp(); }
+	static __device__ void amax(int32_t *p, int32_t v) { atomicMax(p, v); }
+	static __device__ void aadd(int32_t *p, int32_t v) { atomicAdd(p, v); }
 };
 #endif
 
@@ -658,63 +662,130 @@ MMG_HD uint32_t hit_range_word(int s, int e, int word)
 #ifndef HIT_PRIM_CACHE
 #define HIT_PRIM_CACHE 96   // primaries whose query interval and counters are kept in fast memory (shared memory on the device)
 #endif
+#define HIT_FAST_WORDS (5 * HIT_PRIM_CACHE + 64)   // ints of fast scratch a warp needs: 5 per cached primary + the coverage bitmap
 
 // n hits with 0 <= qs < qe <= HIT_COVER_BITS, no alignment records yet.  w[]: n ints (the primaries, as in hit_set_parent);
-// pc[]: 4 * HIT_PRIM_CACHE ints of fast scratch (qs, qe, subsc, n_sub of the first primaries).  Result == hit_set_parent's.
+// fast[]: HIT_FAST_WORDS ints of fast scratch.  Result == hit_set_parent's.
+// Hits are judged 32 at a time, one per lane, against the primaries known so far: what a masked hit does to its primary (a
+// maximum and a count) does not depend on the order, so a group of hits that all find a masking primary is committed at once.
+// The first hit of a group that finds none becomes a primary; the hits after it are judged again with it in place.
 template <class W>
-MMG_HDN inline void hit_set_parent_warp(const W &wp, float mask_level, int n, HitRec *r, bool hard_mask_level, int32_t *w, int32_t *pc)
+MMG_HDN inline void hit_set_parent_warp(const W &wp, float mask_level, int n, HitRec *r, bool hard_mask_level, int32_t *w, int32_t *fast)
 {
 	if (n <= 0) return;
-	typename W::template Var<uint32_t> c0, c1; // query positions covered by a primary: lane l holds positions [32 l, 32 l + 32) and [1024 + 32 l, ...)
-	wp.each([&](int l) { for (int i = l; i < n; i += 32) r[i].id = i; c0(l) = hit_range_word(r[0].qs, r[0].qe, l), c1(l) = hit_range_word(r[0].qs, r[0].qe, l + 32); });
-	wp.one([&]() { w[0] = 0, r[0].parent = 0; pc[0] = r[0].qs, pc[1] = r[0].qe, pc[2] = r[0].subsc, pc[3] = r[0].n_sub; });
+	int32_t *pc = fast;                                              // qs, qe, subsc, n_sub, cnt of the first primaries
+	uint32_t *cbm = reinterpret_cast<uint32_t*>(fast + 5 * HIT_PRIM_CACHE); // query positions covered by any primary
+	wp.each([&](int l) { for (int i = l; i < n; i += 32) r[i].id = i; cbm[l] = hit_range_word(r[0].qs, r[0].qe, l), cbm[l + 32] = hit_range_word(r[0].qs, r[0].qe, l + 32); });
+	wp.one([&]() { w[0] = 0, r[0].parent = 0; pc[0] = r[0].qs, pc[1] = r[0].qe, pc[2] = r[0].subsc, pc[3] = r[0].n_sub, pc[4] = r[0].cnt; });
 	int k = 1;
-	for (int i = 1; i < n; ++i) {
-		const int si = r[i].qs, ei = r[i].qe;
-		int uncov_len = 0, j = -1;
-		bool judge = true;
-		if (!hard_mask_level) {
-			const int cov = wp.sum([&](int l) { return (int)(mmg_popc(c0(l) & hit_range_word(si, ei, l)) + mmg_popc(c1(l) & hit_range_word(si, ei, l + 32))); });
-			if (cov == 0) judge = false;
-			else uncov_len = (ei - si) - cov;
-		}
-		if (judge)
-			for (int base = 0; base < k && j < 0; base += 32) {
-				const unsigned m = wp.ballot([&](int l) {
-					const int t = base + l;
-					if (t >= k) return false;
+	typename W::template Var<int32_t> verdict;
+	for (int base = 1; base < n;) {
+		wp.each([&](int l) {
+			const int i = base + l;
+			if (i >= n) { verdict(l) = -2; return; }
+			const int si = r[i].qs, ei = r[i].qe;
+			int uncov_len = 0, j = -1;
+			bool judge = true;
+			if (!hard_mask_level) {
+				int cov = 0;
+				for (int wd = si >> 5; wd <= (ei - 1) >> 5; ++wd) cov += mmg_popc(cbm[wd] & hit_range_word(si, ei, wd));
+				if (cov == 0) judge = false;
+				else uncov_len = (ei - si) - cov;
+			}
+			if (judge)
+				for (int t = 0; t < k; ++t) {
 					int sj, ej;
-					if (t < HIT_PRIM_CACHE) sj = pc[4 * t], ej = pc[4 * t + 1];
+					if (t < HIT_PRIM_CACHE) sj = pc[5 * t], ej = pc[5 * t + 1];
 					else sj = r[w[t]].qs, ej = r[w[t]].qe;
-					if (ej <= si || sj >= ei) return false;
+					if (ej <= si || sj >= ei) continue;
 					const int mn = ej - sj < ei - si ? ej - sj : ei - si, mx = ej - sj > ei - si ? ej - sj : ei - si;
 					const int ol = si < sj ? (ei < sj ? 0 : ei < ej ? ei - sj : ej - sj) : (ej < si ? 0 : ej < ei ? ej - si : ei - si);
-					return (float)ol / mn - (float)uncov_len / mx > mask_level;
-				});
-				if (m) j = base + mmg_ffs(m) - 1;
-			}
-		if (j >= 0) {
-			wp.one([&]() {
-				HitRec *ri = &r[i];
-				const int pi = w[j];
-				ri->parent = pi; // a primary is its own parent
-				if (j < HIT_PRIM_CACHE) {
-					if (pc[4 * j + 2] < ri->score) pc[4 * j + 2] = ri->score;
-					if (ri->cnt >= r[pi].cnt) ++pc[4 * j + 3];
-				} else {
-					HitRec *rp = &r[pi];
-					rp->subsc = rp->subsc > ri->score ? rp->subsc : ri->score;
-					if (ri->cnt >= rp->cnt) ++rp->n_sub;
+					if ((float)ol / mn - (float)uncov_len / mx > mask_level) { j = t; break; }
 				}
-			});
-		} else {
+			verdict(l) = j;
+		});
+		const unsigned m_new = wp.ballot([&](int l) { return verdict(l) == -1; });
+		const int first_new = m_new ? mmg_ffs(m_new) - 1 : 32;
+		wp.each([&](int l) { // the hits before the first new primary are masked: commit them
+			const int i = base + l, j = verdict(l);
+			if (l >= first_new || j < 0) return;
+			HitRec *ri = &r[i];
+			ri->parent = w[j]; // a primary is its own parent
+			if (j < HIT_PRIM_CACHE) { W::amax(&pc[5 * j + 2], ri->score); if (ri->cnt >= pc[5 * j + 4]) W::aadd(&pc[5 * j + 3], 1); }
+			else { HitRec *rp = &r[w[j]]; W::amax(&rp->subsc, ri->score); if (ri->cnt >= rp->cnt) W::aadd(&rp->n_sub, 1); }
+		});
+		if (first_new < 32) {
+			const int i = base + first_new, si = r[i].qs, ei = r[i].qe;
 			wp.one([&]() {
 				w[k] = i, r[i].parent = i, r[i].n_sub = 0;
-				if (k < HIT_PRIM_CACHE) pc[4 * k] = si, pc[4 * k + 1] = ei, pc[4 * k + 2] = r[i].subsc, pc[4 * k + 3] = 0;
+				if (k < HIT_PRIM_CACHE) pc[5 * k] = si, pc[5 * k + 1] = ei, pc[5 * k + 2] = r[i].subsc, pc[5 * k + 3] = 0, pc[5 * k + 4] = r[i].cnt;
 			});
-			wp.each([&](int l) { c0(l) |= hit_range_word(si, ei, l), c1(l) |= hit_range_word(si, ei, l + 32); });
+			wp.each([&](int l) { cbm[l] |= hit_range_word(si, ei, l), cbm[l + 32] |= hit_range_word(si, ei, l + 32); });
 			++k;
-		}
+			base = i + 1;
+		} else base += 32;
 	}
-	wp.each([&](int l) { for (int t = l; t < k && t < HIT_PRIM_CACHE; t += 32) r[w[t]].subsc = pc[4 * t + 2], r[w[t]].n_sub = pc[4 * t + 3]; });
+	wp.each([&](int l) { for (int t = l; t < k && t < HIT_PRIM_CACHE; t += 32) r[w[t]].subsc = pc[5 * t + 2], r[w[t]].n_sub = pc[5 * t + 3]; });
+}
+
+// pe.c:6-43 for a long hit list, by a warp.  The reference compacts the list in place while it reads the parents' records from
+// it, so a hit's verdict can depend on what was kept before it; but almost every hit of a repeat-family fragment is dropped,
+// and a group of 32 hits in which nothing is kept changes nothing.  Such groups are decided in one step; any other group runs
+// the reference's loop on one lane.  map[]: n ints.
+template <class W>
+MMG_HDN inline int hit_select_sub_multi_warp(const W &wp, float pri_ratio, float pri1, float pri2, int max_gap_ref, int min_diff, int best_n, int n_segs, const int32_t *qlens,
+                                             int n, HitRec *r, int32_t *map, int32_t *state /* 2 ints of fast scratch */)
+{
+	if (!(pri_ratio > 0.0f && n > 0)) return n;
+	const int max_dist = n_segs == 2 ? qlens[0] + qlens[1] + max_gap_ref : 0;
+	auto verdict = [&](int i) -> int { // 0: dropped, 1: primary, 2: secondary that passes the score rules (pe.c:17-33)
+		if (r[i].parent == i) return 1;
+		if (r[i].score + min_diff >= r[r[i].parent].score) return 2;
+		const HitRec *p = &r[r[i].parent], *q = &r[i];
+		const bool prev = p->bits & HB_REV, qrev = q->bits & HB_REV;
+		if (prev == qrev && p->rid == q->rid && q->re - p->rs < max_dist && p->re - q->rs < max_dist) return q->score >= p->score * pri1 ? 2 : 0;
+		const int par_both = (n_segs == 2 && p->qs < qlens[0] && p->qe > qlens[0]);
+		const int chi_both = (n_segs == 2 && q->qs < qlens[0] && q->qe > qlens[0]);
+		if (chi_both || chi_both == par_both) return q->score >= p->score * pri_ratio ? 2 : 0;
+		return q->score >= p->score * pri2 ? 2 : 0;
+	};
+	wp.one([&]() { state[0] = 0, state[1] = 0; }); // k, n_2nd
+	for (int base = 0; base < n; base += 32) {
+		const int k = state[0], n_2nd = state[1];
+		const unsigned m_pri = wp.ballot([&](int l) { return base + l < n && verdict(base + l) == 1; });
+		const unsigned m_2nd = wp.ballot([&](int l) { return base + l < n && verdict(base + l) == 2; });
+		if (m_pri == 0 && (m_2nd == 0 || n_2nd >= best_n)) { // nothing of this group survives: no record moves
+			wp.one([&]() { state[1] = n_2nd + mmg_popc(m_2nd); });
+			continue;
+		}
+		wp.one([&]() {
+			int kk = k, n2 = n_2nd;
+			const int end = base + 32 < n ? base + 32 : n;
+			for (int i = base; i < end; ++i) {
+				const int v = verdict(i);
+				bool keep = v != 0;
+				if (keep && r[i].parent != i && n2++ >= best_n) keep = false;
+				if (keep) r[kk++] = r[i];
+			}
+			state[0] = kk, state[1] = n2;
+		});
+	}
+	const int k = state[0];
+	if (k != n) { // mm_sync_regs (hit.c:214-236)
+		int max_id = -1;
+		for (int i = 0; i < k; ++i) max_id = max_id > r[i].id ? max_id : r[i].id;
+		wp.each([&](int l) { for (int i = l; i <= max_id; i += 32) map[i] = -1; });
+		wp.one([&]() {
+			for (int i = 0; i < k; ++i) if (r[i].id >= 0) map[r[i].id] = i;
+			for (int i = 0; i < k; ++i) {
+				HitRec *h = &r[i];
+				h->id = i;
+				if (h->parent == HIT_PARENT_TMP_PRI) h->parent = i;
+				else if (h->parent >= 0 && map[h->parent] >= 0) h->parent = map[h->parent];
+				else h->parent = HIT_PARENT_UNSET;
+			}
+			hit_set_sam_pri(k, r);
+		});
+	}
+	return k;
 }

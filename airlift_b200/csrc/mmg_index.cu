@@ -53,7 +53,7 @@ extern "C" void mmg_destroy(mmg_ctx_t *c)
 	for (DevBuf *b : bufs) b->release();
 	for (DevBuf &b : c->pb) b.release();
 	PinBuf *pins[] = {&c->h_in, &c->h_meta, &c->h_out_meta, &c->h_out_u, &c->h_out_a, &c->h_out_mini, &c->h_k_jobs, &c->h_k_res, &c->h_k_cig,
-	                  &c->h_p_hash, &c->h_p_nreg, &c->h_p_offs, &c->h_p_blob, &c->h_p_rep};
+	                  &c->h_p_hash, &c->h_p_nreg, &c->h_p_offs, &c->h_p_blob, &c->h_p_rep, &c->h_path};
 	for (PinBuf *b : pins) b->release();
 	for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (const ProfRec &r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -73,6 +73,11 @@ extern "C" void mmg_copy_bytes(mmg_ctx_t *c, uint64_t *h2d, uint64_t *d2h, int r
 }
 
 extern "C" void mmg_profile_enable(mmg_ctx_t *c, int on) { c->prof_on = on != 0; }
+
+extern "C" void mmg_path_counts(mmg_ctx_t *c, uint64_t out[8], int reset)
+{
+	for (int i = 0; i < 8; ++i) { out[i] = c->path[i]; if (reset) c->path[i] = 0; }
+}
 
 // per-kernel device time since the last fetch, from CUDA events recorded around every launch on the ctx stream.
 // Fills up to max entries (name pointers are static strings); returns the number of distinct kernels.

@@ -70,8 +70,9 @@ __global__ void __launch_bounds__(128) k_post_select_warp(const PostShard *__res
 	if (t >= shp->nf) return;
 	const int f = perm[t];
 	if (shp->nu[f] <= POST_WARP_MIN_CHAINS) return;
-	__shared__ int32_t s_fast[4][4 * HIT_PRIM_CACHE];
+	__shared__ int32_t s_fast[4][HIT_FAST_WORDS + 2];
 	WarpDev wp = {(int)(threadIdx.x & 31)};
+	if (wp.lane == 0) atomicAdd(shp->ctr + 3, 1u);
 	post_hits_select_warp(wp, *shp, f, s_fast[threadIdx.x >> 5]);
 }
 
@@ -339,7 +340,9 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 				if (e != cudaSuccess) { mmg_set_error("post-chaining stages: %s", cudaGetErrorString(e)); return MMG_ECUDA; }
 			}
 			if (ctr[1] & POST_ERR_SLOTS) { mmg_set_error("post-chaining stages: a read was cut at z-drops more often than its hit slots allow"); return MMG_ELIMIT; }
+			c->path[5] += ctr[0];
 			if (ctr[0] == 0) break; // no hit was cut: every hit is aligned
+			c->path[4] += 1;
 			if (round > 64) { mmg_set_error("post-chaining stages: alignment made no progress"); return MMG_ECUDA; }
 		}
 		MMG_LAUNCH(c, k_post_final, mmg_blocks(n_seq, 128), 128, 0, d_sh);
@@ -356,6 +359,7 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 	MMG_D2H(c, &blob_bytes, B[X::PB_OFFS].as<int64_t>() + n_seq, 8);
 	MMG_D2H(c, ctr, hs.ctr, 16);
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
+	c->path[3] += ctr[3];
 	if (ctr[1] & POST_ERR_LOGTAB) { mmg_set_error("post-chaining stages: a MAPQ argument lies outside the logf table (alignment score above %d)", POST_LOGTAB_N); return MMG_ELIMIT; }
 	MMG_TRY(B[X::PB_BLOB].ensure((size_t)blob_bytes + 64));
 	MMG_LAUNCH(c, k_post_pack, mmg_blocks(n_seq, 128), 128, 0, d_sh, B[X::PB_OFFS].as<int64_t>(), B[X::PB_BLOB].as<unsigned char>());

@@ -152,7 +152,7 @@ MMG_HDN inline void post_hits_select(const PostShard &sh, int f)
 // selection stays with one lane (it is a single pass whose reads depend on its own earlier writes, pe.c:13-40)
 #define POST_WARP_MIN_CHAINS 32
 template <class W>
-MMG_HDN inline void post_hits_select_warp(const W &wp, const PostShard &sh, int f, int32_t *fast /* 4 * HIT_PRIM_CACHE ints */)
+MMG_HDN inline void post_hits_select_warp(const W &wp, const PostShard &sh, int f, int32_t *fast /* HIT_FAST_WORDS + 2 ints */)
 {
 	const int ns = sh.n_seg[f], qlen_sum = post_qlen_sum(sh, f);
 	const int64_t o = sh.uoff[f];
@@ -163,16 +163,17 @@ MMG_HDN inline void post_hits_select_warp(const W &wp, const PostShard &sh, int 
 		if (qlen_sum <= HIT_COVER_BITS) hit_set_parent_warp(wp, sh.opt.mask_level, n_in, sh.r0 + o, (sh.opt.flag & HIT_F_HARD_MLEVEL) != 0, sh.w + o, fast);
 		else wp.one([&]() { hit_set_parent(sh.opt.mask_level, n_in, sh.r0 + o, sh.opt.a * 2 + sh.opt.b, (sh.opt.flag & HIT_F_HARD_MLEVEL) != 0, sh.w + o, sh.cov + o, nullptr); });
 	}
-	wp.one([&]() {
-		int n = n_in;
-		if (tree) {
-			if (ns <= 1) n = hit_select_sub(sh.opt.pri_ratio, sh.idx_k * 2, sh.opt.best_n, n, sh.r0 + o, sh.w + o);
-			else {
-				int32_t ql[8];
-				for (int j = 0; j < ns; ++j) ql[j] = sh.seq_len[sh.seg_off[f] + j];
-				n = hit_select_sub_multi(sh.opt.pri_ratio, 0.2f, 0.7f, post_frag_gap(sh.opt, qlen_sum), sh.idx_k * 2, sh.opt.best_n, ns, ql, n, sh.r0 + o, sh.w + o);
-			}
+	int n = n_in;
+	if (tree) {
+		if (ns <= 1) wp.one([&]() { fast[HIT_FAST_WORDS] = hit_select_sub(sh.opt.pri_ratio, sh.idx_k * 2, sh.opt.best_n, n_in, sh.r0 + o, sh.w + o); });
+		else {
+			int32_t ql[8];
+			for (int j = 0; j < ns; ++j) ql[j] = sh.seq_len[sh.seg_off[f] + j];
+			n = hit_select_sub_multi_warp(wp, sh.opt.pri_ratio, 0.2f, 0.7f, post_frag_gap(sh.opt, qlen_sum), sh.idx_k * 2, sh.opt.best_n, ns, ql, n_in, sh.r0 + o, sh.w + o, fast + HIT_FAST_WORDS);
 		}
+		if (ns <= 1) n = fast[HIT_FAST_WORDS];
+	}
+	wp.one([&]() {
 		sh.n0[f] = n;
 		for (int j = 0; j < ns; ++j) sh.cap[sh.seg_off[f] + j] = n > 0 ? POST_SLOTS(n) : 0;
 	});

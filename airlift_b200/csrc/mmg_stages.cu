@@ -183,10 +183,75 @@ __global__ void k_heap_rank(int n_list, const int64_t *__restrict__ aoff, const 
 __global__ void k_heap_list(int n_list, const uint8_t *__restrict__ replay, int32_t *__restrict__ out, int32_t *__restrict__ counters)
 {
 	const int li = blockIdx.x * blockDim.x + threadIdx.x;
-	if (li < n_list && replay[li] == 1) out[atomicAdd(&counters[0], 1)] = li;
+	if (li >= n_list) return;
+	if (replay[li] == 1) out[atomicAdd(&counters[0], 1)] = li;
+	else if (replay[li] == 2) atomicAdd(&counters[2], 1); // left to the literal replay of k_fill
 }
 
 #define HEAP_MAX_LISTS 256
+
+// mmg_heap_replay_ranks (mmg_core.h) tuned for one lane: the same pops in the same order.  The serial chain per pop is what
+// bounds a fragment with 10^5 hits, so (a) the root stays in a register, (b) the next rank of every list is fetched into
+// shared memory by an asynchronous copy while the previous sift runs, (c) the sift loads a node's children and grandchildren
+// together and descends two levels per round of shared-memory latency.
+__device__ __forceinline__ void heap_sift_root(uint32_t *l, uint32_t n, uint32_t tmp, uint32_t *root_out)
+{
+	uint32_t i = 0, root = tmp;
+	const uint32_t INF = 0xffffffffu;
+	for (;;) {
+		const uint32_t c = 2 * i + 1;
+		if (c >= n) break;
+		const uint32_t g = 2 * c + 1; // grandchildren g .. g + 3
+		const uint32_t a = l[c], b = c + 1 < n ? l[c + 1] : INF;
+		const uint32_t g0 = g < n ? l[g] : INF, g1 = g + 1 < n ? l[g + 1] : INF, g2 = g + 2 < n ? l[g + 2] : INF, g3 = g + 3 < n ? l[g + 3] : INF;
+		// level 1: the smaller child (the left one on ties); it moves up unless it is larger than tmp (ksort.h:47-51)
+		const bool right = c + 1 < n && (a >> 8) > (b >> 8);
+		const uint32_t k = right ? c + 1 : c, v = right ? b : a;
+		if ((v >> 8) > (tmp >> 8)) break;
+		l[i] = v;
+		if (i == 0) root = v;
+		i = k;
+		// level 2 from registers
+		const uint32_t c2 = 2 * k + 1;
+		if (c2 >= n) break;
+		const uint32_t a2 = right ? g2 : g0, b2 = right ? g3 : g1;
+		const bool right2 = c2 + 1 < n && (a2 >> 8) > (b2 >> 8);
+		const uint32_t k2 = right2 ? c2 + 1 : c2, v2 = right2 ? b2 : a2;
+		if ((v2 >> 8) > (tmp >> 8)) break;
+		l[i] = v2;
+		i = k2;
+	}
+	l[i] = tmp;
+	*root_out = i == 0 ? tmp : root;
+}
+
+__device__ int64_t heap_replay_lane(int n_lists, const int32_t *first, const int32_t *cnt, const uint32_t *__restrict__ K, uint32_t *heap, uint32_t *cur, uint32_t *nxt,
+                                    uint32_t *__restrict__ pop)
+{
+	uint32_t hs = 0;
+	int64_t t = 0;
+	for (int j = 0; j < n_lists; ++j) { heap[hs++] = K[first[j]] << 8 | (uint32_t)j; cur[j] = 0; nxt[j] = cnt[j] > 1 ? K[first[j] + 1] : 0; }
+	if (hs > 1) for (int32_t j = (int32_t)(hs >> 1) - 1; j >= 0; --j) mmg_rank_heap_down((uint32_t)j, hs, heap);
+	uint32_t root = hs ? heap[0] : 0;
+	while (hs > 0) {
+		const uint32_t j = root & 0xff, c = cur[j], f0 = (uint32_t)first[j], n = (uint32_t)cnt[j];
+		pop[t++] = f0 + c;
+		uint32_t tmp;
+		if (c + 1 < n) {
+			asm volatile("cp.async.wait_all;" ::: "memory"); // the copy issued one pop ago has had a whole sift to land
+			tmp = nxt[j] << 8 | j;
+			cur[j] = c + 1;
+			if (c + 2 < n) {
+				const unsigned dst = (unsigned)__cvta_generic_to_shared(&nxt[j]);
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(K + f0 + c + 2) : "memory");
+			}
+		} else { tmp = heap[hs - 1]; --hs; }
+		if (hs > 0) heap_sift_root(heap, hs, tmp, &root);
+	}
+	asm volatile("cp.async.wait_all;" ::: "memory");
+	return t;
+}
+
 // one warp per listed fragment, pulled from a counter: lane 0 replays the heap (state in shared memory), then the warp turns the
 // pop order into anchors -- forward-strand hits in pop order, then reverse-strand hits in pop order (map.c:176-211)
 __global__ void __launch_bounds__(64)
@@ -194,7 +259,7 @@ k_heap_replay(FragTab ft, const int32_t *__restrict__ list, const int32_t *__res
               const int32_t *__restrict__ m_n, const uint64_t *__restrict__ m_val, const int32_t *__restrict__ m_aoff, const uint64_t *__restrict__ pos, int max_occ,
               int64_t flag, const int64_t *__restrict__ aoff, const uint32_t *__restrict__ K, uint32_t *__restrict__ P, int32_t *__restrict__ na, mm128 *__restrict__ a)
 {
-	__shared__ uint32_t s_heap[2][HEAP_MAX_LISTS], s_cur[2][HEAP_MAX_LISTS];
+	__shared__ uint32_t s_heap[2][HEAP_MAX_LISTS], s_cur[2][HEAP_MAX_LISTS], s_nxt[2][HEAP_MAX_LISTS];
 	__shared__ int32_t s_first[2][HEAP_MAX_LISTS], s_cnt[2][HEAP_MAX_LISTS], s_m[2][HEAP_MAX_LISTS];
 	const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const unsigned FULL = 0xffffffffu;
@@ -211,7 +276,7 @@ k_heap_replay(FragTab ft, const int32_t *__restrict__ list, const int32_t *__res
 		if (lane == 0) {
 			for (int i = 0; i < n_mv; ++i)
 				if (m_n[b + i] > 0 && m_n[b + i] < max_occ) s_first[wi][n_lists] = m_aoff[b + i], s_cnt[wi][n_lists] = m_n[b + i], s_m[wi][n_lists] = i, ++n_lists;
-			mmg_heap_replay_ranks(n_lists, s_first[wi], s_cnt[wi], K + ao, s_heap[wi], s_cur[wi], P + ao);
+			heap_replay_lane(n_lists, s_first[wi], s_cnt[wi], K + ao, s_heap[wi], s_cur[wi], s_nxt[wi], P + ao);
 		}
 		n_lists = __shfl_sync(FULL, n_lists, 0);
 		__syncwarp();
@@ -702,6 +767,7 @@ __device__ __forceinline__ int block_incl_scan(int v, int *s, int *total)
 	return r;
 }
 
+#define TAIL_BLOCK_SMEM (96 * 1024)
 __global__ void __launch_bounds__(1024)
 k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
                    const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
@@ -786,17 +852,30 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
 			for (int kk = tid; kk < n_u; kk += NT) W[kk].x = B[V[kk]].x;
 			__syncthreads();
 			// 7. order chains by the position of their first anchor (chain.c:150): unique for distinct keys, literal replay otherwise
-			if (n_u <= 64) {
-				if (tid == 0) mmg_rs_sort_exact(W, (int64_t)n_u, stack + ao / 65 + 2 * (int64_t)li, KeyX());
-			} else {
+			if (n_u > 64) {
 				block_bitonic(W, n_u, M128ByX());
 				for (int kk = tid + 1; kk < n_u; kk += NT) if (W[kk].x == W[kk - 1].x) s_tie = 1;
 				__syncthreads();
-				if (s_tie) {
+				if (s_tie) { // back to the order klib's sort starts from
 					for (int kk = tid; kk < n_u; kk += NT) { const int off = V[kk]; W[kk].x = B[off].x; W[kk].y = (uint64_t)off << 32 | (uint32_t)kk; }
 					__syncthreads();
-					if (tid == 0) mmg_rs_sort_exact(W, (int64_t)n_u, stack + ao / 65 + 2 * (int64_t)li, KeyX());
 				}
+			}
+			if (n_u <= 64 || s_tie) {
+				// the literal replay is one thread's work; on a copy in shared memory its element moves cost tens of cycles instead of
+				// a trip to L2 each (a fragment from a repeat family has thousands of chains, and ties are common there: two query
+				// minimizers with the same hash start chains on the same reference position)
+				extern __shared__ __align__(16) unsigned char dyn_tail[];
+				const size_t frames = (size_t)n_u / 65 + 4;
+				if ((size_t)n_u * sizeof(mm128) + frames * sizeof(RsFrame) <= TAIL_BLOCK_SMEM) {
+					mm128 *sw = reinterpret_cast<mm128*>(dyn_tail);
+					RsFrame *sf = reinterpret_cast<RsFrame*>(dyn_tail + (size_t)n_u * sizeof(mm128));
+					for (int kk = tid; kk < n_u; kk += NT) sw[kk] = W[kk];
+					__syncthreads();
+					if (tid == 0) mmg_rs_sort_exact(sw, (int64_t)n_u, sf, KeyX());
+					__syncthreads();
+					for (int kk = tid; kk < n_u; kk += NT) W[kk] = sw[kk];
+				} else if (tid == 0) mmg_rs_sort_exact(W, (int64_t)n_u, stack + ao / 65 + 2 * (int64_t)li, KeyX());
 			}
 			__syncthreads();
 			// 8. write chains back to a[] in that order (chain.c:152-159)
@@ -1032,6 +1111,8 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		MMG_LAUNCH(c, k_heap_replay, 148 * 4, 64, 0, ft, d_list, rlist, counters, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
 		           c->d_m_aoff.as<int32_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_hrank.as<uint32_t>(), c->d_hpop.as<uint32_t>(),
 		           pb.na->as<int32_t>(), pb.a->as<mm128>());
+		MMG_TRY(c->h_path.ensure(64));
+		MMG_D2H(c, c->h_path.as<int32_t>() + (d_flag ? 0 : 4), counters, 16); // read after the pass has synchronised (mmg_seed_chain_resident)
 	}
 	// literal replay: the heap merge for the few fragments the rank replay does not take; fill + klib radix sort for the non-heap presets
 	{
@@ -1082,8 +1163,12 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		MMG_LAUNCH(c, k_chain_fill, 148 * 8, 128, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(),
 		           pb.a->as<mm128>(), pb.work->as<int32_t>(), c->d_seg_avg.as<float>(), seg_start, d_nseg, d_next, c->d_frag_iter.as<unsigned long long>());
 	}
+	{
+		static bool attr_set = false;
+		if (!attr_set) { MMG_CUDA(cudaFuncSetAttribute(k_chain_tail_block, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_BLOCK_SMEM)); attr_set = true; }
+	}
 	if (d_flag == nullptr) // the re-chain pass: few, very large fragments -> one CTA each
-		MMG_LAUNCH(c, k_chain_tail_block, n_list, 1024, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+		MMG_LAUNCH(c, k_chain_tail_block, n_list, 1024, TAIL_BLOCK_SMEM, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
 		           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
 		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>());
 	else
@@ -1119,6 +1204,8 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 	MMG_TRY(c->d_frag_iter.ensure(16));
 	MMG_CUDA(cudaMemsetAsync(c->d_frag_flag.p, 0, (size_t)nf + 16, c->stream));
 	MMG_CUDA(cudaMemsetAsync(c->d_frag_iter.p, 0, 16, c->stream));
+	MMG_TRY(c->h_path.ensure(64));
+	memset(c->h_path.p, 0, 64);
 	PassBufs p1 = {&c->d_frag_na, &c->d_frag_aoff, &c->d_frag_rep, &c->d_frag_nmini, &c->d_mini, &c->d_a, &c->d_work, &c->d_u, &c->d_b,
 	               &c->d_stack, &c->d_frag_nu, &c->d_frag_nv};
 	int64_t n_anch1 = 0, n_anch2 = 0;
@@ -1200,6 +1287,10 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 		float ms = 0;
 		cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->t_d2h_ms = ms;
 	} else MMG_CUDA(cudaStreamSynchronize(c->stream));
+	{ // path counters of this batch (the stream is idle here)
+		const int32_t *hp = c->h_path.as<int32_t>();
+		c->path[0] += (uint64_t)n2, c->path[1] += (uint64_t)(hp[0] + hp[4]), c->path[2] += (uint64_t)(hp[2] + hp[6]);
+	}
 	float ms = 0;
 	cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); out->t_kernels_ms = ms;
 	out->n_chain_iter = iters;

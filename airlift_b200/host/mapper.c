@@ -1018,6 +1018,23 @@ void mm_b200_report(const mm_idx_t *mi, FILE *fp)
 			(unsigned long)s.n_dp_jobs, (unsigned long)s.n_dp_rounds, (unsigned long)s.n_dp_cells, (unsigned long)s.h2d_bytes, (unsigned long)s.d2h_bytes);
 	n = mm_b200_profile_fetch(mi, 64, nm, t, l);
 	for (i = 0; i < n; ++i) fprintf(fp, "[M::b200] kernel %-18s %8ld launches %10.3f ms\n", nm[i], l[i], t[i]);
+	{
+		uint64_t pc[8];
+		mm_b200_path_counts(mi, pc, 0);
+		fprintf(fp, "[M::b200] paths: rechained %lu, heap_rank_replay %lu, heap_literal_replay %lu, warp_tree %lu, zdrop_rounds %lu, zdrop_cuts %lu\n",
+				(unsigned long)pc[0], (unsigned long)pc[1], (unsigned long)pc[2], (unsigned long)pc[3], (unsigned long)pc[4], (unsigned long)pc[5]);
+	}
+}
+
+void mm_b200_path_counts(const mm_idx_t *mi, uint64_t out[8], int reset)
+{ /* work items that took each data-dependent device path (mmg_path_counts), summed over the shards' contexts */
+	int d, i;
+	for (i = 0; i < 8; ++i) out[i] = 0;
+	for (d = 0; d < mi->B->n_dev * mi->B->lanes; ++d) {
+		uint64_t t[8];
+		mmg_path_counts(mi->B->ctx[d], t, reset);
+		for (i = 0; i < 8; ++i) out[i] += t[i];
+	}
 }
 
 long mm_b200_launch_count(const mm_idx_t *mi, int reset)

@@ -214,6 +214,7 @@ uint64_t mm_b200_batch_digest(const mm_b200_batch_t *b, int64_t *n_hits);
 void mm_b200_write_batch(const mm_idx_t *mi, const mm_mapopt_t *opt, mm_b200_batch_t *b); /* prints and frees */
 void mm_b200_free_batch(mm_b200_batch_t *b);
 int  mm_b200_n_devices(const mm_idx_t *mi);
+void mm_b200_path_counts(const mm_idx_t *mi, uint64_t out[8], int reset); /* see mmg_path_counts (mmg.h) */
 
 typedef struct { /* accumulated over mm_b200_map_batch / mm_map_file_frag calls; seconds and counts */
 	double t_total, t_upload, t_seedchain, t_seedchain_kernels, t_hits, t_align_host, t_ksw_total, t_ksw_kernel, t_finish;

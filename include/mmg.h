@@ -48,6 +48,10 @@ void mmg_copy_bytes(mmg_ctx_t *ctx, uint64_t *h2d, uint64_t *d2h, int reset);
 /* per-kernel device time (CUDA events around every launch of this ctx); names[] receives static strings */
 void mmg_profile_enable(mmg_ctx_t *ctx, int on);
 int  mmg_profile_fetch(mmg_ctx_t *ctx, int max, const char **names, double *ms, long *launches);
+/* work items that took each data-dependent path since the last reset: out[0] fragments re-chained with max_occ (map.c:353-375),
+ * [1] fragments whose seed-merge order was replayed on ranks, [2] ... literally, [3] fragments whose hit tree was built by a warp,
+ * [4] extra DP rounds after z-drop cuts, [5] hits cut at a z-drop; [6], [7] reserved */
+void mmg_path_counts(mmg_ctx_t *ctx, uint64_t out[8], int reset);
 
 /* ------------------------------------------------------------------ index */
 /* Build the index on the device from n_seq ASCII sequences (not NUL-terminated; lens[] given).

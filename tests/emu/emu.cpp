@@ -227,7 +227,7 @@ extern "C" int emu_post_frag(const HitOpt *opt, int idx_k, uint32_t hash, int n_
 		for (int i = 0; i < n_u; ++i) key[i] = key_in[ord[i]], ascnt[i] = val_in[ord[i]];
 		for (int g = 0; g < n_u; ++g) post_hit_record(sh, g);
 	}
-	if (getenv("EMU_WARP") && n_u >= atoi(getenv("EMU_WARP"))) { std::vector<int32_t> fast(4 * HIT_PRIM_CACHE); post_hits_select_warp(WarpEmu(), sh, 0, fast.data()); } // the warp-cooperative form, lanes emulated one after the other
+	if (getenv("EMU_WARP") && n_u >= atoi(getenv("EMU_WARP"))) { std::vector<int32_t> fast(HIT_FAST_WORDS + 2); post_hits_select_warp(WarpEmu(), sh, 0, fast.data()); } // the warp-cooperative form, lanes emulated one after the other
 	else post_hits_select(sh, 0);
 	for (int j = 0; j < n_segs; ++j) roff[j + 1] = roff[j] + cap[j];
 	const int64_t slots = roff[n_segs] + 1;
