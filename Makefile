@@ -24,9 +24,9 @@ emu: $(BUILD)/libmmg_emu.so
 $(BUILD):
 	mkdir -p $(BUILD)
 
-$(BUILD)/mmg_post.o: $(CSRC)/mmg_hits.h $(CSRC)/mmg_aln.h $(CSRC)/mmg_post.h
+CUHDR    := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh)
 
-$(BUILD)/%.o: $(CSRC)/%.cu $(CSRC)/mmg_core.h $(CSRC)/mmg_ctx.cuh include/mmg.h | $(BUILD)
+$(BUILD)/%.o: $(CSRC)/%.cu $(CUHDR) include/mmg.h | $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; false)
 
 $(BUILD)/host_%.o: $(HOST)/%.c $(wildcard $(HOST)/*.h) include/mmg.h | $(BUILD)
@@ -42,7 +42,7 @@ $(BUILD)/mmsynth: tools/mmsynth.c | $(BUILD)
 	$(CC) -O2 -Wno-misleading-indentation -o $@ $< -lm
 
 # CPU emulation of the per-thread device code (test harness only; never linked into the product)
-$(BUILD)/libmmg_emu.so: tests/emu/emu.cpp $(CSRC)/mmg_core.h $(CSRC)/mmg_hits.h $(CSRC)/mmg_aln.h $(CSRC)/mmg_post.h | $(BUILD)
+$(BUILD)/libmmg_emu.so: tests/emu/emu.cpp $(CUHDR) | $(BUILD)
 	g++ -O2 -g -std=c++17 -fPIC -shared -ffp-contract=off -I$(CSRC) $< -o $@
 
 oracle:

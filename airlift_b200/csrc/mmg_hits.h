@@ -14,6 +14,7 @@
 //   pairing                   mm_pair, mm_set_pe_thru       pe.c:45-177
 #pragma once
 #include "mmg_core.h"
+#include "mmg_warp.h"
 
 // == mm_reg1_t (minimap.h:83-98), 80 bytes; `p` holds 1 + the index of the hit's alignment record instead of a pointer
 struct HitRec {
@@ -64,23 +65,6 @@ struct HitOpt {   // the fields of mm_mapopt_t / mm_idx_t these stages read
 #define HIT_F_ALL_CHAINS   0x800000LL
 #define HIT_F_HARD_MLEVEL  0x20000000LL
 #define HIT_F_SR           0x1000LL
-
-MMG_HD int mmg_popc(uint32_t x)
-{
-#ifdef __CUDA_ARCH__
-	return __popc(x);
-#else
-	return __builtin_popcount(x);
-#endif
-}
-MMG_HD int mmg_ffs(uint32_t x) // 1-based index of the lowest set bit, 0 if none
-{
-#ifdef __CUDA_ARCH__
-	return __ffs((int)x);
-#else
-	return __builtin_ffs((int)x);
-#endif
-}
 
 MMG_HD HitExtra *hit_ext(uint32_t *xw, uint64_t p) { return reinterpret_cast<HitExtra*>(xw + (p - 1)); }
 
@@ -627,28 +611,6 @@ MMG_HDN inline bool hit_pair(int max_gap_ref, int pe_bonus, int sub_diff, int ma
 //   * the first primary that masks hit i (hit.c:143-161) is found by one ballot over 32 primaries at a time.
 // The code is written against a tiny warp interface so that tests/emu/ can run it on the CPU: ballot(f) / sum(f) evaluate f(lane)
 // on every lane and combine; each(f) runs f(lane) on every lane; everything else is computed redundantly by all lanes.
-struct WarpEmu { // 32 lanes, one after the other; per-lane variables are arrays
-	template <class T> struct Var { T v[32]; T &operator()(int l) { return v[l]; } const T &operator()(int l) const { return v[l]; } };
-	template <class F> unsigned ballot(F &&f) const { unsigned m = 0; for (int l = 0; l < 32; ++l) if (f(l)) m |= 1u << l; return m; }
-	template <class F> int sum(F &&f) const { int s = 0; for (int l = 0; l < 32; ++l) s += f(l); return s; }
-	template <class F> void each(F &&f) const { for (int l = 0; l < 32; ++l) f(l); }
-	template <class F> void one(F &&f) const { f(); }
-	static void amax(int32_t *p, int32_t v) { if (*p < v) *p = v; }
-	static void aadd(int32_t *p, int32_t v) { *p += v; }
-};
-#ifdef __CUDACC__
-struct WarpDev { // per-lane variables are registers
-	int lane;
-	template <class T> struct Var { T v; __device__ T &operator()(int) { return v; } __device__ const T &operator()(int) const { return v; } };
-	template <class F> __device__ unsigned ballot(F &&f) const { return __ballot_sync(0xffffffffu, f(lane)); }
-	template <class F> __device__ int sum(F &&f) const { return __reduce_add_sync(0xffffffffu, f(lane)); }
-	template <class F> __device__ void each(F &&f) const { f(lane); __syncwarp(); }
-	template <class F> __device__ void one(F &&f) const { if (lane == 0) f(); __syncwarp(); }
-	static __device__ void amax(int32_t *p, int32_t v) { atomicMax(p, v); }
-	static __device__ void aadd(int32_t *p, int32_t v) { atomicAdd(p, v); }
-};
-#endif
-
 #define HIT_COVER_BITS 2048  // query positions the coverage bitmap holds (two words per lane)
 
 MMG_HD uint32_t hit_range_word(int s, int e, int word)

@@ -2,6 +2,7 @@
 // single-call test entry points.  Reference path: mm_map_frag, map.c:272-377.
 #include <cub/cub.cuh>
 #include "mmg_ctx.cuh"
+#include "mmg_regheap.h"
 
 int mmg_run_sketch(mmg_ctx_t *c, const uint32_t *d_S, const SketchUnit *d_units, int n_units, int w, int k, int is_hpc,
                    DevBuf &cnt, DevBuf &off, DevBuf &out, int64_t *total);
@@ -189,11 +190,17 @@ __global__ void k_heap_list(int n_list, const uint8_t *__restrict__ replay, int3
 }
 
 #define HEAP_MAX_LISTS 256
+#define HEAP_RING 16   // ranks of every list staged ahead of the replay in shared memory (a power of two)
 
 // mmg_heap_replay_ranks (mmg_core.h) tuned for one lane: the same pops in the same order.  The serial chain per pop is what
-// bounds a fragment with 10^5 hits, so (a) the root stays in a register, (b) the next rank of every list is fetched into
-// shared memory by an asynchronous copy while the previous sift runs, (c) the sift loads a node's children and grandchildren
-// together and descends two levels per round of shared-memory latency.
+// bounds a fragment with 10^5 hits (one lane, ~1.5 x 10^5 dependent pops), so nothing on that chain may wait for global memory:
+// (a) the root stays in a register; (b) the next HEAP_RING ranks of every list sit in a shared-memory ring that asynchronous
+// copies refill one element per pop, HEAP_RING pops of that list ahead of their use (a copy issued one pop ahead, as before,
+// cost the full L2/HBM latency on every pop: 400 ns per pop); (c) the key the popped list puts back is read from nxt[], which is
+// refreshed from the ring off the critical path; (d) the sift loads a node's children and grandchildren together and descends
+// two levels per round of shared-memory latency.
+struct HeapList { int32_t first, cnt, cur, m; };
+
 __device__ __forceinline__ void heap_sift_root(uint32_t *l, uint32_t n, uint32_t tmp, uint32_t *root_out)
 {
 	uint32_t i = 0, root = tmp;
@@ -225,26 +232,33 @@ __device__ __forceinline__ void heap_sift_root(uint32_t *l, uint32_t n, uint32_t
 	*root_out = i == 0 ? tmp : root;
 }
 
-__device__ int64_t heap_replay_lane(int n_lists, const int32_t *first, const int32_t *cnt, const uint32_t *__restrict__ K, uint32_t *heap, uint32_t *cur, uint32_t *nxt,
-                                    uint32_t *__restrict__ pop)
+// lists[], ring[] (first HEAP_RING ranks of every list) and nxt[] (rank 1 of every list) are set up by the warp; heap[] holds
+// rank 0 of every list, not yet ordered
+__device__ int64_t heap_replay_lane(int n_lists, HeapList *lists, const uint32_t *__restrict__ K, uint32_t *heap, uint32_t *nxt, uint32_t *ring, uint32_t *__restrict__ pop)
 {
-	uint32_t hs = 0;
+	uint32_t hs = (uint32_t)n_lists;
 	int64_t t = 0;
-	for (int j = 0; j < n_lists; ++j) { heap[hs++] = K[first[j]] << 8 | (uint32_t)j; cur[j] = 0; nxt[j] = cnt[j] > 1 ? K[first[j] + 1] : 0; }
 	if (hs > 1) for (int32_t j = (int32_t)(hs >> 1) - 1; j >= 0; --j) mmg_rank_heap_down((uint32_t)j, hs, heap);
 	uint32_t root = hs ? heap[0] : 0;
 	while (hs > 0) {
-		const uint32_t j = root & 0xff, c = cur[j], f0 = (uint32_t)first[j], n = (uint32_t)cnt[j];
+		const uint32_t j = root & 0xff;
+		const uint32_t key1 = nxt[j];      // rank of the list's element c + 1, if there is one
+		const HeapList L = lists[j];
+		const uint32_t c = (uint32_t)L.cur, n = (uint32_t)L.cnt, f0 = (uint32_t)L.first;
 		pop[t++] = f0 + c;
 		uint32_t tmp;
 		if (c + 1 < n) {
-			asm volatile("cp.async.wait_all;" ::: "memory"); // the copy issued one pop ago has had a whole sift to land
-			tmp = nxt[j] << 8 | j;
-			cur[j] = c + 1;
-			if (c + 2 < n) {
-				const unsigned dst = (unsigned)__cvta_generic_to_shared(&nxt[j]);
-				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(K + f0 + c + 2) : "memory");
+			tmp = key1 << 8 | j;
+			lists[j].cur = (int32_t)(c + 1);
+			// element c + 2 was requested when element c + 2 - HEAP_RING was popped; this list alone has committed HEAP_RING - 3
+			// groups since, so at most that many younger groups may still be in flight
+			asm volatile("cp.async.wait_group %0;" :: "n"(HEAP_RING - 3) : "memory");
+			if (c + 2 < n) nxt[j] = ring[j * HEAP_RING + ((c + 2) & (HEAP_RING - 1))];
+			if (c + HEAP_RING < n) { // into the slot of element c, which is in the past
+				const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[j * HEAP_RING + (c & (HEAP_RING - 1))]);
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(K + f0 + c + HEAP_RING) : "memory");
 			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
 		} else { tmp = heap[hs - 1]; --hs; }
 		if (hs > 0) heap_sift_root(heap, hs, tmp, &root);
 	}
@@ -252,16 +266,64 @@ __device__ int64_t heap_replay_lane(int n_lists, const int32_t *first, const int
 	return t;
 }
 
-// one warp per listed fragment, pulled from a counter: lane 0 replays the heap (state in shared memory), then the warp turns the
-// pop order into anchors -- forward-strand hits in pop order, then reverse-strand hits in pop order (map.c:176-211)
-__global__ void __launch_bounds__(64)
+// The warp form of the replay (mmg_regheap.h) with the lists' cursors in registers too: list j belongs to lane j & 31, which
+// keeps its cursor and the rank of its next element in registers, so handing the next key to the heap is one shuffle and
+// nothing the owner does afterwards (recording the pop, reading the rank after next from its ring, requesting the ring's next
+// element) is waited for by the other lanes' next step.  Ring slots of a list are read and refilled by its owner only.
+template <int NREG>
+__device__ void heap_replay_warp(int n_lists, const HeapList *s_lists, const uint32_t *__restrict__ Kf, uint32_t *__restrict__ Pf, const uint32_t *s_heap, uint32_t *s_ring, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	uint32_t cur[NREG], cnt[NREG], first[NREG], nxt[NREG];
+#pragma unroll
+	for (int q = 0; q < NREG; ++q) {
+		const int j = lane + 32 * q;
+		cur[q] = 0, cnt[q] = 0, first[q] = 0, nxt[q] = RH_NONE;
+		if (j < n_lists) { const HeapList L = s_lists[j]; cnt[q] = (uint32_t)L.cnt, first[q] = (uint32_t)L.first; if (L.cnt > 1) nxt[q] = s_ring[j * HEAP_RING + 1]; }
+	}
+	const WarpDev wp = {lane};
+	const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(s_ring); // taken once: the conversion reads a special register
+	auto advance = [&](uint32_t j, int64_t t) -> uint32_t { // pop t is the current element of list j; hands out the rank of its next one
+		const int q = (int)(j >> 5), ol = (int)(j & 31);
+		uint32_t nk = RH_NONE;
+#pragma unroll
+		for (int qq = 0; qq < NREG; ++qq) { const uint32_t v = __shfl_sync(FULL, nxt[qq], ol); if (qq == q) nk = v; }
+		if (lane == ol) {
+#pragma unroll
+			for (int qq = 0; qq < NREG; ++qq)
+				if (qq == q) {
+					const uint32_t c = cur[qq], n = cnt[qq];
+					Pf[t] = first[qq] + c;
+					if (c + 1 < n) {
+						cur[qq] = c + 1;
+						// element c + 2 was requested when element c + 2 - HEAP_RING was popped; this list alone has committed
+						// HEAP_RING - 3 groups of this lane since, so at most that many younger groups may still be in flight
+						asm volatile("cp.async.wait_group %0;" :: "n"(HEAP_RING - 3) : "memory");
+						uint32_t v = RH_NONE;
+						if (c + 2 < n) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring_sa + 4u * (j * HEAP_RING + ((c + 2) & (HEAP_RING - 1)))) : "memory");
+						nxt[qq] = v;
+						if (c + HEAP_RING < n) // into the slot of element c, which is in the past
+							asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ring_sa + 4u * (j * HEAP_RING + (c & (HEAP_RING - 1)))), "l"(Kf + first[qq] + c + HEAP_RING) : "memory");
+						asm volatile("cp.async.commit_group;" ::: "memory");
+					}
+				}
+		}
+		return nk;
+	};
+	regheap_replay<WarpDev, NREG>(wp, n_lists, s_heap, advance);
+	asm volatile("cp.async.wait_all;" ::: "memory");
+	__syncwarp();
+}
+
+// one warp per listed fragment, pulled from a counter: the pop order of the fragment's heap merge, as planned slots, into P[]
+__global__ void __launch_bounds__(32)
 k_heap_replay(FragTab ft, const int32_t *__restrict__ list, const int32_t *__restrict__ rlist, int32_t *__restrict__ counters, const mm128 *__restrict__ mv,
               const int32_t *__restrict__ m_n, const uint64_t *__restrict__ m_val, const int32_t *__restrict__ m_aoff, const uint64_t *__restrict__ pos, int max_occ,
-              int64_t flag, const int64_t *__restrict__ aoff, const uint32_t *__restrict__ K, uint32_t *__restrict__ P, int32_t *__restrict__ na, mm128 *__restrict__ a)
+              int64_t flag, const int64_t *__restrict__ aoff, const uint32_t *__restrict__ K, uint32_t *__restrict__ P)
 {
-	__shared__ uint32_t s_heap[2][HEAP_MAX_LISTS], s_cur[2][HEAP_MAX_LISTS], s_nxt[2][HEAP_MAX_LISTS];
-	__shared__ int32_t s_first[2][HEAP_MAX_LISTS], s_cnt[2][HEAP_MAX_LISTS], s_m[2][HEAP_MAX_LISTS];
-	const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	__shared__ uint32_t s_heap[HEAP_MAX_LISTS], s_nxt[HEAP_MAX_LISTS], s_ring[HEAP_MAX_LISTS * HEAP_RING];
+	__shared__ __align__(16) HeapList s_lists[HEAP_MAX_LISTS];
+	const int lane = threadIdx.x & 31;
 	const unsigned FULL = 0xffffffffu;
 	const int n_work = counters[0];
 	for (;;) {
@@ -271,56 +333,126 @@ k_heap_replay(FragTab ft, const int32_t *__restrict__ list, const int32_t *__res
 		if (t >= n_work) break;
 		const int li = rlist[t], f = list ? list[li] : li;
 		const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]], ao = aoff[li];
-		const int n_mv = (int)(e - b), qlen = ft.qlen[f];
+		const int n_mv = (int)(e - b);
 		int n_lists = 0;
-		if (lane == 0) {
-			for (int i = 0; i < n_mv; ++i)
-				if (m_n[b + i] > 0 && m_n[b + i] < max_occ) s_first[wi][n_lists] = m_aoff[b + i], s_cnt[wi][n_lists] = m_n[b + i], s_m[wi][n_lists] = i, ++n_lists;
-			heap_replay_lane(n_lists, s_first[wi], s_cnt[wi], K + ao, s_heap[wi], s_cur[wi], s_nxt[wi], P + ao);
-		}
-		n_lists = __shfl_sync(FULL, n_lists, 0);
-		__syncwarp();
-		const int n_a = n_lists ? s_first[wi][n_lists - 1] + s_cnt[wi][n_lists - 1] : 0;
-		// pass 1: strand class of every pop (kept in the two top bits of its word), totals
-		int n_for = 0, n_rev = 0;
-		for (int t0 = 0; t0 < n_a; t0 += 32) {
-			const int tt = t0 + lane;
-			int cls = 0;
-			if (tt < n_a) {
-				const uint32_t slot = P[ao + tt];
-				int lo = 0, hi = n_lists - 1; // list of the slot
-				while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((uint32_t)s_first[wi][mid] <= slot) lo = mid; else hi = mid - 1; }
-				const int m = s_m[wi][lo];
-				const uint64_t r = mmg_hit_pos(pos, m_n[b + m], m_val[b + m], slot - (uint32_t)s_first[wi][lo]);
-				const uint32_t qp = (uint32_t)mv[b + m].y;
-				cls = mmg_skip_seed(flag, r, qp) ? 0 : ((r & 1) == (qp & 1) ? 1 : 2);
-				P[ao + tt] = slot | (uint32_t)cls << 30;
-			}
-			n_for += __popc(__ballot_sync(FULL, cls == 1)), n_rev += __popc(__ballot_sync(FULL, cls == 2));
+		for (int i0 = 0; i0 < n_mv; i0 += 32) { // the kept minimizers, in query order
+			const int i = i0 + lane;
+			const bool kept = i < n_mv && m_n[b + i] > 0 && m_n[b + i] < max_occ;
+			const unsigned mk = __ballot_sync(FULL, kept);
+			if (kept) { HeapList L; L.first = m_aoff[b + i], L.cnt = m_n[b + i], L.cur = 0, L.m = i; s_lists[n_lists + __popc(mk & ((1u << lane) - 1u))] = L; }
+			n_lists += __popc(mk);
 		}
 		__syncwarp();
-		// pass 2: anchors
-		int run_for = 0, run_rev = 0;
-		for (int t0 = 0; t0 < n_a; t0 += 32) {
-			const int tt = t0 + lane;
-			int cls = 0; uint32_t slot = 0;
-			if (tt < n_a) { const uint32_t w = P[ao + tt]; cls = (int)(w >> 30), slot = w & 0x3fffffffu; }
-			const unsigned mf = __ballot_sync(FULL, cls == 1), mr = __ballot_sync(FULL, cls == 2);
-			if (cls) {
-				int lo = 0, hi = n_lists - 1;
-				while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((uint32_t)s_first[wi][mid] <= slot) lo = mid; else hi = mid - 1; }
-				const int m = s_m[wi][lo];
-				const uint64_t r = mmg_hit_pos(pos, m_n[b + m], m_val[b + m], slot - (uint32_t)s_first[wi][lo]);
-				const mm128 an = mmg_make_anchor(r, mv[b + m], mmg_is_tandem(mv + b, n_mv, m), qlen);
-				const unsigned below = (1u << lane) - 1u;
-				if (cls == 1) a[ao + run_for + __popc(mf & below)] = an;
-				else a[ao + n_for + run_rev + __popc(mr & below)] = an;
+		for (int x = lane; x < n_lists * HEAP_RING; x += 32) { // the first ranks of every list
+			const int j = x / HEAP_RING, e2 = x % HEAP_RING;
+			if (e2 < s_lists[j].cnt) {
+				const uint32_t k = K[ao + s_lists[j].first + e2];
+				s_ring[x] = k;
+				if (e2 == 0) s_heap[j] = k << 8 | (uint32_t)j;
+				if (e2 == 1) s_nxt[j] = k;
 			}
-			run_for += __popc(mf), run_rev += __popc(mr);
 		}
-		if (lane == 0) na[li] = n_for + n_rev;
+		__syncwarp();
+		if (n_lists <= 127) { // the heap in the warp's registers (mmg_regheap.h): a pop costs a fixed number of warp-wide steps
+			if (lane == 0 && n_lists > 1) for (int32_t j = (n_lists >> 1) - 1; j >= 0; --j) mmg_rank_heap_down((uint32_t)j, (uint32_t)n_lists, s_heap);
+			__syncwarp();
+			if (n_lists <= 31) heap_replay_warp<1>(n_lists, s_lists, K + ao, P + ao, s_heap, s_ring, lane);
+			else if (n_lists <= 63) heap_replay_warp<2>(n_lists, s_lists, K + ao, P + ao, s_heap, s_ring, lane);
+			else heap_replay_warp<4>(n_lists, s_lists, K + ao, P + ao, s_heap, s_ring, lane);
+		} else if (lane == 0) heap_replay_lane(n_lists, s_lists, K + ao, s_heap, s_nxt, s_ring, P + ao);
 		__syncwarp();
 	}
+}
+
+// exclusive scan of v over the CTA (blockDim.x a multiple of 32, <= 1024); s_w: 32 ints
+__device__ __forceinline__ int block_excl_scan(int v, int *s_w, int *total)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	int incl = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+	if (lane == 31) s_w[wid] = incl;
+	__syncthreads();
+	if (wid == 0) {
+		int w = lane < nw ? s_w[lane] : 0;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, w, d); if (lane >= d) w += o; }
+		s_w[lane] = w;
+	}
+	__syncthreads();
+	const int r = (wid ? s_w[wid - 1] : 0) + incl - v;
+	*total = s_w[nw - 1];
+	__syncthreads();
+	return r;
+}
+
+// one CTA per replayed fragment: the pop order becomes anchors -- forward-strand hits in pop order, then reverse-strand hits in
+// pop order (map.c:176-211).  (One warp did this after its replay: 2 x 5 000 rounds of dependent global loads for a fragment
+// with 1.6 x 10^5 hits, as long as the replay itself.)
+#define HEAP_EMIT_THREADS 512
+__global__ void __launch_bounds__(HEAP_EMIT_THREADS)
+k_heap_emit(FragTab ft, const int32_t *__restrict__ list, const int32_t *__restrict__ rlist, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
+            const uint64_t *__restrict__ m_val, const int32_t *__restrict__ m_aoff, const uint64_t *__restrict__ pos, int max_occ, int64_t flag,
+            const int64_t *__restrict__ aoff, uint32_t *__restrict__ P, int32_t *__restrict__ na, mm128 *__restrict__ a)
+{
+	__shared__ int32_t s_first[HEAP_MAX_LISTS], s_m[HEAP_MAX_LISTS], s_w[32], s_tot[3];
+	const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
+	const unsigned FULL = 0xffffffffu;
+	const int li = rlist[blockIdx.x], f = list ? list[li] : li;
+	const int64_t b = ft.unit_off[ft.unit0[f]], e = ft.unit_off[ft.unit0[f + 1]], ao = aoff[li];
+	const int n_mv = (int)(e - b), qlen = ft.qlen[f];
+	if (tid < 32) { // the kept minimizers, in query order (as in k_heap_replay)
+		int n_lists = 0, n_a = 0;
+		for (int i0 = 0; i0 < n_mv; i0 += 32) {
+			const int i = i0 + lane;
+			const bool kept = i < n_mv && m_n[b + i] > 0 && m_n[b + i] < max_occ;
+			const unsigned mk = __ballot_sync(FULL, kept);
+			if (kept) { const int j = n_lists + __popc(mk & ((1u << lane) - 1u)); s_first[j] = m_aoff[b + i], s_m[j] = i; }
+			n_lists += __popc(mk);
+			n_a += __reduce_add_sync(FULL, kept ? m_n[b + i] : 0);
+		}
+		if (lane == 0) s_tot[0] = n_lists, s_tot[1] = 0, s_tot[2] = n_a;
+	}
+	__syncthreads();
+	const int n_lists = s_tot[0], n_a = s_tot[2];
+	// pass 1: strand class of every pop (kept in the two top bits of its word), number of forward-strand hits
+	int my_for = 0;
+	for (int tt = tid; tt < n_a; tt += NT) {
+		const uint32_t slot = P[ao + tt];
+		int lo = 0, hi = n_lists - 1; // list of the slot
+		while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((uint32_t)s_first[mid] <= slot) lo = mid; else hi = mid - 1; }
+		const int m = s_m[lo];
+		const uint64_t r = mmg_hit_pos(pos, m_n[b + m], m_val[b + m], slot - (uint32_t)s_first[lo]);
+		const uint32_t qp = (uint32_t)mv[b + m].y;
+		const int cls = mmg_skip_seed(flag, r, qp) ? 0 : ((r & 1) == (qp & 1) ? 1 : 2);
+		P[ao + tt] = slot | (uint32_t)cls << 30;
+		my_for += cls == 1;
+	}
+	my_for = __reduce_add_sync(FULL, my_for);
+	if (lane == 0 && my_for) atomicAdd(&s_tot[1], my_for);
+	__syncthreads();
+	const int n_for = s_tot[1];
+	// pass 2: anchors; forward hits in the low half of the packed scan value, reverse hits in the high half
+	int run_for = 0, run_rev = 0;
+	for (int t0 = 0; t0 < n_a; t0 += NT) {
+		const int tt = t0 + tid;
+		int cls = 0; uint32_t slot = 0;
+		if (tt < n_a) { const uint32_t w = P[ao + tt]; cls = (int)(w >> 30), slot = w & 0x3fffffffu; }
+		int tot;
+		const int ex = block_excl_scan(cls == 1 ? 1 : cls == 2 ? 1 << 16 : 0, s_w, &tot);
+		if (cls) {
+			int lo = 0, hi = n_lists - 1;
+			while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((uint32_t)s_first[mid] <= slot) lo = mid; else hi = mid - 1; }
+			const int m = s_m[lo];
+			const uint64_t r = mmg_hit_pos(pos, m_n[b + m], m_val[b + m], slot - (uint32_t)s_first[lo]);
+			const mm128 an = mmg_make_anchor(r, mv[b + m], mmg_is_tandem(mv + b, n_mv, m), qlen);
+			if (cls == 1) a[ao + run_for + (ex & 0xffff)] = an;
+			else a[ao + n_for + run_rev + (ex >> 16)] = an;
+		}
+		run_for += tot & 0xffff, run_rev += tot >> 16;
+	}
+	if (tid == 0) na[li] = run_for + run_rev;
 }
 
 // mmg_fill_heap (mmg_core.h) for one fragment per warp: same pops in the same order; the heap and the next position of every
@@ -421,7 +553,7 @@ __device__ __forceinline__ ChainParams mmg_chain_params(const ChainOptDev &o, in
 // flag the first anchor of every segment; zero the t[] array of chain.c:39
 __global__ void k_chain_heads(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
                               const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, const mm128 *__restrict__ a, int64_t n_total,
-                              uint8_t *__restrict__ head, int32_t *__restrict__ work)
+                              uint8_t *__restrict__ head, int32_t *__restrict__ work, int32_t *__restrict__ head_li)
 {
 	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= n_total) return;
@@ -433,6 +565,7 @@ __global__ void k_chain_heads(FragTab ft, const int32_t *__restrict__ list, int 
 		const ChainParams P = mmg_chain_params(co, ft.qlen[f], n_seg[f]);
 		h = (i == 0 || a[g].x > a[g - 1].x + (uint64_t)P.max_dist_x) ? 1 : 0;
 		work[ao * 8 + 2 * n + i] = 0; // t[i]
+		if (h) head_li[g] = li;       // the fill kernels find a segment's fragment here instead of bisecting aoff[] again
 	}
 	head[g] = h;
 }
@@ -449,36 +582,99 @@ __global__ void k_chain_avgspan(int n_list, const int64_t *__restrict__ aoff, co
 	if (lane == 0) avg[li] = n > 0 ? (float)sum / (float)(int64_t)n : 0.f;
 }
 
+// A segment's place: fragment slot, anchor range inside the fragment
+struct SegPlace { int li, f, s, e, n; int64_t ao; };
+__device__ __forceinline__ SegPlace seg_place(int sidx, int n_segments, const int64_t *__restrict__ seg_start, const int32_t *__restrict__ head_li,
+                                              const int32_t *__restrict__ list, const int64_t *__restrict__ aoff, const int32_t *__restrict__ na)
+{
+	SegPlace sp;
+	const int64_t g0 = seg_start[sidx];
+	sp.li = head_li[g0];
+	sp.f = list ? list[sp.li] : sp.li;
+	sp.ao = aoff[sp.li], sp.n = na[sp.li];
+	const int64_t frag_end = sp.ao + sp.n;
+	int64_t g1 = frag_end;
+	if (sidx + 1 < n_segments) { const int64_t nx = seg_start[sidx + 1]; if (nx < frag_end) g1 = nx; }
+	sp.s = (int)(g0 - sp.ao), sp.e = (int)(g1 - sp.ao);
+	return sp;
+}
+
+// one THREAD per short segment.  A read pair from a repeat family meets ~10^4 copies, each contributing a handful of
+// anchors: 2 x 10^7 segments of ~6 anchors per 10^6 reads.  A warp per segment spent its time fetching the segment (a counter,
+// a bisection, the parameters) and then used 3 of its 32 lanes; here every lane walks its own segment with the sequential
+// loop of chain.c:45-85, and only the segments longer than CHAIN_SMALL_SEG are left, as a list, for the warp form below.
+#define CHAIN_SMALL_SEG 24
+__global__ void __launch_bounds__(128)
+k_chain_fill_small(FragTab ft, const int32_t *__restrict__ list, const int32_t *__restrict__ n_seg, ChainOptDev co,
+                   const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, const mm128 *__restrict__ a, int32_t *__restrict__ work,
+                   const float *__restrict__ avg, const int64_t *__restrict__ seg_start, const int32_t *__restrict__ head_li,
+                   const int32_t *__restrict__ n_seg_total, int32_t *__restrict__ long_list, int32_t *__restrict__ n_long,
+                   unsigned long long *__restrict__ iter_total)
+{
+	const int n_segments = *n_seg_total;
+	unsigned long long iters = 0;
+	for (int sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < n_segments; sidx += gridDim.x * blockDim.x) {
+		const SegPlace sp = seg_place(sidx, n_segments, seg_start, head_li, list, aoff, na);
+		if (sp.e - sp.s > CHAIN_SMALL_SEG) { long_list[atomicAdd(n_long, 1)] = sidx; continue; }
+		const ChainParams P = mmg_chain_params(co, ft.qlen[sp.f], n_seg[sp.f]);
+		const float avg_qspan = avg[sp.li];
+		const mm128 *A = a + sp.ao;
+		int32_t *F = work + sp.ao * 8, *Pp = F + sp.n, *T = Pp + sp.n, *V = T + sp.n;
+		int st = sp.s;
+		for (int i = sp.s; i < sp.e; ++i) {
+			const mm128 ai = A[i];
+			const uint64_t ri = ai.x;
+			const int32_t qi = (int32_t)ai.y, q_span = (int32_t)(ai.y >> 32 & 0xff);
+			const int32_t sidi = (int32_t)((ai.y & MMG_SEED_SEG_MASK) >> MMG_SEED_SEG_SHIFT);
+			int32_t max_f = q_span, max_j = -1, n_skip = 0;
+			while (st < i && ri > A[st].x + (uint64_t)P.max_dist_x) ++st;
+			if (i - st > P.max_iter) st = i - P.max_iter;
+			for (int j = i - 1; j >= st; --j) {
+				int32_t sc;
+				++iters;
+				if (!mmg_chain_score(P, ri, qi, q_span, sidi, A[j], avg_qspan, &sc)) continue;
+				sc += F[j];
+				if (sc > max_f) {
+					max_f = sc, max_j = j;
+					if (n_skip > 0) --n_skip;
+				} else if (T[j] == i) {
+					if (++n_skip > P.max_skip) break;
+				}
+				const int pj = Pp[j];
+				if (pj >= 0) T[pj] = i;
+			}
+			F[i] = max_f, Pp[i] = max_j;
+			V[i] = (max_j >= 0 && V[max_j] > max_f) ? V[max_j] : max_f; // chain.c:84
+		}
+	}
+	for (int d = 16; d >= 1; d >>= 1) iters += __shfl_xor_sync(0xffffffffu, iters, d);
+	if ((threadIdx.x & 31) == 0 && iters) atomicAdd(iter_total, iters);
+}
+
 // one warp per segment: lanes evaluate 32 predecessors at a time; the order-dependent parts of the inner loop
 // (strict-max winner, n_skip counter, early break, t[] marks; chain.c:53-82) are resolved from ballots so that the
 // result is the sequential one
 __global__ void __launch_bounds__(128)
 k_chain_fill(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
              const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, const mm128 *__restrict__ a, int32_t *__restrict__ work,
-             const float *__restrict__ avg, const int64_t *__restrict__ seg_start, const int32_t *__restrict__ n_seg_total,
+             const float *__restrict__ avg, const int64_t *__restrict__ seg_start, const int32_t *__restrict__ head_li,
+             const int32_t *__restrict__ n_seg_total, const int32_t *__restrict__ long_list, const int32_t *__restrict__ n_long,
              int32_t *__restrict__ next_seg, unsigned long long *__restrict__ iter_total)
 {
 	const int lane = threadIdx.x & 31;
-	const int n_segments = *n_seg_total;
+	const int n_segments = *n_seg_total, n_work = *n_long;
 	unsigned long long iters = 0;
 	for (;;) {
-		int sidx = 0;
-		if (lane == 0) sidx = atomicAdd(next_seg, 1);
-		sidx = __shfl_sync(0xffffffffu, sidx, 0);
-		if (sidx >= n_segments) break;
-		const int64_t g0 = seg_start[sidx];
-		const int li = frag_of_anchor(aoff, n_list, g0);
-		const int f = list ? list[li] : li;
-		const int64_t ao = aoff[li];
-		const int n = na[li];
-		const int64_t frag_end = ao + n;
-		int64_t g1 = frag_end;
-		if (sidx + 1 < n_segments) { const int64_t nx = seg_start[sidx + 1]; if (nx < frag_end) g1 = nx; }
-		const ChainParams P = mmg_chain_params(co, ft.qlen[f], n_seg[f]);
-		const float avg_qspan = avg[li];
-		const mm128 *A = a + ao;
-		int32_t *F = work + ao * 8, *Pp = F + n, *T = Pp + n, *V = T + n;
-		const int s = (int)(g0 - ao), e = (int)(g1 - ao);
+		int w = 0;
+		if (lane == 0) w = atomicAdd(next_seg, 1);
+		w = __shfl_sync(0xffffffffu, w, 0);
+		if (w >= n_work) break;
+		const SegPlace sp = seg_place(long_list[w], n_segments, seg_start, head_li, list, aoff, na);
+		const int n = sp.n, s = sp.s, e = sp.e;
+		const ChainParams P = mmg_chain_params(co, ft.qlen[sp.f], n_seg[sp.f]);
+		const float avg_qspan = avg[sp.li];
+		const mm128 *A = a + sp.ao;
+		int32_t *F = work + sp.ao * 8, *Pp = F + n, *T = Pp + n, *V = T + n;
 		int st = s;
 		for (int i = s; i < e; ++i) {
 			const mm128 ai = A[i];
@@ -755,6 +951,20 @@ __device__ __forceinline__ void block_bitonic(T *a, int n, Before before)
 	}
 }
 
+// the same sort on a copy in shared memory when it fits: every one of the log^2 n stages of the network is then a round of
+// shared-memory accesses instead of a trip to L2 (a re-chained repeat-family fragment ranks ~10^4 chain ends)
+template <class T, class Before>
+__device__ __forceinline__ void block_bitonic_staged(T *a, int n, Before before, unsigned char *smem, size_t smem_bytes)
+{
+	if ((size_t)n * sizeof(T) > smem_bytes) { block_bitonic(a, n, before); return; }
+	T *sa = reinterpret_cast<T*>(smem);
+	for (int i = threadIdx.x; i < n; i += blockDim.x) sa[i] = a[i];
+	__syncthreads();
+	block_bitonic(sa, n, before);
+	for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = sa[i];
+	__syncthreads();
+}
+
 __device__ __forceinline__ int block_incl_scan(int v, int *s, int *total)
 { // every thread of the CTA calls; blockDim.x <= 1024
 	const int tid = threadIdx.x, nt = blockDim.x;
@@ -767,7 +977,7 @@ __device__ __forceinline__ int block_incl_scan(int v, int *s, int *total)
 	return r;
 }
 
-#define TAIL_BLOCK_SMEM (96 * 1024)
+#define TAIL_BLOCK_SMEM (216 * 1024)
 __global__ void __launch_bounds__(1024)
 k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
                    const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
@@ -775,6 +985,7 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
                    int32_t *__restrict__ nv_out)
 {
 	__shared__ int s_scan[1024], s_nu, s_tie;
+	extern __shared__ __align__(16) unsigned char dyn_tail[];
 	const int li = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
 	if (li >= n_list) return;
 	const int f = list ? list[li] : li;
@@ -805,7 +1016,7 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
 		n_u = s_nu;
 		if (n_u > 0) {
 			// 3. rank by (peak score, anchor) descending (chain.c:107-111)
-			block_bitonic(U1, n_u, U64Desc());
+			block_bitonic_staged(U1, n_u, U64Desc(), dyn_tail, TAIL_BLOCK_SMEM);
 			for (int e = tid; e < n_u; e += NT) U0[e] = U1[e];
 			// 4. ownership: lowest rank whose walk passes through the anchor
 			for (int i = tid; i < n; i += NT) T[i] = 0x7fffffff;
@@ -853,7 +1064,7 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
 			__syncthreads();
 			// 7. order chains by the position of their first anchor (chain.c:150): unique for distinct keys, literal replay otherwise
 			if (n_u > 64) {
-				block_bitonic(W, n_u, M128ByX());
+				block_bitonic_staged(W, n_u, M128ByX(), dyn_tail, TAIL_BLOCK_SMEM);
 				for (int kk = tid + 1; kk < n_u; kk += NT) if (W[kk].x == W[kk - 1].x) s_tie = 1;
 				__syncthreads();
 				if (s_tie) { // back to the order klib's sort starts from
@@ -865,7 +1076,6 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
 				// the literal replay is one thread's work; on a copy in shared memory its element moves cost tens of cycles instead of
 				// a trip to L2 each (a fragment from a repeat family has thousands of chains, and ties are common there: two query
 				// minimizers with the same hash start chains on the same reference position)
-				extern __shared__ __align__(16) unsigned char dyn_tail[];
 				const size_t frames = (size_t)n_u / 65 + 4;
 				if ((size_t)n_u * sizeof(mm128) + frames * sizeof(RsFrame) <= TAIL_BLOCK_SMEM) {
 					mm128 *sw = reinterpret_cast<mm128*>(dyn_tail);
@@ -1061,6 +1271,15 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	           pb.na->as<int32_t>(), pb.rep->as<int32_t>(), pb.nmini->as<int32_t>(), want_mini ? pb.mini->as<uint64_t>() : nullptr,
 	           heap_path ? c->d_replay.as<uint8_t>() : nullptr, c->d_m_aoff.as<int32_t>());
 	MMG_TRY(scan_i32_to_i64(c, pb.na->as<int32_t>(), pb.aoff->as<int64_t>(), n_list + 1));
+	int32_t *hp_counters = nullptr, *rlist = nullptr, *hp = nullptr;
+	if (heap_path) { // the fragments whose heap order has to be replayed: their number rides on the synchronisation below
+		MMG_TRY(c->d_hlist.ensure(((size_t)n_list + 8) * 4));
+		MMG_TRY(c->h_path.ensure(64));
+		hp_counters = c->d_hlist.as<int32_t>(), rlist = hp_counters + 4, hp = c->h_path.as<int32_t>() + (d_flag ? 0 : 4);
+		MMG_CUDA(cudaMemsetAsync(hp_counters, 0, 16, c->stream));
+		MMG_LAUNCH(c, k_heap_list, mmg_blocks(n_list, 256), 256, 0, n_list, c->d_replay.as<uint8_t>(), rlist, hp_counters);
+		MMG_D2H(c, hp, hp_counters, 16);
+	}
 	int64_t tot = 0;
 	MMG_D2H(c, &tot, pb.aoff->as<int64_t>() + n_list, 8);
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
@@ -1102,17 +1321,15 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	if (heap_path && tot > 0) { // fragments where equal positions meet in the heap: replay it on the ranks the sort just produced
 		MMG_TRY(c->d_hrank.ensure(((size_t)tot + 1) * 4));
 		MMG_TRY(c->d_hpop.ensure(((size_t)tot + 1) * 4));
-		MMG_TRY(c->d_hlist.ensure(((size_t)n_list + 8) * 4));
-		int32_t *counters = c->d_hlist.as<int32_t>(), *rlist = counters + 4;
+		int32_t *counters = hp_counters;
 		const uint64_t *k1 = c->d_skey.as<uint64_t>() + tot + 1, *v1 = c->d_sval.as<uint64_t>() + tot + 1;
-		MMG_CUDA(cudaMemsetAsync(counters, 0, 16, c->stream));
-		MMG_LAUNCH(c, k_heap_rank, mmg_blocks(tot, 256), 256, 0, n_list, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), tot, k1, v1, c->d_hrank.as<uint32_t>());
-		MMG_LAUNCH(c, k_heap_list, mmg_blocks(n_list, 256), 256, 0, n_list, c->d_replay.as<uint8_t>(), rlist, counters);
-		MMG_LAUNCH(c, k_heap_replay, 148 * 4, 64, 0, ft, d_list, rlist, counters, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
-		           c->d_m_aoff.as<int32_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_hrank.as<uint32_t>(), c->d_hpop.as<uint32_t>(),
-		           pb.na->as<int32_t>(), pb.a->as<mm128>());
-		MMG_TRY(c->h_path.ensure(64));
-		MMG_D2H(c, c->h_path.as<int32_t>() + (d_flag ? 0 : 4), counters, 16); // read after the pass has synchronised (mmg_seed_chain_resident)
+		if (hp[0] > 0) {
+			MMG_LAUNCH(c, k_heap_rank, mmg_blocks(tot, 256), 256, 0, n_list, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), tot, k1, v1, c->d_hrank.as<uint32_t>());
+			MMG_LAUNCH(c, k_heap_replay, hp[0] < 148 * 8 ? hp[0] : 148 * 8, 32, 0, ft, d_list, rlist, counters, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
+			           c->d_m_aoff.as<int32_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_hrank.as<uint32_t>(), c->d_hpop.as<uint32_t>());
+			MMG_LAUNCH(c, k_heap_emit, hp[0], HEAP_EMIT_THREADS, 0, ft, d_list, rlist, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
+			           c->d_m_aoff.as<int32_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_hpop.as<uint32_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>());
+		}
 	}
 	// literal replay: the heap merge for the few fragments the rank replay does not take; fill + klib radix sort for the non-heap presets
 	{
@@ -1145,10 +1362,12 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		MMG_TRY(c->d_seg_start.ensure(((size_t)tot + 2) * 8 + 64));
 		MMG_TRY(c->d_seg_avg.ensure((size_t)(n_list + 1) * 4));
 		int64_t *seg_start = c->d_seg_start.as<int64_t>();
-		int32_t *d_nseg = reinterpret_cast<int32_t*>(seg_start + tot + 1), *d_next = d_nseg + 1;
-		MMG_CUDA(cudaMemsetAsync(d_nseg, 0, 8, c->stream));
+		int32_t *d_nseg = reinterpret_cast<int32_t*>(seg_start + tot + 1), *d_next = d_nseg + 1, *d_nlong = d_nseg + 2;
+		MMG_CUDA(cudaMemsetAsync(d_nseg, 0, 16, c->stream));
+		MMG_TRY(c->d_seg_li.ensure(((size_t)tot + 1) * 4));   // fragment slot of every segment head (sparse)
+		MMG_TRY(c->d_seg_long.ensure(((size_t)tot / CHAIN_SMALL_SEG + 2) * 4)); // segments left to the warp form
 		MMG_LAUNCH(c, k_chain_heads, mmg_blocks(tot, 256), 256, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
-		           pb.na->as<int32_t>(), pb.a->as<mm128>(), tot, c->d_seg_head.as<uint8_t>(), pb.work->as<int32_t>());
+		           pb.na->as<int32_t>(), pb.a->as<mm128>(), tot, c->d_seg_head.as<uint8_t>(), pb.work->as<int32_t>(), c->d_seg_li.as<int32_t>());
 		MMG_LAUNCH(c, k_chain_avgspan, mmg_blocks((size_t)n_list * 32, 128), 128, 0, n_list, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(),
 		           pb.a->as<mm128>(), c->d_seg_avg.as<float>());
 		{
@@ -1159,9 +1378,13 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 			MMG_CUDA(cub::DeviceSelect::Flagged(c->d_cub.p, tmp, it, c->d_seg_head.as<uint8_t>(), seg_start, d_nseg, tot, c->stream));
 			++c->launches;
 		}
-		// persistent warps pull segments from a counter: 148 SMs x 16 warps x 4 CTAs in flight
+		// short segments: a thread each; the others: persistent warps pull them from the list the first kernel leaves
+		MMG_LAUNCH(c, k_chain_fill_small, 148 * 16, 128, 0, ft, d_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(),
+		           pb.a->as<mm128>(), pb.work->as<int32_t>(), c->d_seg_avg.as<float>(), seg_start, c->d_seg_li.as<int32_t>(), d_nseg,
+		           c->d_seg_long.as<int32_t>(), d_nlong, c->d_frag_iter.as<unsigned long long>());
 		MMG_LAUNCH(c, k_chain_fill, 148 * 8, 128, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(),
-		           pb.a->as<mm128>(), pb.work->as<int32_t>(), c->d_seg_avg.as<float>(), seg_start, d_nseg, d_next, c->d_frag_iter.as<unsigned long long>());
+		           pb.a->as<mm128>(), pb.work->as<int32_t>(), c->d_seg_avg.as<float>(), seg_start, c->d_seg_li.as<int32_t>(), d_nseg,
+		           c->d_seg_long.as<int32_t>(), d_nlong, d_next, c->d_frag_iter.as<unsigned long long>());
 	}
 	{
 		static bool attr_set = false;

@@ -9,6 +9,7 @@
 static long g_ksw_range_viol; // values of valid cells that left the int8 range (must stay 0: the fast form computes in 32 bits)
 #define MMG_KSW_RANGE(v) do { if ((v) < -128 || (v) > 127) ++g_ksw_range_viol; } while (0)
 #include "mmg_core.h"
+#include "mmg_regheap.h"
 
 extern "C" {
 
@@ -104,6 +105,27 @@ int64_t emu_collect_ranked(void *idx, int64_t flag, int max_occ, int n_mv, const
 	std::copy(fw.begin(), fw.end(), a);
 	std::copy(rv.begin(), rv.end(), a + fw.size());
 	return (int64_t)(fw.size() + rv.size());
+}
+
+// the heap merge on ranks: nreg == 0 runs the serial reference (mmg_heap_replay_ranks), nreg in {1, 2, 4} the warp form with the heap
+// in registers (mmg_regheap.h), lanes emulated one after the other.  first/cnt: the lists' slots; K: rank of every slot.
+int64_t emu_heap_replay(int n_lists, const int32_t *first, const int32_t *cnt, const uint32_t *K, uint32_t *pop, int nreg)
+{
+	std::vector<uint32_t> heap(n_lists + 1), cur(n_lists + 1);
+	if (nreg == 0) return mmg_heap_replay_ranks(n_lists, first, cnt, K, heap.data(), cur.data(), pop);
+	if (n_lists > 32 * nreg - 1) return -1;
+	for (int j = 0; j < n_lists; ++j) heap[j] = K[first[j]] << 8 | (uint32_t)j, cur[j] = 0;
+	if (n_lists > 1) for (int j = n_lists / 2 - 1; j >= 0; --j) mmg_rank_heap_down((uint32_t)j, (uint32_t)n_lists, heap.data());
+	auto adv = [&](uint32_t j, int64_t t) -> uint32_t {
+		pop[t] = (uint32_t)first[j] + cur[j];
+		if (cur[j] + 1 < (uint32_t)cnt[j]) { ++cur[j]; return K[(uint32_t)first[j] + cur[j]]; }
+		return RH_NONE;
+	};
+	WarpEmu wp;
+	if (nreg == 1) return regheap_replay<WarpEmu, 1>(wp, n_lists, heap.data(), adv);
+	if (nreg == 2) return regheap_replay<WarpEmu, 2>(wp, n_lists, heap.data(), adv);
+	if (nreg == 4) return regheap_replay<WarpEmu, 4>(wp, n_lists, heap.data(), adv);
+	return -1;
 }
 
 int emu_chain(int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc, int is_cdna, int n_segs,

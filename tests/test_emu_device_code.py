@@ -188,3 +188,45 @@ def test_ksw_fast_form(emu, preset):
                 assert a == b, (len(q), len(t), fl, w)
                 n_fast += 1
     assert n_fast > 1500 and (preset != "sr" or n_skip > 0)
+
+
+def _heap_case(rng, n_lists, max_cnt, dup_frac):
+    """lists of strictly increasing values; a share of the lists are copies of another one (the overlapping-mate / tandem case),
+    so equal values meet in the heap.  Returns first[], cnt[], K[] (rank of every slot = index of the first slot with its value
+    in sorted order) exactly as k_heap_rank derives them."""
+    lists = []
+    for j in range(n_lists):
+        if lists and rng.random() < dup_frac:
+            src = lists[int(rng.integers(0, len(lists)))]
+            lists.append(src.copy() if rng.random() < 0.7 else src[: max(1, len(src) // 2)].copy())
+        else:
+            c = int(rng.integers(1, max_cnt + 1))
+            lists.append(np.sort(rng.choice(max_cnt * n_lists * 4, size=c, replace=False)).astype(np.int64))
+    cnt = np.array([len(x) for x in lists], dtype=np.int32)
+    first = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32)
+    vals = np.concatenate(lists)
+    order = np.argsort(vals, kind="stable")
+    sv = vals[order]
+    start = np.concatenate([[True], sv[1:] != sv[:-1]])
+    rank_sorted = np.maximum.accumulate(np.where(start, np.arange(len(sv)), 0))
+    K = np.zeros(len(vals), dtype=np.uint32)
+    K[order] = rank_sorted.astype(np.uint32)
+    return first, cnt, K
+
+
+@pytest.mark.parametrize("nreg", [1, 2, 4])
+def test_heap_replay_in_registers_equals_serial_heap(emu, nreg):
+    """mmg_regheap.h (a warp, heap nodes in registers) pops in the order of klib's heap on every input, ties included"""
+    emu.emu_heap_replay.restype = C.c_int64
+    emu.emu_heap_replay.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(500 + nreg)
+    cap = 32 * nreg - 1
+    sizes = [1, 2, 3, cap, cap - 1, max(1, cap // 2), 16, 15, 17] + [int(rng.integers(1, cap + 1)) for _ in range(60)]
+    for it, n_lists in enumerate(sizes):
+        n_lists = min(n_lists, cap)
+        first, cnt, K = _heap_case(rng, n_lists, [1, 3, 40, 200][it % 4], [0.0, 0.3, 0.6, 0.9][(it // 4) % 4])
+        n = int(cnt.sum())
+        want, got = np.zeros(n + 1, dtype=np.uint32), np.zeros(n + 1, dtype=np.uint32)
+        assert emu.emu_heap_replay(n_lists, first.ctypes.data, cnt.ctypes.data, K.ctypes.data, want.ctypes.data, 0) == n
+        assert emu.emu_heap_replay(n_lists, first.ctypes.data, cnt.ctypes.data, K.ctypes.data, got.ctypes.data, nreg) == n
+        assert (want == got).all(), f"case {it}: n_lists={n_lists} n={n}, first difference at pop {int(np.argmax(want != got))}"
