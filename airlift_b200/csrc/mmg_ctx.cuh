@@ -23,6 +23,7 @@ struct DevBuf {
 		p = nullptr; cap = 0;
 		size_t want = bytes + bytes / 2 + 256; // generous: a re-allocation in the middle of a run costs a device synchronisation
 		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess) { cudaGetLastError(); want = bytes + 256; e = cudaMalloc(&p, want); } // HBM is short: take what is needed, no headroom
 		if (e != cudaSuccess) { mmg_set_error("cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); p = nullptr; return MMG_ENOMEM; }
 		cap = want;
 		return MMG_OK;
@@ -85,8 +86,7 @@ struct mmg_idx_s {
 struct ResidentBatch {
 	int32_t n_frag = 0, n_seq = 0, n_units = 0;
 	uint64_t n_bases = 0, q_words = 0;
-	std::vector<int32_t> n_seg, seg_off, seq_len, frag_unit0, frag_qlen;
-	std::vector<uint64_t> q_off; // packed (8-base aligned) offset of each read
+	std::vector<int32_t> n_seg, seg_off, seq_len;
 };
 
 struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -106,7 +106,7 @@ struct mmg_ctx_s {
 	DevBuf d_ascii, d_Q, d_seq_len, d_seq_off, d_q_off, d_flip, d_units, d_unit_cnt, d_unit_off, d_mv, d_m_n, d_m_val,
 	       d_frag_unit0, d_frag_qlen, d_frag_na, d_frag_aoff, d_frag_rep, d_frag_nmini, d_mini, d_a, d_work, d_u, d_b, d_heap,
 	       d_stack, d_frag_nu, d_frag_nv, d_frag_flag, d_frag_iter, d_cub, d_out_u, d_out_a, d_out_mini, d_uoff, d_voff, d_moff,
-	       d_frag_list, d_misc, d_seg_head, d_seg_start, d_seg_avg, d_replay, d_skey, d_sval, d_sseg, d_tie, d_m_aoff, d_hrank, d_hpop, d_hlist, d_seg_li, d_seg_long;
+	       d_frag_list, d_misc, d_seg_head, d_seg_start, d_seg_avg, d_replay, d_skey, d_sval, d_sseg, d_tie, d_m_aoff, d_hrank, d_hpop, d_hlist, d_seg_li, d_seg_long, d_unit0, d_fseg_off;
 	// second-pass (re-chain with max_occ) arenas
 	DevBuf d2_frag_na, d2_frag_aoff, d2_frag_rep, d2_frag_nmini, d2_mini, d2_a, d2_work, d2_u, d2_b, d2_stack, d2_frag_nu, d2_frag_nv;
 	// ksw arenas
@@ -124,6 +124,7 @@ struct mmg_ctx_s {
 	// heap order was replayed on ranks, [2] ... replayed literally, [3] fragments whose hit tree was built by a warp, [4] extra DP rounds
 	// after z-drop cuts, [5] hits cut at a z-drop
 	uint64_t path[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	PinBuf h_tab, h_tab_b, h_in_b;     // input tables of the batch being uploaded (mmg_staging_tables); second staging slot
 	PinBuf h_path;                     // device counters of the pass in flight land here
 	PinBuf h_p_hash, h_p_nreg, h_p_offs, h_p_blob, h_p_rep;
 	PinBuf h_in, h_meta, h_out_meta, h_out_u, h_out_a, h_out_mini, h_k_jobs, h_k_res, h_k_cig;

@@ -1158,12 +1158,14 @@ static int scan_i32_to_i64(mmg_ctx_t *c, const int32_t *d_in, int64_t *d_out, in
 	return MMG_OK;
 }
 
-extern "C" void *mmg_staging(mmg_ctx_t *c, size_t bytes)
-{ // pinned host buffer owned by the ctx; valid until the next mmg_staging / mmg_batch_upload of another size
+extern "C" void *mmg_staging_slot(mmg_ctx_t *c, int slot, size_t bytes)
+{ // pinned host buffer owned by the ctx (one of two, so that the next batch can be staged while the current one is mapped)
 	cudaSetDevice(c->dev);
-	if (c->h_in.ensure(bytes + 64) != MMG_OK) return nullptr;
-	return c->h_in.p;
+	PinBuf &in = slot ? c->h_in_b : c->h_in;
+	if (in.ensure(bytes + 64) != MMG_OK) return nullptr;
+	return in.p;
 }
+extern "C" void *mmg_staging(mmg_ctx_t *c, size_t bytes) { return mmg_staging_slot(c, 0, bytes); }
 
 extern "C" int mmg_job_buffers(mmg_ctx_t *c, size_t n_jobs, mmg_ksw_job_t **jobs, mmg_ksw_res_t **res)
 { // page-locked, owned by the ctx, grown on demand and kept across batches (allocating pinned memory is slow)
@@ -1174,73 +1176,132 @@ extern "C" int mmg_job_buffers(mmg_ctx_t *c, size_t n_jobs, mmg_ksw_job_t **jobs
 	return MMG_OK;
 }
 
+// pinned table block of the ctx: seq_len[n_seq+1] | seq_off[n_seq+1] | n_seg[n_frag] | seg_off[n_frag]; callers that fill it in place
+// (and pass these pointers in mmg_batch_t) save mmg_batch_upload a copy
+static void tab_layout(void *base, int n_seq, int n_frag, int32_t **seq_len, uint64_t **seq_off, int32_t **n_seg, int32_t **seg_off)
+{
+	uint8_t *p = static_cast<uint8_t*>(base);
+	*seq_off = reinterpret_cast<uint64_t*>(p); p += ((size_t)n_seq + 2) * 8;
+	*seq_len = reinterpret_cast<int32_t*>(p); p += (((size_t)n_seq + 2) * 4 + 15) & ~(size_t)15;
+	*n_seg = reinterpret_cast<int32_t*>(p); p += (((size_t)n_frag + 2) * 4 + 15) & ~(size_t)15;
+	*seg_off = reinterpret_cast<int32_t*>(p);
+}
+static size_t tab_bytes(int n_seq, int n_frag) { return ((size_t)n_seq + 2) * 12 + ((size_t)n_frag + 2) * 8 + 64; }
+
+extern "C" int mmg_staging_tables_slot(mmg_ctx_t *c, int slot, int n_seq, int n_frag, int32_t **seq_len, uint64_t **seq_off, int32_t **n_seg, int32_t **seg_off)
+{
+	cudaSetDevice(c->dev);
+	PinBuf &tab = slot ? c->h_tab_b : c->h_tab;
+	MMG_TRY(tab.ensure(tab_bytes(n_seq, n_frag)));
+	tab_layout(tab.p, n_seq, n_frag, seq_len, seq_off, n_seg, seg_off);
+	return MMG_OK;
+}
+extern "C" int mmg_staging_tables(mmg_ctx_t *c, int n_seq, int n_frag, int32_t **seq_len, uint64_t **seq_off, int32_t **n_seg, int32_t **seg_off)
+{
+	return mmg_staging_tables_slot(c, 0, n_seq, n_frag, seq_len, seq_off, n_seg, seg_off);
+}
+
+struct PadLen8 { __host__ __device__ uint64_t operator()(int32_t len) const { return ((uint64_t)len + 7) / 8 * 8; } };
+struct UnitsOfLen { __host__ __device__ int64_t operator()(int32_t len) const { return ((int64_t)len + MMG_READ_CHUNK - 1) / MMG_READ_CHUNK; } };
+
+// what the sketch and the later stages need per read and per fragment, from the lengths alone: the sketch work units
+// (one per MMG_READ_CHUNK positions of a read), the mates to flip (pe_ori, map.c:467-469), the fragments' unit ranges and
+// query lengths.  (The host used to build these 60 bytes per read and copy them over from pageable memory, every batch.)
+__global__ void k_batch_tables(int n_frag, int n_seq, const int32_t *__restrict__ n_seg, const int32_t *__restrict__ seg_off,
+                               const int32_t *__restrict__ seq_len, const uint64_t *__restrict__ q_off, const int64_t *__restrict__ unit0, int pe_ori,
+                               SketchUnit *__restrict__ units, uint8_t *__restrict__ flip, int32_t *__restrict__ frag_unit0, int32_t *__restrict__ frag_qlen)
+{
+	const int f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f > n_frag) return;
+	if (f == n_frag) { frag_unit0[f] = (int32_t)unit0[n_seq]; return; }
+	const int off = seg_off[f], ns = n_seg[f];
+	int sum = 0;
+	frag_unit0[f] = (int32_t)unit0[off];
+	for (int j = 0; j < ns; ++j) {
+		const int r = off + j, len = seq_len[r];
+		flip[r] = (ns == 2 && ((j == 0 && (pe_ori >> 1 & 1)) || (j == 1 && (pe_ori & 1)))) ? 1 : 0;
+		int64_t uu = unit0[r];
+		for (int st = 0; st < len; st += MMG_READ_CHUNK) {
+			SketchUnit u;
+			u.off = q_off[r], u.len = len, u.rid = (uint32_t)j, u.y_add = (uint64_t)sum << 1;
+			u.emit_start = st, u.emit_end = st + MMG_READ_CHUNK < len ? st + MMG_READ_CHUNK : len;
+			units[uu++] = u;
+		}
+		sum += len;
+	}
+	frag_qlen[f] = sum;
+}
+
 extern "C" int mmg_batch_upload(mmg_ctx_t *c, const mmg_mapopt_t *opt, const mmg_batch_t *b)
 {
 	MMG_CUDA(cudaSetDevice(c->dev));
 	ResidentBatch &rb = c->rb;
-	// the reads go first: their copy runs while the host builds the per-read tables below
+	// the reads go first: their copy runs while the host looks at the lengths below
 	const size_t sz_bases = (b->n_bases + 15) & ~(size_t)15;
-	if ((const void*)b->bases != c->h_in.p) { // callers that filled mmg_staging() skip this copy
+	const void *src_bases = b->bases;
+	if (src_bases != c->h_in.p && src_bases != c->h_in_b.p) { // callers that filled mmg_staging() skip this copy
 		MMG_TRY(c->h_in.ensure(sz_bases + 64));
 		memcpy(c->h_in.p, b->bases, b->n_bases);
+		src_bases = c->h_in.p;
 	}
 	MMG_TRY(c->d_ascii.ensure(sz_bases + 64));
-	MMG_H2D(c, c->d_ascii.p, c->h_in.p, b->n_bases);
-	rb.n_frag = b->n_frag, rb.n_seq = b->n_seq, rb.n_bases = b->n_bases;
-	rb.n_seg.assign(b->n_seg, b->n_seg + b->n_frag);
-	rb.seg_off.assign(b->seg_off, b->seg_off + b->n_frag);
-	rb.seq_len.assign(b->seq_len, b->seq_len + b->n_seq);
-	rb.q_off.resize(b->n_seq + 1);
-	rb.frag_unit0.resize(b->n_frag + 1);
-	rb.frag_qlen.resize(b->n_frag);
-	std::vector<uint8_t> flip(b->n_seq, 0);
-	std::vector<SketchUnit> units;
-	units.reserve(b->n_seq);
-	uint64_t qo = 0;
-	for (int r = 0; r < b->n_seq; ++r) { rb.q_off[r] = qo; qo += ((uint64_t)b->seq_len[r] + 7) / 8 * 8; }
-	rb.q_off[b->n_seq] = qo;
-	rb.q_words = qo / 8;
-	for (int f = 0; f < b->n_frag; ++f) {
-		const int off = b->seg_off[f], ns = b->n_seg[f];
-		int sum = 0;
-		rb.frag_unit0[f] = (int32_t)units.size();
-		for (int j = 0; j < ns; ++j) {
-			const int r = off + j, len = b->seq_len[r];
-			if (ns == 2 && ((j == 0 && (opt->pe_ori >> 1 & 1)) || (j == 1 && (opt->pe_ori & 1)))) flip[r] = 1;
-			for (int s = 0; s < len; s += MMG_READ_CHUNK) {
-				SketchUnit u;
-				u.off = rb.q_off[r], u.len = len, u.rid = (uint32_t)j, u.y_add = (uint64_t)sum << 1;
-				u.emit_start = s, u.emit_end = s + MMG_READ_CHUNK < len ? s + MMG_READ_CHUNK : len;
-				units.push_back(u);
-			}
-			sum += len;
-		}
-		rb.frag_qlen[f] = sum;
+	MMG_H2D(c, c->d_ascii.p, src_bases, b->n_bases);
+	const int n_seq = b->n_seq, n_frag = b->n_frag;
+	rb.n_frag = n_frag, rb.n_seq = n_seq, rb.n_bases = b->n_bases;
+	rb.n_seg.assign(b->n_seg, b->n_seg + n_frag);
+	rb.seg_off.assign(b->seg_off, b->seg_off + n_frag);
+	rb.seq_len.assign(b->seq_len, b->seq_len + n_seq);
+	// the four input tables in pinned memory (in place already when the caller used mmg_staging_tables)
+	int32_t *t_len, *t_nseg, *t_segoff; uint64_t *t_off;
+	if (c->h_tab_b.p && c->h_tab_b.cap >= tab_bytes(n_seq, n_frag) && (const void*)b->seq_off == c->h_tab_b.p) // filled in place in the second slot
+		tab_layout(c->h_tab_b.p, n_seq, n_frag, &t_len, &t_off, &t_nseg, &t_segoff);
+	else {
+		MMG_TRY(c->h_tab.ensure(tab_bytes(n_seq, n_frag)));
+		tab_layout(c->h_tab.p, n_seq, n_frag, &t_len, &t_off, &t_nseg, &t_segoff);
 	}
-	rb.frag_unit0[b->n_frag] = (int32_t)units.size();
-	rb.n_units = (int)units.size();
+	if (b->seq_len != t_len) memcpy(t_len, b->seq_len, (size_t)n_seq * 4);
+	if (b->seq_off != t_off) memcpy(t_off, b->seq_off, (size_t)n_seq * 8);
+	if (b->n_seg != t_nseg) memcpy(t_nseg, b->n_seg, (size_t)n_frag * 4);
+	if (b->seg_off != t_segoff) memcpy(t_segoff, b->seg_off, (size_t)n_frag * 4);
+	t_len[n_seq] = 0, t_off[n_seq] = b->n_bases; // the scans below run over n_seq + 1 items
+	uint64_t qo = 0; int64_t nu = 0;
+	for (int r = 0; r < n_seq; ++r) { qo += PadLen8()(t_len[r]); nu += UnitsOfLen()(t_len[r]); }
+	rb.q_words = qo / 8;
+	rb.n_units = (int)nu;
 
 	MMG_TRY(c->d_Q.ensure((rb.q_words + 8) * 4));
-	MMG_TRY(c->d_seq_len.ensure((size_t)(b->n_seq + 1) * 4));
-	MMG_TRY(c->d_seq_off.ensure((size_t)(b->n_seq + 1) * 8));
-	MMG_TRY(c->d_q_off.ensure((size_t)(b->n_seq + 1) * 8));
-	MMG_TRY(c->d_flip.ensure((size_t)b->n_seq + 16));
+	MMG_TRY(c->d_seq_len.ensure((size_t)(n_seq + 2) * 4));
+	MMG_TRY(c->d_seq_off.ensure((size_t)(n_seq + 2) * 8));
+	MMG_TRY(c->d_q_off.ensure((size_t)(n_seq + 2) * 8));
+	MMG_TRY(c->d_unit0.ensure((size_t)(n_seq + 2) * 8));
+	MMG_TRY(c->d_flip.ensure((size_t)n_seq + 16));
 	MMG_TRY(c->d_units.ensure((size_t)(rb.n_units + 1) * sizeof(SketchUnit)));
-	MMG_TRY(c->d_frag_unit0.ensure((size_t)(b->n_frag + 1) * 4));
-	MMG_TRY(c->d_frag_qlen.ensure((size_t)(b->n_frag + 1) * 4));
-	MMG_TRY(c->d_misc.ensure((size_t)(b->n_frag + 1) * 4)); // n_seg
-	MMG_H2D(c, c->d_seq_len.p, b->seq_len, (size_t)b->n_seq * 4);
-	MMG_H2D(c, c->d_seq_off.p, b->seq_off, (size_t)b->n_seq * 8);
-	MMG_H2D(c, c->d_q_off.p, rb.q_off.data(), (size_t)(b->n_seq + 1) * 8);
-	MMG_H2D(c, c->d_flip.p, flip.data(), (size_t)b->n_seq);
-	MMG_H2D(c, c->d_units.p, units.data(), (size_t)rb.n_units * sizeof(SketchUnit));
-	MMG_H2D(c, c->d_frag_unit0.p, rb.frag_unit0.data(), (size_t)(b->n_frag + 1) * 4);
-	MMG_H2D(c, c->d_frag_qlen.p, rb.frag_qlen.data(), (size_t)b->n_frag * 4);
-	MMG_H2D(c, c->d_misc.p, b->n_seg, (size_t)b->n_frag * 4);
+	MMG_TRY(c->d_frag_unit0.ensure((size_t)(n_frag + 2) * 4));
+	MMG_TRY(c->d_frag_qlen.ensure((size_t)(n_frag + 2) * 4));
+	MMG_TRY(c->d_misc.ensure((size_t)(n_frag + 2) * 4));     // n_seg
+	MMG_TRY(c->d_fseg_off.ensure((size_t)(n_frag + 2) * 4));
+	MMG_H2D(c, c->d_seq_len.p, t_len, (size_t)(n_seq + 1) * 4);
+	MMG_H2D(c, c->d_seq_off.p, t_off, (size_t)(n_seq + 1) * 8);
+	MMG_H2D(c, c->d_misc.p, t_nseg, (size_t)n_frag * 4);
+	MMG_H2D(c, c->d_fseg_off.p, t_segoff, (size_t)n_frag * 4);
+	{ // packed (8-base aligned) offset of every read, first sketch unit of every read
+		cub::TransformInputIterator<uint64_t, PadLen8, const int32_t*> it_q(c->d_seq_len.as<int32_t>(), PadLen8());
+		cub::TransformInputIterator<int64_t, UnitsOfLen, const int32_t*> it_u(c->d_seq_len.as<int32_t>(), UnitsOfLen());
+		size_t t1 = 0, t2 = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, t1, it_q, c->d_q_off.as<uint64_t>(), n_seq + 1, c->stream);
+		cub::DeviceScan::ExclusiveSum(nullptr, t2, it_u, c->d_unit0.as<int64_t>(), n_seq + 1, c->stream);
+		MMG_TRY(c->d_cub.ensure(t1 > t2 ? t1 : t2));
+		MMG_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, t1, it_q, c->d_q_off.as<uint64_t>(), n_seq + 1, c->stream));
+		MMG_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, t2, it_u, c->d_unit0.as<int64_t>(), n_seq + 1, c->stream));
+		c->launches += 2;
+	}
+	MMG_LAUNCH(c, k_batch_tables, mmg_blocks((size_t)n_frag + 1, 256), 256, 0, n_frag, n_seq, c->d_misc.as<int32_t>(), c->d_fseg_off.as<int32_t>(),
+	           c->d_seq_len.as<int32_t>(), c->d_q_off.as<uint64_t>(), c->d_unit0.as<int64_t>(), opt->pe_ori, c->d_units.as<SketchUnit>(),
+	           c->d_flip.as<uint8_t>(), c->d_frag_unit0.as<int32_t>(), c->d_frag_qlen.as<int32_t>());
 	if (rb.q_words)
 		MMG_LAUNCH(c, k_encode_reads, mmg_blocks(rb.q_words, 256), 256, 0, c->d_ascii.as<uint8_t>(), c->d_seq_off.as<uint64_t>(),
-		           c->d_seq_len.as<int32_t>(), c->d_q_off.as<uint64_t>(), c->d_flip.as<uint8_t>(), b->n_seq, rb.q_words, c->d_Q.as<uint32_t>());
-	MMG_CUDA(cudaStreamSynchronize(c->stream)); // units/flip live on this stack frame
+		           c->d_seq_len.as<int32_t>(), c->d_q_off.as<uint64_t>(), c->d_flip.as<uint8_t>(), n_seq, rb.q_words, c->d_Q.as<uint32_t>());
+	// no synchronisation: every source of the copies above is pinned memory the ctx owns until its next upload
 	return MMG_OK;
 }
 

@@ -96,6 +96,8 @@ typedef struct {          /* one GPU's share of a mini-batch */
 	char *stage_dst; const uint64_t *stage_off;
 	size_t m_jobs;
 	int rc;
+	int slot, stage_mode; /* staging slot of the ctx; 0: stage and upload, 1: stage only (host), 2: upload what an earlier stage-only call left in the slot */
+	const void *batch;    /* the mini-batch the shard belongs to (identifies what a slot holds) */
 } shard_t;
 
 static inline int mate_is_flipped(const mm_mapopt_t *opt, int n_segs, int j)
@@ -280,12 +282,15 @@ static void stage_copy_read(void *data, long i, int tid)
 	memcpy(sh->stage_dst + sh->stage_off[i], t->seq, t->l_seq);
 }
 
-/* stage the reads of fragments [f0,f1) on the shard's GPU (H2D + 4-bit encode) */
+/* stage the reads of fragments [f0,f1) on the shard's GPU: the host part fills one of the ctx's two pinned staging slots
+ * (concatenated reads and the four tables), the device part is mmg_batch_upload (H2D + 4-bit encode).  mm_b200_map_batches
+ * runs the host part of a lane group's next mini-batch while the current one is mapped. */
 static void *shard_upload(void *data)
 {
 	shard_t *sh = (shard_t*)data;
-	const int nf = sh->f1 - sh->f0;
-	int i, n_seq = 0;
+	const int nf = sh->f1 - sh->f0, mode = sh->stage_mode;
+	struct mm_idx_bucket_s *B = sh->mi->B;
+	int i, n_seq = 0, ci;
 	uint64_t n_bases = 0, o;
 	char *bases;
 	int32_t *n_seg, *seg_off, *seq_len;
@@ -294,27 +299,38 @@ static void *shard_upload(void *data)
 	double t0;
 	sh->rc = 0;
 	if (nf <= 0) return 0;
-	if (sh->up_token) pthread_mutex_lock(sh->up_token);
+	for (ci = 0; ci < 16 * MM_B200_MAX_LANES && B->ctx[ci] != sh->ctx; ++ci) {}
+	if (mode != 1 && sh->up_token) pthread_mutex_lock(sh->up_token);
 	t0 = realtime();
 	sh->s0 = sh->seg_off[sh->f0];
-	for (i = sh->f0; i < sh->f1; ++i) n_seq += sh->n_seg[i];
-	for (i = 0; i < n_seq; ++i) n_bases += sh->seq[sh->s0 + i].l_seq;
-	bases = (char*)mmg_staging(sh->ctx, n_bases + 1);
-	if (bases == 0) { shard_fail(sh, "cannot allocate the staging buffer"); if (sh->up_token) pthread_mutex_unlock(sh->up_token); return 0; }
-	n_seg = (int32_t*)malloc((size_t)nf * 4), seg_off = (int32_t*)malloc((size_t)nf * 4);
-	seq_len = (int32_t*)malloc((size_t)(n_seq + 1) * 4), seq_off = (uint64_t*)malloc((size_t)(n_seq + 1) * 8);
-	for (i = 0, o = 0; i < n_seq; ++i) {
-		seq_len[i] = sh->seq[sh->s0 + i].l_seq, seq_off[i] = o;
-		o += seq_len[i];
+	if (mode == 2 && B->staged[ci][sh->slot].batch == sh->batch && B->staged[ci][sh->slot].f0 == sh->f0 && B->staged[ci][sh->slot].f1 == sh->f1) {
+		n_seq = B->staged[ci][sh->slot].n_seq, n_bases = B->staged[ci][sh->slot].n_bases;
+		bases = (char*)mmg_staging_slot(sh->ctx, sh->slot, n_bases + 1);
+		mmg_staging_tables_slot(sh->ctx, sh->slot, n_seq, nf, &seq_len, &seq_off, &n_seg, &seg_off);
+	} else {
+		for (i = sh->f0; i < sh->f1; ++i) n_seq += sh->n_seg[i];
+		for (i = 0; i < n_seq; ++i) n_bases += sh->seq[sh->s0 + i].l_seq;
+		bases = (char*)mmg_staging_slot(sh->ctx, sh->slot, n_bases + 1);
+		if (bases == 0 || mmg_staging_tables_slot(sh->ctx, sh->slot, n_seq, nf, &seq_len, &seq_off, &n_seg, &seg_off) != MMG_OK) {
+			shard_fail(sh, "cannot allocate the staging buffers"); if (mode != 1 && sh->up_token) pthread_mutex_unlock(sh->up_token); return 0;
+		}
+		for (i = 0, o = 0; i < n_seq; ++i) {
+			seq_len[i] = sh->seq[sh->s0 + i].l_seq, seq_off[i] = o;
+			o += seq_len[i];
+		}
+		sh->stage_dst = bases, sh->stage_off = seq_off;
+		parallel_for(sh->n_threads, stage_copy_read, sh, n_seq);
+		for (i = 0; i < nf; ++i) n_seg[i] = sh->n_seg[sh->f0 + i], seg_off[i] = sh->seg_off[sh->f0 + i] - sh->s0;
+		if (getenv("MM2_B200_TRACE")) fprintf(stderr, "[T::upload] staged %d reads in %.4f s\n", n_seq, realtime() - t0);
+		if (mode == 1) {
+			B->staged[ci][sh->slot].batch = sh->batch, B->staged[ci][sh->slot].f0 = sh->f0, B->staged[ci][sh->slot].f1 = sh->f1;
+			B->staged[ci][sh->slot].n_seq = n_seq, B->staged[ci][sh->slot].n_bases = n_bases;
+			sh->st.t_upload += realtime() - t0;
+			return 0;
+		}
 	}
-	sh->stage_dst = bases, sh->stage_off = seq_off;
-	{ const double tq = realtime(); if (getenv("MM2_B200_TRACE")) fprintf(stderr, "[T::upload] tables %.4f s\n", tq - t0); }
-	parallel_for(sh->n_threads, stage_copy_read, sh, n_seq);
-	{ const double tq = realtime(); if (getenv("MM2_B200_TRACE")) fprintf(stderr, "[T::upload] +staging copy %.4f s\n", tq - t0); }
-	for (i = 0; i < nf; ++i) n_seg[i] = sh->n_seg[sh->f0 + i], seg_off[i] = sh->seg_off[sh->f0 + i] - sh->s0;
 	b.n_frag = nf, b.n_seq = n_seq, b.n_seg = n_seg, b.seg_off = seg_off, b.seq_len = seq_len, b.seq_off = seq_off, b.bases = bases, b.n_bases = n_bases;
 	if (mmg_batch_upload(sh->ctx, &sh->dopt, &b) != MMG_OK) shard_fail(sh, "read upload failed");
-	free(n_seg); free(seg_off); free(seq_len); free(seq_off);
 	if (getenv("MM2_B200_TRACE")) fprintf(stderr, "[T::upload] +device upload %.4f s\n", realtime() - t0);
 	sh->st.n_frag += nf, sh->st.n_reads += n_seq, sh->st.n_bases += n_bases;
 	sh->st.t_upload += realtime() - t0;
@@ -542,11 +558,14 @@ static step_t *step_read(pipeline_t *p)
 
 static void *shard_both(void *data) { shard_upload(data); return map_shard(data); }
 
-/* mode 0: upload + map; 1: upload only; 2: map the batch uploaded by an earlier mode-1 call */
-static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, step_t *s, int mode)
+/* mode 0: upload + map; 1: upload only; 2: map the batch uploaded by an earlier mode-1 call.
+ * group/n_groups: the lanes of every GPU are split into n_groups sets and this call uses set `group`, so that calls on
+ * different groups may run at the same time (mm_b200_map_batches) */
+static int map_step_group(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, step_t *s, int mode, int group, int n_groups, int slot, int stage_mode)
 {
 	struct mm_idx_bucket_s *B = mi->B;
-	const int n_dev = B->n_dev * B->lanes; /* shards: `lanes` per GPU, each with its own stream */
+	const int lanes = B->lanes / n_groups;  /* shards per GPU of this call, each with its own stream */
+	const int n_dev = B->n_dev * lanes;
 	shard_t *sh = (shard_t*)calloc(n_dev, sizeof(shard_t));
 	pthread_t *tid = (pthread_t*)calloc(n_dev, sizeof(pthread_t));
 	int d, f = 0, rc = 0, pass;
@@ -559,16 +578,18 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		shard_t *h = &sh[d];
 		/* device path with two shards per GPU: the first shard is the smaller one, so that its upload (the only one no kernel
 		 * can hide) is short and the second, larger upload runs under its kernels */
-		const int64_t goal = (B->lanes == 2 && use_device_path(mi, opt)) ? (tot * (d / 2) + (d % 2 == 0 ? tot * 3 / 10 : tot)) / B->n_dev : tot * (d + 1) / n_dev;
-		h->mi = mi, h->opt = opt, h->ctx = B->ctx[d], h->didx = B->didx[d / B->lanes];
+		const int64_t goal = (lanes == 2 && use_device_path(mi, opt)) ? (tot * (d / 2) + (d % 2 == 0 ? tot * 3 / 10 : tot)) / B->n_dev : tot * (d + 1) / n_dev;
+		const int gpu = d / lanes;
+		h->mi = mi, h->opt = opt, h->ctx = B->ctx[gpu * B->lanes + group * lanes + d % lanes], h->didx = B->didx[gpu];
 		mm_mapopt_to_dev(opt, &h->dopt);
 		mm_arena_init(&h->arena);
 		/* lanes of one GPU alternate between device and host stages, so each may use that GPU's whole share of host threads */
 		h->n_threads = n_threads / B->n_dev > 0 ? n_threads / B->n_dev : 1;
 		/* host path: the lanes of a GPU take turns on the device while the others run host stages; device path: their kernels
 		 * may overlap freely (the latency-bound tails of one shard fill the gaps of the other) */
-		h->gpu_token = B->lanes > 1 && (!use_device_path(mi, opt) || g_serial_shards) ? &B->gpu_token[d / B->lanes] : 0;
-		h->up_token = B->lanes > 1 && use_device_path(mi, opt) ? &B->gpu_token[d / B->lanes] : 0;
+		h->gpu_token = B->lanes > 1 && (!use_device_path(mi, opt) || g_serial_shards) ? &B->gpu_token[gpu] : 0;
+		h->up_token = B->lanes > 1 && use_device_path(mi, opt) ? &B->up_token[gpu] : 0;
+		h->slot = slot, h->stage_mode = stage_mode, h->batch = s;
 		h->seq = s->seq, h->n_seg = s->n_seg, h->seg_off = s->seg_off, h->n_reg = s->n_reg, h->rep_len = s->rep_len, h->frag_gap = s->frag_gap, h->reg = s->reg;
 		h->f0 = f;
 		while (f < s->n_frag && (acc < goal || d == n_dev - 1)) {
@@ -579,6 +600,7 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 		h->f1 = f;
 		if (h->f1 > h->f0) h->s0 = s->seg_off[h->f0];
 	}
+	if (stage_mode == 1) mode = 1; /* host staging only */
 	for (pass = 0; pass < 2; ++pass) {
 		void *(*fn)(void*) = mode == 0 ? shard_both : pass == 0 ? shard_upload : map_shard;
 		if ((pass == 0 && mode == 2) || (pass == 1 && mode == 1) || (pass == 1 && mode == 0)) continue;
@@ -614,7 +636,67 @@ static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, s
 	return rc;
 }
 
+static int map_step(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, step_t *s, int mode) { return map_step_group(mi, opt, n_threads, s, mode, 0, 1, 0, 0); }
+
 static int step_map(pipeline_t *p, step_t *s) { return map_step(p->mi, p->opt, p->n_threads, s, 0); }
+
+/* Several mini-batches, two in flight: batch i runs on lane group i % 2 of every GPU, so the upload, the latency-bound tails
+ * (the serial replays of a few repeat-family fragments) and the host finish of one batch run under the kernels of the other.
+ * This is worker_pipeline's overlap of its three steps (map.c:553-652, kt_pipeline with n_threads = 3) carried into the
+ * mapping step itself.  Results are complete, batch by batch, when the call returns. */
+static int g_in_flight = 2;
+int mm_b200_set_in_flight(int n) { if (n < 1 || n > MM_B200_MAX_LANES) return -1; g_in_flight = n; return 0; }
+typedef struct { const mm_idx_t *mi; const mm_mapopt_t *opt; int n_threads, mode, group, n_groups, n; step_t **b; int rc; } mb_arg_t;
+typedef struct { mb_arg_t *a; int i, slot, n_threads; } mb_stage_t;
+static void *map_batches_stage(void *data)
+{ /* host staging of batch i into the pinned slot the lane group does not map from */
+	mb_stage_t *t = (mb_stage_t*)data;
+	map_step_group(t->a->mi, t->a->opt, t->n_threads, t->a->b[t->i], 1, t->a->group, t->a->n_groups, t->slot, 1);
+	return 0;
+}
+
+static void *map_batches_main(void *data)
+{
+	mb_arg_t *a = (mb_arg_t*)data;
+	int i, slot = 0;
+	if (a->mode != 0) { /* upload only / map resident: nothing to overlap */
+		for (i = a->group; i < a->n; i += a->n_groups)
+			if (map_step_group(a->mi, a->opt, a->n_threads, a->b[i], a->mode, a->group, a->n_groups, 0, 0) != 0) a->rc = -1;
+		return 0;
+	}
+	{ mb_stage_t t0 = {a, a->group, 0, a->n_threads}; if (a->group < a->n) map_batches_stage(&t0); }
+	for (i = a->group; i < a->n; i += a->n_groups, slot ^= 1) {
+		const int nx = i + a->n_groups;
+		pthread_t tid;
+		mb_stage_t t = {a, nx, slot ^ 1, a->n_threads > 2 ? a->n_threads / 2 : 1};
+		if (nx < a->n) pthread_create(&tid, 0, map_batches_stage, &t); /* the next batch of this group is staged while this one is mapped */
+		if (map_step_group(a->mi, a->opt, a->n_threads, a->b[i], 0, a->group, a->n_groups, slot, 2) != 0) a->rc = -1;
+		if (nx < a->n) pthread_join(tid, 0);
+	}
+	return 0;
+}
+
+int mm_b200_map_batches(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, mm_b200_batch_t **b, int n, int mode)
+{
+	int n_groups = g_in_flight < n ? g_in_flight : n;
+	mb_arg_t a[MM_B200_MAX_LANES];
+	pthread_t tid[MM_B200_MAX_LANES];
+	int g, rc = 0;
+	if (n_threads < 1) n_threads = 1;
+	while (n_groups > 1 && mi->B->lanes % n_groups) --n_groups;
+	if (!use_device_path(mi, opt) || g_serial_shards || n_groups < 1) n_groups = 1;
+	for (g = 0; g < n_groups; ++g) {
+		a[g].mi = mi, a[g].opt = opt, a[g].n_threads = n_threads / n_groups > 0 ? n_threads / n_groups : 1, a[g].mode = mode;
+		a[g].group = g, a[g].n_groups = n_groups, a[g].n = n, a[g].b = (step_t**)b, a[g].rc = 0;
+	}
+	if (n_groups == 1) map_batches_main(&a[0]);
+	else {
+		for (g = 0; g < n_groups; ++g) pthread_create(&tid[g], 0, map_batches_main, &a[g]);
+		for (g = 0; g < n_groups; ++g) pthread_join(tid[g], 0);
+	}
+	for (g = 0; g < n_groups; ++g) if (a[g].rc) rc = -1;
+	return rc;
+}
 
 /* Step 2 (map.c:594-650, no --split-prefix).  Records are formatted by the worker threads, one output buffer per block of
  * fragments, and the buffers leave through stdout in input order: the bytes are those of one puts() per record. */

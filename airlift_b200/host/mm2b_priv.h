@@ -51,12 +51,14 @@ typedef struct mm_bseq_file_s mm_bseq_file_t;
 typedef struct { int n_u, n_a; uint64_t *u; mm128_t *a; } mm_seg_t;
 
 /* hidden part of mm_idx_t */
-#define MM_B200_MAX_LANES 4  /* a batch is cut in `lanes` shards per GPU (own stream each) so that one shard's host work overlaps another's kernels */
+#define MM_B200_MAX_LANES 8  /* a batch is cut in `lanes` shards per GPU (own stream each) so that one shard's host work overlaps another's kernels */
 struct mm_idx_bucket_s {
 	int n_dev, lanes;
 	int dev_id[16];
 	mmg_ctx_t *ctx[16 * MM_B200_MAX_LANES]; /* ctx[d * lanes + lane]: own stream and arenas, same device */
 	mmg_idx_t *didx[16];
+	struct { const void *batch; int f0, f1, n_seq; uint64_t n_bases; } staged[16 * MM_B200_MAX_LANES][2]; /* what the ctx's staging slots hold (mm_b200_map_batches) */
+	pthread_mutex_t up_token[16];  /* device path: the shards of a GPU stage their reads one after the other */
 	pthread_mutex_t gpu_token[16]; /* with lanes > 1: one shard per GPU runs device stages at a time, the others do their host stages */
 	int32_t max_occ_cache_set; float max_occ_cache_f; int32_t max_occ_cache;
 	pthread_mutex_t api_mu; /* mm_map_frag()/mm_map() share ctx[0]: concurrent callers take turns */

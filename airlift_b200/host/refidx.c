@@ -52,6 +52,7 @@ static mm_idx_t *idx_from_seqs(int w, int k, int b, int flag, int n, char **seq,
 	for (d = 0; d < g_n_dev; ++d) {
 		int l;
 		pthread_mutex_init(&B->gpu_token[d], 0);
+		pthread_mutex_init(&B->up_token[d], 0);
 		B->dev_id[d] = g_dev[d];
 		for (l = 0; l < B->lanes; ++l)
 			if (mmg_init(g_dev[d], &B->ctx[d * B->lanes + l]) != MMG_OK) die_gpu("cannot initialise the GPU");
@@ -441,6 +442,7 @@ mm_idx_t *mm_b200_idx_alloc_named(const mm_idxopt_t *opt, int n_seq, const char 
 	B->n_dev = 1, B->lanes = g_lanes, B->dev_id[0] = g_dev[0];
 	pthread_mutex_init(&B->api_mu, 0);
 	pthread_mutex_init(&B->gpu_token[0], 0);
+	pthread_mutex_init(&B->up_token[0], 0);
 	for (i = 0; i < B->lanes; ++i)
 		if (mmg_init(g_dev[0], &B->ctx[i]) != MMG_OK) die_gpu("cannot initialise the GPU");
 	*ptrs = *shape;

@@ -94,6 +94,7 @@ def load_lib():
     L.mm_b200_read_batch.argtypes = [C.c_void_p, C.POINTER(MapOptFull), C.c_int]
     L.mm_b200_batch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     L.mm_b200_map_batch.argtypes = [C.c_void_p, C.POINTER(MapOptFull), C.c_int, C.c_void_p, C.c_int]
+    L.mm_b200_map_batches.argtypes = [C.c_void_p, C.POINTER(MapOptFull), C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int]
     L.mm_b200_reset_batch.argtypes = [C.c_void_p]
     L.mm_b200_free_batch.argtypes = [C.c_void_p]
     L.mm_b200_write_batch.argtypes = [C.c_void_p, C.POINTER(MapOptFull), C.c_void_p]
@@ -326,7 +327,7 @@ def first_difference(p1, p2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sr", choices=["sr", "ont"])
@@ -337,7 +338,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the SAM-identity gate against oracle/_ref/minimap2_B")
     ap.add_argument("--no-cli", action="store_true", help="skip the whole-CLI (parse + map + SAM) timing at N=1")
-    ap.add_argument("--lanes", type=int, default=2, help="shards (streams) per GPU a batch is cut into")
+    ap.add_argument("--lanes", type=int, default=4, help="streams per GPU: two mini-batches in flight, each cut into lanes/2 shards")
+    ap.add_argument("--in-flight", type=int, default=2, help="mini-batches in flight (each on lanes/in_flight streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -402,6 +404,7 @@ def main():
     dev = (C.c_int * 1)(local_rank)
     L.mm_b200_set_devices(1, dev)
     L.mm_b200_set_lanes(args.lanes)
+    L.mm_b200_set_in_flight(args.in_flight)
     ipt, opt = IdxOpt(), MapOptFull()
     L.mm_set_opt(None, C.byref(ipt), C.byref(opt))
     L.mm_set_opt(wl.preset.encode(), C.byref(ipt), C.byref(opt))
@@ -514,10 +517,15 @@ def main():
             torch.cuda.synchronize()
 
     # ---- warm-up (full path, host buffers)
-    for _ in range(args.warmup):
-        b = next_batch()
-        if L.mm_b200_map_batch(mi, C.byref(opt), n_threads, b, 0) != 0:
+    # (through the same two-in-flight call as the timed passes, so that every lane's arenas reach their working size here)
+    wb = [next_batch() for _ in range(args.warmup)]
+    for rep in range(2):
+        if L.mm_b200_map_batches(mi, C.byref(opt), n_threads, (C.c_void_p * len(wb))(*wb), len(wb), 0) != 0:
             raise SystemExit("mapping failed")
+        for b in wb:
+            L.mm_b200_reset_batch(b)
+        wb = wb[1:] + wb[:1]   # the other lane group sees the other batches
+    for b in wb:
         L.mm_b200_free_batch(b)
 
     # the K mini-batches of the timed passes: parsed once, mapped three times (host buffers; resident; kernel profile)
@@ -528,8 +536,9 @@ def main():
         L.mm_b200_batch_info(b, C.byref(ns), None, None)
         n_reads += ns.value
 
-    def timed(mode_resident):
-        """K steps; returns (seconds max over ranks, reads of all ranks, stats, kernel profile, launches, clocks, digest)."""
+    def timed(mode_resident, in_flight=1):
+        """K steps; returns (seconds max over ranks, reads of all ranks, stats, kernel profile, launches, clocks, digest).
+        in_flight: mini-batches resident at a time in the resident pass (1 when the shards take turns on the device)."""
         L.mm_b200_stats(None, 1)
         L.mm_b200_launch_count(mi, 1)
         L.mm_b200_profile(mi, 1)
@@ -538,22 +547,26 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dev_ms = 0.0
         sync_all()
+        arr = (C.c_void_p * len(batches))(*batches)
         if not mode_resident:
+            # the K mini-batches through the batch C-ABI, two in flight (mm_b200_map_batches): host buffers in, malloc'd hits out
             ev0.record(stream)
-            for b in batches:
-                if L.mm_b200_map_batch(mi, C.byref(opt), n_threads, b, 0) != 0:
-                    raise SystemExit("mapping failed")
+            if L.mm_b200_map_batches(mi, C.byref(opt), n_threads, arr, len(batches), 0) != 0:
+                raise SystemExit("mapping failed")
             ev1.record(stream)
             sync_all()
             dev_ms = ev0.elapsed_time(ev1)
         else:
-            for b in batches:  # stage the reads in HBM outside the timed region, then time the resident pass
-                if L.mm_b200_map_batch(mi, C.byref(opt), n_threads, b, 1) != 0:
+            # the reads of up to two mini-batches (one per lane group) are staged in HBM outside the timed region, then the resident
+            # pass of those batches is timed
+            for i in range(0, len(batches), in_flight):
+                pair = (C.c_void_p * len(batches[i:i + in_flight]))(*batches[i:i + in_flight])
+                if L.mm_b200_map_batches(mi, C.byref(opt), n_threads, pair, len(pair), 1) != 0:
                     raise SystemExit("upload failed")
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                if L.mm_b200_map_batch(mi, C.byref(opt), n_threads, b, 2) != 0:
+                if L.mm_b200_map_batches(mi, C.byref(opt), n_threads, pair, len(pair), 2) != 0:
                     raise SystemExit("mapping failed")
                 e1.record(stream)
                 torch.cuda.synchronize()
@@ -591,12 +604,12 @@ def main():
         return secs, total_reads, st, prof, launches, clocks, digest
 
     secs_e2e, reads_e2e, st_e2e, prof_e2e, launches_e2e, clocks_e2e, dig_e2e = timed(False)
-    secs_res, reads_res, st_res, prof_val, launches_res, clocks_res, dig_res = timed(True)
+    secs_res, reads_res, st_res, prof_val, launches_res, clocks_res, dig_res = timed(True, in_flight=args.in_flight)
     per_rank_ms = timed.per_rank_ms
     # Kernel profile: a third pass in which the shards of a GPU take turns on the device.  In the timed passes the two shards'
     # kernels overlap on purpose, which stretches every per-kernel CUDA-event interval; the roofline figures need clean ones.
     L.mm_b200_set_serial(1)
-    _, _, st_res, prof_res, _, _, dig_prof = timed(True)
+    _, _, st_res, prof_res, _, _, dig_prof = timed(True, in_flight=1)
     L.mm_b200_set_serial(0)
     for b in batches:
         L.mm_b200_free_batch(b)
@@ -653,7 +666,7 @@ def main():
             "e2e": {"value": reads_e2e / secs_e2e, "unit": "reads/s", "h2d_bytes_per_step": st_e2e.h2d_bytes // args.steps,
                     "d2h_bytes_per_step": st_e2e.d2h_bytes // args.steps, "ms_per_step": secs_e2e * 1e3 / args.steps},
             "gpu_launches": int(launches_res), "roofline": roof, "parity": parity,
-            "passes_digest_equal": bool(dig_e2e == dig_res == dig_prof),
+            "passes_digest_equal": bool(dig_e2e == dig_res == dig_prof), "passes_digest": [f"{x:016x}" for x in (dig_e2e, dig_res, dig_prof)],
             "ksw_gcups": k4["gcups"], "k4": k4,
             "seed_lookup_gbs": algo["k_lookup"] / (lookup_ms * 1e-3) / 1e9 if lookup_ms else None,
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof_res.items(), key=lambda kv: -kv[1][0])},
@@ -670,7 +683,8 @@ def main():
                                     "total": st_e2e.t_total / args.steps},
             "per_rank_ms_per_step": per_rank_ms, "host_threads": n_threads, "host_cores": cores,
             "setup_s": {"synthetic_data": t_data, "index_build": t_build, "index_build_and_broadcast": t_index},
-            "index_broadcast_bytes": bcast_bytes, "clocks": clocks_res,
+            "index_broadcast_bytes": bcast_bytes, "clocks": clocks_res, "lanes": args.lanes, "batches_in_flight": args.in_flight,
+            "hbm_used_gb": (lambda fr_to: (fr_to[1] - fr_to[0]) / 1e9)(torch.cuda.mem_get_info()),
         }
     # ---- CPU baseline next to it (rank 0, N=1 only): the reference fork's mapping step on a bounded sample of the same files
     if rank == 0:

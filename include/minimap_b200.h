@@ -197,7 +197,7 @@ int mm_b200_idx_finalize(mm_idx_t *mi);
  * ignored: 0 if opt can be mapped with, else -1 after an [ERROR] line.  mm_map_frag()/mm_map() take turns on a lock (one
  * resident batch per GPU context), so concurrent callers are safe but serialised. */
 int mm_b200_check_opt(const mm_mapopt_t *opt);
-int mm_b200_set_lanes(int lanes); /* shards (streams) per GPU a batch is cut into, 1..4; before building the index */
+int mm_b200_set_lanes(int lanes); /* streams (with their arenas) per GPU, 1..8; before building the index */
 
 /* Batch interface = the drop-in cut point of SURVEY.md §8b (worker_pipeline step 1, map.c:590-593): a mini-batch of
  * fragments with HOST buffers in, malloc'd mm_reg1_t arrays out.  mode 0 maps (upload + all stages); modes 1 / 2 split
@@ -213,6 +213,10 @@ void mm_b200_reset_batch(mm_b200_batch_t *b);
 uint64_t mm_b200_batch_digest(const mm_b200_batch_t *b, int64_t *n_hits);
 void mm_b200_write_batch(const mm_idx_t *mi, const mm_mapopt_t *opt, mm_b200_batch_t *b); /* prints and frees */
 void mm_b200_free_batch(mm_b200_batch_t *b);
+/* n mini-batches through mm_b200_map_batch with two of them in flight (needs an even number of lanes >= 2): batch i uses lane
+ * group i % 2 of every GPU, so one batch's upload, serial tails and host finish run under the other's kernels */
+int  mm_b200_set_in_flight(int n); /* mini-batches mm_b200_map_batches keeps in flight (default 2); must divide the number of lanes */
+int  mm_b200_map_batches(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, mm_b200_batch_t **b, int n, int mode);
 int  mm_b200_n_devices(const mm_idx_t *mi);
 void mm_b200_path_counts(const mm_idx_t *mi, uint64_t out[8], int reset); /* see mmg_path_counts (mmg.h) */
 

@@ -159,6 +159,12 @@ int  mmg_seed_chain_batch(mmg_ctx_t *ctx, const mmg_idx_t *idx, const mmg_mapopt
 int  mmg_batch_upload(mmg_ctx_t *ctx, const mmg_mapopt_t *opt, const mmg_batch_t *batch);
 /* pinned staging buffer of the ctx: fill it with the concatenated reads and pass it as batch->bases to skip one host copy */
 void *mmg_staging(mmg_ctx_t *ctx, size_t bytes);
+/* pinned arrays of the ctx for the four tables of mmg_batch_t (seq_len and seq_off with n_seq entries, n_seg and seg_off with n_frag):
+ * fill them and pass the same pointers in the batch to skip another host copy */
+int  mmg_staging_tables(mmg_ctx_t *ctx, int n_seq, int n_frag, int32_t **seq_len, uint64_t **seq_off, int32_t **n_seg, int32_t **seg_off);
+/* the same with an explicit slot (0 or 1): a caller can fill slot 1 for its next batch while the batch staged in slot 0 is mapped */
+void *mmg_staging_slot(mmg_ctx_t *ctx, int slot, size_t bytes);
+int  mmg_staging_tables_slot(mmg_ctx_t *ctx, int slot, int n_seq, int n_frag, int32_t **seq_len, uint64_t **seq_off, int32_t **n_seg, int32_t **seg_off);
 /* page-locked job / result arrays owned by the ctx (kept across batches) for mmg_ksw_batch; plain malloc'd arrays work too, slower */
 
 int  mmg_seed_chain_resident(mmg_ctx_t *ctx, const mmg_idx_t *idx, const mmg_mapopt_t *opt, mmg_chains_t *out, int download);
