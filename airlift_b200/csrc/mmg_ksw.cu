@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cub/cub.cuh>
 #include "mmg_ctx.cuh"
+#include "mmg_kswdpx.h"
 
 struct KswJobDev {       // a job as the kernel sees it: mmg_ksw_job_t resolved against the resident batch and the index
 	uint64_t q_base;      // packed base offset of the read in Q
@@ -24,6 +25,8 @@ struct KswResDev { KswEz ez; uint64_t cigar_off; };   // == mmg_ksw_res_t
 #define KSW_GROUP 16
 #define KSW_JOBS_PER_BLOCK 8
 #define KSW_SMEM_PER_JOB 4096
+#define KSWDPX_SMEM_PER_JOB 5120    /* pair layout (mmg_kswdpx.h): 14 B per target column + query + 16 */
+#define KSWDPX_JOBS_PER_BLOCK 4     /* one warp per job */
 
 __device__ __forceinline__ uint8_t ksw_qbase(const uint32_t *Q, const KswJobDev &jb, int j)
 { // element j of the query handed to ksw (align.c:691-697,721,761): a slice of qseq0[rev], possibly reversed
@@ -109,6 +112,7 @@ __global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, KswSco
 					  if (bw > 32 && !g.bail && mmg_ksw_mem_bytes(qlen, tlen) + (size_t)((tlen + 15) / 16) * 64 <= KSW_SMEM_PER_JOB) cls = KSW_CLS_LITERAL_WIDE; }
 					const size_t mem_bytes = mmg_ksw_mem_bytes(qlen, tlen), H_bytes = (size_t)((tlen + 15) / 16) * 64;
 					if (mem_bytes + H_bytes > KSW_SMEM_PER_JOB) m = (mem_bytes + H_bytes + 63) & ~(size_t)63;
+					if (mmg_kswdpx_mem_bytes(qlen, tlen) > KSWDPX_SMEM_PER_JOB) { const size_t md = (mmg_kswdpx_mem_bytes(qlen, tlen) + 63) & ~(size_t)63; if (md > m) m = md; }
 					if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = ((uint64_t)(qlen + tlen - 1) * ksw_ncol(qlen, tlen, j.w) + 1) * 16;
 					const uint64_t est = (uint64_t)(qlen + tlen) * (uint64_t)(qlen < tlen ? qlen : tlen);
 					k = (uint32_t)cls << 28 | (63u - (uint32_t)(63 - __clzll((long long)(est | 1)))); // big jobs first
@@ -305,6 +309,170 @@ k_ksw(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order,
 	else if (!(jb.flag & MMG_EZ_RIGHT)) ksw_run<1, G>(g, jb, mem, H, p, ez, lane, gmask);
 	else ksw_run<2, G>(g, jb, mem, H, p, ez, lane, gmask);
 	__syncwarp(gmask);
+	if (lane == 0) {
+		int i0, j0;
+		if (with_cigar && mmg_ksw_trace_start(g, jb.flag, jb.end_bonus, &ez, &i0, &j0))
+			ez.n_cigar = mmg_ksw_backtrack(g, !!(jb.flag & MMG_EZ_REV_CIGAR), p, i0, j0, gcig + jb.cig_off);
+		res[ji] = ez;
+	}
+}
+
+// ---- K4, literal form on 16x2 SIMD: one warp per job, two adjacent cells per lane (mmg_kswdpx.h) ------------------------
+// The same program as ksw_run above -- widened band, stale lanes, block carry-in, score refresh in 16-byte chunks from st0 with
+// its spill into sf[], exact-max tie order -- with four 16-lane SSE blocks side by side in the warp: lane L holds cells 2(L & 7)
+// and 2(L & 7) + 1 of block st_ + 4 i + (L >> 3) in step i.  (Eight lanes per job, four jobs per warp, was no faster than the
+// byte-lane kernel: jobs of different shapes in one warp diverge and issue one after the other.)
+template <int kMode>
+__device__ __forceinline__ void ksw_run_dpx(const KswGeom &g, const KswJobDev &jb, uint8_t *mem, int32_t *H, uint8_t *p, KswEz &ez, const int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int tl16 = g.tlen_ * 16;
+	uint4 *PK = reinterpret_cast<uint4*>(mem);
+	int8_t *sm = reinterpret_cast<int8_t*>(mem), *s = sm + (size_t)tl16 * 8;
+	const uint8_t *sf = reinterpret_cast<const uint8_t*>(s + tl16), *qr = sf + tl16;
+	const int qlen = g.qlen, tlen = g.tlen, flag = jb.flag;
+	const bool approx = (flag & MMG_EZ_APPROX_MAX) != 0;
+	const int n1 = -g.q - g.e, n2 = -g.q2 - g.e2;
+	const KswDpxConst cst = mmg_kswdpx_const<kMode>(g);
+	int last_st = -1, last_en = -1;
+	int32_t H0 = 0, last_H0_t = 0;
+	for (int r = 0; r < qlen + tlen - 1; ++r) {
+		int st0, en0;
+		if (!mmg_ksw_band(g, r, &st0, &en0)) { ez.zdropped = 1; break; }
+		const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
+		int x1, x21, v1;
+		if (st > 0) {
+			if (st - 1 >= last_st && st - 1 <= last_en) x1 = sm[KSWDPX_X(st - 1)], x21 = sm[KSWDPX_X2(st - 1)], v1 = sm[KSWDPX_V(st - 1)];
+			else x1 = n1, x21 = n2, v1 = n1;
+		} else {
+			x1 = n1, x21 = n2;
+			v1 = mmg_ksw_first_col(g, r);
+		}
+		if (en >= r && lane == 0) { // bytes of cell r; nobody reads them before the barrier below
+			sm[KSWDPX_Y(r)] = (int8_t)n1, sm[KSWDPX_Y2(r)] = (int8_t)n2;
+			sm[KSWDPX_U(r)] = (int8_t)mmg_ksw_first_col(g, r);
+		}
+		{ // scores, 16-byte chunks starting at st0 (ksw2_extd2_sse.c:158-172): two chunks per step
+			const uint8_t *qrr = qr + (qlen - 1 - r);
+			for (int t = st0 + (lane >> 4) * 16; t <= en0; t += 32) s[t + (lane & 15)] = mmg_ksw_score(g, sf[t + (lane & 15)], qrr[t + (lane & 15)]);
+		}
+		__syncwarp();
+		const int st_ = st / 16, en_ = en / 16;
+		uint32_t cin = mmg_kswdpx_carry_of(x1, v1, x21);
+		for (int b0 = st_; b0 <= en_; b0 += 4) {
+			const int blk = b0 + (lane >> 3), pi = blk * 8 + (lane & 7);
+			const bool act = blk <= en_;
+			KswPair o = {0u, 0u, 0u};
+			uint32_t s2 = 0;
+			if (act) { const uint4 w = PK[pi]; o.w0 = w.x, o.w1 = w.y, o.w2 = w.z; s2 = *reinterpret_cast<const uint16_t*>(s + 2 * pi); }
+			const uint32_t cw = mmg_kswdpx_carry(o);
+			uint32_t prev = __shfl_up_sync(FULL, cw, 1);
+			if (lane == 0) prev = cin;
+			cin = __shfl_sync(FULL, cw, 31);
+			if (act) {
+				uint32_t d2 = 0;
+				const KswPair nw = mmg_kswdpx_pair<kMode>(cst, o, s2, prev, &d2);
+				PK[pi] = make_uint4(nw.w0, nw.w1, nw.w2, 0u);
+				if (kMode) *reinterpret_cast<uint16_t*>(p + ((size_t)r * g.n_col_ + (blk - st_)) * 16 + 2 * (lane & 7)) = (uint16_t)d2;
+			}
+		}
+		__syncwarp();
+		if (!approx) { // exact max over the band with the reference's tie order (ksw2_extd2_sse.c:315-358)
+			int32_t max_H, max_t, H_en0;
+			if (r > 0) {
+				H_en0 = en0 > 0 ? H[en0 - 1] + sm[KSWDPX_U(en0)] : H[en0] + sm[KSWDPX_V(en0)];
+				__syncwarp();
+				int32_t bh = H_en0, bt = en0; uint32_t br = 0;
+				for (int t = st0 + lane; t < en0; t += 32) {
+					const int32_t h = H[t] + sm[KSWDPX_V(t)];
+					H[t] = h;
+					const uint32_t rk = mmg_ksw_max_rank(t, st0, en0);
+					if (h > bh || (h == bh && rk < br)) bh = h, bt = t, br = rk;
+				}
+				if (lane == 0) H[en0] = H_en0;
+#pragma unroll
+				for (int d = 16; d >= 1; d >>= 1) {
+					const int32_t oh = __shfl_xor_sync(FULL, bh, d), ot = __shfl_xor_sync(FULL, bt, d);
+					const uint32_t orank = __shfl_xor_sync(FULL, br, d);
+					if (oh > bh || (oh == bh && orank < br)) bh = oh, bt = ot, br = orank;
+				}
+				max_H = bh, max_t = bt;
+			} else {
+				H_en0 = sm[KSWDPX_V(0)] - g.qe_pre;
+				if (lane == 0) H[0] = H_en0;
+				max_H = H_en0, max_t = 0;
+			}
+			__syncwarp();
+			if (en0 == tlen - 1 && H_en0 > ez.mte) ez.mte = H_en0, ez.mte_q = r - en;
+			if (r - st0 == qlen - 1) { const int32_t hs = H[st0]; if (hs > ez.mqe) ez.mqe = hs, ez.mqe_t = st0; }
+			if (mmg_ksw_zdrop(&ez, max_H, r, max_t, jb.zdrop, g.e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H[tlen - 1];
+		} else { // ksw2_extd2_sse.c:359-375
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					const int32_t d0 = sm[KSWDPX_V(last_H0_t)], d1 = sm[KSWDPX_U(last_H0_t + 1)];
+					if (d0 > d1) H0 += d0;
+					else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
+					H0 += sm[KSWDPX_V(last_H0_t)];
+				} else {
+					++last_H0_t, H0 += sm[KSWDPX_U(last_H0_t)];
+				}
+			} else H0 = sm[KSWDPX_V(0)] - g.qe_pre, last_H0_t = 0;
+			if ((flag & MMG_EZ_APPROX_DROP) && mmg_ksw_zdrop(&ez, H0, r, last_H0_t, jb.zdrop, g.e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
+		}
+		last_st = st, last_en = en;
+	}
+}
+
+__global__ void __launch_bounds__(32 * KSWDPX_JOBS_PER_BLOCK)
+k_ksw_dpx(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order, int n_jobs, KswScore sc, const uint32_t *__restrict__ Q,
+          const uint32_t *__restrict__ S, const uint64_t *__restrict__ q_off, const int32_t *__restrict__ read_len, const uint64_t *__restrict__ ref_off,
+          const uint64_t *__restrict__ mem_off, const uint64_t *__restrict__ p_off, const uint64_t *__restrict__ cig_off,
+          int8_t *__restrict__ gmem, uint8_t *__restrict__ gp, uint32_t *__restrict__ gcig, KswEz *__restrict__ res)
+{
+	extern __shared__ __align__(16) uint8_t smem[];
+	const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int slot = blockIdx.x * KSWDPX_JOBS_PER_BLOCK + grp;
+	if (slot >= n_jobs) return;
+	const int ji = order[slot];
+	const mmg_ksw_job_t hj = jobs[ji];
+	KswJobDev jb;
+	jb.q_base = q_off[hj.seq_id], jb.q_readlen = read_len[hj.seq_id], jb.q_rev = hj.q_rev, jb.q_start = hj.q_start, jb.q_len = hj.q_len;
+	jb.t_base = ref_off[hj.rid] + (uint64_t)hj.t_start, jb.t_len = hj.t_len, jb.reversed = hj.reversed;
+	jb.w = hj.w, jb.zdrop = hj.zdrop, jb.end_bonus = hj.end_bonus, jb.flag = hj.flag;
+	jb.mem_off = mem_off[ji], jb.p_off = p_off[ji], jb.cig_off = cig_off[ji];
+	const KswGeom g = mmg_ksw_geom(jb.q_len, jb.t_len, sc.m, sc.mat, sc.q, sc.e, sc.q2, sc.e2, jb.w);
+	KswEz ez;
+	mmg_ksw_reset(&ez);
+	if (g.bail) { if (lane == 0) res[ji] = ez; return; }
+	const int tl16 = g.tlen_ * 16;
+	const size_t lane_bytes = (mmg_kswdpx_lane_bytes(jb.q_len, jb.t_len) + 15) & ~(size_t)15;
+	uint8_t *mem = mmg_kswdpx_mem_bytes(jb.q_len, jb.t_len) <= KSWDPX_SMEM_PER_JOB ? smem + (size_t)grp * KSWDPX_SMEM_PER_JOB
+	                                                                              : reinterpret_cast<uint8_t*>(gmem) + jb.mem_off; // arena slot sized in k_ksw_prep
+	int32_t *H = reinterpret_cast<int32_t*>(mem + lane_bytes);
+	{ // initial lane state (ksw2_extd2_sse.c:99-121) in the pair layout
+		const uint32_t w1 = 0x01010101u * (uint8_t)(int8_t)(-g.q - g.e), w2 = 0x01010101u * (uint8_t)(int8_t)(-g.q2 - g.e2);
+		uint4 *PK = reinterpret_cast<uint4*>(mem);
+		for (int i = lane; i < tl16 / 2; i += 32) PK[i] = make_uint4(w1, w1, w2, 0u);
+		int8_t *s = reinterpret_cast<int8_t*>(mem) + (size_t)tl16 * 8;
+		for (int i = lane; i < tl16; i += 32) {
+			s[i] = 0;                                                           // s (kcalloc)
+			s[tl16 + i] = i < jb.t_len ? (int8_t)ksw_tbase(S, jb, i) : 0;       // sf
+			H[i] = MMG_KSW_NEG_INF;
+		}
+		int8_t *qr = s + 2 * tl16;
+		const int qn = g.qlen_ * 16 + 16;
+		for (int i = lane; i < qn; i += 32) qr[i] = i < jb.q_len ? (int8_t)ksw_qbase(Q, jb, jb.q_len - 1 - i) : 0;
+	}
+	__syncwarp();
+	uint8_t *p = gp + jb.p_off;
+	const bool with_cigar = !(jb.flag & MMG_EZ_SCORE_ONLY);
+	if (!with_cigar) ksw_run_dpx<0>(g, jb, mem, H, p, ez, lane);
+	else if (!(jb.flag & MMG_EZ_RIGHT)) ksw_run_dpx<1>(g, jb, mem, H, p, ez, lane);
+	else ksw_run_dpx<2>(g, jb, mem, H, p, ez, lane);
+	__syncwarp();
 	if (lane == 0) {
 		int i0, j0;
 		if (with_cigar && mmg_ksw_trace_start(g, jb.flag, jb.end_bonus, &ez, &i0, &j0))
@@ -612,13 +780,27 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 			           c->k_p.as<uint8_t>(), c->k_cig.as<uint32_t>(), d_ez);
 		first += nq;
 	}
-	if (h_cls[KSW_CLS_LITERAL])
+	static const bool legacy_literal = getenv("MMG_KSW_LEGACY") != nullptr; // the one-lane-per-byte-lane kernels, kept for A/B runs
+	if (!legacy_literal) {
+		static bool dpx_attr[16] = {false};
+		if (c->dev < 16 && !dpx_attr[c->dev]) {
+			MMG_CUDA(cudaFuncSetAttribute(k_ksw_dpx, cudaFuncAttributeMaxDynamicSharedMemorySize, KSWDPX_SMEM_PER_JOB * KSWDPX_JOBS_PER_BLOCK));
+			dpx_attr[c->dev] = true;
+		}
+		const uint32_t nl = h_cls[KSW_CLS_LITERAL] + h_cls[KSW_CLS_LITERAL_WIDE]; // consecutive in the scheduling order
+		if (nl)
+			MMG_LAUNCH(c, k_ksw_dpx, mmg_blocks(nl, KSWDPX_JOBS_PER_BLOCK), 32 * KSWDPX_JOBS_PER_BLOCK, KSWDPX_SMEM_PER_JOB * KSWDPX_JOBS_PER_BLOCK,
+			           d_jobs, order + first, (int)nl, sc, d_Q, d_S, d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off),
+			           reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(),
+			           c->k_cig.as<uint32_t>(), d_ez);
+	}
+	if (legacy_literal && h_cls[KSW_CLS_LITERAL])
 		MMG_LAUNCH(c, k_ksw<16>, mmg_blocks(h_cls[KSW_CLS_LITERAL], KSW_JOBS_PER_BLOCK), 16 * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
 		           d_jobs, order + first, (int)h_cls[KSW_CLS_LITERAL], sc, d_Q, d_S, d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off),
 		           reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(),
 		           c->k_cig.as<uint32_t>(), d_ez);
 	first += h_cls[KSW_CLS_LITERAL];
-	if (h_cls[KSW_CLS_LITERAL_WIDE])
+	if (legacy_literal && h_cls[KSW_CLS_LITERAL_WIDE])
 		MMG_LAUNCH(c, k_ksw<32>, mmg_blocks(h_cls[KSW_CLS_LITERAL_WIDE], KSW_JOBS_PER_BLOCK), 32 * KSW_JOBS_PER_BLOCK, KSW_SMEM_PER_JOB * KSW_JOBS_PER_BLOCK,
 		           d_jobs, order + first, (int)h_cls[KSW_CLS_LITERAL_WIDE], sc, d_Q, d_S, d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off),
 		           reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(),

@@ -10,6 +10,7 @@ static long g_ksw_range_viol; // values of valid cells that left the int8 range 
 #define MMG_KSW_RANGE(v) do { if ((v) < -128 || (v) > 127) ++g_ksw_range_viol; } while (0)
 #include "mmg_core.h"
 #include "mmg_regheap.h"
+#include "mmg_kswdpx.h"
 
 extern "C" {
 
@@ -163,6 +164,25 @@ int emu_ksw(int qlen, const uint8_t *query, int tlen, const uint8_t *target, con
 	for (int i = 0; i < tlen; ++i) sf[i] = target[i];
 	for (int i = 0; i < qlen; ++i) qr[i] = query[qlen - 1 - i];
 	mmg_ksw_scalar(g, flag, zdrop, end_bonus, mem.data(), H.data(), p.data(), ez_out, cigar);
+	return 0;
+}
+
+// the literal form in the pair layout on 16x2 SIMD arithmetic (mmg_kswdpx.h), one thread walking the eight lanes of every block
+int emu_ksw_dpx(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int q, int e, int q2, int e2, int w,
+                int zdrop, int end_bonus, int flag, KswEz *ez_out, uint32_t *cigar)
+{
+	KswGeom g = mmg_ksw_geom(qlen, tlen, 5, mat, q, e, q2, e2, w);
+	KswEz ez; mmg_ksw_reset(&ez);
+	if (g.bail) { *ez_out = ez; return 0; }
+	const int tl16 = g.tlen_ * 16;
+	std::vector<uint32_t> mem32((mmg_kswdpx_mem_bytes(qlen, tlen) + 64) / 4, 0);
+	uint8_t *mem = (uint8_t*)mem32.data();
+	std::vector<int32_t> H(tl16);
+	std::vector<uint8_t> p(((size_t)(qlen + tlen - 1) * g.n_col_ + 1) * 16);
+	uint8_t *sf = mem + (size_t)tl16 * 9, *qr = sf + tl16;
+	for (int i = 0; i < tlen; ++i) sf[i] = target[i];
+	for (int i = 0; i < qlen; ++i) qr[i] = query[qlen - 1 - i];
+	mmg_kswdpx_scalar(g, flag, zdrop, end_bonus, mem, H.data(), p.data(), ez_out, cigar);
 	return 0;
 }
 

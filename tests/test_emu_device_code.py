@@ -230,3 +230,36 @@ def test_heap_replay_in_registers_equals_serial_heap(emu, nreg):
         assert emu.emu_heap_replay(n_lists, first.ctypes.data, cnt.ctypes.data, K.ctypes.data, want.ctypes.data, 0) == n
         assert emu.emu_heap_replay(n_lists, first.ctypes.data, cnt.ctypes.data, K.ctypes.data, got.ctypes.data, nreg) == n
         assert (want == got).all(), f"case {it}: n_lists={n_lists} n={n}, first difference at pop {int(np.argmax(want != got))}"
+
+
+def emu_ksw_dpx(E, q, t, mat, pen, w, zd, eb, fl):
+    E.emu_ksw_dpx.restype = C.c_int
+    E.emu_ksw_dpx.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.POINTER(Ez), C.c_void_p]
+    ez = Ez()
+    cig = np.zeros(len(q) + len(t) + 4, dtype=np.uint32)
+    q = np.ascontiguousarray(q, dtype=np.uint8); t = np.ascontiguousarray(t, dtype=np.uint8)
+    E.emu_ksw_dpx(len(q), q.ctypes.data, len(t), t.ctypes.data, mat.ctypes.data, *pen, w, zd, eb, fl, C.byref(ez), cig.ctypes.data)
+    return dict(max=ez.max, zdropped=ez.zdropped, max_q=ez.max_q, max_t=ez.max_t, mqe=ez.mqe, mqe_t=ez.mqe_t, mte=ez.mte,
+                mte_q=ez.mte_q, score=ez.score, reach_end=ez.reach_end, cigar=cig[:ez.n_cigar].tolist())
+
+
+@pytest.mark.parametrize("preset", ["sr", "ont"])
+def test_ksw_literal_form_on_16x2_simd(emu, preset):
+    """The literal form in the pair layout (two cells per lane, 16x2 arithmetic, direction from one max over value*8+preference)
+    equals ksw_extd2 bit for bit: all flags, bands that clip (stale lanes are read), w=-1, N bases."""
+    from test_oracle_vs_ref import _ksw_cases
+    rng = np.random.default_rng(4242)
+    if preset == "sr":
+        mat, pen, bw, zd, eb = L.simple_mat(2, 8, 1), (12, 2, 24, 1), 151, 100, 10
+    else:
+        mat, pen, bw, zd, eb = L.simple_mat(2, 4, 1), (4, 2, 24, 1), 751, 400, -1
+    n = 0
+    for q, t in _ksw_cases(rng, 200):
+        for fl in [0xC2, 0x40, 0x08, 0x18, 0x00, 0x01, 0x02, 0x80]:
+            for w in ([bw, 20, 7, -1] if n % 3 == 0 else [bw, 20]):
+                a = L.orc_ksw(q, t, mat, *pen, w, zd, eb if fl & 0x40 else -1, fl)
+                b = emu_ksw_dpx(emu, q, t, mat, pen, w, zd, eb if fl & 0x40 else -1, fl)
+                if fl & 0x01:
+                    a["cigar"] = []
+                assert a == b, (len(q), len(t), fl, w)
+        n += 1

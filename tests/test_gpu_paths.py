@@ -110,7 +110,7 @@ def test_repeat_family_pairs(data):
     assert paths.get("warp_tree", 0) > 100, paths             # hit trees of fragments with more than 32 chains
     assert paths.get("heap_rank_replay", 0) > 100, paths      # equal positions in the seed merge
     assert paths.get("zdrop_cuts", 0) > 10 and paths.get("zdrop_rounds", 0) >= 1, paths
-    assert kern.get("k_ksw_tpj", 0) >= 1 and (kern.get("k_ksw<16>", 0) + kern.get("k_ksw<32>", 0)) >= 1, kern   # both DP forms
+    assert kern.get("k_ksw_tpj", 0) >= 1 and kern.get("k_ksw_dpx", 0) >= 1, kern   # both DP forms
 
 
 def test_kilobase_reads_short_read_preset(data):
