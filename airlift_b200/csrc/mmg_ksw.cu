@@ -334,6 +334,7 @@ __device__ __forceinline__ void ksw_run_dpx(const KswGeom &g, const KswJobDev &j
 	const bool approx = (flag & MMG_EZ_APPROX_MAX) != 0;
 	const int n1 = -g.q - g.e, n2 = -g.q2 - g.e2;
 	const KswDpxConst cst = mmg_kswdpx_const<kMode>(g);
+	const bool small_keys = mmg_ksw_fast_ok(g); // |H| * 2048 fits 32 bits and an anti-diagonal has at most 1023 cells
 	int last_st = -1, last_en = -1;
 	int32_t H0 = 0, last_H0_t = 0;
 	for (int r = 0; r < qlen + tlen - 1; ++r) {
@@ -382,21 +383,39 @@ __device__ __forceinline__ void ksw_run_dpx(const KswGeom &g, const KswJobDev &j
 			if (r > 0) {
 				H_en0 = en0 > 0 ? H[en0 - 1] + sm[KSWDPX_U(en0)] : H[en0] + sm[KSWDPX_V(en0)];
 				__syncwarp();
-				int32_t bh = H_en0, bt = en0; uint32_t br = 0;
-				for (int t = st0 + lane; t < en0; t += 32) {
-					const int32_t h = H[t] + sm[KSWDPX_V(t)];
-					H[t] = h;
-					const uint32_t rk = mmg_ksw_max_rank(t, st0, en0);
-					if (h > bh || (h == bh && rk < br)) bh = h, bt = t, br = rk;
-				}
-				if (lane == 0) H[en0] = H_en0;
+				if (small_keys) { // score and tie preference in one word (as mmg_ksw_fast_run): one warp-wide integer max
+					const int en1k = (en0 - st0) / 4 * 4;
+					int32_t best = H_en0 * 2048 + 2047; // the cell en0 wins every tie (ksw2_extd2_sse.c:319-349 starts from it)
+					for (int t = st0 + lane; t < en0; t += 32) {
+						const int32_t h = H[t] + sm[KSWDPX_V(t)];
+						H[t] = h;
+						const int k = t - st0, rk = k < en1k ? ((k & 3) << 8 | k >> 2) : (4 << 8 | (k - en1k));
+						const int32_t key = h * 2048 + (2046 - rk);
+						best = best > key ? best : key;
+					}
+					if (lane == 0) H[en0] = H_en0;
+					best = __reduce_max_sync(FULL, best);
+					const int32_t low = best & 2047;
+					max_H = (best - low) >> 11; // exact: best - low is a multiple of 2048
+					if (low == 2047) max_t = en0;
+					else { const int32_t rk = 2046 - low; max_t = (rk >> 8) == 4 ? st0 + en1k + (rk & 255) : st0 + ((rk & 255) << 2) + (rk >> 8); }
+				} else {
+					int32_t bh = H_en0, bt = en0; uint32_t br = 0;
+					for (int t = st0 + lane; t < en0; t += 32) {
+						const int32_t h = H[t] + sm[KSWDPX_V(t)];
+						H[t] = h;
+						const uint32_t rk = mmg_ksw_max_rank(t, st0, en0);
+						if (h > bh || (h == bh && rk < br)) bh = h, bt = t, br = rk;
+					}
+					if (lane == 0) H[en0] = H_en0;
 #pragma unroll
-				for (int d = 16; d >= 1; d >>= 1) {
-					const int32_t oh = __shfl_xor_sync(FULL, bh, d), ot = __shfl_xor_sync(FULL, bt, d);
-					const uint32_t orank = __shfl_xor_sync(FULL, br, d);
-					if (oh > bh || (oh == bh && orank < br)) bh = oh, bt = ot, br = orank;
+					for (int d = 16; d >= 1; d >>= 1) {
+						const int32_t oh = __shfl_xor_sync(FULL, bh, d), ot = __shfl_xor_sync(FULL, bt, d);
+						const uint32_t orank = __shfl_xor_sync(FULL, br, d);
+						if (oh > bh || (oh == bh && orank < br)) bh = oh, bt = ot, br = orank;
+					}
+					max_H = bh, max_t = bt;
 				}
-				max_H = bh, max_t = bt;
 			} else {
 				H_en0 = sm[KSWDPX_V(0)] - g.qe_pre;
 				if (lane == 0) H[0] = H_en0;

@@ -394,7 +394,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_w, int *total)
 __global__ void __launch_bounds__(HEAP_EMIT_THREADS)
 k_heap_emit(FragTab ft, const int32_t *__restrict__ list, const int32_t *__restrict__ rlist, const mm128 *__restrict__ mv, const int32_t *__restrict__ m_n,
             const uint64_t *__restrict__ m_val, const int32_t *__restrict__ m_aoff, const uint64_t *__restrict__ pos, int max_occ, int64_t flag,
-            const int64_t *__restrict__ aoff, uint32_t *__restrict__ P, int32_t *__restrict__ na, mm128 *__restrict__ a)
+            const int64_t *__restrict__ aoff, uint32_t *__restrict__ P, int32_t *__restrict__ na, mm128 *__restrict__ a, unsigned long long *__restrict__ n_pops)
 {
 	__shared__ int32_t s_first[HEAP_MAX_LISTS], s_m[HEAP_MAX_LISTS], s_w[32], s_tot[3];
 	const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
@@ -452,7 +452,7 @@ k_heap_emit(FragTab ft, const int32_t *__restrict__ list, const int32_t *__restr
 		}
 		run_for += tot & 0xffff, run_rev += tot >> 16;
 	}
-	if (tid == 0) na[li] = run_for + run_rev;
+	if (tid == 0) { na[li] = run_for + run_rev; atomicAdd(n_pops, (unsigned long long)n_a); }
 }
 
 // mmg_fill_heap (mmg_core.h) for one fragment per warp: same pops in the same order; the heap and the next position of every
@@ -1389,7 +1389,8 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 			MMG_LAUNCH(c, k_heap_replay, hp[0] < 148 * 8 ? hp[0] : 148 * 8, 32, 0, ft, d_list, rlist, counters, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
 			           c->d_m_aoff.as<int32_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_hrank.as<uint32_t>(), c->d_hpop.as<uint32_t>());
 			MMG_LAUNCH(c, k_heap_emit, hp[0], HEAP_EMIT_THREADS, 0, ft, d_list, rlist, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(), c->d_m_val.as<uint64_t>(),
-			           c->d_m_aoff.as<int32_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_hpop.as<uint32_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>());
+			           c->d_m_aoff.as<int32_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), c->d_hpop.as<uint32_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>(),
+			           c->d_frag_iter.as<unsigned long long>() + 1);
 		}
 	}
 	// literal replay: the heap merge for the few fragments the rank replay does not take; fill + klib radix sort for the non-heap presets
@@ -1540,6 +1541,7 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 	MMG_CUDA(cudaEventRecord(c->ev[1], c->stream));
 	unsigned long long iters = 0;
 	MMG_D2H(c, &iters, c->d_frag_iter.p, 8);
+	MMG_D2H(c, c->h_path.as<unsigned long long>() + 5, c->d_frag_iter.as<unsigned long long>() + 1, 8); // hits whose merge order was replayed
 	out->n_minimizers = (uint64_t)n_mv, out->n_anchors = (uint64_t)(n_anch1 + n_anch2);
 	if (download) {
 		// meta: n_u | n_a | rep_len | n_mini | rechained (int32 each) then u_off | a_off | mini_off (uint64 each, nf+1)
@@ -1574,6 +1576,7 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 	{ // path counters of this batch (the stream is idle here)
 		const int32_t *hp = c->h_path.as<int32_t>();
 		c->path[0] += (uint64_t)n2, c->path[1] += (uint64_t)(hp[0] + hp[4]), c->path[2] += (uint64_t)(hp[2] + hp[6]);
+		c->path[6] += c->h_path.as<unsigned long long>()[5];
 	}
 	float ms = 0;
 	cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); out->t_kernels_ms = ms;

@@ -676,6 +676,14 @@ static void *map_batches_main(void *data)
 	return 0;
 }
 
+int mm_b200_batches_in_flight(const mm_idx_t *mi, const mm_mapopt_t *opt)
+{ /* how many mini-batches mm_b200_map_batches overlaps for these options (1: one after the other) */
+	int n_groups = g_in_flight;
+	while (n_groups > 1 && mi->B->lanes % n_groups) --n_groups;
+	if (!use_device_path(mi, opt) || g_serial_shards || n_groups < 1) n_groups = 1;
+	return n_groups;
+}
+
 int mm_b200_map_batches(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, mm_b200_batch_t **b, int n, int mode)
 {
 	int n_groups = g_in_flight < n ? g_in_flight : n;

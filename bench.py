@@ -95,6 +95,7 @@ def load_lib():
     L.mm_b200_batch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     L.mm_b200_map_batch.argtypes = [C.c_void_p, C.POINTER(MapOptFull), C.c_int, C.c_void_p, C.c_int]
     L.mm_b200_map_batches.argtypes = [C.c_void_p, C.POINTER(MapOptFull), C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int]
+    L.mm_b200_batches_in_flight.argtypes = [C.c_void_p, C.POINTER(MapOptFull)]
     L.mm_b200_reset_batch.argtypes = [C.c_void_p]
     L.mm_b200_free_batch.argtypes = [C.c_void_p]
     L.mm_b200_write_batch.argtypes = [C.c_void_p, C.POINTER(MapOptFull), C.c_void_p]
@@ -114,6 +115,7 @@ def load_lib():
     L.mm_b200_ctx.argtypes = [C.c_void_p, C.c_int]
     L.mmg_stream.restype = C.c_void_p
     L.mmg_stream.argtypes = [C.c_void_p]
+    L.mm_b200_path_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
     L.mm_b200_launch_count.restype = C.c_long
     L.mm_b200_launch_count.argtypes = [C.c_void_p, C.c_int]
     return L
@@ -540,6 +542,7 @@ def main():
         """K steps; returns (seconds max over ranks, reads of all ranks, stats, kernel profile, launches, clocks, digest).
         in_flight: mini-batches resident at a time in the resident pass (1 when the shards take turns on the device)."""
         L.mm_b200_stats(None, 1)
+        L.mm_b200_path_counts(mi, (C.c_uint64 * 8)(), 1)
         L.mm_b200_launch_count(mi, 1)
         L.mm_b200_profile(mi, 1)
         sampler = ClockSampler(local_rank)
@@ -583,6 +586,10 @@ def main():
             prof[nm] = (prof.get(nm, (0.0, 0))[0] + ms[i], prof.get(nm, (0.0, 0))[1] + ln[i])
         L.mm_b200_profile(mi, 0)
         launches = L.mm_b200_launch_count(mi, 0)
+        pc = (C.c_uint64 * 8)()
+        L.mm_b200_path_counts(mi, pc, 0)
+        timed.paths = {"rechained": pc[0], "heap_rank_replay": pc[1], "heap_literal_replay": pc[2], "warp_tree": pc[3], "zdrop_rounds": pc[4],
+                       "zdrop_cuts": pc[5], "replayed_hits": pc[6]}
         digest = 0
         for b in batches:  # the three passes must produce the same hits
             digest ^= L.mm_b200_batch_digest(b, None)
@@ -604,7 +611,8 @@ def main():
         return secs, total_reads, st, prof, launches, clocks, digest
 
     secs_e2e, reads_e2e, st_e2e, prof_e2e, launches_e2e, clocks_e2e, dig_e2e = timed(False)
-    secs_res, reads_res, st_res, prof_val, launches_res, clocks_res, dig_res = timed(True, in_flight=args.in_flight)
+    in_flight = L.mm_b200_batches_in_flight(mi, C.byref(opt))   # 1 for the presets whose post-chaining stages run on the host
+    secs_res, reads_res, st_res, prof_val, launches_res, clocks_res, dig_res = timed(True, in_flight=in_flight)
     per_rank_ms = timed.per_rank_ms
     # Kernel profile: a third pass in which the shards of a GPU take turns on the device.  In the timed passes the two shards'
     # kernels overlap on purpose, which stretches every per-kernel CUDA-event interval; the roofline figures need clean ones.
@@ -629,7 +637,10 @@ def main():
         # algorithmic HBM bytes of each kernel over the timed region (bytes per unit x units from the live counters)
         nmv, nanch, cells, jobs = st_res.n_minimizers, st_res.n_anchors, st_res.n_dp_cells, st_res.n_dp_jobs
         cells_fast, jobs_fast = st_res.n_dp_cells_fast, st_res.n_dp_jobs_fast
+        paths = timed.paths
         algo = {
+            # serial merge replay: a rank in, a slot out per replayed hit (latency-bound: one dependent pop after the other)
+            "k_heap_replay": paths["replayed_hits"] * 8.0,
             "k_sketch_count": st_res.n_bases * 0.5, "k_sketch_fill": st_res.n_bases * 0.5 + nmv * 16, "k_sketch_reads": st_res.n_bases * 0.5 + nmv * 16,
             "k_lookup": nmv * (16 + 16 + 12), "k_fill": nmv * 28 + nanch * (8 + 16), "k_expand": nmv * 28 + nanch * (8 + 16),
             "k_chain_fill": nanch * (16 + 16), "k_chain_tail_warp": nanch * (16 + 16 + 16 + 16),
@@ -673,6 +684,7 @@ def main():
             "kernel_launches_per_step": {k: v[1] / args.steps for k, v in sorted(prof_res.items(), key=lambda kv: -kv[1][0])},
             "kernel_profile": "CUDA events around every launch in a separate pass of the same K steps with the two shards of a GPU serialised "
                               "(in the timed passes their kernels overlap, which stretches per-kernel intervals)",
+            "paths_per_step": {k: v / args.steps for k, v in paths.items()},
             "work_per_step": {"reads": n_reads / args.steps, "bases": st_res.n_bases / args.steps, "minimizers": nmv / args.steps, "anchors": nanch / args.steps,
                               "chain_iterations": st_res.n_chain_iter / args.steps, "dp_jobs": jobs / args.steps, "dp_cells": cells / args.steps},
             "host_s_per_step": {"seed_chain_call": st_res.t_seedchain / args.steps, "hits": st_res.t_hits / args.steps,
@@ -683,7 +695,7 @@ def main():
                                     "total": st_e2e.t_total / args.steps},
             "per_rank_ms_per_step": per_rank_ms, "host_threads": n_threads, "host_cores": cores,
             "setup_s": {"synthetic_data": t_data, "index_build": t_build, "index_build_and_broadcast": t_index},
-            "index_broadcast_bytes": bcast_bytes, "clocks": clocks_res, "lanes": args.lanes, "batches_in_flight": args.in_flight,
+            "index_broadcast_bytes": bcast_bytes, "clocks": clocks_res, "lanes": args.lanes, "batches_in_flight": in_flight,
             "hbm_used_gb": (lambda fr_to: (fr_to[1] - fr_to[0]) / 1e9)(torch.cuda.mem_get_info()),
         }
     # ---- CPU baseline next to it (rank 0, N=1 only): the reference fork's mapping step on a bounded sample of the same files

@@ -216,6 +216,7 @@ void mm_b200_free_batch(mm_b200_batch_t *b);
 /* n mini-batches through mm_b200_map_batch with two of them in flight (needs an even number of lanes >= 2): batch i uses lane
  * group i % 2 of every GPU, so one batch's upload, serial tails and host finish run under the other's kernels */
 int  mm_b200_set_in_flight(int n); /* mini-batches mm_b200_map_batches keeps in flight (default 2); must divide the number of lanes */
+int  mm_b200_batches_in_flight(const mm_idx_t *mi, const mm_mapopt_t *opt); /* what mm_b200_map_batches overlaps for these options */
 int  mm_b200_map_batches(const mm_idx_t *mi, const mm_mapopt_t *opt, int n_threads, mm_b200_batch_t **b, int n, int mode);
 int  mm_b200_n_devices(const mm_idx_t *mi);
 void mm_b200_path_counts(const mm_idx_t *mi, uint64_t out[8], int reset); /* see mmg_path_counts (mmg.h) */

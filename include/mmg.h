@@ -50,7 +50,7 @@ void mmg_profile_enable(mmg_ctx_t *ctx, int on);
 int  mmg_profile_fetch(mmg_ctx_t *ctx, int max, const char **names, double *ms, long *launches);
 /* work items that took each data-dependent path since the last reset: out[0] fragments re-chained with max_occ (map.c:353-375),
  * [1] fragments whose seed-merge order was replayed on ranks, [2] ... literally, [3] fragments whose hit tree was built by a warp,
- * [4] extra DP rounds after z-drop cuts, [5] hits cut at a z-drop; [6], [7] reserved */
+ * [4] extra DP rounds after z-drop cuts, [5] hits cut at a z-drop, [6] seed hits whose merge order was replayed (pops of [1]); [7] reserved */
 void mmg_path_counts(mmg_ctx_t *ctx, uint64_t out[8], int reset);
 
 /* ------------------------------------------------------------------ index */
