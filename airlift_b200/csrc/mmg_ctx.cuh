@@ -15,12 +15,16 @@ void mmg_set_error(const char *fmt, ...);
 	mmg_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return MMG_ECUDA; } } while (0)
 #define MMG_TRY(call) do { int r_ = (call); if (r_ != MMG_OK) return r_; } while (0)
 
+// how often a device / pinned buffer had to be re-allocated (each time costs a device-wide synchronisation): [0] device, [1] pinned
+extern unsigned long long g_mmg_grow[2];
+
 struct DevBuf {
 	void *p = nullptr; size_t cap = 0;
 	int ensure(size_t bytes) {
 		if (bytes <= cap) return MMG_OK;
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
+		__atomic_fetch_add(&g_mmg_grow[0], 1ULL, __ATOMIC_RELAXED);
 		size_t want = bytes + bytes / 2 + 256; // generous: a re-allocation in the middle of a run costs a device synchronisation
 		cudaError_t e = cudaMalloc(&p, want);
 		if (e != cudaSuccess) { cudaGetLastError(); want = bytes + 256; e = cudaMalloc(&p, want); } // HBM is short: take what is needed, no headroom
@@ -50,6 +54,7 @@ struct PinBuf {
 		if (bytes <= cap) return MMG_OK;
 		if (p) cudaFreeHost(p);
 		p = nullptr; cap = 0;
+		__atomic_fetch_add(&g_mmg_grow[1], 1ULL, __ATOMIC_RELAXED);
 		size_t want = bytes + bytes / 2 + 256; // page-locking hundreds of MB again takes ~0.1 s
 		cudaError_t e = cudaMallocHost(&p, want);
 		if (e != cudaSuccess) { mmg_set_error("cudaMallocHost(%zu): %s", want, cudaGetErrorString(e)); p = nullptr; return MMG_ENOMEM; }

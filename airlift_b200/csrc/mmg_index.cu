@@ -72,6 +72,12 @@ extern "C" void mmg_copy_bytes(mmg_ctx_t *c, uint64_t *h2d, uint64_t *d2h, int r
 	if (reset) c->h2d_bytes = c->d2h_bytes = 0;
 }
 
+unsigned long long g_mmg_grow[2] = {0, 0};
+extern "C" void mmg_growth_counts(uint64_t out[2], int reset)
+{
+	for (int i = 0; i < 2; ++i) { out[i] = g_mmg_grow[i]; if (reset) g_mmg_grow[i] = 0; }
+}
+
 extern "C" void mmg_profile_enable(mmg_ctx_t *c, int on) { c->prof_on = on != 0; }
 
 extern "C" void mmg_path_counts(mmg_ctx_t *c, uint64_t out[8], int reset)

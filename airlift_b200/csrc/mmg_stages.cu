@@ -1163,6 +1163,7 @@ extern "C" void *mmg_staging_slot(mmg_ctx_t *c, int slot, size_t bytes)
 	cudaSetDevice(c->dev);
 	PinBuf &in = slot ? c->h_in_b : c->h_in;
 	if (in.ensure(bytes + 64) != MMG_OK) return nullptr;
+	if ((c->h_in_b.p || slot) && (slot ? c->h_in : c->h_in_b).ensure(bytes + 64) != MMG_OK) return nullptr; // both slots grow together
 	return in.p;
 }
 extern "C" void *mmg_staging(mmg_ctx_t *c, size_t bytes) { return mmg_staging_slot(c, 0, bytes); }
@@ -1193,6 +1194,7 @@ extern "C" int mmg_staging_tables_slot(mmg_ctx_t *c, int slot, int n_seq, int n_
 	cudaSetDevice(c->dev);
 	PinBuf &tab = slot ? c->h_tab_b : c->h_tab;
 	MMG_TRY(tab.ensure(tab_bytes(n_seq, n_frag)));
+	if (c->h_tab_b.p || slot) MMG_TRY((slot ? c->h_tab : c->h_tab_b).ensure(tab_bytes(n_seq, n_frag))); // both slots grow together: page-locking is slow and synchronises the device
 	tab_layout(tab.p, n_seq, n_frag, seq_len, seq_off, n_seg, seg_off);
 	return MMG_OK;
 }

@@ -116,6 +116,7 @@ def load_lib():
     L.mmg_stream.restype = C.c_void_p
     L.mmg_stream.argtypes = [C.c_void_p]
     L.mm_b200_path_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+    L.mmg_growth_counts.argtypes = [C.POINTER(C.c_uint64), C.c_int]
     L.mm_b200_launch_count.restype = C.c_long
     L.mm_b200_launch_count.argtypes = [C.c_void_p, C.c_int]
     return L
@@ -350,7 +351,7 @@ def main():
     wl = Workload(args)
 
     ensure_tools()
-    n_steps = args.warmup + args.steps
+    n_steps = max(args.warmup, 4) + args.steps * (2 if os.environ.get("BENCH_E2E_TWICE") else 1)   # the b200 arm warms up on at least four mini-batches
     bytes_per_unit = 700 if wl.kind == "sr" else 20_500
     d = workdir(int(wl.G * 1.02) + 10 * (1 << 30) + world * wl.units * n_steps * bytes_per_unit)
     if args.impl == "reference":
@@ -520,7 +521,16 @@ def main():
 
     # ---- warm-up (full path, host buffers)
     # (through the same two-in-flight call as the timed passes, so that every lane's arenas reach their working size here)
-    wb = [next_batch() for _ in range(args.warmup)]
+    wb = [next_batch() for _ in range(max(args.warmup, 4))]   # at least two per lane group: both staging slots of every stream get used
+    # the K mini-batches of the timed passes: parsed once, mapped three times (host buffers; resident; kernel profile).  They are
+    # parsed BEFORE the warm-up, so that the timed region starts right behind it: two seconds of FASTQ parsing in between let
+    # the GPU fall back to its idle clocks, and the ramp back up cost the first timed pass 30-50 ms per step.
+    batches = [next_batch() for _ in range(args.steps)]
+    n_reads = 0
+    for b in batches:
+        ns = C.c_int(0)
+        L.mm_b200_batch_info(b, C.byref(ns), None, None)
+        n_reads += ns.value
     for rep in range(2):
         if L.mm_b200_map_batches(mi, C.byref(opt), n_threads, (C.c_void_p * len(wb))(*wb), len(wb), 0) != 0:
             raise SystemExit("mapping failed")
@@ -530,21 +540,14 @@ def main():
     for b in wb:
         L.mm_b200_free_batch(b)
 
-    # the K mini-batches of the timed passes: parsed once, mapped three times (host buffers; resident; kernel profile)
-    batches = [next_batch() for _ in range(args.steps)]
-    n_reads = 0
-    for b in batches:
-        ns = C.c_int(0)
-        L.mm_b200_batch_info(b, C.byref(ns), None, None)
-        n_reads += ns.value
-
-    def timed(mode_resident, in_flight=1):
+    def timed(mode_resident, in_flight=1, profile=False):
         """K steps; returns (seconds max over ranks, reads of all ranks, stats, kernel profile, launches, clocks, digest).
         in_flight: mini-batches resident at a time in the resident pass (1 when the shards take turns on the device)."""
         L.mm_b200_stats(None, 1)
+        L.mmg_growth_counts((C.c_uint64 * 2)(), 1)
         L.mm_b200_path_counts(mi, (C.c_uint64 * 8)(), 1)
         L.mm_b200_launch_count(mi, 1)
-        L.mm_b200_profile(mi, 1)
+        L.mm_b200_profile(mi, 1 if profile else 0)   # CUDA events around every launch: only in the separate profile pass
         sampler = ClockSampler(local_rank)
         sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -586,6 +589,9 @@ def main():
             prof[nm] = (prof.get(nm, (0.0, 0))[0] + ms[i], prof.get(nm, (0.0, 0))[1] + ln[i])
         L.mm_b200_profile(mi, 0)
         launches = L.mm_b200_launch_count(mi, 0)
+        gr = (C.c_uint64 * 2)()
+        L.mmg_growth_counts(gr, 0)
+        timed.growths = [int(gr[0]), int(gr[1])]
         pc = (C.c_uint64 * 8)()
         L.mm_b200_path_counts(mi, pc, 0)
         timed.paths = {"rechained": pc[0], "heap_rank_replay": pc[1], "heap_literal_replay": pc[2], "warp_tree": pc[3], "zdrop_rounds": pc[4],
@@ -611,13 +617,27 @@ def main():
         return secs, total_reads, st, prof, launches, clocks, digest
 
     secs_e2e, reads_e2e, st_e2e, prof_e2e, launches_e2e, clocks_e2e, dig_e2e = timed(False)
+    growths_e2e = timed.growths
+    if os.environ.get("BENCH_E2E_TWICE"):   # diagnostic: the same batches again, every arena at its final size
+        r2 = timed(False)
+        s2 = r2[0]
+        keep = batches
+        batches = [next_batch() for _ in range(args.steps)]   # a second set of new batches
+        r3 = timed(False)
+        sys.stderr.write(f"[bench] e2e pass 3 (other new batches) {r3[0] * 1e3 / args.steps:.1f} ms/step\n")
+        for b in batches:
+            L.mm_b200_free_batch(b)
+        batches = keep
+        for nm, st in (("pass 1", st_e2e), ("pass 2", r2[2])):
+            sys.stderr.write(f"[bench] {nm}: total {st.t_total:.3f} upload {st.t_upload:.3f} seed/chain {st.t_seedchain:.3f} (kernels {st.t_seedchain_kernels:.3f}) dp {st.t_ksw_total:.3f} (kernel {st.t_ksw_kernel:.3f}) finish {st.t_finish:.3f}\n")
+        sys.stderr.write(f"[bench] e2e pass 1 {secs_e2e * 1e3 / args.steps:.1f} ms/step (buffer re-allocations {growths_e2e}), pass 2 {s2 * 1e3 / args.steps:.1f} ms/step ({timed.growths})\n")
     in_flight = L.mm_b200_batches_in_flight(mi, C.byref(opt))   # 1 for the presets whose post-chaining stages run on the host
     secs_res, reads_res, st_res, prof_val, launches_res, clocks_res, dig_res = timed(True, in_flight=in_flight)
     per_rank_ms = timed.per_rank_ms
     # Kernel profile: a third pass in which the shards of a GPU take turns on the device.  In the timed passes the two shards'
     # kernels overlap on purpose, which stretches every per-kernel CUDA-event interval; the roofline figures need clean ones.
     L.mm_b200_set_serial(1)
-    _, _, st_res, prof_res, _, _, dig_prof = timed(True, in_flight=1)
+    _, _, st_res, prof_res, _, _, dig_prof = timed(True, in_flight=1, profile=True)
     L.mm_b200_set_serial(0)
     for b in batches:
         L.mm_b200_free_batch(b)
@@ -695,7 +715,7 @@ def main():
                                     "total": st_e2e.t_total / args.steps},
             "per_rank_ms_per_step": per_rank_ms, "host_threads": n_threads, "host_cores": cores,
             "setup_s": {"synthetic_data": t_data, "index_build": t_build, "index_build_and_broadcast": t_index},
-            "index_broadcast_bytes": bcast_bytes, "clocks": clocks_res, "lanes": args.lanes, "batches_in_flight": in_flight,
+            "index_broadcast_bytes": bcast_bytes, "clocks": clocks_res, "lanes": args.lanes, "batches_in_flight": in_flight, "buffer_reallocations_in_e2e_pass": {"device": growths_e2e[0], "pinned": growths_e2e[1]},
             "hbm_used_gb": (lambda fr_to: (fr_to[1] - fr_to[0]) / 1e9)(torch.cuda.mem_get_info()),
         }
     # ---- CPU baseline next to it (rank 0, N=1 only): the reference fork's mapping step on a bounded sample of the same files

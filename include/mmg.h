@@ -52,6 +52,9 @@ int  mmg_profile_fetch(mmg_ctx_t *ctx, int max, const char **names, double *ms, 
  * [1] fragments whose seed-merge order was replayed on ranks, [2] ... literally, [3] fragments whose hit tree was built by a warp,
  * [4] extra DP rounds after z-drop cuts, [5] hits cut at a z-drop, [6] seed hits whose merge order was replayed (pops of [1]); [7] reserved */
 void mmg_path_counts(mmg_ctx_t *ctx, uint64_t out[8], int reset);
+/* process-wide: how often a device ([0]) or pinned host ([1]) buffer of any ctx was re-allocated since the last reset; a
+ * re-allocation synchronises the whole device, so a steady state should show none */
+void mmg_growth_counts(uint64_t out[2], int reset);
 
 /* ------------------------------------------------------------------ index */
 /* Build the index on the device from n_seq ASCII sequences (not NUL-terminated; lens[] given).
