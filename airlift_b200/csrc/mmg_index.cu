@@ -8,6 +8,7 @@
 #include <stdarg.h>
 #include <cub/cub.cuh>
 #include "mmg_ctx.cuh"
+#include "mmg_sketchwarp.h"
 
 static thread_local char g_err[512] = "";
 void mmg_set_error(const char *fmt, ...)
@@ -47,7 +48,7 @@ extern "C" void mmg_destroy(mmg_ctx_t *c)
 		&c->d_unit_off, &c->d_mv, &c->d_m_n, &c->d_m_val, &c->d_frag_unit0, &c->d_frag_qlen, &c->d_frag_na, &c->d_frag_aoff,
 		&c->d_frag_rep, &c->d_frag_nmini, &c->d_mini, &c->d_a, &c->d_work, &c->d_u, &c->d_b, &c->d_heap, &c->d_stack, &c->d_frag_nu,
 		&c->d_frag_nv, &c->d_frag_flag, &c->d_frag_iter, &c->d_cub, &c->d_out_u, &c->d_out_a, &c->d_out_mini, &c->d_uoff, &c->d_voff,
-		&c->d_moff, &c->d_frag_list, &c->d_misc, &c->d_seg_head, &c->d_seg_start, &c->d_seg_avg, &c->d_replay, &c->d_skey, &c->d_sval, &c->d_sseg, &c->d_tie, &c->d_m_aoff, &c->d_hrank, &c->d_hpop, &c->d_hlist, &c->d_seg_li, &c->d_seg_long, &c->d_unit0, &c->d_fseg_off, &c->d2_frag_na, &c->d2_frag_aoff, &c->d2_frag_rep, &c->d2_frag_nmini, &c->d2_mini,
+		&c->d_moff, &c->d_frag_list, &c->d_misc, &c->d_seg_head, &c->d_seg_start, &c->d_seg_avg, &c->d_replay, &c->d_skey, &c->d_sval, &c->d_sseg, &c->d_tie, &c->d_m_aoff, &c->d_hrank, &c->d_hpop, &c->d_hlist, &c->d_seg_li, &c->d_seg_long, &c->d_unit0, &c->d_fseg_off, &c->d_sk_stage, &c->d2_frag_na, &c->d2_frag_aoff, &c->d2_frag_rep, &c->d2_frag_nmini, &c->d2_mini,
 		&c->d2_a, &c->d2_work, &c->d2_u, &c->d2_b, &c->d2_stack, &c->d2_frag_nu, &c->d2_frag_nv, &c->k_jobs, &c->k_mem, &c->k_H,
 		&c->k_p, &c->k_cig, &c->k_res, &c->k_cig_out, &c->k_cig_off};
 	for (DevBuf *b : bufs) b->release();
@@ -148,6 +149,41 @@ __global__ void k_sketch_fill(const uint32_t *__restrict__ S, const SketchUnit *
 	mmg_sketch_unit<true>(S, units[u], w, k, is_hpc, out + off[u]);
 }
 
+// K1, short reads: one warp per read (mmg_sketchwarp.h).  Count pass (out == nullptr) and fill pass; a read the warp form does
+// not take (ambiguous base, odd geometry) is sketched by lane 0 with the state machine.
+#define SKW_WARPS 4
+template <bool kWrite>
+__global__ void __launch_bounds__(32 * SKW_WARPS)
+k_sketch_warp(const uint32_t *__restrict__ S, const SketchUnit *__restrict__ units, int n_units, int w, int k, int is_hpc,
+              int32_t *__restrict__ cnt, const int64_t *__restrict__ off, mm128 *__restrict__ out)
+{
+	__shared__ uint64_t s_words[SKW_WARPS][SKW_MAX_LEN / 32 + 2], s_xs[SKW_WARPS][SKW_MAX_LEN];
+	__shared__ uint8_t s_zs[SKW_WARPS][SKW_MAX_LEN];
+	const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int u = blockIdx.x * SKW_WARPS + wi;
+	if (u >= n_units) return;
+	const SketchUnit un = units[u];
+	const WarpDev wp = {lane};
+	// kWrite with off == nullptr: single pass into a staging area with one slot per base of the read (a read cannot emit more
+	// minimizers than it has bases), compacted by k_sketch_compact once the counts have been scanned
+	mm128 *o = kWrite ? (off ? out + off[u] : out + un.off) : nullptr;
+	int n = -1;
+	if (skw_eligible(un, w, k, is_hpc)) n = mmg_sketch_warp<WarpDev, kWrite>(wp, S, un, w, k, s_words[wi], s_xs[wi], s_zs[wi], o);
+	if (n < 0 && lane == 0) n = mmg_sketch_unit<kWrite>(S, un, w, k, is_hpc, o);
+	if (cnt && lane == 0) cnt[u] = n;
+}
+
+// staging area -> dense output, one warp per read
+__global__ void k_sketch_compact(const SketchUnit *__restrict__ units, int n_units, const int32_t *__restrict__ cnt, const int64_t *__restrict__ off,
+                                 const mm128 *__restrict__ stage, mm128 *__restrict__ out)
+{
+	const int u = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (u >= n_units) return;
+	const mm128 *src = stage + units[u].off;
+	mm128 *dst = out + off[u];
+	for (int i = lane; i < cnt[u]; i += 32) dst[i] = src[i];
+}
+
 __global__ void k_split_kv(const mm128 *__restrict__ mv, int64_t n, uint64_t *__restrict__ key, uint64_t *__restrict__ val)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,14 +230,18 @@ __global__ void k_idx_get(IdxView ix, int n_q, const uint64_t *__restrict__ mini
 // ------------------------------------------------------------------ build
 
 int mmg_run_sketch(mmg_ctx_t *c, const uint32_t *d_S, const SketchUnit *d_units, int n_units, int w, int k, int is_hpc,
-                   DevBuf &cnt, DevBuf &off, DevBuf &out, int64_t *total)
-{ // count -> exclusive scan -> fill; leaves off[n_units] = total
+                   DevBuf &cnt, DevBuf &off, DevBuf &out, int64_t *total, bool short_reads, uint64_t stage_slots)
+{ // count -> exclusive scan -> fill; leaves off[n_units] = total.  short_reads: every unit is a whole read of at most SKW_MAX_LEN bases
+  // that starts at its own 8-aligned offset of d_S (stage_slots = the padded bases of all reads): one pass into a staging area, then compaction
+	const bool warp_form = short_reads && !is_hpc && (k & 1) && w <= 64 && stage_slots > 0;
+	if (warp_form) MMG_TRY(c->d_sk_stage.ensure((stage_slots + 8) * sizeof(mm128)));
 	*total = 0;
 	MMG_TRY(cnt.ensure((size_t)(n_units + 1) * 4));
 	MMG_TRY(off.ensure((size_t)(n_units + 1) * 8));
 	if (n_units == 0) return MMG_OK;
 	MMG_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)(n_units + 1) * 4, c->stream));
-	MMG_LAUNCH(c, k_sketch_count, mmg_blocks(n_units, 128), 128, 0, d_S, d_units, n_units, w, k, is_hpc, cnt.as<int32_t>());
+	if (warp_form) MMG_LAUNCH(c, k_sketch_warp<true>, mmg_blocks(n_units, SKW_WARPS), 32 * SKW_WARPS, 0, d_S, d_units, n_units, w, k, is_hpc, cnt.as<int32_t>(), nullptr, c->d_sk_stage.as<mm128>());
+	else MMG_LAUNCH(c, k_sketch_count, mmg_blocks(n_units, 128), 128, 0, d_S, d_units, n_units, w, k, is_hpc, cnt.as<int32_t>());
 	size_t tmp_bytes = 0;
 	cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.as<int32_t>(), off.as<int64_t>(), n_units + 1, c->stream);
 	MMG_TRY(c->d_cub.ensure(tmp_bytes));
@@ -210,7 +250,8 @@ int mmg_run_sketch(mmg_ctx_t *c, const uint32_t *d_S, const SketchUnit *d_units,
 	MMG_CUDA(cudaMemcpyAsync(total, off.as<int64_t>() + n_units, 8, cudaMemcpyDeviceToHost, c->stream));
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	MMG_TRY(out.ensure((size_t)(*total + 1) * sizeof(mm128)));
-	MMG_LAUNCH(c, k_sketch_fill, mmg_blocks(n_units, 128), 128, 0, d_S, d_units, n_units, w, k, is_hpc, off.as<int64_t>(), out.as<mm128>());
+	if (warp_form) MMG_LAUNCH(c, k_sketch_compact, mmg_blocks((size_t)n_units * 32, 256), 256, 0, d_units, n_units, cnt.as<int32_t>(), off.as<int64_t>(), c->d_sk_stage.as<mm128>(), out.as<mm128>());
+	else MMG_LAUNCH(c, k_sketch_fill, mmg_blocks(n_units, 128), 128, 0, d_S, d_units, n_units, w, k, is_hpc, off.as<int64_t>(), out.as<mm128>());
 	return MMG_OK;
 }
 
@@ -314,7 +355,7 @@ extern "C" int mmg_idx_build(mmg_ctx_t *c, int w, int k, int is_hpc, int n_seq, 
 
 	// 3. sketch
 	int64_t n_mini = 0;
-	IDX_TRY(mmg_run_sketch(c, mi->d_S, d_units, n_units, w, k, is_hpc, cnt, off, mv, &n_mini));
+	IDX_TRY(mmg_run_sketch(c, mi->d_S, d_units, n_units, w, k, is_hpc, cnt, off, mv, &n_mini, false, 0));
 	IDX_CUDA(cudaStreamSynchronize(c->stream));
 	cudaFree(d_units); d_units = nullptr; cnt.release(); off.release();
 	mi->n_pos = (uint64_t)n_mini;

@@ -3,9 +3,10 @@
 #include <cub/cub.cuh>
 #include "mmg_ctx.cuh"
 #include "mmg_regheap.h"
+#include "mmg_sketchwarp.h"
 
 int mmg_run_sketch(mmg_ctx_t *c, const uint32_t *d_S, const SketchUnit *d_units, int n_units, int w, int k, int is_hpc,
-                   DevBuf &cnt, DevBuf &off, DevBuf &out, int64_t *total);
+                   DevBuf &cnt, DevBuf &off, DevBuf &out, int64_t *total, bool short_reads, uint64_t stage_slots);
 
 #define MMG_READ_CHUNK 4096   // reads longer than this are sketched in chunks
 
@@ -1267,7 +1268,9 @@ extern "C" int mmg_batch_upload(mmg_ctx_t *c, const mmg_mapopt_t *opt, const mmg
 	if (b->seg_off != t_segoff) memcpy(t_segoff, b->seg_off, (size_t)n_frag * 4);
 	t_len[n_seq] = 0, t_off[n_seq] = b->n_bases; // the scans below run over n_seq + 1 items
 	uint64_t qo = 0; int64_t nu = 0;
-	for (int r = 0; r < n_seq; ++r) { qo += PadLen8()(t_len[r]); nu += UnitsOfLen()(t_len[r]); }
+	int max_len = 0;
+	for (int r = 0; r < n_seq; ++r) { qo += PadLen8()(t_len[r]); nu += UnitsOfLen()(t_len[r]); max_len = max_len > t_len[r] ? max_len : t_len[r]; }
+	rb.max_len = max_len;
 	rb.q_words = qo / 8;
 	rb.n_units = (int)nu;
 
@@ -1478,7 +1481,7 @@ extern "C" int mmg_seed_chain_resident(mmg_ctx_t *c, const mmg_idx_t *mi, const 
 	// K1
 	int64_t n_mv = 0;
 	MMG_TRY(mmg_run_sketch(c, c->d_Q.as<uint32_t>(), c->d_units.as<SketchUnit>(), rb.n_units, mi->w, mi->k, mi->is_hpc, c->d_unit_cnt,
-	                       c->d_unit_off, c->d_mv, &n_mv));
+	                       c->d_unit_off, c->d_mv, &n_mv, rb.max_len <= SKW_MAX_LEN, rb.q_words * 8));
 	// K2a
 	MMG_TRY(c->d_m_n.ensure((size_t)(n_mv + 1) * 4));
 	MMG_TRY(c->d_m_val.ensure((size_t)(n_mv + 1) * 8));
@@ -1619,7 +1622,7 @@ extern "C" int mmg_sketch(mmg_ctx_t *c, const char *str, int len, int w, int k, 
 	MMG_TRY(c->d_units.ensure(units.size() * sizeof(SketchUnit)));
 	MMG_H2D(c, c->d_units.p, units.data(), units.size() * sizeof(SketchUnit));
 	int64_t n = 0;
-	MMG_TRY(mmg_run_sketch(c, c->d_Q.as<uint32_t>(), c->d_units.as<SketchUnit>(), (int)units.size(), w, k, is_hpc, c->d_unit_cnt, c->d_unit_off, c->d_mv, &n));
+	MMG_TRY(mmg_run_sketch(c, c->d_Q.as<uint32_t>(), c->d_units.as<SketchUnit>(), (int)units.size(), w, k, is_hpc, c->d_unit_cnt, c->d_unit_off, c->d_mv, &n, false, 0));
 	*n_out = (int)n;
 	const int64_t m = n < cap ? n : cap;
 	if (m > 0) MMG_D2H(c, out, c->d_mv.p, (size_t)m * 16);

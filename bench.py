@@ -340,6 +340,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="pairs (sr) or reads (ont) per step; default 500000 / 10000")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the SAM-identity gate against oracle/_ref/minimap2_B")
+    ap.add_argument("--no-long-read", action="store_true", help="skip the map-ont run appended to the short-read line at N=1")
     ap.add_argument("--no-cli", action="store_true", help="skip the whole-CLI (parse + map + SAM) timing at N=1")
     ap.add_argument("--lanes", type=int, default=4, help="streams per GPU: two mini-batches in flight, each cut into lanes/2 shards")
     ap.add_argument("--in-flight", type=int, default=2, help="mini-batches in flight (each on lanes/in_flight streams)")
@@ -741,6 +742,21 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and world == 1 and wl.kind == "sr" and not args.no_long_read:
+        # BASELINE.json configs[3] next to the headline: 10 kb ONT-shaped reads overlapping the same updated regions, -ax map-ont, in a
+        # process of its own (another index: k=15, w=10) now that this one has released the GPU
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--workload", "ont", "--steps", "3", "--warmup", "3", "--no-cli", "--no-parity",
+                   "--no-cpu-baseline", "--no-long-read", "--genome-bp", str(args.genome_bp), "--contigs", str(args.contigs)]
+            p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+            lr = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+            out["long_read"] = {"workload": lr["config"]["workload"], "value": lr["value"], "unit": lr["unit"], "ms_per_step": lr["ms_per_step"],
+                                "e2e": lr["e2e"], "ksw_gcups": lr["ksw_gcups"], "passes_digest_equal": lr["passes_digest_equal"],
+                                "kernel_ms_per_step": dict(list(lr["kernel_ms_per_step"].items())[:6]),
+                                "note": "post-chaining stages of the long-read presets run on the host (DESIGN.md section 1); parity of this preset is held by "
+                                        "tests/test_gpu_e2e.py, tests/test_gpu_paths.py and the golden CLI cases"}
+        except Exception as e:  # noqa
+            out["long_read"] = {"value": None, "why": f"failed: {e}"}
     if rank == 0:
         print(json.dumps(out))
 

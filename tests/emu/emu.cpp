@@ -11,6 +11,7 @@ static long g_ksw_range_viol; // values of valid cells that left the int8 range 
 #include "mmg_core.h"
 #include "mmg_regheap.h"
 #include "mmg_kswdpx.h"
+#include "mmg_sketchwarp.h"
 
 extern "C" {
 
@@ -106,6 +107,26 @@ int64_t emu_collect_ranked(void *idx, int64_t flag, int max_occ, int n_mv, const
 	std::copy(fw.begin(), fw.end(), a);
 	std::copy(rv.begin(), rv.end(), a + fw.size());
 	return (int64_t)(fw.size() + rv.size());
+}
+
+// K1, warp form (mmg_sketchwarp.h), lanes emulated one after the other; returns -1 when the read must take the state machine
+int emu_sketch_warp(const char *str, int len, int w, int k, uint32_t rid, mm128 *out, int cap)
+{
+	std::vector<uint32_t> S((len + 7) / 8 + 4, 0x44444444u);
+	for (int i = 0; i < len; ++i) { const int c = mmg_nt4((uint8_t)str[i]); S[i >> 3] = (S[i >> 3] & ~(0xfu << ((i & 7) * 4))) | (uint32_t)c << ((i & 7) * 4); }
+	SketchUnit u; u.off = 0, u.len = len, u.rid = rid, u.y_add = 0, u.emit_start = 0, u.emit_end = len;
+	if (!skw_eligible(u, w, k, 0)) return -1;
+	std::vector<uint64_t> words(SKW_MAX_LEN / 32 + 2), xs(SKW_MAX_LEN);
+	std::vector<uint8_t> zs(SKW_MAX_LEN);
+	std::vector<mm128> tmp(len + 8);
+	WarpEmu wp;
+	const int n = mmg_sketch_warp<WarpEmu, true>(wp, S.data(), u, w, k, words.data(), xs.data(), zs.data(), tmp.data());
+	if (n < 0) return -1;
+	const int nc = mmg_sketch_warp<WarpEmu, false>(wp, S.data(), u, w, k, words.data(), xs.data(), zs.data(), nullptr);
+	if (nc != n) return -3;
+	if (n > cap) return -2;
+	for (int i = 0; i < n; ++i) out[i] = tmp[i];
+	return n;
 }
 
 // the heap merge on ranks: nreg == 0 runs the serial reference (mmg_heap_replay_ranks), nreg in {1, 2, 4} the warp form with the heap

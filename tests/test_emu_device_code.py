@@ -263,3 +263,31 @@ def test_ksw_literal_form_on_16x2_simd(emu, preset):
                     a["cigar"] = []
                 assert a == b, (len(q), len(t), fl, w)
         n += 1
+
+
+@pytest.mark.parametrize("w,k", [(11, 21), (10, 15), (5, 19), (19, 19), (3, 5), (1, 15), (4, 7), (32, 27)])
+def test_sketch_warp_form_equals_oracle(emu, w, k):
+    """K1 with the positions of a read spread over the lanes (mmg_sketchwarp.h) emits what mm_sketch emits, in its order:
+    random reads, tandem repeats and homopolymers (equal hashes inside a window), reads shorter than a window."""
+    emu.emu_sketch_warp.restype = C.c_int
+    emu.emu_sketch_warp.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(900 + w + k)
+    n_done = 0
+    for it in range(300):
+        n = int(rng.integers(1, 513)) if it % 7 else int(rng.integers(1, w + k + 3))
+        s = L.rand_seq(rng, n)
+        if it % 5 == 0:
+            unit = L.rand_seq(rng, int(rng.integers(1, 9)))
+            s = (unit * n)[:n]
+        if it % 11 == 0:
+            s = s[: n // 2] + s[: n - n // 2]
+        out = np.zeros(n + 8, dtype=L.mm128)
+        got_n = emu.emu_sketch_warp(s, n, w, k, it & 1, out.ctypes.data, len(out))
+        assert got_n >= 0, (got_n, n)
+        want = L.orc_sketch(s, w, k, it & 1, 0)
+        assert got_n == len(want) and out[:got_n].tobytes() == want.tobytes(), (it, n, s[:80])
+        n_done += 1
+    assert n_done == 300
+    # a read with an ambiguous base is handed back
+    s = L.rand_seq(rng, 150); s = s[:70] + b"N" + s[71:]
+    assert emu.emu_sketch_warp(s, 150, w, k, 0, np.zeros(200, dtype=L.mm128).ctypes.data, 200) == -1
