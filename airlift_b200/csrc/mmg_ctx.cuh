@@ -142,6 +142,13 @@ struct mmg_ctx_s {
 	if ((ctx)->prof_on) { cudaEventRecord(pr_.b, (ctx)->stream); (ctx)->prof.push_back(pr_); } \
 	cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { mmg_set_error("launch %s: %s", #kern, cudaGetErrorString(e_)); return MMG_ECUDA; } } while (0)
 
+// a library call (cub) on the context's stream, timed like a launch when profiling is on
+#define MMG_TIMED(ctx, label, call) do { \
+	ProfRec pr_ = {label, nullptr, nullptr}; \
+	if ((ctx)->prof_on) { pr_.a = (ctx)->prof_event(); pr_.b = (ctx)->prof_event(); cudaEventRecord(pr_.a, (ctx)->stream); } \
+	MMG_CUDA(call); ++(ctx)->launches; \
+	if ((ctx)->prof_on) { cudaEventRecord(pr_.b, (ctx)->stream); (ctx)->prof.push_back(pr_); } } while (0)
+
 // account a host<->device copy issued on the context's stream
 #define MMG_H2D(ctx, dst, src, n) do { (ctx)->h2d_bytes += (uint64_t)(n); MMG_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyHostToDevice, (ctx)->stream)); } while (0)
 #define MMG_D2H(ctx, dst, src, n) do { (ctx)->d2h_bytes += (uint64_t)(n); MMG_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyDeviceToHost, (ctx)->stream)); } while (0)

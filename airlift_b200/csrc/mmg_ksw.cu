@@ -758,8 +758,7 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 		size_t tmp = 0;
 		cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, order, n, 0, 31, c->stream);
 		MMG_TRY(c->d_cub.ensure(tmp));
-		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, order, n, 0, 31, c->stream));
-		++c->launches;
+		MMG_TIMED(c, "cub_radix_sort(dp jobs)", cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, order, n, 0, 31, c->stream));
 	}
 	int64_t tot[3]; unsigned long long h_cells[1 + KSW_N_CLS]; uint32_t h_cls[KSW_N_CLS];
 	MMG_D2H(c, &tot[0], mem_off + n, 8); MMG_D2H(c, &tot[1], p_off + n, 8); MMG_D2H(c, &tot[2], cg_off + n, 8);

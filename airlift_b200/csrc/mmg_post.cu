@@ -264,8 +264,7 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 		size_t tmp = 0;
 		cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, idx, perm, nf, 0, 32, c->stream);
 		MMG_TRY(c->d_cub.ensure(tmp));
-		MMG_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, perm, nf, 0, 32, c->stream));
-		++c->launches;
+		MMG_TIMED(c, "cub_radix_sort(fragments)", cub::DeviceRadixSort::SortPairs(c->d_cub.p, tmp, key, key2, idx, perm, nf, 0, 32, c->stream));
 	}
 	if (tot_u > 0) { // keys -> hit order -> records
 		MMG_LAUNCH(c, k_post_cnt, mmg_blocks(tot_u, 256), 256, 0, hs.u, tot_u, B[X::PB_CNT].as<int32_t>());
@@ -274,8 +273,7 @@ extern "C" int mmg_post_chain(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapop
 		size_t tmp = 0;
 		cub::DeviceSegmentedSort::StableSortPairsDescending(nullptr, tmp, hs.key_in, hs.key, B[X::PB_VAL_IN].as<uint64_t>(), hs.ascnt, tot_u, nf, hs.uoff, hs.uoff + 1, c->stream);
 		MMG_TRY(c->d_cub.ensure(tmp));
-		MMG_CUDA(cub::DeviceSegmentedSort::StableSortPairsDescending(c->d_cub.p, tmp, hs.key_in, hs.key, B[X::PB_VAL_IN].as<uint64_t>(), hs.ascnt, tot_u, nf, hs.uoff, hs.uoff + 1, c->stream));
-		++c->launches;
+		MMG_TIMED(c, "cub_segmented_sort(chains)", cub::DeviceSegmentedSort::StableSortPairsDescending(c->d_cub.p, tmp, hs.key_in, hs.key, B[X::PB_VAL_IN].as<uint64_t>(), hs.ascnt, tot_u, nf, hs.uoff, hs.uoff + 1, c->stream));
 		MMG_LAUNCH(c, k_post_records, mmg_blocks(tot_u, 128), 128, 0, d_sh, tot_u);
 	}
 	MMG_LAUNCH(c, k_post_select_warp, mmg_blocks((size_t)nf * 32, 128), 128, 0, d_sh, perm);

@@ -1378,8 +1378,7 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 			size_t tmp = 0;
 			cub::DeviceSegmentedSort::SortPairs(nullptr, tmp, k0, k1, v0, v1, tot, n_list, seg_b, seg_e, c->stream);
 			MMG_TRY(c->d_cub.ensure(tmp));
-			MMG_CUDA(cub::DeviceSegmentedSort::SortPairs(c->d_cub.p, tmp, k0, k1, v0, v1, tot, n_list, seg_b, seg_e, c->stream));
-			++c->launches;
+			MMG_TIMED(c, "cub_segmented_sort(seed hits)", cub::DeviceSegmentedSort::SortPairs(c->d_cub.p, tmp, k0, k1, v0, v1, tot, n_list, seg_b, seg_e, c->stream));
 		}
 		MMG_LAUNCH(c, k_emit_sorted, mmg_blocks(tot, 256), 256, 0, n_list, pb.aoff->as<int64_t>(), c->d_replay.as<uint8_t>(), tot, k1, v1, n_skipped,
 		           pb.na->as<int32_t>(), pb.a->as<mm128>(), d_tie);
