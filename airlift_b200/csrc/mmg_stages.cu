@@ -4,6 +4,7 @@
 #include "mmg_ctx.cuh"
 #include "mmg_regheap.h"
 #include "mmg_sketchwarp.h"
+#include "mmg_rswarp.h"
 
 int mmg_run_sketch(mmg_ctx_t *c, const uint32_t *d_S, const SketchUnit *d_units, int n_units, int w, int k, int is_hpc,
                    DevBuf &cnt, DevBuf &off, DevBuf &out, int64_t *total, bool short_reads, uint64_t stage_slots);
@@ -161,6 +162,41 @@ __global__ void k_emit_sorted(int n_list, const int64_t *__restrict__ aoff, cons
 		const uint64_t kp = key[g - 1], rp = kp & ~(1ULL << 63);
 		if (((kp & (1ULL << 63)) | (rp & 0xffffffff00000000ULL) | ((uint32_t)rp >> 1)) == an.x) tie[li] = 1;
 	}
+}
+
+// K2c, radix-sort form, fragments in which two anchors share x: the anchors in query order (the planned slots k_expand filled,
+// minus the skipped seeds) and klib's radix sort replayed by a warp (mmg_rswarp.h).  work[] is free until the chain fill.
+__global__ void __launch_bounds__(128)
+k_fill_flat_warp(int n_list, const int64_t *__restrict__ aoff, const uint8_t *__restrict__ tie, const uint64_t *__restrict__ key,
+                 const uint64_t *__restrict__ val, int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work, RsFrame *__restrict__ stack)
+{
+	__shared__ int32_t s_head[4][256], s_tail[4][256];
+	const int li = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+	if (li >= n_list || tie[li] != 1) return;
+	const int64_t ao = aoff[li];
+	const int32_t n_plan = (int32_t)(aoff[li + 1] - ao);
+	mm128 *A = a + ao;
+	int32_t o = 0;
+	for (int32_t i0 = 0; i0 < n_plan; i0 += 32) {
+		const int32_t i = i0 + lane;
+		const uint64_t k = i < n_plan ? key[ao + i] : MMG_NONE;
+		const unsigned m = __ballot_sync(0xffffffffu, k != MMG_NONE);
+		if (k != MMG_NONE) {
+			const uint64_t r = k & ~(1ULL << 63);
+			mm128 an;
+			an.x = (k & (1ULL << 63)) | (r & 0xffffffff00000000ULL) | ((uint32_t)r >> 1);
+			an.y = val[ao + i];
+			A[o + __popc(m & ((1u << lane) - 1u))] = an;
+		}
+		o += __popc(m);
+	}
+	__syncwarp();
+	mm128 *tmp = reinterpret_cast<mm128*>(work + ao * 8);
+	int32_t *dst = reinterpret_cast<int32_t*>(tmp + n_plan);
+	uint8_t *dig = reinterpret_cast<uint8_t*>(dst + n_plan);
+	const WarpDev wp = {lane};
+	mmg_rs_sort_warp(wp, A, (int64_t)o, tmp, dst, dig, stack + ao / 65 + 2 * (int64_t)li, s_head[wi], s_tail[wi], KeyX());
+	if (lane == 0) na[li] = o;
 }
 
 // ---- K2c, heap replay on ranks (fragments in which two kept query minimizers share a hash: equal positions meet in the heap,
@@ -1398,7 +1434,11 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 		}
 	}
 	// literal replay: the heap merge for the few fragments the rank replay does not take; fill + klib radix sort for the non-heap presets
-	{
+	if (!heap_path) {
+		if (tot > 0)
+			MMG_LAUNCH(c, k_fill_flat_warp, mmg_blocks((size_t)n_list * 32, 128), 128, 0, n_list, pb.aoff->as<int64_t>(), d_tie, c->d_skey.as<uint64_t>(),
+			           c->d_sval.as<uint64_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.stack->as<RsFrame>());
+	} else {
 		const int per_warp = d_flag == nullptr || n_list <= 4096 ? 1 : 0; // the re-chain pass (and any small list): spread over warps
 		MMG_LAUNCH(c, k_fill, mmg_blocks(per_warp ? (size_t)n_list * 32 : (size_t)n_list, 64), 64, 0, ft, d_list, n_list, c->d_mv.as<mm128>(), c->d_m_n.as<int32_t>(),
 		           c->d_m_val.as<uint64_t>(), mi->d_pos, max_occ, opt->flag, pb.aoff->as<int64_t>(), pb.na->as<int32_t>(), pb.a->as<mm128>(), c->d_heap.as<mm128>(),

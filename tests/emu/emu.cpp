@@ -12,6 +12,7 @@ static long g_ksw_range_viol; // values of valid cells that left the int8 range 
 #include "mmg_regheap.h"
 #include "mmg_kswdpx.h"
 #include "mmg_sketchwarp.h"
+#include "mmg_rswarp.h"
 
 extern "C" {
 
@@ -168,6 +169,18 @@ void emu_rs_sort_128x(mm128 *a, int64_t n)
 {
 	std::vector<RsFrame> st(n / 65 + 4);
 	mmg_rs_sort_exact(a, n, st.data(), KeyX());
+}
+
+// the warp form of the same replay (mmg_rswarp.h), 32 emulated lanes
+void emu_rs_sort_warp_128x(mm128 *a, int64_t n)
+{
+	std::vector<RsFrame> st(n / 65 + 4);
+	std::vector<mm128> tmp(n + 1);
+	std::vector<int32_t> dst(n + 1);
+	std::vector<uint8_t> dig(n + 1);
+	int32_t head[256], tail[256];
+	WarpEmu wp;
+	mmg_rs_sort_warp(wp, a, n, tmp.data(), dst.data(), dig.data(), st.data(), head, tail, KeyX());
 }
 
 // the one-thread-per-job ksw walk the device runs for small jobs (mmg_ksw_scalar), on the CPU

@@ -34,6 +34,7 @@ def emu():
     E.emu_chain.restype = C.c_int
     E.emu_chain.argtypes = [C.c_int] * 9 + [C.c_int64, C.c_void_p, C.c_void_p]
     E.emu_rs_sort_128x.argtypes = [C.c_void_p, C.c_int64]
+    E.emu_rs_sort_warp_128x.argtypes = [C.c_void_p, C.c_int64]
     E.emu_ksw.restype = C.c_int
     E.emu_ksw.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.POINTER(Ez), C.c_void_p]
     E.emu_ksw_fast.restype = C.c_int
@@ -75,6 +76,34 @@ def test_exact_radix_replay(emu):
             emu.emu_rs_sort_128x(a.ctypes.data, n)
             L.oracle().orc_radix_sort_128x(b.ctypes.data, b.ctypes.data + 16 * n)
             assert a.tobytes() == b.tobytes()
+
+
+def test_exact_radix_replay_warp(emu):
+    """mmg_rs_sort_warp (digits walked by one lane, elements scattered by the warp) ends in klib's order: anchor-shaped keys
+    (strand<<63 | rid<<32 | pos, many equal), few-digit keys, all-equal keys, sizes around the 64-element insertion-sort limit"""
+    rng = np.random.default_rng(5)
+    for n in [0, 1, 2, 63, 64, 65, 66, 129, 300, 4000, 20000, 70000]:
+        for kind in ["bits2", "bits9", "bits33", "bits64", "anchor", "equal", "locus"]:
+            a = np.zeros(n, dtype=L.mm128)
+            if kind.startswith("bits"):
+                a["x"] = rng.integers(0, (1 << int(kind[4:])) - 1, n, dtype=np.uint64, endpoint=True)
+            elif kind == "anchor":
+                strand = rng.integers(0, 2, n, dtype=np.uint64) << np.uint64(63)
+                rid = rng.integers(0, 24, n, dtype=np.uint64) << np.uint64(32)
+                pos = rng.integers(0, max(2, n // 3), n, dtype=np.uint64) * np.uint64(977)
+                a["x"] = strand | rid | pos
+            elif kind == "equal":
+                a["x"] = np.uint64(0x8000000500001234)
+            else:  # one locus: positions within 10 kb, every fourth one doubled
+                pos = np.uint64(123456789) + rng.integers(0, 10000, n, dtype=np.uint64)
+                if n > 8:
+                    pos[::4] = pos[1::4][: len(pos[::4])] if len(pos[1::4]) >= len(pos[::4]) else pos[::4]
+                a["x"] = (np.uint64(7) << np.uint64(32)) | pos
+            a["y"] = np.arange(n)
+            b = a.copy()
+            emu.emu_rs_sort_warp_128x(a.ctypes.data, n)
+            L.oracle().orc_radix_sort_128x(b.ctypes.data, b.ctypes.data + 16 * n)
+            assert a.tobytes() == b.tobytes(), (n, kind)
 
 
 def _index_arrays(seqs, w, k):
