@@ -54,8 +54,14 @@ __device__ __forceinline__ int ksw_ncol(int qlen, int tlen, int w)
 #define KSW_N_FAST 3
 #define KSW_CLS_LITERAL KSW_N_FAST            /* literal form, 16 lanes per job */
 #define KSW_CLS_LITERAL_WIDE (KSW_N_FAST + 1)  /* literal form, 32 lanes per job: bands wider than two SSE blocks */
-#define KSW_CLS_WAVE (KSW_N_FAST + 2)          /* wavefront form: one warp per large job whose band never clips */
-#define KSW_N_CLS (KSW_N_FAST + 3)
+#define KSW_CLS_BLOCK1 (KSW_N_FAST + 2)        /* literal form, one CTA per job: state too large for the warp kernel's shared-memory slot */
+#define KSW_CLS_BLOCK2 (KSW_N_FAST + 3)        /* the same with up to KSWB_SMEM2 bytes of state */
+#define KSW_CLS_WAVE (KSW_N_FAST + 4)          /* wavefront form: one warp per large job whose band never clips */
+#define KSW_N_CLS (KSW_N_FAST + 5)
+#define KSWB_WARPS 8                           /* warps of the CTA form */
+#define KSWB_MAXG 2                            /* groups of four SSE blocks per warp and anti-diagonal: bands up to 64 blocks */
+#define KSWB_SMEM1 (48 * 1024)
+#define KSWB_SMEM2 (200 * 1024)
 struct KswFastClass { int32_t mc, tc, qc, nt; };
 struct KswFastTab { KswFastClass c[KSW_N_FAST]; };
 static inline size_t ksw_fast_smem(const KswFastClass &k) { return (size_t)k.nt * ((size_t)(k.mc + 1) * 8 + (size_t)k.tc + (size_t)k.qc); }
@@ -72,7 +78,7 @@ MMG_HD size_t ksw_wave_mem_bytes(int qlen, int tlen) { return (((size_t)(qlen + 
 // loops), and the true-band cell count
 __global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, KswScore sc, KswFastTab ft, uint64_t *__restrict__ mem_sz,
                            uint64_t *__restrict__ p_sz, uint64_t *__restrict__ cig_sz, uint32_t *__restrict__ key, int32_t *__restrict__ idx,
-                           unsigned long long *__restrict__ cells_total, uint32_t *__restrict__ cls_count)
+                           unsigned long long *__restrict__ cells_total, uint32_t *__restrict__ cls_count, int force_block)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned long long cells = 0;
@@ -114,6 +120,11 @@ __global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, KswSco
 					if (mem_bytes + H_bytes > KSW_SMEM_PER_JOB) m = (mem_bytes + H_bytes + 63) & ~(size_t)63;
 					if (mmg_kswdpx_mem_bytes(qlen, tlen) > KSWDPX_SMEM_PER_JOB) { const size_t md = (mmg_kswdpx_mem_bytes(qlen, tlen) + 63) & ~(size_t)63; if (md > m) m = md; }
 					if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = ((uint64_t)(qlen + tlen - 1) * ksw_ncol(qlen, tlen, j.w) + 1) * 16;
+					{ // state beyond the warp kernel's slot: a CTA walks the job with the state in its own shared memory
+						const size_t md = mmg_kswdpx_mem_bytes(qlen, tlen);
+						if (!g.bail && (md > KSWDPX_SMEM_PER_JOB || force_block) && md <= KSWB_SMEM2 && g.n_col_ <= 4 * KSWB_WARPS * KSWB_MAXG)
+							cls = md <= KSWB_SMEM1 ? KSW_CLS_BLOCK1 : KSW_CLS_BLOCK2, m = 0;
+					}
 					const uint64_t est = (uint64_t)(qlen + tlen) * (uint64_t)(qlen < tlen ? qlen : tlen);
 					k = (uint32_t)cls << 28 | (63u - (uint32_t)(63 - __clzll((long long)(est | 1)))); // big jobs first
 				} else {
@@ -500,6 +511,212 @@ k_ksw_dpx(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ or
 	}
 }
 
+// ---- K4, literal form, one CTA per job -----------------------------------------------------------------------------
+// Long-read end extensions clip their band (w = 500 against thousands of bases) and carry tens of kilobytes of lane state: as
+// one warp with the state in the HBM arena such a job took 16 dependent L2 round trips per anti-diagonal and a launch waited
+// for its longest job (3.9 GCUPS).  Here the state sits in the CTA's shared memory and the SSE blocks of an anti-diagonal are
+// spread over KSWB_WARPS warps: every lane takes the OLD state of its pair (and lane 0 of a warp its left neighbour's, which
+// another warp owns) into registers, a barrier, then everybody writes.  The exact-max pass runs on all threads with one
+// block-wide max over the packed (score, tie preference) keys.  Same program as ksw_run_dpx otherwise, four barriers per
+// anti-diagonal.
+template <int kMode>
+__device__ __forceinline__ void ksw_run_dpx_block(const KswGeom &g, const KswJobDev &jb, uint8_t *mem, int32_t *H, uint8_t *p, KswEz &ez, int32_t *s_red)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = 32 * KSWB_WARPS;
+	const int tl16 = g.tlen_ * 16;
+	uint4 *PK = reinterpret_cast<uint4*>(mem);
+	int8_t *sm = reinterpret_cast<int8_t*>(mem), *s = sm + (size_t)tl16 * 8;
+	const uint8_t *sf = reinterpret_cast<const uint8_t*>(s + tl16), *qr = sf + tl16;
+	const int qlen = g.qlen, tlen = g.tlen, flag = jb.flag;
+	const bool approx = (flag & MMG_EZ_APPROX_MAX) != 0;
+	const int n1 = -g.q - g.e, n2 = -g.q2 - g.e2;
+	const KswDpxConst cst = mmg_kswdpx_const<kMode>(g);
+	const bool small_keys = mmg_ksw_fast_ok(g);
+	int last_st = -1, last_en = -1;
+	int32_t H0 = 0, last_H0_t = 0;
+	for (int r = 0; r < qlen + tlen - 1; ++r) {
+		int st0, en0;
+		if (!mmg_ksw_band(g, r, &st0, &en0)) { ez.zdropped = 1; break; }
+		const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
+		int x1, x21, v1;
+		if (st > 0) {
+			if (st - 1 >= last_st && st - 1 <= last_en) x1 = sm[KSWDPX_X(st - 1)], x21 = sm[KSWDPX_X2(st - 1)], v1 = sm[KSWDPX_V(st - 1)];
+			else x1 = n1, x21 = n2, v1 = n1;
+		} else {
+			x1 = n1, x21 = n2;
+			v1 = mmg_ksw_first_col(g, r);
+		}
+		// H of the cell the last one of this anti-diagonal derives from: nobody writes H before the max pass below
+		const int32_t H_from = (!approx && r > 0) ? (en0 > 0 ? H[en0 - 1] : H[en0]) : 0;
+		if (en >= r && tid == 0) {
+			sm[KSWDPX_Y(r)] = (int8_t)n1, sm[KSWDPX_Y2(r)] = (int8_t)n2;
+			sm[KSWDPX_U(r)] = (int8_t)mmg_ksw_first_col(g, r);
+		}
+		{ // scores, 16-byte chunks starting at st0 (ksw2_extd2_sse.c:158-172)
+			const uint8_t *qrr = qr + (qlen - 1 - r);
+			for (int t = st0 + (tid >> 4) * 16; t <= en0; t += NT) s[t + (tid & 15)] = mmg_ksw_score(g, sf[t + (tid & 15)], qrr[t + (tid & 15)]);
+		}
+		__syncthreads();
+		const int st_ = st / 16, en_ = en / 16;
+		KswPair o[KSWB_MAXG]; uint32_t s2[KSWB_MAXG], prev[KSWB_MAXG];
+#pragma unroll
+		for (int gi = 0; gi < KSWB_MAXG; ++gi) {
+			const int b0 = st_ + 4 * (warp + gi * KSWB_WARPS), blk = b0 + (lane >> 3), pi = blk * 8 + (lane & 7);
+			const bool act = blk <= en_;
+			o[gi].w0 = o[gi].w1 = o[gi].w2 = 0u, s2[gi] = 0;
+			if (act) { const uint4 w = PK[pi]; o[gi].w0 = w.x, o[gi].w1 = w.y, o[gi].w2 = w.z; s2[gi] = *reinterpret_cast<const uint16_t*>(s + 2 * pi); }
+			uint32_t pv = __shfl_up_sync(FULL, mmg_kswdpx_carry(o[gi]), 1);
+			if (lane == 0) {
+				if (b0 == st_) pv = mmg_kswdpx_carry_of(x1, v1, x21);
+				else if (act) { const uint4 w = PK[pi - 1]; const KswPair ol = {w.x, w.y, w.z}; pv = mmg_kswdpx_carry(ol); }
+			}
+			prev[gi] = pv;
+		}
+		__syncthreads(); // every old state this anti-diagonal reads is in registers
+#pragma unroll
+		for (int gi = 0; gi < KSWB_MAXG; ++gi) {
+			const int b0 = st_ + 4 * (warp + gi * KSWB_WARPS), blk = b0 + (lane >> 3), pi = blk * 8 + (lane & 7);
+			if (blk <= en_) {
+				uint32_t d2 = 0;
+				const KswPair nw = mmg_kswdpx_pair<kMode>(cst, o[gi], s2[gi], prev[gi], &d2);
+				PK[pi] = make_uint4(nw.w0, nw.w1, nw.w2, 0u);
+				if (kMode) *reinterpret_cast<uint16_t*>(p + ((size_t)r * g.n_col_ + (blk - st_)) * 16 + 2 * (lane & 7)) = (uint16_t)d2;
+			}
+		}
+		__syncthreads();
+		if (!approx) { // exact max over the band with the reference's tie order (ksw2_extd2_sse.c:315-358)
+			int32_t max_H, max_t, H_en0;
+			if (r > 0) {
+				H_en0 = H_from + (en0 > 0 ? sm[KSWDPX_U(en0)] : sm[KSWDPX_V(en0)]);
+				if (small_keys) {
+					const int en1k = (en0 - st0) / 4 * 4;
+					int32_t best = H_en0 * 2048 + 2047;
+					for (int t = st0 + tid; t < en0; t += NT) {
+						const int32_t h = H[t] + sm[KSWDPX_V(t)];
+						H[t] = h;
+						const int k = t - st0, rk = k < en1k ? ((k & 3) << 8 | k >> 2) : (4 << 8 | (k - en1k));
+						const int32_t key = h * 2048 + (2046 - rk);
+						best = best > key ? best : key;
+					}
+					if (tid == 0) H[en0] = H_en0;
+					best = __reduce_max_sync(FULL, best);
+					if (lane == 0) s_red[warp] = best;
+					__syncthreads();
+#pragma unroll
+					for (int q = 0; q < KSWB_WARPS; ++q) { const int32_t v = s_red[q]; best = best > v ? best : v; }
+					const int32_t low = best & 2047;
+					max_H = (best - low) >> 11;
+					if (low == 2047) max_t = en0;
+					else { const int32_t rk = 2046 - low; max_t = (rk >> 8) == 4 ? st0 + en1k + (rk & 255) : st0 + ((rk & 255) << 2) + (rk >> 8); }
+				} else {
+					int32_t bh = H_en0, bt = en0; uint32_t br = 0;
+					for (int t = st0 + tid; t < en0; t += NT) {
+						const int32_t h = H[t] + sm[KSWDPX_V(t)];
+						H[t] = h;
+						const uint32_t rk = mmg_ksw_max_rank(t, st0, en0);
+						if (h > bh || (h == bh && rk < br)) bh = h, bt = t, br = rk;
+					}
+					if (tid == 0) H[en0] = H_en0;
+#pragma unroll
+					for (int d = 16; d >= 1; d >>= 1) {
+						const int32_t oh = __shfl_xor_sync(FULL, bh, d), ot = __shfl_xor_sync(FULL, bt, d);
+						const uint32_t orank = __shfl_xor_sync(FULL, br, d);
+						if (oh > bh || (oh == bh && orank < br)) bh = oh, bt = ot, br = orank;
+					}
+					if (lane == 0) s_red[warp] = bh, s_red[KSWB_WARPS + warp] = bt, s_red[2 * KSWB_WARPS + warp] = (int32_t)br;
+					__syncthreads();
+#pragma unroll
+					for (int q = 0; q < KSWB_WARPS; ++q) {
+						const int32_t oh = s_red[q], ot = s_red[KSWB_WARPS + q];
+						const uint32_t orank = (uint32_t)s_red[2 * KSWB_WARPS + q];
+						if (oh > bh || (oh == bh && orank < br)) bh = oh, bt = ot, br = orank;
+					}
+					max_H = bh, max_t = bt;
+				}
+			} else {
+				H_en0 = sm[KSWDPX_V(0)] - g.qe_pre;
+				if (tid == 0) H[0] = H_en0;
+				__syncthreads();
+				max_H = H_en0, max_t = 0;
+			}
+			if (en0 == tlen - 1 && H_en0 > ez.mte) ez.mte = H_en0, ez.mte_q = r - en;
+			if (r - st0 == qlen - 1) { const int32_t hs = H[st0]; if (hs > ez.mqe) ez.mqe = hs, ez.mqe_t = st0; }
+			const bool stop = mmg_ksw_zdrop(&ez, max_H, r, max_t, jb.zdrop, g.e2);
+			if (stop) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H[tlen - 1];
+			// no barrier here: the next anti-diagonal writes H and s_red only behind its own three barriers
+		} else { // ksw2_extd2_sse.c:359-375
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					const int32_t d0 = sm[KSWDPX_V(last_H0_t)], d1 = sm[KSWDPX_U(last_H0_t + 1)];
+					if (d0 > d1) H0 += d0;
+					else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
+					H0 += sm[KSWDPX_V(last_H0_t)];
+				} else {
+					++last_H0_t, H0 += sm[KSWDPX_U(last_H0_t)];
+				}
+			} else H0 = sm[KSWDPX_V(0)] - g.qe_pre, last_H0_t = 0;
+			if ((flag & MMG_EZ_APPROX_DROP) && mmg_ksw_zdrop(&ez, H0, r, last_H0_t, jb.zdrop, g.e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
+		}
+		last_st = st, last_en = en;
+	}
+}
+
+__global__ void __launch_bounds__(32 * KSWB_WARPS)
+k_ksw_dpx_block(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order, int n_jobs, KswScore sc, const uint32_t *__restrict__ Q,
+                const uint32_t *__restrict__ S, const uint64_t *__restrict__ q_off, const int32_t *__restrict__ read_len, const uint64_t *__restrict__ ref_off,
+                const uint64_t *__restrict__ p_off, const uint64_t *__restrict__ cig_off, uint8_t *__restrict__ gp, uint32_t *__restrict__ gcig,
+                KswEz *__restrict__ res)
+{
+	extern __shared__ __align__(16) uint8_t smem[];
+	__shared__ int32_t s_red[3 * KSWB_WARPS];
+	const int tid = threadIdx.x, NT = 32 * KSWB_WARPS;
+	const int ji = order[blockIdx.x];
+	const mmg_ksw_job_t hj = jobs[ji];
+	KswJobDev jb;
+	jb.q_base = q_off[hj.seq_id], jb.q_readlen = read_len[hj.seq_id], jb.q_rev = hj.q_rev, jb.q_start = hj.q_start, jb.q_len = hj.q_len;
+	jb.t_base = ref_off[hj.rid] + (uint64_t)hj.t_start, jb.t_len = hj.t_len, jb.reversed = hj.reversed;
+	jb.w = hj.w, jb.zdrop = hj.zdrop, jb.end_bonus = hj.end_bonus, jb.flag = hj.flag;
+	jb.mem_off = 0, jb.p_off = p_off[ji], jb.cig_off = cig_off[ji];
+	const KswGeom g = mmg_ksw_geom(jb.q_len, jb.t_len, sc.m, sc.mat, sc.q, sc.e, sc.q2, sc.e2, jb.w);
+	KswEz ez;
+	mmg_ksw_reset(&ez);
+	const int tl16 = g.tlen_ * 16;
+	const size_t lane_bytes = (mmg_kswdpx_lane_bytes(jb.q_len, jb.t_len) + 15) & ~(size_t)15;
+	uint8_t *mem = smem;
+	int32_t *H = reinterpret_cast<int32_t*>(mem + lane_bytes);
+	{ // initial lane state (ksw2_extd2_sse.c:99-121) in the pair layout
+		const uint32_t w1 = 0x01010101u * (uint8_t)(int8_t)(-g.q - g.e), w2 = 0x01010101u * (uint8_t)(int8_t)(-g.q2 - g.e2);
+		uint4 *PK = reinterpret_cast<uint4*>(mem);
+		for (int i = tid; i < tl16 / 2; i += NT) PK[i] = make_uint4(w1, w1, w2, 0u);
+		int8_t *s = reinterpret_cast<int8_t*>(mem) + (size_t)tl16 * 8;
+		for (int i = tid; i < tl16; i += NT) {
+			s[i] = 0;
+			s[tl16 + i] = i < jb.t_len ? (int8_t)ksw_tbase(S, jb, i) : 0;
+			H[i] = MMG_KSW_NEG_INF;
+		}
+		int8_t *qr = s + 2 * tl16;
+		const int qn = g.qlen_ * 16 + 16;
+		for (int i = tid; i < qn; i += NT) qr[i] = i < jb.q_len ? (int8_t)ksw_qbase(Q, jb, jb.q_len - 1 - i) : 0;
+	}
+	__syncthreads();
+	uint8_t *p = gp + jb.p_off;
+	const bool with_cigar = !(jb.flag & MMG_EZ_SCORE_ONLY);
+	if (!with_cigar) ksw_run_dpx_block<0>(g, jb, mem, H, p, ez, s_red);
+	else if (!(jb.flag & MMG_EZ_RIGHT)) ksw_run_dpx_block<1>(g, jb, mem, H, p, ez, s_red);
+	else ksw_run_dpx_block<2>(g, jb, mem, H, p, ez, s_red);
+	__syncthreads();
+	if (tid == 0) {
+		int i0, j0;
+		if (with_cigar && mmg_ksw_trace_start(g, jb.flag, jb.end_bonus, &ez, &i0, &j0))
+			ez.n_cigar = mmg_ksw_backtrack(g, !!(jb.flag & MMG_EZ_REV_CIGAR), p, i0, j0, gcig + jb.cig_off);
+		res[ji] = ez;
+	}
+}
+
 // K4, fast form: one thread per job whose band never clips (mmg_ksw_fast, mmg_core.h).  The threads of a CTA interleave
 // their per-job arrays in shared memory ([element][thread]): a warp's accesses fall on consecutive banks.
 __global__ void __launch_bounds__(128)
@@ -749,8 +966,9 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 	uint32_t *key = d_cls + 8, *key2 = key + n1;
 	int32_t *idx = reinterpret_cast<int32_t*>(key2 + n1), *order = idx + n1, *ncig = order + n1;
 	static const KswFastTab ftab = {{{24, 56, 56, 128}, {48, 104, 104, 128}, {80, 160, 160, 64}}};
+	static const bool force_block = getenv("MMG_KSW_FORCE_BLOCK") != nullptr; // test aid: every literal job the CTA form can take goes through it
 	MMG_CUDA(cudaMemsetAsync(d_cells, 0, (2 + KSW_N_CLS) * 8 + 32, c->stream));
-	MMG_LAUNCH(c, k_ksw_prep, mmg_blocks(n1, 128), 128, 0, d_jobs, n, sc, ftab, mem_sz, p_sz, cig_sz, key, idx, d_cells, d_cls);
+	MMG_LAUNCH(c, k_ksw_prep, mmg_blocks(n1, 128), 128, 0, d_jobs, n, sc, ftab, mem_sz, p_sz, cig_sz, key, idx, d_cells, d_cls, force_block ? 1 : 0);
 	MMG_TRY(scan_excl(c, mem_sz, mem_off, (int)n1));
 	MMG_TRY(scan_excl(c, p_sz, p_off, (int)n1));
 	MMG_TRY(scan_excl(c, cig_sz, cg_off, (int)n1));
@@ -765,8 +983,8 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 	MMG_D2H(c, h_cells, d_cells, sizeof(h_cells)); MMG_D2H(c, h_cls, d_cls, sizeof(h_cls));
 	MMG_CUDA(cudaStreamSynchronize(c->stream));
 	if (cells) *cells = h_cells[0];
-	c->k_last_jobs_literal = h_cls[KSW_CLS_LITERAL] + h_cls[KSW_CLS_LITERAL_WIDE]; // the wavefront form counts as a fast form
-	c->k_last_cells_literal = h_cells[1 + KSW_CLS_LITERAL] + h_cells[1 + KSW_CLS_LITERAL_WIDE];
+	c->k_last_jobs_literal = h_cls[KSW_CLS_LITERAL] + h_cls[KSW_CLS_LITERAL_WIDE] + h_cls[KSW_CLS_BLOCK1] + h_cls[KSW_CLS_BLOCK2]; // the wavefront form counts as a fast form
+	c->k_last_cells_literal = h_cells[1 + KSW_CLS_LITERAL] + h_cells[1 + KSW_CLS_LITERAL_WIDE] + h_cells[1 + KSW_CLS_BLOCK1] + h_cells[1 + KSW_CLS_BLOCK2];
 	c->k_last_jobs_fast = (uint64_t)n - c->k_last_jobs_literal, c->k_last_cells_fast = h_cells[0] - c->k_last_cells_literal;
 	if (getenv("MMG_KSW_DEBUG")) {
 		fprintf(stderr, "[mmg_ksw] %d jobs, %llu cells:", n, h_cells[0]);
@@ -824,6 +1042,18 @@ static int ksw_launch(mmg_ctx_t *c, const mmg_ksw_job_t *d_jobs, int n, const ui
 		           reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_mem.as<int8_t>(), c->k_p.as<uint8_t>(),
 		           c->k_cig.as<uint32_t>(), d_ez);
 	first += h_cls[KSW_CLS_LITERAL_WIDE];
+	for (int q = KSW_CLS_BLOCK1; q <= KSW_CLS_BLOCK2; ++q) { // literal jobs with more state than a warp's slot: a CTA each, state in its shared memory
+		static bool blk_attr[16] = {false};
+		if (c->dev < 16 && !blk_attr[c->dev]) {
+			MMG_CUDA(cudaFuncSetAttribute(k_ksw_dpx_block, cudaFuncAttributeMaxDynamicSharedMemorySize, KSWB_SMEM2));
+			blk_attr[c->dev] = true;
+		}
+		if (h_cls[q])
+			MMG_LAUNCH(c, k_ksw_dpx_block, h_cls[q], 32 * KSWB_WARPS, q == KSW_CLS_BLOCK1 ? KSWB_SMEM1 : KSWB_SMEM2, d_jobs, order + first, (int)h_cls[q], sc, d_Q, d_S,
+			           d_q_off, d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off), c->k_p.as<uint8_t>(),
+			           c->k_cig.as<uint32_t>(), d_ez);
+		first += h_cls[q];
+	}
 	if (h_cls[KSW_CLS_WAVE])
 		MMG_LAUNCH(c, k_ksw_wave, mmg_blocks(h_cls[KSW_CLS_WAVE], KW_WARPS), 32 * KW_WARPS, 0, d_jobs, order + first, (int)h_cls[KSW_CLS_WAVE], sc, d_Q, d_S, d_q_off,
 		           d_read_len, d_ref_off, reinterpret_cast<const uint64_t*>(mem_off), reinterpret_cast<const uint64_t*>(p_off), reinterpret_cast<const uint64_t*>(cg_off),

@@ -665,7 +665,8 @@ def main():
             "k_sketch_count": st_res.n_bases * 0.5, "k_sketch_fill": st_res.n_bases * 0.5 + nmv * 16, "k_sketch_reads": st_res.n_bases * 0.5 + nmv * 16,
             "k_lookup": nmv * (16 + 16 + 12), "k_fill": nmv * 28 + nanch * (8 + 16), "k_expand": nmv * 28 + nanch * (8 + 16),
             "k_chain_fill": nanch * (16 + 16), "k_chain_tail_warp": nanch * (16 + 16 + 16 + 16),
-            "k_ksw": (cells - cells_fast) * 1.0 + (jobs - jobs_fast) * 64, "k_ksw_dpx": (cells - cells_fast) * 1.0 + (jobs - jobs_fast) * 64, "k_ksw_tpj": cells_fast * 1.0 + jobs_fast * 64,
+            "k_ksw": (cells - cells_fast) * 1.0 + (jobs - jobs_fast) * 64, "k_ksw_dpx": (cells - cells_fast) * 1.0 + (jobs - jobs_fast) * 64,
+            "k_ksw_dpx_block": (cells - cells_fast) * 1.0 + (jobs - jobs_fast) * 64, "k_ksw_tpj": cells_fast * 1.0 + jobs_fast * 64,
             "k_ksw_wave": cells_fast * 1.0 + jobs_fast * 64,
             "k_encode_reads": st_res.n_bases * 1.5,
             # post-chaining bookkeeping: chained anchors in, query + target windows as 4-bit codes, hits out
@@ -682,7 +683,7 @@ def main():
                 "share_of_kernel_time": dms / step_dev_ms if step_dev_ms else None,
                 "note": "the chaining and DP kernels are integer/latency-bound, not HBM-bound: their HBM fraction is small by construction; "
                         "see k4 (GCUPS against the integer-pipe roofline) and DESIGN.md section 4"}
-        ksw_lit_ms = prof_res.get("k_ksw", (0.0, 0))[0] + prof_res.get("k_ksw_dpx", (0.0, 0))[0]
+        ksw_lit_ms = prof_res.get("k_ksw", (0.0, 0))[0] + prof_res.get("k_ksw_dpx", (0.0, 0))[0] + prof_res.get("k_ksw_dpx_block", (0.0, 0))[0]
         ksw_fast_ms = prof_res.get("k_ksw_tpj", (0.0, 0))[0] + prof_res.get("k_ksw_wave", (0.0, 0))[0]
         ksw_ms = ksw_lit_ms + ksw_fast_ms
         lookup_ms = prof_res.get("k_lookup", (0.0, 0))[0]
