@@ -107,13 +107,13 @@ MMG_HD void post_hit_record(const PostShard &sh, int64_t g)
 }
 
 // fragments of more than 64 chains: equal keys leave klib's radix sort in an order only its replay gives (hit_order_desc)
-MMG_HDN inline void post_hits_fix_order(const PostShard &sh, int f)
+MMG_HDN inline void post_hits_fix_order(const PostShard &sh, int f, int known_tie = -1 /* 1: the caller found equal keys; 0: none; -1: look */)
 {
 	const int n = sh.nu[f];
 	if (n <= 64) return;
 	const int64_t o = sh.uoff[f];
-	bool tie = false;
-	for (int i = 1; i < n && !tie; ++i) tie = sh.key[o + i] == sh.key[o + i - 1];
+	bool tie = known_tie > 0;
+	if (known_tie < 0) for (int i = 1; i < n && !tie; ++i) tie = sh.key[o + i] == sh.key[o + i - 1];
 	if (!tie) return;
 	// original order: key_in holds the chains back to front
 	uint64_t *k = sh.cov + o;
@@ -158,7 +158,12 @@ MMG_HDN inline void post_hits_select_warp(const W &wp, const PostShard &sh, int 
 	const int64_t o = sh.uoff[f];
 	const int n_in = post_frag_mapped(sh, f, qlen_sum) ? sh.nu[f] : 0;
 	const bool tree = n_in > 0 && !(sh.opt.flag & HIT_F_ALL_CHAINS);
-	if (n_in > 0) wp.one([&]() { post_hits_fix_order(sh, f); });
+	if (n_in > 64) { // equal keys among the sorted chain keys?  (one lane reading them one after the other held a 10^4-chain fragment for most of its time here)
+		bool tie = false;
+		for (int i0 = 1; i0 < n_in && !tie; i0 += 32)
+			tie = wp.ballot([&](int l) { const int i = i0 + l; return i < n_in && sh.key[o + i] == sh.key[o + i - 1]; }) != 0;
+		if (tie) wp.one([&]() { post_hits_fix_order(sh, f, 1); });
+	}
 	if (tree) {
 		if (qlen_sum <= HIT_COVER_BITS) hit_set_parent_warp(wp, sh.opt.mask_level, n_in, sh.r0 + o, (sh.opt.flag & HIT_F_HARD_MLEVEL) != 0, sh.w + o, fast);
 		else wp.one([&]() { hit_set_parent(sh.opt.mask_level, n_in, sh.r0 + o, sh.opt.a * 2 + sh.opt.b, (sh.opt.flag & HIT_F_HARD_MLEVEL) != 0, sh.w + o, sh.cov + o, nullptr); });

@@ -803,6 +803,29 @@ __device__ __forceinline__ void warp_bitonic(T *a, int n, int lane, Before befor
 struct U64Desc { __device__ bool operator()(uint64_t x, uint64_t y) const { return x > y; } };
 struct M128ByX { __device__ bool operator()(const mm128 &x, const mm128 &y) const { return x.x < y.x; } };
 
+// does the fragment go through the second pass with the higher occurrence cut-off? (map.c:353-370)
+__device__ __forceinline__ uint8_t chain_wants_rechain(bool candidate, int n_u, const uint64_t *U0, const mm128 *A, int segs)
+{
+	if (!candidate) return 0;
+	if (n_u == 0) return 1;
+	int n_chained = 1, max = 0, max_i = -1, max_off = -1, off = 0; // does the best chain span every segment? (map.c:355-365)
+	for (int i = 0; i < n_u; ++i) {
+		if (max < (int)(U0[i] >> 32)) max = (int)(U0[i] >> 32), max_i = i, max_off = off;
+		off += (int32_t)U0[i];
+	}
+	if (max_i >= 0)
+		for (int i = 1; i < (int32_t)U0[max_i]; ++i)
+			if ((A[max_off + i].y & MMG_SEED_SEG_MASK) != (A[max_off + i - 1].y & MMG_SEED_SEG_MASK)) ++n_chained;
+	return n_chained < segs ? 1 : 0;
+}
+
+// fragments of the first pass with more anchors than one warp should walk
+__global__ void k_tail_heavy_list(int n_list, const int32_t *__restrict__ na, int heavy_n, int32_t *__restrict__ heavy, int32_t *__restrict__ n_heavy)
+{
+	const int li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li < n_list && na[li] > heavy_n) heavy[atomicAdd(n_heavy, 1)] = li;
+}
+
 // K3 tail, one warp per fragment: chain ends and peaks, ranking by peak score, backtracking, output order
 // (chain.c:87-160).  The sequential backtrack marks anchors as used chain by chain in rank order; the same
 // ownership is obtained in parallel as "the lowest rank whose path passes through the anchor" (atomicMin while
@@ -812,7 +835,7 @@ __global__ void __launch_bounds__(128)
 k_chain_tail_warp(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
                   const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
                   uint64_t *__restrict__ u, mm128 *__restrict__ bb, RsFrame *__restrict__ stack, int32_t *__restrict__ nu_out,
-                  int32_t *__restrict__ nv_out, const int32_t *__restrict__ rep, int rechain_enabled, uint8_t *__restrict__ flag_out)
+                  int32_t *__restrict__ nv_out, const int32_t *__restrict__ rep, int rechain_enabled, uint8_t *__restrict__ flag_out, int heavy_n)
 {
 	const int li = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
 	if (li >= n_list) return;
@@ -820,6 +843,7 @@ k_chain_tail_warp(FragTab ft, const int32_t *__restrict__ list, int n_list, cons
 	const int f = list ? list[li] : li;
 	const int64_t ao = aoff[li];
 	const int n = na[li], segs = n_seg[f];
+	if (n > heavy_n) return; // left to k_chain_tail_block: thousands of chains ranked and walked by 32 lanes held the launch
 	int n_u = 0, n_v = 0;
 	mm128 *A = a + ao, *B = bb + ao;
 	uint64_t *U0 = u + ao * 2, *U1 = U0 + n;
@@ -944,23 +968,7 @@ k_chain_tail_warp(FragTab ft, const int32_t *__restrict__ list, int n_list, cons
 	}
 	if (lane != 0) return;
 	nu_out[li] = n_u, nv_out[li] = n_v;
-	if (flag_out) {
-		uint8_t rechain = 0;
-		if (rechain_enabled && rep[li] > 0) {
-			if (n_u > 0) { // does the best chain span every segment? (map.c:355-365)
-				int n_chained = 1, max = 0, max_i = -1, max_off = -1, off = 0;
-				for (int i = 0; i < n_u; ++i) {
-					if (max < (int)(U0[i] >> 32)) max = (int)(U0[i] >> 32), max_i = i, max_off = off;
-					off += (int32_t)U0[i];
-				}
-				if (max_i >= 0)
-					for (int i = 1; i < (int32_t)U0[max_i]; ++i)
-						if ((A[max_off + i].y & MMG_SEED_SEG_MASK) != (A[max_off + i - 1].y & MMG_SEED_SEG_MASK)) ++n_chained;
-				if (n_chained < segs) rechain = 1;
-			} else rechain = 1;
-		}
-		flag_out[f] = rechain;
-	}
+	if (flag_out) flag_out[f] = chain_wants_rechain(rechain_enabled && rep[li] > 0, n_u, U0, A, segs);
 }
 
 
@@ -1015,16 +1023,22 @@ __device__ __forceinline__ int block_incl_scan(int v, int *s, int *total)
 }
 
 #define TAIL_BLOCK_SMEM (216 * 1024)
+#define TAIL_HEAVY_N 2048               /* first-pass fragments with more anchors go to the CTA form */
+#define TAIL_HEAVY_SMEM (64 * 1024)     /* staging area of the CTA form in the first pass: three CTAs of 512 threads per SM */
 __global__ void __launch_bounds__(1024)
 k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
                    const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
                    uint64_t *__restrict__ u, mm128 *__restrict__ bb, RsFrame *__restrict__ stack, int32_t *__restrict__ nu_out,
-                   int32_t *__restrict__ nv_out)
+                   int32_t *__restrict__ nv_out, const int32_t *__restrict__ heavy /* null: every fragment of the list */,
+                   const int32_t *__restrict__ n_heavy, size_t smem_cap, const int32_t *__restrict__ rep, int rechain_enabled,
+                   uint8_t *__restrict__ flag_out /* first pass only */)
 {
 	__shared__ int s_scan[1024], s_nu, s_tie;
 	extern __shared__ __align__(16) unsigned char dyn_tail[];
-	const int li = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
-	if (li >= n_list) return;
+	const int tid = threadIdx.x, NT = blockDim.x;
+	const int n_items = heavy ? *n_heavy : n_list;
+	for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+	const int li = heavy ? heavy[it] : it;
 	const int f = list ? list[li] : li;
 	const int64_t ao = aoff[li];
 	const int n = na[li], segs = n_seg[f];
@@ -1053,7 +1067,7 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
 		n_u = s_nu;
 		if (n_u > 0) {
 			// 3. rank by (peak score, anchor) descending (chain.c:107-111)
-			block_bitonic_staged(U1, n_u, U64Desc(), dyn_tail, TAIL_BLOCK_SMEM);
+			block_bitonic_staged(U1, n_u, U64Desc(), dyn_tail, smem_cap);
 			for (int e = tid; e < n_u; e += NT) U0[e] = U1[e];
 			// 4. ownership: lowest rank whose walk passes through the anchor
 			for (int i = tid; i < n; i += NT) T[i] = 0x7fffffff;
@@ -1101,7 +1115,7 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
 			__syncthreads();
 			// 7. order chains by the position of their first anchor (chain.c:150): unique for distinct keys, literal replay otherwise
 			if (n_u > 64) {
-				block_bitonic_staged(W, n_u, M128ByX(), dyn_tail, TAIL_BLOCK_SMEM);
+				block_bitonic_staged(W, n_u, M128ByX(), dyn_tail, smem_cap);
 				for (int kk = tid + 1; kk < n_u; kk += NT) if (W[kk].x == W[kk - 1].x) s_tie = 1;
 				__syncthreads();
 				if (s_tie) { // back to the order klib's sort starts from
@@ -1114,7 +1128,7 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
 				// a trip to L2 each (a fragment from a repeat family has thousands of chains, and ties are common there: two query
 				// minimizers with the same hash start chains on the same reference position)
 				const size_t frames = (size_t)n_u / 65 + 4;
-				if ((size_t)n_u * sizeof(mm128) + frames * sizeof(RsFrame) <= TAIL_BLOCK_SMEM) {
+				if ((size_t)n_u * sizeof(mm128) + frames * sizeof(RsFrame) <= smem_cap) {
 					mm128 *sw = reinterpret_cast<mm128*>(dyn_tail);
 					RsFrame *sf = reinterpret_cast<RsFrame*>(dyn_tail + (size_t)n_u * sizeof(mm128));
 					for (int kk = tid; kk < n_u; kk += NT) sw[kk] = W[kk];
@@ -1142,7 +1156,12 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
 			__syncthreads();
 		}
 	}
-	if (tid == 0) nu_out[li] = n_u, nv_out[li] = n_v;
+	if (tid == 0) {
+		nu_out[li] = n_u, nv_out[li] = n_v;
+		if (flag_out) flag_out[f] = chain_wants_rechain(rechain_enabled && rep[li] > 0, n_u, U0, A, segs);
+	}
+	__syncthreads(); // s_nu, s_tie and the staging area belong to the next fragment from here
+	}
 }
 
 // gather per-fragment results (first or second pass) into dense output arrays
@@ -1158,7 +1177,19 @@ __global__ void k_gather(int n_frag, const int32_t *__restrict__ src_li /* secon
 	const uint64_t *U = s >= 0 ? u2 + aoff2[s] * 2 : u1 + aoff1[f] * 2;
 	const mm128 *A = s >= 0 ? a2 + aoff2[s] : a1 + aoff1[f];
 	for (int i = threadIdx.x; i < nu[f]; i += blockDim.x) out_u[uoff[f] + i] = U[i];
-	for (int i = threadIdx.x; i < nv[f]; i += blockDim.x) out_a[voff[f] + i] = A[i];
+	// a re-chained fragment carries ~10^5 anchors: eight independent loads per thread and round, or its CTA holds the launch
+	// for a millisecond of one-at-a-time round trips
+	const int n = nv[f], nt = blockDim.x;
+	mm128 *O = out_a + voff[f];
+	int i = threadIdx.x;
+	for (; i + 7 * nt < n; i += 8 * nt) {
+		mm128 v[8];
+#pragma unroll
+		for (int q = 0; q < 8; ++q) v[q] = A[i + q * nt];
+#pragma unroll
+		for (int q = 0; q < 8; ++q) O[i + q * nt] = v[q];
+	}
+	for (; i < n; i += nt) O[i] = A[i];
 }
 
 __global__ void k_gather_mini(int n_frag, FragTab ft, const int32_t *__restrict__ src_li, const uint64_t *__restrict__ mini1,
@@ -1499,11 +1530,23 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	if (d_flag == nullptr) // the re-chain pass: few, very large fragments -> one CTA each
 		MMG_LAUNCH(c, k_chain_tail_block, n_list, 1024, TAIL_BLOCK_SMEM, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
 		           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
-		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>());
-	else
+		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), nullptr, nullptr, (size_t)TAIL_BLOCK_SMEM, nullptr, 0, nullptr);
+	else {
+		// first pass: the fragments with thousands of anchors (a few per thousand) get a CTA each, with its sorts staged in shared memory,
+		// ahead of the warp kernel that takes everything else
+		static const int heavy_n = getenv("MMG_TAIL_HEAVY_N") ? atoi(getenv("MMG_TAIL_HEAVY_N")) : TAIL_HEAVY_N;
+		const int rechain_enabled = opt->max_occ > opt->mid_occ ? 1 : 0;
+		MMG_TRY(c->d_heavy.ensure(((size_t)n_list + 4) * 4));
+		int32_t *n_heavy = c->d_heavy.as<int32_t>(), *heavy = n_heavy + 4;
+		MMG_CUDA(cudaMemsetAsync(n_heavy, 0, 16, c->stream));
+		MMG_LAUNCH(c, k_tail_heavy_list, mmg_blocks(n_list, 256), 256, 0, n_list, pb.na->as<int32_t>(), heavy_n, heavy, n_heavy);
+		MMG_LAUNCH(c, k_chain_tail_block, 148 * 3, 512, TAIL_HEAVY_SMEM, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+		           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
+		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), heavy, n_heavy, (size_t)TAIL_HEAVY_SMEM, pb.rep->as<int32_t>(), rechain_enabled, d_flag);
 		MMG_LAUNCH(c, k_chain_tail_warp, mmg_blocks((size_t)n_list * 32, 128), 128, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
 		           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
-		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), pb.rep->as<int32_t>(), opt->max_occ > opt->mid_occ ? 1 : 0, d_flag);
+		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), pb.rep->as<int32_t>(), rechain_enabled, d_flag, heavy_n);
+	}
 	return MMG_OK;
 }
 
