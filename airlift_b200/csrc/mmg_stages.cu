@@ -1023,6 +1023,7 @@ __device__ __forceinline__ int block_incl_scan(int v, int *s, int *total)
 }
 
 #define TAIL_BLOCK_SMEM (216 * 1024)
+__device__ int g_tail_walk = 0;        /* 1: the chain tail walks every chain (the form before the level-by-level one); MMG_TAIL_WALK=1 */
 #define TAIL_HEAVY_N 2048               /* first-pass fragments with more anchors go to the CTA form */
 #define TAIL_HEAVY_SMEM (64 * 1024)     /* staging area of the CTA form in the first pass: three CTAs of 512 threads per SM */
 __global__ void __launch_bounds__(1024)
@@ -1069,46 +1070,164 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
 			// 3. rank by (peak score, anchor) descending (chain.c:107-111)
 			block_bitonic_staged(U1, n_u, U64Desc(), dyn_tail, smem_cap);
 			for (int e = tid; e < n_u; e += NT) U0[e] = U1[e];
-			// 4. ownership: lowest rank whose walk passes through the anchor
-			for (int i = tid; i < n; i += NT) T[i] = 0x7fffffff;
-			__syncthreads();
-			for (int k = tid; k < n_u; k += NT) {
-				int j = (int32_t)U0[k];
-				while (j >= 0) { const int old = atomicMin(&T[j], k); if (old < k) break; j = Pp[j]; }
-			}
-			__syncthreads();
-			// 5. what each chain keeps (chain.c:115-129)
-			for (int k = tid; k < n_u; k += NT) {
-				const int j0 = (int32_t)U0[k];
-				const int32_t sc = (int32_t)(U0[k] >> 32);
-				int cnt = 1, j = Pp[j0];
-				while (j >= 0 && T[j] == k) ++cnt, j = Pp[j];
-				bool keep; int32_t score;
-				if (j < 0) keep = cnt >= P.min_cnt, score = sc;
-				else keep = (sc - F[j] >= P.min_sc) && cnt >= P.min_cnt, score = sc - F[j];
-				U1[k] = keep ? ((uint64_t)(uint32_t)score << 32 | (uint32_t)cnt) : 0;
-			}
-			__syncthreads();
-			// 6. kept chains in rank order -> b[], compacted u, chain-order keys w
+			// The backtracking of chain.c:112-129 walks every chain from its peak towards its root, best chain first, and stops at the
+			// first anchor a better chain took.  Walked literally that is a dependent load per step (two thirds of this kernel's time
+			// on a fragment whose state does not fit L2).  The same result without walking: with depth[] (distance to the root, by
+			// pointer jumping) an anchor's owner is the lowest rank among the peaks in its subtree -- pushed up level by level, one
+			// fire-and-forget atomic per anchor -- a chain keeps exactly the anchors it owns (they are consecutive on its path), and an
+			// owned anchor's slot in b[] follows from the two depths.
 			int n_keep = 0;
-			for (int k0 = 0; k0 < n_u; k0 += NT) {
-				const int k = k0 + tid;
-				const uint64_t uk = k < n_u ? U1[k] : 0;
-				const int cnt = (int32_t)(uint32_t)uk;
-				int tot_cnt, tot_keep;
-				const int incl = block_incl_scan(cnt, s_scan, &tot_cnt), inclk = block_incl_scan(cnt > 0 ? 1 : 0, s_scan, &tot_keep);
-				const int kk = n_keep + inclk - 1;
-				if (cnt > 0) {
-					const int off = n_v + incl - cnt;
-					int j = (int32_t)U0[k];
-					for (int q = cnt - 1; q >= 0; --q) { B[off + q] = A[j]; j = Pp[j]; }
-					V[kk] = off;
-					W[kk].y = (uint64_t)off << 32 | (uint32_t)kk;
+			bool par = P.min_cnt >= 2 && !g_tail_walk;
+			int maxd = 0;
+			if (par) {
+				unsigned long long *P2 = reinterpret_cast<unsigned long long*>(W); // (jump << 32 | distance) per anchor
+				for (int x = tid; x < n; x += NT) { const int pj = Pp[x]; P2[x] = pj >= 0 ? ((unsigned long long)(uint32_t)pj << 32 | 1ull) : (0xffffffffull << 32); }
+				__syncthreads();
+				for (;;) {
+					int any = 0;
+					for (int x = tid; x < n; x += NT) {
+						const unsigned long long w = P2[x];
+						const int j = (int32_t)(w >> 32);
+						if (j >= 0) {
+							const unsigned long long w2 = P2[j]; // an 8-byte word read at once: some valid (ancestor, distance) pair of j, whatever round it is from
+							P2[x] = (w2 & 0xffffffff00000000ull) | (unsigned long long)((uint32_t)w + (uint32_t)w2);
+							any |= (int32_t)(w2 >> 32) >= 0;
+						}
+					}
+					if (!__syncthreads_or(any)) break;
+				}
+				if (tid == 0) s_tie = 0; // borrowed as the maximum depth until step 7 resets it
+				__syncthreads();
+				int md = 0;
+				for (int x = tid; x < n; x += NT) { const int d = (int32_t)(uint32_t)P2[x]; V[x] = d; md = md > d ? md : d; }
+				md = __reduce_max_sync(0xffffffffu, md);
+				if ((tid & 31) == 0) atomicMax(&s_tie, md);
+				__syncthreads();
+				maxd = s_tie;
+				__syncthreads();
+				if (tid == 0) s_tie = 0;
+				par = (size_t)(maxd + 2) * 8 <= smem_cap;
+			}
+			if (par) {
+				int32_t *lvl_start = reinterpret_cast<int32_t*>(dyn_tail), *lvl_cur = lvl_start + maxd + 2; // anchors grouped by depth
+				int32_t *order = reinterpret_cast<int32_t*>(W), *cntk = order + n, *lastk = cntk + n;
+				for (int d = tid; d < maxd + 2; d += NT) lvl_start[d] = 0;
+				__syncthreads();
+				for (int x = tid; x < n; x += NT) atomicAdd(&lvl_start[V[x] + 1], 1);
+				__syncthreads();
+				if (tid == 0) { int acc = 0; for (int d = 0; d < maxd + 2; ++d) { acc += lvl_start[d]; lvl_start[d] = acc; lvl_cur[d] = acc; } }
+				__syncthreads(); // lvl_start[d] = first slot of depth d; lvl_start[maxd + 1] = n
+				for (int x = tid; x < n; x += NT) { order[atomicAdd(&lvl_cur[V[x]], 1)] = x; T[x] = 0x7fffffff; }
+				for (int k = tid; k < n_u; k += NT) cntk[k] = 0;
+				__syncthreads();
+				for (int k = tid; k < n_u; k += NT) atomicMin(&T[(int32_t)U0[k]], k);
+				__syncthreads();
+				for (int d = maxd; d >= 1; --d) { // owners move up one level per step
+					for (int i = lvl_start[d] + tid; i < lvl_start[d + 1]; i += NT) {
+						const int x = order[i], t = T[x];
+						if (t != 0x7fffffff) atomicMin(&T[Pp[x]], t);
+					}
+					__syncthreads();
+				}
+				// 5. what each chain keeps (chain.c:115-129): its peak, then the anchors it owns
+				for (int x = tid; x < n; x += NT) {
+					const int k = T[x];
+					if (k != 0x7fffffff) {
+						atomicAdd(&cntk[k], 1);
+						const int pj = Pp[x];
+						if (pj < 0 || T[pj] != k) lastk[k] = x; // the owned anchor closest to the root: one per chain
+					}
 				}
 				__syncthreads();
-				if (cnt > 0) U1[kk] = uk; // kk <= k, and every entry of this block of ranks was read above
-				n_v += tot_cnt, n_keep += tot_keep;
+				for (int k = tid; k < n_u; k += NT) {
+					const int j0 = (int32_t)U0[k];
+					const int32_t sc = (int32_t)(U0[k] >> 32);
+					int cnt, j;
+					if (T[j0] == k) cnt = cntk[k], j = Pp[lastk[k]];
+					else cnt = 1, j = Pp[j0]; // the peak belongs to a better chain: it is still taken (the do-while of chain.c:118-122), nothing else
+					bool keep; int32_t score;
+					if (j < 0) keep = cnt >= P.min_cnt, score = sc;
+					else keep = (sc - F[j] >= P.min_sc) && cnt >= P.min_cnt, score = sc - F[j];
+					U1[k] = keep ? ((uint64_t)(uint32_t)score << 32 | (uint32_t)cnt) : 0;
+				}
 				__syncthreads();
+				// 6. kept chains in rank order -> b[]: offsets by a scan over the ranks (F and Pp are free from here: F[k] = first slot of
+				// chain k in b[], Pp[k] = its index among the kept chains), then every owned anchor goes to its slot
+				for (int k0 = 0; k0 < n_u; k0 += NT) {
+					const int k = k0 + tid;
+					const int cnt = k < n_u ? (int32_t)(uint32_t)U1[k] : 0;
+					int tot_cnt, tot_keep;
+					const int incl = block_incl_scan(cnt, s_scan, &tot_cnt), inclk = block_incl_scan(cnt > 0 ? 1 : 0, s_scan, &tot_keep);
+					if (cnt > 0) F[k] = n_v + incl - cnt, Pp[k] = n_keep + inclk - 1;
+					n_v += tot_cnt, n_keep += tot_keep;
+				}
+				__syncthreads();
+				int32_t *cid = reinterpret_cast<int32_t*>(W) + 2 * (int64_t)n; // rank of the chain that owns b[t]; the kept chains' W entries end below it (>= 2 anchors each)
+				for (int x = tid; x < n; x += NT) {
+					const int k = T[x];
+					if (k == 0x7fffffff) continue;
+					const int cnt = (int32_t)(uint32_t)U1[k];
+					if (cnt == 0) continue;
+					const int slot = F[k] + cnt - 1 - (V[(int32_t)U0[k]] - V[x]);
+					B[slot] = A[x], cid[slot] = k;
+				}
+				__syncthreads();
+				for (int k0 = 0; k0 < n_u; k0 += NT) { // per kept chain: start in b[], chain-order key, compacted u
+					const int k = k0 + tid;
+					const uint64_t uk = k < n_u ? U1[k] : 0;
+					const int cnt = (int32_t)(uint32_t)uk;
+					int kk = 0;
+					if (cnt > 0) {
+						kk = Pp[k];
+						const int off = F[k];
+						V[kk] = off;
+						W[kk].y = (uint64_t)off << 32 | (uint32_t)kk;
+					}
+					__syncthreads();
+					if (cnt > 0) U1[kk] = uk; // kk <= k, and every entry of this block of ranks was read above
+					__syncthreads();
+				}
+			} else {
+				// 4. ownership: lowest rank whose walk passes through the anchor
+				for (int i = tid; i < n; i += NT) T[i] = 0x7fffffff;
+				__syncthreads();
+				for (int k = tid; k < n_u; k += NT) {
+					int j = (int32_t)U0[k];
+					while (j >= 0) { const int old = atomicMin(&T[j], k); if (old < k) break; j = Pp[j]; }
+				}
+				__syncthreads();
+				// 5. what each chain keeps (chain.c:115-129)
+				for (int k = tid; k < n_u; k += NT) {
+					const int j0 = (int32_t)U0[k];
+					const int32_t sc = (int32_t)(U0[k] >> 32);
+					int cnt = 1, j = Pp[j0];
+					while (j >= 0 && T[j] == k) ++cnt, j = Pp[j];
+					bool keep; int32_t score;
+					if (j < 0) keep = cnt >= P.min_cnt, score = sc;
+					else keep = (sc - F[j] >= P.min_sc) && cnt >= P.min_cnt, score = sc - F[j];
+					U1[k] = keep ? ((uint64_t)(uint32_t)score << 32 | (uint32_t)cnt) : 0;
+				}
+				__syncthreads();
+				// 6. kept chains in rank order -> b[], compacted u, chain-order keys w
+				for (int k0 = 0; k0 < n_u; k0 += NT) {
+					const int k = k0 + tid;
+					const uint64_t uk = k < n_u ? U1[k] : 0;
+					const int cnt = (int32_t)(uint32_t)uk;
+					int tot_cnt, tot_keep;
+					const int incl = block_incl_scan(cnt, s_scan, &tot_cnt), inclk = block_incl_scan(cnt > 0 ? 1 : 0, s_scan, &tot_keep);
+					const int kk = n_keep + inclk - 1;
+					if (cnt > 0) {
+						const int off = n_v + incl - cnt;
+						int j = (int32_t)U0[k];
+						for (int q = cnt - 1; q >= 0; --q) { B[off + q] = A[j]; j = Pp[j]; }
+						V[kk] = off;
+						W[kk].y = (uint64_t)off << 32 | (uint32_t)kk;
+					}
+					__syncthreads();
+					if (cnt > 0) U1[kk] = uk; // kk <= k, and every entry of this block of ranks was read above
+					n_v += tot_cnt, n_keep += tot_keep;
+					__syncthreads();
+				}
 			}
 			n_u = n_keep;
 			for (int kk = tid; kk < n_u; kk += NT) W[kk].x = B[V[kk]].x;
@@ -1140,18 +1259,35 @@ k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, con
 			}
 			__syncthreads();
 			// 8. write chains back to a[] in that order (chain.c:152-159)
-			int dst = 0;
-			for (int i0 = 0; i0 < n_u; i0 += NT) {
-				const int i = i0 + tid;
-				uint64_t uk = 0; int src = 0;
-				if (i < n_u) { const uint64_t wy = W[i].y; uk = U1[(int32_t)(uint32_t)wy]; src = (int)(wy >> 32); }
-				const int nn = (int32_t)(uint32_t)uk;
-				int tot;
-				const int incl = block_incl_scan(nn, s_scan, &tot);
-				const int off = dst + incl - nn;
-				for (int q = 0; q < nn; ++q) A[off + q] = B[src + q];
-				if (i < n_u) U0[i] = uk;
-				dst += tot;
+			if (!par) {
+				int dst = 0;
+				for (int i0 = 0; i0 < n_u; i0 += NT) {
+					const int i = i0 + tid;
+					uint64_t uk = 0; int src = 0;
+					if (i < n_u) { const uint64_t wy = W[i].y; uk = U1[(int32_t)(uint32_t)wy]; src = (int)(wy >> 32); }
+					const int nn = (int32_t)(uint32_t)uk;
+					int tot;
+					const int incl = block_incl_scan(nn, s_scan, &tot);
+					const int off = dst + incl - nn;
+					for (int q = 0; q < nn; ++q) A[off + q] = B[src + q];
+					if (i < n_u) U0[i] = uk;
+					dst += tot;
+				}
+			} else { // the same offsets; anchors moved by all threads: b[t] belongs to chain cid[t], whose anchors shift by T[kk]
+				int32_t *cid = reinterpret_cast<int32_t*>(W) + 2 * (int64_t)n;
+				int dst = 0;
+				for (int i0 = 0; i0 < n_u; i0 += NT) {
+					const int i = i0 + tid;
+					uint64_t uk = 0; int src = 0, kk = 0;
+					if (i < n_u) { const uint64_t wy = W[i].y; kk = (int32_t)(uint32_t)wy; uk = U1[kk]; src = (int)(wy >> 32); }
+					const int nn = (int32_t)(uint32_t)uk;
+					int tot;
+					const int incl = block_incl_scan(nn, s_scan, &tot);
+					if (i < n_u) T[kk] = dst + incl - nn - src, U0[i] = uk;
+					dst += tot;
+				}
+				__syncthreads();
+				for (int t = tid; t < n_v; t += NT) A[t + T[Pp[cid[t]]]] = B[t];
 			}
 			__syncthreads();
 		}
@@ -1525,7 +1661,11 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 	}
 	{
 		static bool attr_set = false;
-		if (!attr_set) { MMG_CUDA(cudaFuncSetAttribute(k_chain_tail_block, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_BLOCK_SMEM)); attr_set = true; }
+		if (!attr_set) {
+			MMG_CUDA(cudaFuncSetAttribute(k_chain_tail_block, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_BLOCK_SMEM));
+			if (getenv("MMG_TAIL_WALK")) { const int one = 1; MMG_CUDA(cudaMemcpyToSymbol(g_tail_walk, &one, sizeof(one))); } // A/B aid
+			attr_set = true;
+		}
 	}
 	if (d_flag == nullptr) // the re-chain pass: few, very large fragments -> one CTA each
 		MMG_LAUNCH(c, k_chain_tail_block, n_list, 1024, TAIL_BLOCK_SMEM, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
