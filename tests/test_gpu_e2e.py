@@ -46,6 +46,9 @@ def _run(binary, args, cwd):
     ["-x", "map-ont", "-t", "8", "ref.fa", "long.fq"],
     ["-ax", "map-ont", "-t", "8", "ref.fa", "long.fq"],
     ["-cx", "map-ont", "-t", "8", "--cs=long", "ref.fa", "long.fq"],
+    # q == q2 && e == e2: the reference switches to ksw_extz2_sse (align.c:328-329); served by the extd2 kernels, see tests/test_extz2_identity.py
+    ["-ax", "sr", "-t", "8", "-O", "12,12", "-E", "2,2", "ref.fa", "r1.fq", "r2.fq"],
+    ["-ax", "map-ont", "-t", "8", "-O", "4,4", "-E", "2,2", "ref.fa", "long.fq"],
 ], ids=lambda a: " ".join(a[:-2]))
 def test_cli_identical_to_reference(data, args):
     want = _run(L.REF_BIN_B, args, data)
