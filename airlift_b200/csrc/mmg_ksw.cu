@@ -10,6 +10,7 @@
 #include <cub/cub.cuh>
 #include "mmg_ctx.cuh"
 #include "mmg_kswdpx.h"
+#include "mmg_kswfast2.h"
 
 struct KswJobDev {       // a job as the kernel sees it: mmg_ksw_job_t resolved against the resident batch and the index
 	uint64_t q_base;      // packed base offset of the read in Q
@@ -64,7 +65,8 @@ __device__ __forceinline__ int ksw_ncol(int qlen, int tlen, int w)
 #define KSWB_SMEM2 (200 * 1024)
 struct KswFastClass { int32_t mc, tc, qc, nt; };
 struct KswFastTab { KswFastClass c[KSW_N_FAST]; };
-static inline size_t ksw_fast_smem(const KswFastClass &k) { return (size_t)k.nt * ((size_t)(k.mc + 1) * 8 + (size_t)k.tc + (size_t)k.qc); }
+// per thread: the window of pair slots (mmg_kswfast2.h), the target bases, the query bases with a padding element at either end
+static inline size_t ksw_fast_smem(const KswFastClass &k) { return (size_t)k.nt * ((size_t)((k.mc >> 1) + 3) * 16 + (size_t)k.tc + (size_t)k.qc + 2); }
 
 // wavefront form (k_ksw_wave below): geometry of its traceback rows and of its per-job arena
 #define KW_S 8
@@ -128,7 +130,7 @@ __global__ void k_ksw_prep(const mmg_ksw_job_t *__restrict__ jobs, int n, KswSco
 					const uint64_t est = (uint64_t)(qlen + tlen) * (uint64_t)(qlen < tlen ? qlen : tlen);
 					k = (uint32_t)cls << 28 | (63u - (uint32_t)(63 - __clzll((long long)(est | 1)))); // big jobs first
 				} else {
-					if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = mmg_ksw_fast_p_bytes(qlen, tlen);
+					if (!(j.flag & MMG_EZ_SCORE_ONLY)) p = mmg_ksw_fast2_p_bytes(qlen, tlen);
 					const uint32_t mode = (j.flag & MMG_EZ_SCORE_ONLY) ? 0u : (j.flag & MMG_EZ_RIGHT) ? 2u : 1u;
 					k = (uint32_t)cls << 28 | mode << 26 | (uint32_t)(1023 - tlen) << 10 | (uint32_t)(1023 - qlen);
 				}
@@ -717,8 +719,9 @@ k_ksw_dpx_block(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restric
 	}
 }
 
-// K4, fast form: one thread per job whose band never clips (mmg_ksw_fast, mmg_core.h).  The threads of a CTA interleave
-// their per-job arrays in shared memory ([element][thread]): a warp's accesses fall on consecutive banks.
+// K4, fast form: one thread per job whose band never clips, two cells per instruction (mmg_ksw_fast2, mmg_kswfast2.h).  The
+// threads of a CTA interleave their per-job arrays in shared memory ([element][thread]): a warp's accesses fall on consecutive
+// banks (16-byte pair slots: one LDS.128 / STS.128 per two cells).
 __global__ void __launch_bounds__(128)
 k_ksw_tpj(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ order, int n_jobs, KswScore sc, KswFastClass fc,
           const uint32_t *__restrict__ Q, const uint32_t *__restrict__ S, const uint64_t *__restrict__ q_off, const int32_t *__restrict__ read_len,
@@ -729,8 +732,8 @@ k_ksw_tpj(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ or
 	const int NT = blockDim.x, tid = threadIdx.x;
 	const int slot = blockIdx.x * NT + tid;
 	if (slot >= n_jobs) return;
-	uint64_t *st = reinterpret_cast<uint64_t*>(smem) + tid;
-	uint8_t *tb = smem + (size_t)(fc.mc + 1) * NT * 8 + tid, *qb = tb + (size_t)fc.tc * NT;
+	KswSlot *st = reinterpret_cast<KswSlot*>(smem) + tid;
+	uint8_t *tb = smem + (size_t)((fc.mc >> 1) + 3) * NT * 16 + tid, *qb = tb + (size_t)fc.tc * NT + NT; // qb[-1] and qb[qlen] are padding
 	const int ji = order[slot];
 	const mmg_ksw_job_t hj = jobs[ji];
 	const int qlen = hj.q_len, tlen = hj.t_len;
@@ -764,8 +767,9 @@ k_ksw_tpj(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ or
 			}
 		}
 	}
+	qb[-(ptrdiff_t)NT] = 4, qb[(size_t)qlen * NT] = 4;
 	KswEz ez;
-	mmg_ksw_fast(g, hj.flag, hj.zdrop, hj.end_bonus, st, tb, qb, NT, reinterpret_cast<uint32_t*>(gp + p_off[ji]), &ez, gcig + cig_off[ji]);
+	mmg_ksw_fast2(g, hj.flag, hj.zdrop, hj.end_bonus, st, tb, qb - NT, NT, reinterpret_cast<uint32_t*>(gp + p_off[ji]), &ez, gcig + cig_off[ji]);
 	res[ji] = ez;
 }
 

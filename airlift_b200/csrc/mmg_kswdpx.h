@@ -90,7 +90,7 @@ MMG_HD uint32_t mmg_kswdpx_carry_of(int x, int v, int x2) { return (uint32_t)(x 
 
 // two cells of ksw2_extd2_sse.c:184-313.  o: old state of the pair; s2: its two scores (bytes); prev: carry of the pair on the
 // left (or the block's carry-in).  Returns the new state; *d2 = the two traceback bytes (kMode != 0).
-template <int kMode>
+template <int kMode, bool kFold = true /* false: the fast forms, where no stale lane is read and valid cells stay inside int8 */>
 MMG_HD KswPair mmg_kswdpx_pair(const KswDpxConst &c, const KswPair &o, uint32_t s2, uint32_t prev, uint32_t *d2)
 {
 	// sign-extended operands
@@ -100,7 +100,7 @@ MMG_HD KswPair mmg_kswdpx_pair(const KswDpxConst &c, const KswPair &o, uint32_t 
 	// The reference's lanes are int8 and the STALE ones do overflow (a lane left of the band keeps re-evaluating the recurrence on
 	// its own old outputs and drifts: y = 94, 106, -150 -> 106 ...), so every sum and difference is folded back to int8 the way
 	// _mm_add_epi8 / _mm_sub_epi8 wrap: one byte permute with sign replication per result.
-#define W8(v) dpx_prmt((v), 0, 0xA280)
+#define W8(v) (kFold ? dpx_prmt((v), 0, 0xA280) : (v))
 	uint32_t a = W8(dpx_add(xt1, vt1)), b = W8(dpx_add(yt, ut)), a2 = W8(dpx_add(x2t1, vt1)), b2 = W8(dpx_add(y2t, ut));
 	uint32_t d = 0;
 	if (kMode == 0) z = dpx_max3(dpx_max3(z, a, b), a2, b2);

@@ -13,6 +13,7 @@ static long g_ksw_range_viol; // values of valid cells that left the int8 range 
 #include "mmg_kswdpx.h"
 #include "mmg_sketchwarp.h"
 #include "mmg_rswarp.h"
+#include "mmg_kswfast2.h"
 
 extern "C" {
 
@@ -217,6 +218,26 @@ int emu_ksw_dpx(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
 	for (int i = 0; i < tlen; ++i) sf[i] = target[i];
 	for (int i = 0; i < qlen; ++i) qr[i] = query[qlen - 1 - i];
 	mmg_kswdpx_scalar(g, flag, zdrop, end_bonus, mem, H.data(), p.data(), ez_out, cigar);
+	return 0;
+}
+
+// the pair form of the fast path (mmg_kswfast2.h): returns -1 when the job does not qualify
+int emu_ksw_fast2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int q, int e, int q2, int e2, int w,
+                  int zdrop, int end_bonus, int flag, int stride, KswEz *ez_out, uint32_t *cigar)
+{
+	KswGeom g = mmg_ksw_geom(qlen, tlen, 5, mat, q, e, q2, e2, w);
+	KswEz ez; mmg_ksw_reset(&ez);
+	if (g.bail) { *ez_out = ez; return 0; }
+	for (int r = 0; r < qlen + tlen - 1; ++r) if (mmg_ksw_band_clips(g, r)) return -1;
+	if (!mmg_ksw_fast_ok(g)) return -1;
+	const int Wp = mmg_ksw_fast2_wp(qlen, tlen);
+	std::vector<KswSlot> S((size_t)Wp * stride);
+	memset(S.data(), 0x5a, S.size() * sizeof(KswSlot)); // garbage: a valid cell must never depend on an unwritten slot
+	std::vector<uint8_t> tb((size_t)tlen * stride, 9), qb((size_t)(qlen + 2) * stride, 9);
+	std::vector<uint32_t> p(mmg_ksw_fast2_p_bytes(qlen, tlen) / 4 + 4, 0xa5a5a5a5u);
+	for (int i = 0; i < tlen; ++i) tb[(size_t)i * stride] = target[i];
+	for (int i = 0; i < qlen; ++i) qb[(size_t)(i + 1) * stride] = query[i];
+	mmg_ksw_fast2(g, flag, zdrop, end_bonus, S.data(), tb.data(), qb.data(), stride, p.data(), ez_out, cigar);
 	return 0;
 }
 

@@ -38,6 +38,8 @@ def emu():
     E.emu_ksw.restype = C.c_int
     E.emu_ksw.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.POINTER(Ez), C.c_void_p]
     E.emu_ksw_fast.restype = C.c_int
+    E.emu_ksw_fast2.restype = C.c_int
+    E.emu_ksw_fast2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.POINTER(Ez), C.c_void_p]
     E.emu_ksw_fast.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.POINTER(Ez), C.c_void_p]
     return E
 
@@ -192,6 +194,48 @@ def emu_ksw_fast(E, q, t, mat, pen, w, zd, eb, fl, stride):
         return None
     return dict(max=ez.max, zdropped=ez.zdropped, max_q=ez.max_q, max_t=ez.max_t, mqe=ez.mqe, mqe_t=ez.mqe_t, mte=ez.mte,
                 mte_q=ez.mte_q, score=ez.score, reach_end=ez.reach_end, cigar=cig[:ez.n_cigar].tolist())
+
+
+def emu_ksw_fast2(E, q, t, mat, pen, w, zd, eb, fl, stride):
+    ez = Ez()
+    cig = np.zeros(len(q) + len(t) + 4, dtype=np.uint32)
+    q = np.ascontiguousarray(q, dtype=np.uint8); t = np.ascontiguousarray(t, dtype=np.uint8)
+    rc = E.emu_ksw_fast2(len(q), q.ctypes.data, len(t), t.ctypes.data, mat.ctypes.data, *pen, w, zd, eb, fl, stride, C.byref(ez), cig.ctypes.data)
+    if rc < 0:
+        return None
+    return dict(max=ez.max, zdropped=ez.zdropped, max_q=ez.max_q, max_t=ez.max_t, mqe=ez.mqe, mqe_t=ez.mqe_t, mte=ez.mte,
+                mte_q=ez.mte_q, score=ez.score, reach_end=ez.reach_end, cigar=cig[:ez.n_cigar].tolist())
+
+
+@pytest.mark.parametrize("preset", ["sr", "ont", "eq"])
+def test_ksw_fast_form_in_pairs(emu, preset):
+    """The thread-per-job form on 16x2 pairs (mmg_kswfast2.h: two cells per instruction, pairs aligned on the target coordinate, the
+    out-of-matrix half of the first / last pair computed and ignored) equals ksw_extd2 bit for bit: all flags, w = -1, odd and
+    even lengths, 1 x n and n x 1 jobs, N bases."""
+    from test_oracle_vs_ref import _ksw_cases
+    rng = np.random.default_rng(4242)
+    if preset == "sr":
+        mat, pen, bw, zd, eb = L.simple_mat(2, 8, 1), (12, 2, 24, 1), 151, 100, 10
+    elif preset == "ont":
+        mat, pen, bw, zd, eb = L.simple_mat(2, 4, 1), (4, 2, 24, 1), 751, 400, -1
+    else:
+        mat, pen, bw, zd, eb = L.simple_mat(1, 4, 1), (6, 1, 6, 1), 200, 200, 5
+    cases = list(_ksw_cases(rng, 240))
+    for ql, tl in [(1, 1), (1, 2), (2, 1), (1, 7), (7, 1), (2, 2), (3, 2), (2, 3), (5, 4), (4, 5), (16, 17), (17, 16), (33, 31)]:
+        cases.append((rng.integers(0, 5, ql, dtype=np.uint8), rng.integers(0, 5, tl, dtype=np.uint8)))
+    n_fast = 0
+    for q, t in cases:
+        for fl in [0xC2, 0x40, 0x08, 0x18, 0x00, 0x01, 0x02, 0x80, 0x4A]:
+            for w in [bw, -1]:
+                b = emu_ksw_fast2(emu, q, t, mat, pen, w, zd, eb if fl & 0x40 else -1, fl, 1 + (n_fast % 3))
+                if b is None:
+                    continue
+                a = L.orc_ksw(q, t, mat, *pen, w, zd, eb if fl & 0x40 else -1, fl)
+                if fl & 0x01:
+                    a["cigar"] = []
+                assert a == b, (len(q), len(t), fl, w)
+                n_fast += 1
+    assert n_fast > 1500
 
 
 @pytest.mark.parametrize("preset", ["sr", "ont"])
