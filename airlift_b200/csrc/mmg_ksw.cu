@@ -66,7 +66,8 @@ __device__ __forceinline__ int ksw_ncol(int qlen, int tlen, int w)
 struct KswFastClass { int32_t mc, tc, qc, nt; };
 struct KswFastTab { KswFastClass c[KSW_N_FAST]; };
 // per thread: the window of pair slots (mmg_kswfast2.h), the target bases, the query bases with a padding element at either end
-static inline size_t ksw_fast_smem(const KswFastClass &k) { return (size_t)k.nt * ((size_t)((k.mc >> 1) + 3) * 16 + (size_t)k.tc + (size_t)k.qc + 2); }
+// (the target bases are read from the packed reference when a cell enters: keeping them too cost a resident CTA per SM)
+static inline size_t ksw_fast_smem(const KswFastClass &k) { return (size_t)k.nt * ((size_t)((k.mc >> 1) + 3) * 16 + (size_t)k.qc + 2); }
 
 // wavefront form (k_ksw_wave below): geometry of its traceback rows and of its per-job arena
 #define KW_S 8
@@ -733,22 +734,15 @@ k_ksw_tpj(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ or
 	const int slot = blockIdx.x * NT + tid;
 	if (slot >= n_jobs) return;
 	KswSlot *st = reinterpret_cast<KswSlot*>(smem) + tid;
-	uint8_t *tb = smem + (size_t)((fc.mc >> 1) + 3) * NT * 16 + tid, *qb = tb + (size_t)fc.tc * NT + NT; // qb[-1] and qb[qlen] are padding
+	uint8_t *qb = smem + (size_t)((fc.mc >> 1) + 3) * NT * 16 + tid + NT; // qb[-1] and qb[qlen] are padding
 	const int ji = order[slot];
 	const mmg_ksw_job_t hj = jobs[ji];
 	const int qlen = hj.q_len, tlen = hj.t_len;
 	const KswGeom g = mmg_ksw_geom(qlen, tlen, sc.m, sc.mat, sc.q, sc.e, sc.q2, sc.e2, hj.w);
-	{ // target slice of S (mm_idx_getseq, index.c:152-162), reversed for left extensions (align.c:694-695)
-		const uint64_t a0 = ref_off[hj.rid] + (uint64_t)hj.t_start, a1 = a0 + (uint64_t)tlen;
-		for (uint64_t wa = a0 >> 3; wa <= (a1 - 1) >> 3; ++wa) {
-			const uint32_t word = S[wa];
-#pragma unroll
-			for (int k = 0; k < 8; ++k) {
-				const uint64_t a = wa * 8 + k;
-				if (a >= a0 && a < a1) { const int i = (int)(a - a0); tb[(size_t)(hj.reversed ? tlen - 1 - i : i) * NT] = (uint8_t)(word >> (4 * k) & 0xf); }
-			}
-		}
-	}
+	// target slice of S (mm_idx_getseq, index.c:152-162), reversed for left extensions (align.c:694-695): read base by base as cells enter
+	const uint64_t t_a0 = ref_off[hj.rid] + (uint64_t)hj.t_start;
+	const bool t_rev = hj.reversed != 0;
+	auto tbase = [&](int i) -> uint32_t { const uint64_t a = t_a0 + (uint64_t)(t_rev ? tlen - 1 - i : i); return __ldg(S + (a >> 3)) >> ((a & 7) << 2) & 0xf; };
 	{ // query slice of qseq0[q_rev] (align.c:865-870)
 		const uint64_t qbase = q_off[hj.seq_id];
 		const int rl = read_len[hj.seq_id];
@@ -769,7 +763,7 @@ k_ksw_tpj(const mmg_ksw_job_t *__restrict__ jobs, const int32_t *__restrict__ or
 	}
 	qb[-(ptrdiff_t)NT] = 4, qb[(size_t)qlen * NT] = 4;
 	KswEz ez;
-	mmg_ksw_fast2(g, hj.flag, hj.zdrop, hj.end_bonus, st, tb, qb - NT, NT, reinterpret_cast<uint32_t*>(gp + p_off[ji]), &ez, gcig + cig_off[ji]);
+	mmg_ksw_fast2(g, hj.flag, hj.zdrop, hj.end_bonus, st, tbase, qb - NT, NT, reinterpret_cast<uint32_t*>(gp + p_off[ji]), &ez, gcig + cig_off[ji]);
 	res[ji] = ez;
 }
 

@@ -50,10 +50,11 @@ MMG_HD int32_t mmg_ksw_fast2_pref(int k, int en1k)
 	return 2046 - rk;
 }
 
-// S: window of mmg_ksw_fast2_wp() slots, slot i of this job at S[i * stride]; tb[t * stride] target bases; qb[(j + 1) * stride]
+// S: window of mmg_ksw_fast2_wp() slots, slot i of this job at S[i * stride]; tb(t) = target base t (asked once per cell, when
+// it enters: the kernel reads it from the packed reference instead of keeping a copy in shared memory); qb[(j + 1) * stride]
 // query bases with one padding element before and after; p: rows of mmg_ksw_fast2_pw() bytes
-template <int kMode>
-MMG_HDN inline void mmg_ksw_fast2_run(const KswGeom &g, int flag, int zdrop, KswSlot *S, const uint8_t *tb, const uint8_t *qb, int stride,
+template <int kMode, class TB>
+MMG_HDN inline void mmg_ksw_fast2_run(const KswGeom &g, int flag, int zdrop, KswSlot *S, TB &&tb, const uint8_t *qb, int stride,
                                       uint32_t *p, KswEz &ez)
 {
 	const int qlen = g.qlen, tlen = g.tlen;
@@ -64,6 +65,7 @@ MMG_HDN inline void mmg_ksw_fast2_run(const KswGeom &g, int flag, int zdrop, Ksw
 	const uint8_t *qbp = qb + stride; // qbp[j * stride], j = -1 .. qlen
 	int P0 = 0, s0 = 0;               // first pair of the anti-diagonal and its window slot
 	int32_t Hst = 0, H0 = 0, last_H0_t = 0;
+	uint32_t tb_next = tb(0); // base of the cell that enters next: asked for one anti-diagonal ahead, so that a load from the packed reference is never waited for
 #define KF2_SLOT(P_) (S + (size_t)((s0 + ((P_) - P0)) >= Wp ? (s0 + ((P_) - P0)) - Wp : (s0 + ((P_) - P0))) * stride)
 #define KF2_U(t_) ((int32_t)(int8_t)(KF2_SLOT((t_) >> 1)->w0 >> (((t_) & 1) << 3)))
 #define KF2_V(t_) ((int32_t)(int8_t)(KF2_SLOT((t_) >> 1)->w0 >> (16 + (((t_) & 1) << 3))))
@@ -85,8 +87,9 @@ MMG_HDN inline void mmg_ksw_fast2_run(const KswGeom &g, int flag, int zdrop, Ksw
 			o.w0 = (o.w0 & ~m8) | ((uint32_t)(fc & 0xff) << sh);                         // u
 			o.w1 = (o.w1 & ~m8h) | ((uint32_t)(n1 & 0xff) << (16 + sh));                 // y
 			o.w2 = (o.w2 & ~m8h) | ((uint32_t)(n2 & 0xff) << (16 + sh));                 // y2
-			o.w3 = (o.w3 & ~m8) | ((uint32_t)tb[(size_t)r * stride] << sh);
+			o.w3 = (o.w3 & ~m8) | (tb_next << sh);
 			mmg_ksw_slot_st(sp, o);
+			if (r + 1 < tlen) tb_next = tb(r + 1);
 		}
 		const int np = (en0 >> 1) - P0 + 1;
 		const int en1k = (n - 1) / 4 * 4;
@@ -191,7 +194,8 @@ MMG_HDN inline int mmg_ksw_backtrack_fast2(const KswGeom &g, int is_rev, const u
 	return n;
 }
 
-MMG_HDN inline void mmg_ksw_fast2(const KswGeom &g, int flag, int zdrop, int end_bonus, KswSlot *S, const uint8_t *tb, const uint8_t *qb, int stride,
+template <class TB>
+MMG_HDN inline void mmg_ksw_fast2(const KswGeom &g, int flag, int zdrop, int end_bonus, KswSlot *S, TB &&tb, const uint8_t *qb, int stride,
                                   uint32_t *p, KswEz *ez_out, uint32_t *cigar)
 {
 	KswEz ez;

@@ -237,7 +237,7 @@ int emu_ksw_fast2(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 	std::vector<uint32_t> p(mmg_ksw_fast2_p_bytes(qlen, tlen) / 4 + 4, 0xa5a5a5a5u);
 	for (int i = 0; i < tlen; ++i) tb[(size_t)i * stride] = target[i];
 	for (int i = 0; i < qlen; ++i) qb[(size_t)(i + 1) * stride] = query[i];
-	mmg_ksw_fast2(g, flag, zdrop, end_bonus, S.data(), tb.data(), qb.data(), stride, p.data(), ez_out, cigar);
+	mmg_ksw_fast2(g, flag, zdrop, end_bonus, S.data(), [&](int t) { return tb[(size_t)t * stride]; }, qb.data(), stride, p.data(), ez_out, cigar);
 	return 0;
 }
 
