@@ -240,22 +240,31 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cli_mapping_phase(cmd, out_path=None):
-    """Run a minimap2-style CLI; return seconds between `loaded/built the index` and `Real time`."""
+def cli_mapping_phase(cmd, out_path=None, detail=None):
+    """Run a minimap2-style CLI; return seconds between `loaded/built the index` and `Real time`.
+    detail (a dict) receives `steady`: reads/s between the second and the last `mapped N sequences` line of the CLI's own log,
+    i.e. without the start-up of the first two mini-batches (buffer growth, pipeline fill)."""
     out = open(out_path, "wb") if out_path else subprocess.DEVNULL
     p = subprocess.run(cmd, stdout=out, stderr=subprocess.PIPE, text=True)
     if out_path:
         out.close()
     t_idx = t_end = None
+    done = []
     for line in p.stderr.splitlines():
         m = re.match(r"\[M::main::([0-9.]+)\*", line)
         if m and "loaded/built the index" in line:
             t_idx = float(m.group(1))
+        m = re.match(r"\[M::worker_pipeline::([0-9.]+)\*[0-9.]+\] mapped (\d+) sequences", line)
+        if m:
+            done.append((float(m.group(1)), int(m.group(2))))
         m = re.search(r"Real time: ([0-9.]+) sec", line)
         if m:
             t_end = float(m.group(1))
     if p.returncode != 0 or t_idx is None or t_end is None:
         raise RuntimeError("CLI run failed: " + p.stderr[-400:])
+    if detail is not None and len(done) >= 4 and done[-1][0] > done[1][0]:
+        detail["steady"] = sum(n for _, n in done[2:]) / (done[-1][0] - done[1][0])
+        detail["steady_sample"] = f"mini-batches 3..{len(done)} by the CLI's own log timestamps"
     return t_end - t_idx
 
 
@@ -289,9 +298,10 @@ def run_reference(args, wl, d):
     cli = None
     if not args.no_cli:
         try:
-            t = cli_mapping_phase([REF_BIN, "-ax", wl.preset, "-t", str(cores), "-K", str(wl.bases_per_step), mmi] + files)
+            det = {}
+            t = cli_mapping_phase([REF_BIN, "-ax", wl.preset, "-t", str(cores), "-K", str(wl.bases_per_step), mmi] + files, detail=det)
             cli = {"value": sum(r["reads"]) / t, "unit": "reads/s", "sample": f"{sum(r['reads'])} reads in {n_steps} mini-batches, minimap2_B -ax {wl.preset} -t {cores} -K {wl.bases_per_step}, "
-                   "mapping phase (index loaded) incl. FASTQ parsing and SAM output"}
+                   "mapping phase (index loaded) incl. FASTQ parsing and SAM output", "steady_state": det.get("steady"), "steady_state_sample": det.get("steady_sample")}
         except Exception as e:  # noqa
             cli = {"value": None, "unit": "reads/s", "sample": f"failed: {e}"}
     sample = (f"{args.steps} timed mini-batches of {wl.units} {'pairs' if wl.kind == 'sr' else 'reads'} after {args.warmup} warm-up ones, the reference's own step 1 "
@@ -373,8 +383,9 @@ def main():
         n_units = wl.units * 8
         cf = make_reads(d, wl, prefix, n_units, 45, f"{wl.kind}_{wl.G}_cli_{n_units}")
         try:
-            t = cli_mapping_phase([CLI_BIN, "-ax", wl.preset, "-t", str(cores), "-K", str(wl.bases_per_step), prefix + ".new.fa"] + cf)
-            cli_result = {"value": wl.reads_per_unit * n_units / t, "unit": "reads/s",
+            det = {}
+            t = cli_mapping_phase([CLI_BIN, "-ax", wl.preset, "-t", str(cores), "-K", str(wl.bases_per_step), prefix + ".new.fa"] + cf, detail=det)
+            cli_result = {"value": wl.reads_per_unit * n_units / t, "unit": "reads/s", "steady_state": det.get("steady"), "steady_state_sample": det.get("steady_sample"),
                           "sample": f"{n_units} {'pairs' if wl.kind == 'sr' else 'reads'} in 8 mini-batches, build/minimap2-b200 -ax {wl.preset} -t {cores} -K {wl.bases_per_step}, "
                                     "mapping phase (after the index is built) incl. FASTQ parsing, first-batch buffer growth and SAM output"}
         except Exception as e:  # noqa
