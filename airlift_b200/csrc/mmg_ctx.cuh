@@ -1,5 +1,6 @@
 // mmg_ctx.cuh -- internal: context, growable device / pinned buffers, error plumbing.
 #pragma once
+#include <time.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -17,17 +18,21 @@ void mmg_set_error(const char *fmt, ...);
 
 // how often a device / pinned buffer had to be re-allocated (each time costs a device-wide synchronisation): [0] device, [1] pinned
 extern unsigned long long g_mmg_grow[2];
+extern unsigned long long g_mmg_grow_ns[2]; // wall time spent in those re-allocations (MM2_B200_TRACE reports it when a context is destroyed)
+static inline unsigned long long mmg_now_ns() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (unsigned long long)ts.tv_sec * 1000000000ULL + (unsigned long long)ts.tv_nsec; }
 
 struct DevBuf {
 	void *p = nullptr; size_t cap = 0;
 	int ensure(size_t bytes) {
 		if (bytes <= cap) return MMG_OK;
+		const unsigned long long t0 = mmg_now_ns();
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
 		__atomic_fetch_add(&g_mmg_grow[0], 1ULL, __ATOMIC_RELAXED);
 		size_t want = bytes + bytes / 2 + 256; // generous: a re-allocation in the middle of a run costs a device synchronisation
 		cudaError_t e = cudaMalloc(&p, want);
 		if (e != cudaSuccess) { cudaGetLastError(); want = bytes + 256; e = cudaMalloc(&p, want); } // HBM is short: take what is needed, no headroom
+		__atomic_fetch_add(&g_mmg_grow_ns[0], mmg_now_ns() - t0, __ATOMIC_RELAXED);
 		if (e != cudaSuccess) { mmg_set_error("cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); p = nullptr; return MMG_ENOMEM; }
 		cap = want;
 		return MMG_OK;
@@ -52,11 +57,13 @@ struct PinBuf {
 	void *p = nullptr; size_t cap = 0;
 	int ensure(size_t bytes) {
 		if (bytes <= cap) return MMG_OK;
+		const unsigned long long t0 = mmg_now_ns();
 		if (p) cudaFreeHost(p);
 		p = nullptr; cap = 0;
 		__atomic_fetch_add(&g_mmg_grow[1], 1ULL, __ATOMIC_RELAXED);
 		size_t want = bytes + bytes / 2 + 256; // page-locking hundreds of MB again takes ~0.1 s
 		cudaError_t e = cudaMallocHost(&p, want);
+		__atomic_fetch_add(&g_mmg_grow_ns[1], mmg_now_ns() - t0, __ATOMIC_RELAXED);
 		if (e != cudaSuccess) { mmg_set_error("cudaMallocHost(%zu): %s", want, cudaGetErrorString(e)); p = nullptr; return MMG_ENOMEM; }
 		cap = want;
 		return MMG_OK;
