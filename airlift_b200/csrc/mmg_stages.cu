@@ -819,11 +819,15 @@ __device__ __forceinline__ uint8_t chain_wants_rechain(bool candidate, int n_u, 
 	return n_chained < segs ? 1 : 0;
 }
 
-// fragments of the first pass with more anchors than one warp should walk
-__global__ void k_tail_heavy_list(int n_list, const int32_t *__restrict__ na, int heavy_n, int32_t *__restrict__ heavy, int32_t *__restrict__ n_heavy)
+// the fragments the CTA form of the tail takes (more than heavy_n anchors): counted here; listed by the descending sort of
+// (anchors, slot) that follows, so that the CTAs, which pull their work from a counter, start with the largest fragments
+__global__ void k_tail_heavy_list(int n_list, const int32_t *__restrict__ na, int heavy_n, uint32_t *__restrict__ key, int32_t *__restrict__ val, int32_t *__restrict__ n_heavy)
 {
 	const int li = blockIdx.x * blockDim.x + threadIdx.x;
-	if (li < n_list && na[li] > heavy_n) heavy[atomicAdd(n_heavy, 1)] = li;
+	if (li >= n_list) return;
+	const int n = na[li];
+	key[li] = (uint32_t)(n > 0 ? n : 0), val[li] = li;
+	if (n > heavy_n) atomicAdd(n_heavy, 1);
 }
 
 // K3 tail, one warp per fragment: chain ends and peaks, ranking by peak score, backtracking, output order
@@ -1030,16 +1034,20 @@ __global__ void __launch_bounds__(1024)
 k_chain_tail_block(FragTab ft, const int32_t *__restrict__ list, int n_list, const int32_t *__restrict__ n_seg, ChainOptDev co,
                    const int64_t *__restrict__ aoff, const int32_t *__restrict__ na, mm128 *__restrict__ a, int32_t *__restrict__ work,
                    uint64_t *__restrict__ u, mm128 *__restrict__ bb, RsFrame *__restrict__ stack, int32_t *__restrict__ nu_out,
-                   int32_t *__restrict__ nv_out, const int32_t *__restrict__ heavy /* null: every fragment of the list */,
-                   const int32_t *__restrict__ n_heavy, size_t smem_cap, const int32_t *__restrict__ rep, int rechain_enabled,
-                   uint8_t *__restrict__ flag_out /* first pass only */)
+                   int32_t *__restrict__ nv_out, const int32_t *__restrict__ heavy /* slots by descending anchor count */,
+                   int32_t *__restrict__ n_heavy /* [0] how many of them this kernel takes, [1] the next one to hand out */, size_t smem_cap,
+                   const int32_t *__restrict__ rep, int rechain_enabled, uint8_t *__restrict__ flag_out /* first pass only */)
 {
-	__shared__ int s_scan[1024], s_nu, s_tie;
+	__shared__ int s_scan[1024], s_nu, s_tie, s_it;
 	extern __shared__ __align__(16) unsigned char dyn_tail[];
 	const int tid = threadIdx.x, NT = blockDim.x;
-	const int n_items = heavy ? *n_heavy : n_list;
-	for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-	const int li = heavy ? heavy[it] : it;
+	const int n_items = n_heavy[0];
+	for (;;) { // largest fragments first, whichever CTA is free takes the next one
+	if (tid == 0) s_it = atomicAdd(n_heavy + 1, 1);
+	__syncthreads();
+	const int it = s_it;
+	if (it >= n_items) break;
+	const int li = heavy[it];
 	const int f = list ? list[li] : li;
 	const int64_t ao = aoff[li];
 	const int n = na[li], segs = n_seg[f];
@@ -1667,22 +1675,34 @@ static int run_pass(mmg_ctx_t *c, const mmg_idx_t *mi, const mmg_mapopt_t *opt, 
 			attr_set = true;
 		}
 	}
-	if (d_flag == nullptr) // the re-chain pass: few, very large fragments -> one CTA each
-		MMG_LAUNCH(c, k_chain_tail_block, n_list, 1024, TAIL_BLOCK_SMEM, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
-		           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
-		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), nullptr, nullptr, (size_t)TAIL_BLOCK_SMEM, nullptr, 0, nullptr);
-	else {
-		// first pass: the fragments with thousands of anchors (a few per thousand) get a CTA each, with its sorts staged in shared memory,
-		// ahead of the warp kernel that takes everything else
-		static const int heavy_n = getenv("MMG_TAIL_HEAVY_N") ? atoi(getenv("MMG_TAIL_HEAVY_N")) : TAIL_HEAVY_N;
-		const int rechain_enabled = opt->max_occ > opt->mid_occ ? 1 : 0;
-		MMG_TRY(c->d_heavy.ensure(((size_t)n_list + 4) * 4));
-		int32_t *n_heavy = c->d_heavy.as<int32_t>(), *heavy = n_heavy + 4;
+	{
+		// The fragments with thousands of anchors get a CTA each, with its sorts staged in shared memory: all fragments of the re-chain
+		// pass (one CTA per SM, the whole shared memory), a few per thousand of the first pass (ahead of the warp kernel that takes
+		// everything else).  The CTAs pull fragments from a counter, largest first.
+		static const int heavy_env = getenv("MMG_TAIL_HEAVY_N") ? atoi(getenv("MMG_TAIL_HEAVY_N")) : TAIL_HEAVY_N;
+		const bool second = d_flag == nullptr;
+		const int heavy_n = second ? -1 : heavy_env, rechain_enabled = opt->max_occ > opt->mid_occ ? 1 : 0;
+		MMG_TRY(c->d_heavy.ensure(((size_t)n_list * 4 + 16) * 4));
+		int32_t *n_heavy = c->d_heavy.as<int32_t>(), *val0 = n_heavy + 4, *heavy = val0 + n_list;
+		uint32_t *key0 = reinterpret_cast<uint32_t*>(heavy + n_list), *key1 = key0 + n_list;
 		MMG_CUDA(cudaMemsetAsync(n_heavy, 0, 16, c->stream));
-		MMG_LAUNCH(c, k_tail_heavy_list, mmg_blocks(n_list, 256), 256, 0, n_list, pb.na->as<int32_t>(), heavy_n, heavy, n_heavy);
-		MMG_LAUNCH(c, k_chain_tail_block, 148 * 3, 512, TAIL_HEAVY_SMEM, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
-		           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
-		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), heavy, n_heavy, (size_t)TAIL_HEAVY_SMEM, pb.rep->as<int32_t>(), rechain_enabled, d_flag);
+		MMG_LAUNCH(c, k_tail_heavy_list, mmg_blocks(n_list, 256), 256, 0, n_list, pb.na->as<int32_t>(), heavy_n, key0, val0, n_heavy);
+		{
+			size_t tmp = 0;
+			cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, key0, key1, val0, heavy, n_list, 0, 32, c->stream);
+			MMG_TRY(c->d_cub.ensure(tmp));
+			MMG_CUDA(cub::DeviceRadixSort::SortPairsDescending(c->d_cub.p, tmp, key0, key1, val0, heavy, n_list, 0, 32, c->stream));
+			++c->launches;
+		}
+		if (second)
+			MMG_LAUNCH(c, k_chain_tail_block, n_list < 148 ? n_list : 148, 1024, TAIL_BLOCK_SMEM, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+			           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
+			           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), heavy, n_heavy, (size_t)TAIL_BLOCK_SMEM, nullptr, 0, nullptr);
+		else
+			MMG_LAUNCH(c, k_chain_tail_block, 148 * 3, 512, TAIL_HEAVY_SMEM, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
+			           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
+			           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), heavy, n_heavy, (size_t)TAIL_HEAVY_SMEM, pb.rep->as<int32_t>(), rechain_enabled, d_flag);
+		if (!second)
 		MMG_LAUNCH(c, k_chain_tail_warp, mmg_blocks((size_t)n_list * 32, 128), 128, 0, ft, d_list, n_list, c->d_misc.as<int32_t>(), co, pb.aoff->as<int64_t>(),
 		           pb.na->as<int32_t>(), pb.a->as<mm128>(), pb.work->as<int32_t>(), pb.u->as<uint64_t>(), pb.b->as<mm128>(), pb.stack->as<RsFrame>(),
 		           pb.nu->as<int32_t>(), pb.nv->as<int32_t>(), pb.rep->as<int32_t>(), rechain_enabled, d_flag, heavy_n);
