@@ -276,7 +276,7 @@ int main(int argc, char *argv[])
 	if (mm_b200_check_opt(&opt) < 0) return 1; /* splice, --no-pairing, -D/-X/--dual=no, -T, --split-prefix: refused, not ignored */
 	/* two shards per GPU: the host stages (or, for the short-read presets whose bookkeeping runs on the GPU, the upload and
 	 * the latency-bound kernel tails) of one overlap the kernels of the other */
-	mm_b200_set_lanes(2);
+	mm_b200_set_lanes(4); /* two lane groups of two streams: two mini-batches in flight on the device path (mm_map_file_frag) */
 	if (getenv("MM2_B200_LANES")) mm_b200_set_lanes(atoi(getenv("MM2_B200_LANES")));
 	if (mm_b200_set_devices(n_gpus, 0) < 0) { fprintf(stderr, "[ERROR] --gpus must be within 1 and 16\n"); return 1; }
 	idx_rdr = mm_idx_reader_open(argv[optind], &ipt, fnw);

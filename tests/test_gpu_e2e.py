@@ -58,6 +58,19 @@ def test_cli_identical_to_reference(data, args):
         assert a == b, f"line {i}:\nref: {a[:300]}\nnew: {b[:300]}"
 
 
+def test_two_mappers_from_the_first_batch(data):
+    """The file driver lets its second mapper (second lane group, two mini-batches in flight) join after 16 mini-batches;
+    MM2_B200_WARM_BATCHES=0 makes it join at once, so that a small input crosses the ordered hand-off many times."""
+    args = ["-ax", "sr", "-t", "6", "-K", "1M", "ref.fa", "r1.fq", "r2.fq"]
+    want = _run(L.REF_BIN_B, args, data)
+    env = dict(os.environ, MM2_B200_WARM_BATCHES="0")
+    p = subprocess.run([NEW] + args, cwd=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert p.returncode == 0, p.stderr.decode()[-800:]
+    got = [l for l in p.stdout.decode().split("\n") if not l.startswith("@PG")]
+    assert got == want
+    assert p.stderr.decode().count("mapped ") >= 8  # really many mini-batches
+
+
 def test_device_post_path_equals_host_build(data):
     """The post-chaining stages compiled for the GPU (csrc/mmg_post.cu) and the host build of the same sources
     (MM2_B200_HOSTPATH=1) must print the same bytes; both are already compared with the reference above."""
