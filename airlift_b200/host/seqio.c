@@ -192,7 +192,7 @@ static void make_bseq(mm_bseq1_t *s, int packed, const char *name, int l_name, c
 		if (qual) { s->qual = (char*)malloc((size_t)l_qual + 1); memcpy(s->qual, qual, l_qual); s->qual[l_qual] = 0; }
 		if (comment) { s->comment = (char*)malloc((size_t)l_comment + 1); memcpy(s->comment, comment, l_comment); s->comment[l_comment] = 0; }
 	}
-	fix_u(s->seq, l_seq);
+	if (memchr(s->seq, 'U', l_seq) || memchr(s->seq, 'u', l_seq)) fix_u(s->seq, l_seq); /* two vector scans instead of a byte loop over every read */
 	s->l_seq = l_seq;
 	s->rid = 0;
 }
@@ -222,7 +222,9 @@ static int fastq_fast_path(mm_bseq_file_t *fp, mm_bseq1_t *out, int with_qual, i
 	if (p1[-1] == '\r' || p2[-1] == '\r' || p4[-1] == '\r') return 0;
 	if (p4 + 1 < e && p4[1] != '@') return 0;                 /* not followed by a record start: leave it to the general parser */
 	if (p4 + 1 >= e && !st->eof) return 0;                     /* cannot see what follows */
-	if (memchr(p1 + 1, '>', l_seq) || memchr(p1 + 1, '@', l_seq) || memchr(p1 + 1, '+', l_seq)) return 0;
+	/* kseq looks at the first character of a sequence line only (kseq.h:186: `while ((c = ks_getc(ks)) >= 0 && c != '>' && c != '+'
+	 * && c != '@')`, the rest of the line goes through ks_getuntil2); l_seq > 0, so p1[1] is that character */
+	if (p1[1] == '>' || p1[1] == '@' || p1[1] == '+') return 0;
 	for (ws = p0 + 1; ws < p1; ++ws) if (isspace(*ws)) break; /* name ends at the first white space; the rest of the line is the comment */
 	l_name = (int)(ws - (p0 + 1));
 	make_bseq(out, fp->packed, (const char*)p0 + 1, l_name, (const char*)p1 + 1, l_seq, with_qual ? (const char*)p3 + 1 : 0, l_seq,
