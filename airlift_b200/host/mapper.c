@@ -340,7 +340,8 @@ static void *shard_upload(void *data)
 
 
 /* ---- device path (short-read presets): hits, per-mate split, alignment walk and CIGAR post-processing run on the GPU
- * (csrc/mmg_post.cu compiles hits.c / aln.c for the device); the host computes the name hash before and MAPQ / pairing after */
+ * (csrc/mmg_post.cu: designed device stages over flat arrays, mmg_hits.h / mmg_aln.h / mmg_post.h, MAPQ and pairing included); the
+ * host computes the name hash before and unpacks the result blob into malloc'd API objects after */
 
 static void stage_dev_hash(void *data, long i, int tid)
 {
